@@ -1,0 +1,170 @@
+// common.cuh — shared host/device helpers for libmixvae_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mixvae_b200.h"
+
+namespace mvae {
+
+constexpr int kMaxH = 128;   // fc_dim
+constexpr int kMaxL = 32;    // lowD_dim
+constexpr int kMaxC = 128;   // n_categories
+constexpr int kMaxS = 8;     // state_dim
+constexpr int kMaxW = 128;   // max width of any narrow layer
+constexpr int kMaxPairs = MVAE_MAX_ARMS * (MVAE_MAX_ARMS - 1) / 2;
+constexpr int kRowWarps = 8;       // warps per CTA in the row-wise kernels
+constexpr int kRowsPerWarp = 4;    // rows a warp processes at once
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern int64_t g_launches;
+
+#define MVAE_CHECK_ARG(cond, ...)                \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::mvae::set_error(__VA_ARGS__);            \
+      return -1;                                 \
+    }                                            \
+  } while (0)
+
+#define MVAE_CUDA(expr)                                                                  \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::mvae::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                       \
+      return (int)_e;                                                                    \
+    }                                                                                    \
+  } while (0)
+
+#define MVAE_LAUNCH_CHECK()                                                              \
+  do {                                                                                   \
+    ::mvae::g_launches++;                                                                \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      ::mvae::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),      \
+                        __FILE__, __LINE__);                                             \
+      return (int)_e;                                                                    \
+    }                                                                                    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// parameter tensor indices (per arm) — order of the reference's ModuleLists, nn_model.py:184-208
+// ---------------------------------------------------------------------------------------------
+enum ParamId {
+  FC1_W = 0, FC1_B, FC2_W, FC2_B, FC3_W, FC3_B, FC4_W, FC4_B, FC5_W, FC5_B,
+  FCC_W, FCC_B, FCMU_W, FCMU_B, FCSIG_W, FCSIG_B, FC6_W, FC6_B, FC7_W, FC7_B,
+  FC8_W, FC8_B, FC9_W, FC9_B, FC10_W, FC10_B, FC11_W, FC11_B
+};
+
+// ---------------------------------------------------------------------------------------------
+// workspace map (offsets in floats from st->work).  Everything that is per arm is laid out
+// [A_local][...]; `acc` is the fp64 accumulator block that is zeroed by memset nodes.
+// ---------------------------------------------------------------------------------------------
+struct Work {
+  // forward activations kept for backward
+  int64_t a[5];        // a1..a4 [A][B][H], a5 [A][B][L]   post-ReLU, pre-BN
+  int64_t bn_mean;     // [5][A][128]  batch mean   (training) or running mean (eval)
+  int64_t bn_rstd;     // [5][A][128]
+  int64_t ysoft;       // [A][B][C]  soft Gumbel sample (== c_smp unless hard)
+  int64_t svar;        // [A][B][S]  sigma^2
+  int64_t yy;          // [A][B][L+C]  state-head input  [x_low | c_smp]
+  int64_t zc;          // [A][B][C+S]  decoder input     [c_smp | dropout(s)]
+  int64_t d[5];        // d6 [A][B][L], d7..d10 [A][B][H]
+  // backward
+  int64_t g_d10;       // [A][B][H]  dLoss/d h10 (post-ReLU), written by the fc11 kernels
+  int64_t gtmp[2];     // [A][B][H]  ping-pong gradient wrt layer inputs
+  int64_t delta_dec[5];// delta6 [A][B][L], delta7..10 [A][B][H]  (pre-activation grads)
+  int64_t delta_mu, delta_sig;  // [A][B][S]
+  int64_t delta_z;     // [A][B][C]
+  int64_t g_xlow;      // [A][B][L]
+  int64_t delta_enc[5];// delta1..4 [A][B][H], delta5 [A][B][L]
+  int64_t delta1_t;    // [A][Hpad128][Bpad]  delta1 transposed (tensor-core fc1 dW operand)
+  int64_t d10_t;       // [A][Hpad128][Bpad]  h10 transposed     (tensor-core fc11 dW operand)
+  int64_t w11_t;       // [A][Hpad128][Dpad]  fc11.weight transposed (tensor-core d h10 operand)
+  int64_t rsum;        // [B][C]  sum over ALL arms of r = log(q+eps)*w
+  int64_t colc;        // [A][4][128]  per category: w, cvar, mean, T   (coupling-gradient constants)
+  int64_t wcat;        // [At][128]    w of every arm of the model
+  int64_t fc1_part;    // [splitk][A][B][Hpad] split-K partials of fc1 (tensor-core path)
+  int64_t big;         // [A][B][D]  materialised x_hat / dY, SIMT path only (else -1)
+  int64_t wg_part;     // [nsplit][A][wg_floats]  weight-gradient partials of the narrow layers
+  // fp64 accumulators (offsets still in floats; 8-byte aligned)
+  int64_t acc_fwd, acc_fwd_floats;   // bn_sum[5][A][2][128], (unused q block), kl_sum[A][16]
+  int64_t acc_loss, acc_loss_floats; // see accl_* below
+  int64_t acc_bwd, acc_bwd_floats;   // bnb_sum[5][A][2][128]
+  int64_t total;
+  int32_t Bpad, Dpad, Hpad, wg_nsplit, wg_rows, fc1_splitk;
+  int64_t wg_floats;   // narrow-layer params per arm (contiguous range FC2_W .. FC10_B), see wgrad
+};
+
+// sub-offsets inside the fp64 accumulator blocks, in doubles
+__host__ __device__ inline int64_t acc_bn(int layer, int A, int a) { return ((int64_t)(layer * A + a)) * 2 * 128; }
+__host__ __device__ inline int64_t acc_q(int A, int a) { return (int64_t)5 * A * 256 + (int64_t)a * 256; }
+__host__ __device__ inline int64_t acc_kl(int A, int a) { return (int64_t)6 * A * 256 + (int64_t)a * 16; }
+__host__ __device__ inline int64_t acc_fwd_doubles(int A) { return (int64_t)6 * A * 256 + (int64_t)A * 16; }
+// acc_loss block (doubles, fixed capacity MVAE_MAX_ARMS): recon[16][2] | ent[16] | pair[120][2] | T[16][128] | qs[16][2][128]
+__host__ __device__ inline int64_t accl_recon(int a) { return (int64_t)a * 2; }
+__host__ __device__ inline int64_t accl_ent(int a) { return 32 + (int64_t)a; }
+__host__ __device__ inline int64_t accl_pair(int p) { return 48 + (int64_t)p * 2; }
+__host__ __device__ inline int64_t accl_T(int a) { return 48 + kMaxPairs * 2 + (int64_t)a * 128; }
+__host__ __device__ inline int64_t accl_qs(int a) { return 48 + kMaxPairs * 2 + 16 * 128 + (int64_t)a * 256; }
+__host__ __device__ inline int64_t acc_loss_doubles() { return 48 + kMaxPairs * 2 + 16 * 128 + 16 * 256; }
+__host__ __device__ inline int64_t accb_bn(int layer, int A, int a) { return ((int64_t)(layer * A + a)) * 2 * 128; }
+__host__ __device__ inline int64_t acc_bwd_doubles(int A) { return (int64_t)5 * A * 256; }
+
+int compute_layout(const mvae_dims& d, mvae_layout* L);
+Work make_work(const mvae_dims& d);
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Counter-based dropout generator: 16 random bits per element from a 32-bit mix of
+// (seed, element pair index).  keep <=> bits >= thresh16, thresh16 = round(p * 65536).
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ bool drop_keep(uint64_t seed, int arm, int64_t row, int64_t col, int64_t D,
+                                          uint32_t thresh16) {
+  uint64_t idx = (uint64_t)row * (uint64_t)D + (uint64_t)col;
+  uint64_t pair = idx >> 1;
+  uint32_t h = mix32((uint32_t)pair * 0x9E3779B1u ^ (uint32_t)(pair >> 32) * 0x7FEB352Du ^
+                     (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x846CA68Bu) ^ ((uint32_t)arm * 0x632BE5ABu));
+  uint32_t bits = (idx & 1) ? (h >> 16) : (h & 0xffffu);
+  return bits >= thresh16;
+}
+#endif
+
+struct DropSpec {
+  const uint8_t* keep;  // injected mask [B][D] for this launch's arm 0, or nullptr
+  int64_t keep_arm_stride;
+  uint64_t seed;        // used when keep == nullptr && mode == 2
+  float scale;          // 1/(1-p)
+  uint32_t thresh16;
+  int mode;             // 0: no dropout, 1: injected mask, 2: in-kernel generator
+  int64_t D;            // genes per row (hash index)
+};
+
+}  // namespace mvae

@@ -1,0 +1,24 @@
+// gemm_tc.h — tcgen05/TMA kernels for the gene-dimension GEMMs (fc1 forward, fc11 fused
+// forward+loss+backward, fc1 weight gradient).
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mvae {
+
+// true when the tensor-core kernels can run this shape (TMA needs 16-byte aligned row pitches)
+bool gemm_tc_supported(int B, int D, int H);
+
+// fc1 partial products into work.fc1_part; fills the split-K description of `epi`.
+int tc_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
+                   const DropSpec& drop, const Work& w, cudaStream_t s, Fc1EpiArgs* epi);
+
+// fc11 GEMM fused with the reconstruction loss and (want_grad) d fc11.weight / d fc11.bias / d h10.
+int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
+                      const Work& w, float gscale, int want_grad, cudaStream_t s);
+
+// d fc1.weight = delta1^T * dropout(x)
+int tc_fc1_wgrad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
+                 const DropSpec& drop, const Work& w, cudaStream_t s);
+
+}  // namespace mvae

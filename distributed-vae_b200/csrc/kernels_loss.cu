@@ -1,0 +1,311 @@
+// kernels_loss.cu — coupling / entropy terms of mixVAE_model.loss, loss finalisation, and the
+// element-wise reconstruction loss used when the reconstruction is materialised.
+//
+// Reference: mmidas/nn_model.py:39-86 (helpers), :539-598 (loss).  All batch reductions are fp64
+// atomics into a block that mvae_loss zeroes first.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mvae {
+
+constexpr int KC = 4;
+
+// ---------------------------------------------------------------------------------------------
+// column sums of q(c|x) of every arm: sum_b q, sum_b q^2  -> inv_var (nn_model.py:75-77)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) qstats_kernel(const CouplingArgs p) {
+  const int arm = blockIdx.y;  // global arm index
+  const int k = threadIdx.x;
+  if (k >= p.C) return;
+  const float* q = p.qc_all + (int64_t)arm * p.B * p.C;
+  const int rows_per = (p.B + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per, r1 = min(p.B, r0 + rows_per);
+  double s1 = 0.0, s2 = 0.0;
+  for (int r = r0; r < r1; ++r) {
+    const double v = (double)q[(int64_t)r * p.C + k];
+    s1 += v;
+    s2 += v * v;
+  }
+  if (r1 > r0) {
+    atomicAdd(p.acc + accl_qs(arm) + k, s1);
+    atomicAdd(p.acc + accl_qs(arm) + 128 + k, s2);
+  }
+}
+
+int launch_qstats(const CouplingArgs& a, cudaStream_t s) {
+  int gx = (a.B + 31) / 32;
+  if (gx > 148) gx = 148;
+  qstats_kernel<<<dim3(gx, a.At), 128, 0, s>>>(a);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per cell: r_a = log(q_a+eps)*w_a, pairwise ||r_a-r_b||^2 and ||c_a-c_b||^2, per-arm entropy,
+// R = sum_a r_a, and for the local arms T_a[k] = sum_b G_a[b,k]*log(q_a[b,k]+eps),
+// G_a = (2 lam / B) (A r_a - R)   (gradient of the distance through inv_var)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const CouplingArgs p) {
+  __shared__ float w[MVAE_MAX_ARMS][128];
+  __shared__ double sT[MVAE_MAX_ARMS][128];
+  __shared__ double sPair[kMaxPairs][2];
+  __shared__ double sEnt[MVAE_MAX_ARMS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int At = p.At, B = p.B, C = p.C;
+  for (int idx = tid; idx < At * 128; idx += blockDim.x) {
+    const int a = idx >> 7, k = idx & 127;
+    float wv = 0.f;
+    if (k < C) {
+      const double s1 = p.acc[accl_qs(a) + k], s2 = p.acc[accl_qs(a) + 128 + k];
+      const double mean = s1 / (double)B;
+      double var = (s2 - s1 * mean) / (double)(B - 1);      // unbiased, torch.var default
+      if (var < 0.0) var = 0.0;
+      wv = (float)sqrt(1.0 / (var + (double)p.eps));
+      if (blockIdx.x == 0) p.wcat[a * 128 + k] = wv;
+    }
+    w[a][k] = wv;
+    if (a < p.A) sT[a][k] = 0.0;
+  }
+  for (int idx = tid; idx < kMaxPairs * 2; idx += blockDim.x) (&sPair[0][0])[idx] = 0.0;
+  if (tid < MVAE_MAX_ARMS) sEnt[tid] = 0.0;
+  __syncthreads();
+
+  const float gcoef = 2.f * p.lam / (float)B;
+  for (int row = blockIdx.x * kRowWarps + warp; row < B; row += gridDim.x * kRowWarps) {
+    float rs[KC] = {0.f, 0.f, 0.f, 0.f};
+    // pass 1: R = sum_a r_a ; entropy per arm
+    for (int a = 0; a < At; ++a) {
+      const float* q = p.qc_all + ((int64_t)a * B + row) * C;
+      float ent = 0.f;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int kk = lane + 32 * k;
+        if (kk < C) {
+          const float qv = q[kk];
+          const float lq = logf(qv + p.eps);
+          rs[k] += lq * w[a][kk];
+          ent = fmaf(qv, lq, ent);
+        }
+      }
+      ent = warp_sum(ent);
+      if (lane == 0) atomicAdd(&sEnt[a], (double)ent);
+    }
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int kk = lane + 32 * k;
+      if (kk < C) p.rsum[(int64_t)row * C + kk] = rs[k];
+    }
+    // pass 2: pairs and T (q rows are L1/L2 resident)
+    int pair = 0;
+    for (int a = 0; a < At; ++a) {
+      const float* qa = p.qc_all + ((int64_t)a * B + row) * C;
+      const float* ca = p.csmp_all + ((int64_t)a * B + row) * C;
+      float ra[KC], ya[KC];
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int kk = lane + 32 * k;
+        ra[k] = 0.f; ya[k] = 0.f;
+        if (kk < C) {
+          const float lq = logf(qa[kk] + p.eps);
+          ra[k] = lq * w[a][kk];
+          ya[k] = ca[kk];
+          const int la = a - p.arm_off;
+          if (la >= 0 && la < p.A) {
+            const float G = gcoef * ((float)At * ra[k] - rs[k]);
+            atomicAdd(&sT[la][kk], (double)(G * lq));
+          }
+        }
+      }
+      for (int b = a + 1; b < At; ++b, ++pair) {
+        const float* qb = p.qc_all + ((int64_t)b * B + row) * C;
+        const float* cb = p.csmp_all + ((int64_t)b * B + row) * C;
+        float dist = 0.f, l2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const int kk = lane + 32 * k;
+          if (kk < C) {
+            const float rb = logf(qb[kk] + p.eps) * w[b][kk];
+            const float d = ra[k] - rb;
+            dist = fmaf(d, d, dist);
+            const float e = ya[k] - cb[kk];
+            l2 = fmaf(e, e, l2);
+          }
+        }
+        dist = warp_sum(dist);
+        l2 = warp_sum(l2);
+        if (lane == 0) {
+          atomicAdd(&sPair[pair][0], (double)dist);
+          atomicAdd(&sPair[pair][1], (double)l2);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int npairs = At * (At - 1) / 2;
+  for (int idx = tid; idx < npairs * 2; idx += blockDim.x) atomicAdd(p.acc + accl_pair(0) + idx, (&sPair[0][0])[idx]);
+  if (tid < At) atomicAdd(p.acc + accl_ent(tid), sEnt[tid]);
+  for (int idx = tid; idx < p.A * 128; idx += blockDim.x) {
+    const int a = idx >> 7, k = idx & 127;
+    if (k < C) atomicAdd(p.acc + accl_T(a) + k, sT[a][k]);
+  }
+}
+
+int launch_coupling_rows(const CouplingArgs& a, cudaStream_t s) {
+  int gx = (a.B + kRowWarps - 1) / kRowWarps;
+  if (gx > 296) gx = 296;
+  coupling_rows_kernel<<<gx, kRowWarps * 32, 0, s>>>(a);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss vector (nn_model.py:579-598) + per-category constants of the coupling gradient
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) loss_finalize_kernel(const LossFinalArgs p) {
+  const int tid = threadIdx.x;
+  const int A = p.A, At = p.At, B = p.B, C = p.C;
+  const double Bd = (double)B;
+  // coupling-gradient constants for the local arms
+  for (int idx = tid; idx < A * 128; idx += blockDim.x) {
+    const int a = idx >> 7, k = idx & 127;
+    float wv = 0.f, cv = 0.f, mn = 0.f, T = 0.f;
+    if (k < C) {
+      const int ga = a + p.arm_off;
+      const double s1 = p.acc_loss[accl_qs(ga) + k], s2 = p.acc_loss[accl_qs(ga) + 128 + k];
+      const double mean = s1 / Bd;
+      double var = (s2 - s1 * mean) / (Bd - 1.0);
+      if (var < 0.0) var = 0.0;
+      const double ve = var + (double)p.eps;
+      wv = (float)sqrt(1.0 / ve);
+      cv = (float)(1.0 / (ve * sqrt(ve)) / (Bd - 1.0));
+      mn = (float)mean;
+      T = (float)p.acc_loss[accl_T(a) + k];
+    }
+    p.colc[(int64_t)a * 512 + k] = wv;
+    p.colc[(int64_t)a * 512 + 128 + k] = cv;
+    p.colc[(int64_t)a * 512 + 256 + k] = mn;
+    p.colc[(int64_t)a * 512 + 384 + k] = T;
+  }
+  if (tid == 0) {
+    const double log2pi = 1.8378770664093453;
+    float* out = p.loss_out;
+    for (int i = 0; i < 5 + 3 * At; ++i) out[i] = 0.f;
+    double sum_ind = 0.0;
+    for (int a = 0; a < A; ++a) {
+      const int ga = a + p.arm_off;
+      const double sse = p.acc_loss[accl_recon(a)], mism = p.acc_loss[accl_recon(a) + 1];
+      const double numel = Bd * (double)p.D;
+      const float rec = (float)(0.5 * sse / Bd + 0.5 * (100.0 * mism / numel));
+      const float ll = (float)(sse / numel + Bd * log2pi);
+      double kl = 0.0;
+      for (int s = 0; s < p.S; ++s) kl += -0.5 * (p.kl_sums[(int64_t)a * 16 + s] / Bd);
+      out[5 + ga] = rec;
+      out[5 + At + ga] = (float)kl;
+      out[5 + 2 * At + ga] = ll;
+      sum_ind += (double)rec + (double)p.beta * kl;
+    }
+    const int npairs = At * (At - 1) / 2;
+    double sum_dist = 0.0, sum_l2 = 0.0, sum_ent = 0.0;
+    for (int i = 0; i < npairs; ++i) {
+      sum_dist += p.acc_loss[accl_pair(i)] / Bd;
+      sum_l2 += p.acc_loss[accl_pair(i) + 1] / Bd;
+    }
+    for (int a = 0; a < At; ++a) sum_ent += (double)(At - 1) * p.acc_loss[accl_ent(a)] / Bd;
+    const double np_f = npairs > 1 ? (double)npairs : 1.0;
+    const double joint = (double)p.lam * sum_dist + sum_ent +
+                         np_f * (((double)C / 2.0) * log2pi - 0.5 * log(2.0 * (double)p.lam));
+    const double scale = At - 1 > 1 ? (double)(At - 1) : 1.0;
+    out[0] = (float)(scale * sum_ind + joint);
+    out[1] = (float)joint;
+    if (npairs > 0) {
+      out[2] = (float)(sum_ent / npairs);
+      out[3] = (float)(sum_dist / npairs);
+      out[4] = (float)(sum_l2 / npairs);
+    }
+  }
+}
+
+int launch_loss_finalize(const LossFinalArgs& a, cudaStream_t s) {
+  loss_finalize_kernel<<<1, 128, 0, s>>>(a);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// element-wise reconstruction loss on a materialised pre-activation (nn_model.py:287, :542-546)
+//   x_hat = relu(pre + b11);  sse += (x_hat-x)^2;  mism += [x_hat>0.1] != [x>0.1]
+//   dY = gscale * (x_hat - x) * [x_hat > 0]   (the BCE half has no gradient: its inputs are constants)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) recon_elem_kernel(const ReconElemArgs p) {
+  __shared__ double red[8][2];
+  const int arm = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* pre = p.pre + (int64_t)arm * p.B * p.D;
+  const float* x = p.x + (int64_t)arm * p.x_arm_stride;
+  const float* bias = p.params + (int64_t)arm * p.p_arm_stride + p.offB;
+  float* xr = p.x_rec ? p.x_rec + (int64_t)arm * p.B * p.D : nullptr;
+  double sse = 0.0, mism = 0.0;
+  const int64_t n = (int64_t)p.B * p.D;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + tid; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = idx / p.D;
+    const int col = (int)(idx - row * p.D);
+    const float xv = x[row * p.x_row_stride + col];
+    const float xh = fmaxf(pre[idx] + bias[col], 0.f);
+    const float d = xh - xv;
+    sse += (double)d * (double)d;
+    mism += ((xh > 0.1f) != (xv > 0.1f)) ? 1.0 : 0.0;
+    if (xr) xr[idx] = xh;
+    if (p.want_grad) pre[idx] = xh > 0.f ? p.gscale * d : 0.f;
+  }
+  sse = warp_sum(sse);
+  mism = warp_sum(mism);
+  if (lane == 0) {
+    red[warp][0] = sse;
+    red[warp][1] = mism;
+  }
+  __syncthreads();
+  if (tid < 2 && p.recon_acc) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w][tid];
+    atomicAdd(p.recon_acc + accl_recon(arm) + tid, s);
+  }
+}
+
+int launch_recon_elem(const ReconElemArgs& a, int A, cudaStream_t s) {
+  int64_t n = (int64_t)a.B * a.D;
+  int gx = (int)((n + 256 * 8 - 1) / (256 * 8));
+  if (gx > 148 * 8) gx = 148 * 8;
+  if (gx < 1) gx = 1;
+  recon_elem_kernel<<<dim3(gx, A), 256, 0, s>>>(a);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// column sums of a [B][D] matrix per arm (d fc11.bias = sum_b dY)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* src, int64_t src_arm_stride, float* dst_base,
+                                                     int64_t dst_arm_stride, int B, int D) {
+  __shared__ float red[8][32];
+  const int arm = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const float* s = src + (int64_t)arm * src_arm_stride;
+  float acc = 0.f;
+  if (col < D)
+    for (int r = warp; r < B; r += 8) acc += s[(int64_t)r * D + col];
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && col < D) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    dst_base[(int64_t)arm * dst_arm_stride + col] = t;
+  }
+}
+
+int launch_colsum(const float* src, int64_t src_arm_stride, float* dst_base, int64_t dst_arm_stride, int B, int D,
+                  int A, cudaStream_t s) {
+  colsum_kernel<<<dim3((D + 31) / 32, A), 256, 0, s>>>(src, src_arm_stride, dst_base, dst_arm_stride, B, D);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mvae

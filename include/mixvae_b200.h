@@ -1,0 +1,166 @@
+/*
+ * mixvae_b200.h — C ABI of libmixvae_b200.so: the coupled mixture-VAE (cpl-mixVAE / MMIDAS)
+ * training step as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (AllenInstitute/distributed-vae) has no FFI for this path: its boundary is the
+ * Python class API of mmidas/nn_model.py (mixVAE_model.forward :297, .loss :495), the autograd
+ * backward at mmidas/cpl_mixvae.py:462 and torch.optim.Adam.step at :463.  Each entry point below
+ * names the reference call it stands in for; distributed-vae_b200/mmidas_b200/ is the Python
+ * mirror that binds them with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device pointer is owned by the caller (PyTorch) and
+ *     borrowed for the duration of a call; the library allocates and frees nothing on the device.
+ *   - all work is enqueued on the cudaStream_t passed in (as void*); no host synchronisation, so
+ *     every call is CUDA-graph capturable.
+ *   - return value: 0 = ok, <0 = argument/shape/arch error, >0 = cudaError_t.  Text of the last
+ *     error of the calling thread: mvae_last_error().
+ *   - fp32 storage everywhere (the reference is fp32); row-major; weights are [out,in] like
+ *     nn.Linear.
+ */
+#ifndef MIXVAE_B200_H_
+#define MIXVAE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVAE_ABI_VERSION 1
+#define MVAE_N_PARAM_TENSORS 28 /* 14 Linear layers x {weight, bias} per arm */
+#define MVAE_MAX_ARMS 16
+
+/* Shapes.  mixVAE_model.__init__ arguments (nn_model.py:112-134). */
+typedef struct mvae_dims {
+  int32_t n_arm;        /* A  n_arm                          */
+  int32_t batch;        /* B  cells per step                 */
+  int32_t input_dim;    /* D  genes                          */
+  int32_t fc_dim;       /* H  hidden width          (<=128)  */
+  int32_t lowD_dim;     /* L  latent width          (<=32)   */
+  int32_t n_categories; /* C  categories            (<=128)  */
+  int32_t state_dim;    /* S  continuous state dim  (<=8)    */
+  int32_t n_arm_total;  /* arms in the whole model (>= n_arm; > n_arm when arms are sharded over ranks) */
+  int32_t arm_offset;   /* index of this rank's first arm in the whole model */
+} mvae_dims;
+
+/* Scalars.  mixVAE_model.__init__ (nn_model.py:160-178) + forward(temp) + Adam defaults. */
+typedef struct mvae_hparams {
+  float tau, temp, beta, lam, eps, momentum, x_drop, s_drop;
+  int32_t hard;       /* straight-through one-hot Gumbel sample (nn_model.py:486-493) */
+  int32_t precision;  /* 0: fc1 3xTF32 + TF32 elsewhere (default), 1: 3xTF32 in every gene GEMM,
+                         2: plain TF32 everywhere, 3: fp32 SIMT kernels (no tensor cores) */
+} mvae_hparams;
+
+/* Per-arm flat parameter layout, in floats.  Tensor order = the reference's per-arm parameter
+ * order: fc1.w fc1.b fc2.w ... fc5.b fcc.w fcc.b fc_mu.w fc_mu.b fc_sigma.w fc_sigma.b fc6.w ...
+ * fc11.w fc11.b.  Arm a's tensor t lives at params + a*arm_stride + offset[t]. */
+typedef struct mvae_layout {
+  int64_t offset[MVAE_N_PARAM_TENSORS];
+  int64_t numel[MVAE_N_PARAM_TENSORS];
+  int64_t arm_stride;   /* floats per arm incl. padding (multiple of 256)                     */
+  int64_t bn_stride;    /* floats per arm of BN running stats: l1..l5,s each {mean,var}       */
+  int64_t bn_offset[6]; /* offset of running_mean of batch_l1..l5, batch_s; var follows mean  */
+  int64_t work_floats;  /* workspace size in floats for (dims)                                */
+} mvae_layout;
+
+/* Device buffers that persist across steps (all owned by the caller). */
+typedef struct mvae_state {
+  float* params;        /* [A][arm_stride]                                           */
+  float* grads;         /* [A][arm_stride]   written (not accumulated) by backward   */
+  float* adam_m;        /* [A][arm_stride]                                           */
+  float* adam_v;        /* [A][arm_stride]                                           */
+  float* bn_running;    /* [A][bn_stride]    running_mean / running_var             */
+  int64_t* bn_batches;  /* [A][6]            num_batches_tracked                     */
+  float* work;          /* [work_floats]     activations + partials                  */
+} mvae_state;
+
+/* Per-step inputs.  Null noise pointers are only legal in eval mode (U, keep_*) — the Python
+ * mirror draws U and E with torch's device RNG; keep_x==NULL in training selects the in-kernel
+ * counter-based dropout generator seeded by (seed, step). */
+typedef struct mvae_inputs {
+  const float* x;          /* [A or 1][B][D]                                                  */
+  int64_t x_arm_stride;    /* floats between arms' inputs; 0 = all arms share x (x.expand)     */
+  int64_t x_row_stride;    /* floats between rows (>= D)                                       */
+  const float* U;          /* [A][B][C] uniforms for the Gumbel noise (nn_model.py:440)        */
+  const float* E;          /* [A][B][S] uniforms for the state sample (nn_model.py:427)        */
+  const uint8_t* keep_x;   /* [A][B][D] input-dropout keep mask or NULL                        */
+  const uint8_t* keep_s;   /* [A][B][S] state-dropout keep mask or NULL (s_drop == 0)          */
+  uint64_t seed;           /* in-kernel dropout generator                                      */
+  uint64_t step;
+  int32_t training;        /* 1: batch-stat BN, dropout, Gumbel; 0: mixVAE_model.forward(eval=True) on .eval() */
+} mvae_inputs;
+
+/* Forward outputs, the tensors mixVAE_model.forward returns (nn_model.py:368); [A][B][.] each. */
+typedef struct mvae_outputs {
+  float* x_low;     /* [A][B][L] */
+  float* c_prob;    /* [A][B][C] */
+  float* qc;        /* [A][B][C] */
+  float* c_smp;     /* [A][B][C] */
+  float* s_mean;    /* [A][B][S] */
+  float* s_logvar;  /* [A][B][S] */
+  float* s_smp;     /* [A][B][S] */
+  float* x_rec;     /* [A][B][D] or NULL: the reconstruction is only materialised on request */
+} mvae_outputs;
+
+/* Layout of the loss vector written by mvae_loss (floats):
+ *   [0] total  [1] joint  [2] neg. joint entropy (avg over pairs)  [3] simplex distance (avg)
+ *   [4] l2 distance of samples (avg)  [5 .. 5+At) rec per arm  [5+At .. 5+2At) KL per arm
+ *   [5+2At .. 5+3At) log-likelihood metric per arm;  At = n_arm_total.
+ * (mixVAE_model.loss return tuple, nn_model.py:588-598) */
+#define MVAE_LOSS_FLOATS(At) (5 + 3 * (At))
+
+const char* mvae_last_error(void);
+int mvae_abi_version(void);
+
+/* Shape bookkeeping (host only). */
+int mvae_compute_layout(const mvae_dims* dims, mvae_layout* out);
+
+/* mixVAE_model.forward (nn_model.py:297-368): encoder, categorical head, Gumbel-softmax, state
+ * head, decoder stack up to fc10; x_rec = relu(fc11(.)) only if out->x_rec != NULL. */
+int mvae_forward(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state* st,
+                 const mvae_inputs* in, const mvae_outputs* out, void* stream);
+
+/* mixVAE_model.loss (nn_model.py:495-598).  Fuses the fc11 GEMM with the reconstruction loss and,
+ * if want_grad, with its own backward (d fc11.weight, d fc11.bias, d h10), and the coupling terms
+ * with the first half of their gradient.  qc_all: [n_arm_total][B][C] posteriors of every arm of
+ * the model in global arm order (== out->qc when arms are not sharded); c_smp_all likewise.
+ * loss_out: MVAE_LOSS_FLOATS(n_arm_total) floats on the device. */
+int mvae_loss(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state* st,
+              const mvae_inputs* in, const mvae_outputs* out, const float* qc_all,
+              const float* c_smp_all, float* loss_out, int want_grad, void* stream);
+
+/* Tensor.backward of the loss (cpl_mixvae.py:462): the rest of the backward chain; fills
+ * st->grads.  grad_scale: device pointer to the upstream gradient of the total loss (NULL = 1). */
+int mvae_backward(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state* st,
+                  const mvae_inputs* in, const mvae_outputs* out, const float* grad_scale,
+                  void* stream);
+
+/* torch.optim.Adam.step (cpl_mixvae.py:463, defaults of :274) over a flat buffer.
+ * step_count: device pointer to the fp32 step counter (incremented by the kernel of block 0) or
+ * NULL, in which case `step` (1-based, already incremented) is used. */
+int mvae_adam(float* params, const float* grads, float* m, float* v, int64_t n, float lr,
+              float beta1, float beta2, float eps, float weight_decay, int32_t adamw,
+              int64_t step, void* stream);
+
+/* zero_grad + forward + loss + backward + Adam in one call (cpl_mixvae.py:434-463). */
+int mvae_train_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state* st,
+                    const mvae_inputs* in, const mvae_outputs* out, float* loss_out, float lr,
+                    float beta1, float beta2, float adam_eps, int64_t step, void* stream);
+
+/* Device-side argmax of q(c|x) -> int32 labels [A][B] (replaces the per-step D2H of
+ * cpl_mixvae.py:476 + mmidas/_utils.py:78 classify). */
+int mvae_argmax(const float* q, int32_t* labels, int64_t rows, int32_t cols, void* stream);
+
+/* The keep-mask [A][B][D] that the in-kernel dropout generator applies for (in->seed, in->step):
+ * the fc1 forward and fc1 weight-gradient kernels regenerate it on the fly instead of reading it. */
+int mvae_dropout_mask(const mvae_dims* dims, const mvae_hparams* hp, const mvae_inputs* in,
+                      uint8_t* keep_out, void* stream);
+
+/* Number of kernels launched by the library in this process (for bench.py's gpu_launches). */
+int64_t mvae_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIXVAE_B200_H_ */

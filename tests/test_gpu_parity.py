@@ -1,0 +1,284 @@
+"""Parity of the CUDA path (through the C ABI, via the Python mirror) against the CPU oracle and the
+golden vectors of the unmodified reference.  Needs a B200: run with ``-m gpu``.
+
+Tolerances (stated per tensor):
+  * argmax of q(c|x) and of the Gumbel sample: bit-exact against the reference goldens;
+  * every floating-point tensor t: err(cuda, fp64 oracle) <= max(K * err(fp32 oracle, fp64 oracle), floor)
+    in relative L2 — i.e. the CUDA result is as close to the exact value as the reference's own fp32
+    arithmetic is, up to the factor K; floors are written next to each check;
+  * parameters after Adam steps: hard bound 2*lr*steps per element, and all but a stated fraction
+    within 1e-5 (Adam's first steps are ~lr*sign(g): elements whose gradient is rounding noise flip).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mixvae_oracle as O
+from golden_cases import CASES, case_inputs, load
+from gpu_utils import build_model, cuda_grads, loss_vector, oracle_step, rel_l2, to_dev_noise
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["fp32_simt", "tf32x3_fc1", "tf32x3"]
+K = 4.0  # allowed multiple of the reference's own fp32-vs-fp64 error
+
+# relative-L2 floors per precision mode for (forward tensors, losses, encoder grads, decoder grads)
+FLOORS = {
+    "fp32_simt": dict(fwd=2e-5, loss=1e-5, genc=5e-5, gdec=2e-5),
+    "tf32x3": dict(fwd=5e-5, loss=2e-5, genc=2e-4, gdec=1e-4),
+    "tf32x3_fc1": dict(fwd=5e-5, loss=1e-3, genc=5e-3, gdec=1e-2),   # plain TF32 on the decoder side
+    "tf32": dict(fwd=5e-2, loss=1e-2, genc=1e-1, gdec=1e-2),
+}
+ENC = ("fc1", "fc2", "fc3", "fc4", "fc5", "fcc")
+
+
+def _fwd_loss_bwd(model, x, noise, temp):
+    model.train()
+    xs = x.expand(model.n_arm, -1, -1)
+    for p in model.parameters():
+        p.grad = None
+    out = model(xs, temp, 0.0, noise=noise)
+    x_recs, _, _, x_lows, cs, s_smps, c_smps, s_means, s_logvars, c_probs = out
+    ls = model.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0)
+    ls[0].backward()
+    return out, ls
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", list(CASES))
+def test_step0_forward_loss_grads(name, precision):
+    hp, x, noises, _, detail = case_inputs(name)
+    g = load(name)
+    fl = FLOORS[precision]
+    sd0 = O.init_state_dict(hp, 546)
+    _, o32 = oracle_step(hp, sd0, x, noises[0], torch.float32)
+    _, o64 = oracle_step(hp, sd0, x, noises[0], torch.float64)
+    model = build_model(hp, precision)
+    out, ls = _fwd_loss_bwd(model, x.cuda(), to_dev_noise(noises[0]), hp.temp)
+    x_recs, _, _, x_lows, cs, s_smps, c_smps, s_means, s_logvars, c_probs = out
+    torch.cuda.synchronize()
+
+    # --- bit-exact assignments against the reference goldens
+    am = torch.stack(cs).argmax(-1).cpu().numpy()
+    np.testing.assert_array_equal(am, g["s0_argmax_qc"])
+    am = torch.stack(c_smps).argmax(-1).cpu().numpy()
+    np.testing.assert_array_equal(am, g["s0_argmax_csmp"])
+    am2 = model.argmax_labels(torch.stack(cs)).cpu().numpy()
+    np.testing.assert_array_equal(am2, g["s0_argmax_qc"])
+
+    # --- forward tensors
+    got = {"qc": cs, "c_smp": c_smps, "s_mean": s_means, "s_logvar": s_logvars, "x_low": x_lows, "s_smp": s_smps,
+           "c_prob": c_probs, "x_rec": x_recs}
+    for key, lst in got.items():
+        c = torch.stack(lst).cpu().numpy()
+        r64 = torch.stack(o64["fw"][key]).numpy()
+        r32 = torch.stack(o32["fw"][key]).numpy()
+        tol = max(K * rel_l2(r32, r64), fl["fwd"])
+        assert rel_l2(c, r64) <= tol, (key, rel_l2(c, r64), tol)
+
+    # --- the 9 loss outputs
+    total, rec, joint, ent, dist, l2, kls, _, lls = ls
+    lv = np.array([total.item(), joint.item(), ent.item(), dist.item(), l2.item()])
+    l64, l32 = loss_vector(o64["loss"]), loss_vector(o32["loss"])
+    for i, nm in enumerate(("total", "joint", "ent", "dist", "l2")):
+        tol = max(K * abs(l32[i] / l64[i] - 1), fl["loss"])
+        assert abs(lv[i] / l64[i] - 1) <= tol, (nm, lv[i], l64[i], tol)
+    for a in range(hp.n_arm):
+        for nm, got_v, key in (("rec", rec[a].item(), "rec"), ("kl", kls[a].item(), "kl"), ("ll", lls[a].item(), "ll")):
+            want = float(o64["loss"][key][a])
+            assert abs(got_v / want - 1) <= max(fl["loss"], 1e-5), (nm, a, got_v, want)
+    # goldens of the reference itself (fp32): same tolerance class
+    np.testing.assert_allclose(lv, g["s0_losses"], rtol=max(10 * fl["loss"], 1e-4))
+
+    # --- all 28*A gradients
+    grads = cuda_grads(model)
+    for n in O.param_names(hp):
+        r64 = o64["grads"][n].numpy()
+        r32 = o32["grads"][n].numpy()
+        floor = fl["genc"] if n.split(".")[0] in ENC else fl["gdec"]
+        tol = max(K * rel_l2(r32, r64), floor)
+        e = rel_l2(grads[n], r64)
+        assert e <= tol, (n, e, tol)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", ["tiny", "a3_hard", "mid"])
+def test_multi_step_training_matches(name, precision):
+    """N optimiser steps through the reference-shaped API (zero_grad, forward, loss, backward, step)."""
+    from mmidas_b200 import FusedAdam
+    hp, x, noises, eval_noise, detail = case_inputs(name)
+    g = load(name)
+    model = build_model(hp, precision)
+    opt = FusedAdam(model.parameters(), lr=hp.lr, model=model)
+    st = O.TrainState(hp, O.init_state_dict(hp, 546))
+    xc = x.cuda()
+    later = {"tiny": 2e-2, "a3_hard": 2e-2, "mid": 1e-3}[name]
+    for step, noise in enumerate(noises):
+        ref = O.train_step(st, [x] * hp.n_arm, noise)
+        opt.zero_grad()
+        _, ls = _fwd_loss_bwd(model, xc, to_dev_noise(noise), hp.temp)
+        opt.step()
+        tol = max(10 * FLOORS[precision]["loss"], 1e-4) if step == 0 else later
+        assert abs(ls[0].item() / float(ref["loss"]["total"]) - 1) <= tol, (step, ls[0].item(), float(ref["loss"]["total"]))
+    torch.cuda.synchronize()
+    sd = model.state_dict()
+    frac = {"tiny": 0.3, "a3_hard": 0.3, "mid": 0.05}[name]
+    for k, v in st.sd.items():
+        got = sd[k].cpu().numpy()
+        if v.is_floating_point():
+            d = np.abs(got.astype(np.float64) - v.numpy())
+            assert d.max() <= 2 * hp.lr * st.step + 1e-5, (k, d.max())
+            assert (d > 1e-5).mean() <= frac, (k, (d > 1e-5).mean())
+        else:
+            assert int(got) == int(v), k            # num_batches_tracked (batch_s stays 0: never used)
+    # optimizer state in torch.optim.Adam layout
+    osd = opt.state_dict()
+    assert len(osd["state"]) == 28 * hp.n_arm and float(osd["state"][0]["step"]) == st.step
+    assert osd["param_groups"][0]["params"] == list(range(28 * hp.n_arm))
+
+
+@pytest.mark.parametrize("name", ["tiny", "a3_hard", "mid"])
+def test_single_adam_step_teacher_forced(name):
+    """One step from identical state: parameters, Adam moments, BN running statistics."""
+    from mmidas_b200 import FusedAdam
+    hp, x, noises, _, _ = case_inputs(name)
+    model = build_model(hp, "fp32_simt")
+    opt = FusedAdam(model.parameters(), lr=hp.lr, model=model)
+    st = O.TrainState(hp, O.init_state_dict(hp, 546))
+    O.train_step(st, [x] * hp.n_arm, noises[0])
+    opt.zero_grad()
+    _fwd_loss_bwd(model, x.cuda(), to_dev_noise(noises[0]), hp.temp)
+    opt.step()
+    sd = model.state_dict()
+    for k, v in st.sd.items():
+        got = sd[k].cpu().numpy()
+        if "running" in k:
+            np.testing.assert_allclose(got, v.numpy(), rtol=2e-5, atol=1e-7, err_msg=k)
+        elif v.is_floating_point():
+            d = np.abs(got.astype(np.float64) - v.numpy())
+            assert d.max() <= 2 * hp.lr + 1e-6, (k, d.max())
+            assert (d > 1e-6).mean() <= 0.02, (k, (d > 1e-6).mean())
+    osd = opt.state_dict()["state"]
+    for i, n in enumerate(O.param_names(hp)):
+        assert rel_l2(osd[i]["exp_avg"].cpu().numpy(), st.m[n].numpy()) <= 2e-3, n
+        assert rel_l2(osd[i]["exp_avg_sq"].cpu().numpy(), st.v[n].numpy()) <= 4e-3, n
+
+
+@pytest.mark.parametrize("name", ["tiny", "a3_hard", "mid"])
+def test_eval_forward_matches_reference(name):
+    """eval=True forward on a model in .eval(): running-stat BN, no Gumbel noise, one-hot sample."""
+    hp, x, noises, eval_noise, detail = case_inputs(name)
+    g = load(name)
+    # reproduce the trained state with the oracle (multi-step CUDA drift would blur the comparison)
+    st = O.TrainState(hp, O.init_state_dict(hp, 546))
+    for noise in noises:
+        O.train_step(st, [x] * hp.n_arm, noise)
+    model = build_model(hp, "fp32_simt")
+    model.load_state_dict(st.sd)
+    model.eval()
+    with torch.no_grad():
+        xs = [x.cuda()] * hp.n_arm
+        out = model(x=xs, temp=hp.temp, prior_c=0.0, eval=True, noise=to_dev_noise(eval_noise))
+        x_recs, _, _, x_lows, cs, s_smps, c_smps, s_means, s_logvars, c_probs = out
+        ls = model.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0)
+        fw = O.forward(st.sd, [x] * hp.n_arm, eval_noise, hp, train=False)
+        lo = O.loss(fw, [x] * hp.n_arm, hp)
+    assert not ls[0].requires_grad
+    for key, lst in (("qc", cs), ("c_smp", c_smps), ("s_mean", s_means), ("s_logvar", s_logvars), ("x_rec", x_recs)):
+        np.testing.assert_allclose(torch.stack(lst).cpu().numpy(), torch.stack(fw[key]).numpy(), rtol=2e-4, atol=2e-5,
+                                   err_msg=key)
+    np.testing.assert_array_equal(torch.stack(c_smps).argmax(-1).cpu().numpy(), torch.stack(fw["c_smp"]).argmax(-1).numpy())
+    got = np.array([ls[0].item(), ls[2].item(), ls[3].item(), ls[4].item(), ls[5].item()])
+    np.testing.assert_allclose(got, loss_vector(lo), rtol=1e-4)
+
+
+def test_fused_step_equals_api_step():
+    """mvae_train_step (one C call) == forward/loss/backward/Adam through the reference-shaped API."""
+    from mmidas_b200 import FusedAdam
+    hp, x, noises, _, _ = case_inputs("mid")
+    xc = x.cuda()
+    res = []
+    for fused in (False, True):
+        model = build_model(hp, "fp32_simt")
+        opt = FusedAdam(model.parameters(), lr=hp.lr, model=model)
+        model.train()
+        for noise in noises:
+            nz = to_dev_noise(noise)
+            if fused:
+                lv = model.fused_train_step(xc.expand(hp.n_arm, -1, -1), hp.temp, opt, noise=nz)
+                total = lv[0].item()
+            else:
+                opt.zero_grad()
+                _, ls = _fwd_loss_bwd(model, xc, nz, hp.temp)
+                opt.step()
+                total = ls[0].item()
+        res.append((total, model.flat_parameters().clone(), model._flat_bn.clone(), model._flat_nbt.clone()))
+    assert abs(res[0][0] / res[1][0] - 1) < 1e-5
+    d = (res[0][1] - res[1][1]).abs()
+    assert d.max().item() <= 4 * hp.lr and (d > 1e-6).float().mean().item() < 0.02
+    torch.testing.assert_close(res[0][2], res[1][2], rtol=1e-5, atol=1e-7)
+    assert torch.equal(res[0][3], res[1][3])
+
+
+def test_in_kernel_dropout_equals_injected_mask():
+    """The counter-based generator used by the fc1 forward and fc1 weight-gradient kernels: same mask
+    in both (checked by injecting the materialised mask), keep rate ~ 1-p."""
+    import ctypes as C
+    from mmidas_b200 import _lib
+    hp, x, noises, _, _ = case_inputs("mid")
+    xc = x.cuda()
+    noise = to_dev_noise(noises[0])
+    m1 = build_model(hp, "fp32_simt")
+    nz = {k: v for k, v in noise.items() if k != "keep_x"}
+    torch.manual_seed(1234)
+    out1, ls1 = _fwd_loss_bwd(m1, xc, nz, hp.temp)
+    ctx = m1._ctx
+    keep = torch.empty(hp.n_arm, x.shape[0], hp.input_dim, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.load().mvae_dropout_mask(C.byref(ctx.dims), C.byref(ctx.hp), C.byref(ctx.inputs), keep.data_ptr(),
+                                             None), "mvae_dropout_mask")
+    torch.cuda.synchronize()
+    rate = keep.float().mean().item()
+    assert abs(rate - (1 - hp.x_drop)) < 0.01, rate
+    assert not torch.equal(keep[0], keep[1])          # arms draw different masks
+    m2 = build_model(hp, "fp32_simt")
+    nz2 = dict(nz, keep_x=keep)
+    out2, ls2 = _fwd_loss_bwd(m2, xc, nz2, hp.temp)
+    assert ls1[0].item() == ls2[0].item()
+    assert torch.equal(m1.flat_grads(), m2.flat_grads())
+
+
+def test_full_size_cfg2_properties():
+    """BASELINE config 2 (A=2, B=5000, D=5032, C=100) against the oracle at full size."""
+    hp = O.HP(input_dim=5032, n_categories=100, state_dim=2, n_arm=2, x_drop=0.5, s_drop=0.0)
+    gen = torch.Generator().manual_seed(546)
+    B = 5000
+    x = O.synth_x(B, hp.input_dim, gen)
+    noise = O.synth_noise(hp, B, gen)
+    sd0 = O.init_state_dict(hp, 546)
+    _, o32 = oracle_step(hp, sd0, x, noise, torch.float32)
+    for precision in ("fp32_simt", "tf32x3_fc1"):
+        model = build_model(hp, precision)
+        out, ls = _fwd_loss_bwd(model, x.cuda(), to_dev_noise(noise), hp.temp)
+        cs = out[4]
+        flips = (torch.stack(cs).argmax(-1).cpu() != torch.stack(o32["fw"]["qc"]).argmax(-1)).sum().item()
+        assert flips == 0, (precision, flips)
+        assert abs(ls[0].item() / float(o32["loss"]["total"]) - 1) < 1e-4
+        grads = cuda_grads(model)
+        for n in ("fc1.0.weight", "fc5.1.weight", "fcc.0.weight", "fc_mu.0.weight", "fc8.1.weight", "fc11.0.weight", "fc11.1.bias"):
+            tol = 1e-3 if precision == "fp32_simt" else 2e-2
+            assert rel_l2(grads[n], o32["grads"][n].numpy()) < tol, (precision, n)
+
+
+def test_rejects_bad_usage():
+    hp, x, noises, _, _ = case_inputs("tiny")
+    model = build_model(hp, "fp32_simt")
+    model.train()
+    xs = x.cuda().expand(hp.n_arm, -1, -1)
+    out = model(xs, 1.0, 0.0, noise=to_dev_noise(noises[0]))
+    out2 = model(xs, 1.0, 0.0, noise=to_dev_noise(noises[0]))
+    with pytest.raises(RuntimeError):
+        model.loss(out[0], [], [], xs, out[7], out[8], out[4], out[6], 0.0)   # stale forward outputs
+    with pytest.raises(NotImplementedError):
+        model(xs, 1.0, 0.0, mask=torch.arange(3))
+    with pytest.raises(ValueError):
+        model([xs[0]], 1.0, 0.0)
