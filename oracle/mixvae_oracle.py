@@ -310,4 +310,5 @@ def train_step(st: TrainState, xs: Sequence[torch.Tensor], noise: Dict[str, torc
 
 
 def cast_state_dict(sd, dtype):
-    return {k: (v.to(dtype) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    """Always a deep copy: train_step updates the state in place."""
+    return {k: (v.detach().clone().to(dtype) if v.is_floating_point() else v.clone()) for k, v in sd.items()}

@@ -30,6 +30,9 @@ FLOORS = {
     "tf32": dict(fwd=5e-2, loss=1e-2, genc=1e-1, gdec=1e-2),
 }
 ENC = ("fc1", "fc2", "fc3", "fc4", "fc5", "fcc")
+# upper bound on the reference's own fp32-vs-fp64 error per case (small-batch cases are ill-conditioned:
+# tau=0.005 and inv_var up to 1e4 amplify rounding); a yardstick above this would make a check vacuous.
+FLOOR_SANITY = {"tiny": 0.05, "a3_hard": 0.05, "mid": 0.02, "cfg1": 1e-3}
 
 
 def _fwd_loss_bwd(model, x, noise, temp):
@@ -73,7 +76,9 @@ def test_step0_forward_loss_grads(name, precision):
         c = torch.stack(lst).cpu().numpy()
         r64 = torch.stack(o64["fw"][key]).numpy()
         r32 = torch.stack(o32["fw"][key]).numpy()
-        tol = max(K * rel_l2(r32, r64), fl["fwd"])
+        floor32 = rel_l2(r32, r64)
+        assert floor32 < FLOOR_SANITY[name], (key, floor32)       # the yardstick itself must be meaningful
+        tol = max(K * floor32, fl["fwd"])
         assert rel_l2(c, r64) <= tol, (key, rel_l2(c, r64), tol)
 
     # --- the 9 loss outputs
@@ -85,8 +90,9 @@ def test_step0_forward_loss_grads(name, precision):
         assert abs(lv[i] / l64[i] - 1) <= tol, (nm, lv[i], l64[i], tol)
     for a in range(hp.n_arm):
         for nm, got_v, key in (("rec", rec[a].item(), "rec"), ("kl", kls[a].item(), "kl"), ("ll", lls[a].item(), "ll")):
-            want = float(o64["loss"][key][a])
-            assert abs(got_v / want - 1) <= max(fl["loss"], 1e-5), (nm, a, got_v, want)
+            want, w32 = float(o64["loss"][key][a]), float(o32["loss"][key][a])
+            tol = max(K * abs(w32 / want - 1), fl["loss"], 1e-5)
+            assert abs(got_v / want - 1) <= tol, (nm, a, got_v, want, tol)
     # goldens of the reference itself (fp32): same tolerance class
     np.testing.assert_allclose(lv, g["s0_losses"], rtol=max(10 * fl["loss"], 1e-4))
 
@@ -96,7 +102,9 @@ def test_step0_forward_loss_grads(name, precision):
         r64 = o64["grads"][n].numpy()
         r32 = o32["grads"][n].numpy()
         floor = fl["genc"] if n.split(".")[0] in ENC else fl["gdec"]
-        tol = max(K * rel_l2(r32, r64), floor)
+        floor32 = rel_l2(r32, r64)
+        assert floor32 < FLOOR_SANITY[name], (n, floor32)
+        tol = max(K * floor32, floor)
         e = rel_l2(grads[n], r64)
         assert e <= tol, (n, e, tol)
 
@@ -248,7 +256,9 @@ def test_in_kernel_dropout_equals_injected_mask():
 
 
 def test_full_size_cfg2_properties():
-    """BASELINE config 2 (A=2, B=5000, D=5032, C=100) against the oracle at full size."""
+    """BASELINE config 2 (A=2, B=5000, D=5032, C=100) against the oracle at full size.  The yardstick
+    is the fp64 oracle: at B=5000 torch's own fp32 batch-norm backward is only good to ~1e-3 on the
+    encoder gradients, so "as close to fp64 as the reference's fp32" is the meaningful bar."""
     hp = O.HP(input_dim=5032, n_categories=100, state_dim=2, n_arm=2, x_drop=0.5, s_drop=0.0)
     gen = torch.Generator().manual_seed(546)
     B = 5000
@@ -256,17 +266,23 @@ def test_full_size_cfg2_properties():
     noise = O.synth_noise(hp, B, gen)
     sd0 = O.init_state_dict(hp, 546)
     _, o32 = oracle_step(hp, sd0, x, noise, torch.float32)
+    _, o64 = oracle_step(hp, sd0, x, noise, torch.float64)
     for precision in ("fp32_simt", "tf32x3_fc1"):
+        fl = FLOORS[precision]
         model = build_model(hp, precision)
         out, ls = _fwd_loss_bwd(model, x.cuda(), to_dev_noise(noise), hp.temp)
         cs = out[4]
         flips = (torch.stack(cs).argmax(-1).cpu() != torch.stack(o32["fw"]["qc"]).argmax(-1)).sum().item()
-        assert flips == 0, (precision, flips)
-        assert abs(ls[0].item() / float(o32["loss"]["total"]) - 1) < 1e-4
+        assert flips == 0, (precision, flips)                       # bit-exact assignments, 10 000 cells
+        assert abs(ls[0].item() / float(o64["loss"]["total"]) - 1) < max(fl["loss"], 1e-5)
         grads = cuda_grads(model)
-        for n in ("fc1.0.weight", "fc5.1.weight", "fcc.0.weight", "fc_mu.0.weight", "fc8.1.weight", "fc11.0.weight", "fc11.1.bias"):
-            tol = 1e-3 if precision == "fp32_simt" else 2e-2
-            assert rel_l2(grads[n], o32["grads"][n].numpy()) < tol, (precision, n)
+        for n in O.param_names(hp):
+            r64 = o64["grads"][n].numpy()
+            floor32 = rel_l2(o32["grads"][n].numpy(), r64)
+            assert floor32 < 5e-3, (n, floor32)
+            floor = fl["genc"] if n.split(".")[0] in ENC else fl["gdec"]
+            e = rel_l2(grads[n], r64)
+            assert e <= max(K * floor32, floor), (precision, n, e, floor32)
 
 
 def test_rejects_bad_usage():
