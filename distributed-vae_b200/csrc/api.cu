@@ -101,6 +101,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   DropSpec drop = make_drop(p, hp, in);
   Fc1EpiArgs epi;
   memset(&epi, 0, sizeof(epi));
+  timing_begin(TG_FC1_FWD, s);
   if (use_tc(p, hp)) {
     RC(tc_fc1_forward(p.d, hp, st, in, drop, w, s, &epi));
   } else {
@@ -117,6 +118,8 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   epi.params = st.params; epi.p_arm_stride = p.L.arm_stride; epi.offB = p.L.offset[FC1_B];
   epi.out = work + w.a[0]; epi.stats_out = acc_fwd + acc_bn(0, A, 0); epi.B = B; epi.H = H;
   RC(launch_fc1_epilogue(epi, A, s));
+  timing_end(TG_FC1_FWD, s);
+  timing_begin(TG_NARROW_FWD, s);
 
   // ---- fc2..fc5 with the BatchNorm of the previous layer folded into the load (:265-268)
   for (int l = 1; l <= 4; ++l) {
@@ -172,6 +175,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   if (training)
     RC(launch_bn_update_running(st.bn_running, p.L.bn_stride, bn_off(p), st.bn_batches, acc_fwd, A, B, H, Ld,
                                 hp.momentum, s));
+  timing_end(TG_NARROW_FWD, s);
 
   // ---- optional materialised reconstruction x_rec = relu(fc11(h10)) (:287)
   if (out.x_rec) {
@@ -207,6 +211,7 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
   const float gscale = (float)(At - 1 > 1 ? At - 1 : 1) / (float)B;
 
   // ---- reconstruction term: fc11 GEMM fused with loss (+ its own backward)
+  timing_begin(TG_FC11, s);
   if (use_tc(p, hp)) {
     RC(tc_fc11_loss_grad(p.d, hp, st, in, w, gscale, want_grad, s));
   } else {
@@ -242,6 +247,8 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
     }
   }
 
+  timing_end(TG_FC11, s);
+  timing_begin(TG_COUPLING, s);
   // ---- coupling terms over every arm of the model (:558-569)
   CouplingArgs c;
   memset(&c, 0, sizeof(c));
@@ -257,6 +264,7 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
   f.acc_loss = acc_loss; f.kl_sums = acc_fwd + acc_kl(A, 0);
   f.colc = work + w.colc; f.loss_out = loss_out; f.eps = hp.eps; f.lam = hp.lam; f.beta = hp.beta;
   RC(launch_loss_finalize(f, s));
+  timing_end(TG_COUPLING, s);
   return 0;
 }
 
@@ -274,6 +282,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   const bool tc = use_tc(p, hp);
 
   // ---- decoder fc10..fc7
+  timing_begin(TG_NARROW_BWD, s);
   const float* g_cur = work + w.g_d10;
   for (int l = 4; l >= 1; --l) {
     DenseBwdArgs a;
@@ -334,8 +343,10 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
     g_cur = a.g_in;
   }
 
+  timing_end(TG_NARROW_BWD, s);
   // ---- d fc1.weight = delta1^T * dropout(x)
   DropSpec drop = make_drop(p, hp, in);
+  timing_begin(TG_FC1_WGRAD, s);
   if (tc) {
     RC(tc_fc1_wgrad(p.d, hp, st, in, drop, w, s));
   } else {
@@ -349,7 +360,9 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
     RC(launch_sgemm_simt(g, A, s));
   }
 
+  timing_end(TG_FC1_WGRAD, s);
   // ---- weight gradients of every narrow layer
+  timing_begin(TG_WGRAD, s);
   WgArgs wg;
   memset(&wg, 0, sizeof(wg));
   int np = 0;
@@ -373,6 +386,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   wg.base_off = p.L.offset[FC1_B];
   wg.grads = st.grads; wg.g_arm_stride = p.L.arm_stride;
   RC(launch_wgrad(wg, s));
+  timing_end(TG_WGRAD, s);
 
   if (grad_scale) RC(launch_scale(st.grads, (int64_t)A * p.L.arm_stride, grad_scale, s));
   return 0;
@@ -433,6 +447,7 @@ int mvae_train_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_st
   RC(forward_impl(p, *hp, *st, *in, o, s));
   RC(loss_impl(p, *hp, *st, *in, o, o.qc, o.c_smp, loss_out, 1, s));
   RC(backward_impl(p, *hp, *st, *in, o, nullptr, s));
+  TimedScope ts(TG_ADAM, s);
   return launch_adam(st->params, st->grads, st->adam_m, st->adam_v, (int64_t)p.A * p.L.arm_stride, lr, beta1, beta2,
                      adam_eps, 0.f, 0, step, s);
 }

@@ -117,6 +117,16 @@ __host__ __device__ inline int64_t acc_loss_doubles() { return 48 + kMaxPairs * 
 __host__ __device__ inline int64_t accb_bn(int layer, int A, int a) { return ((int64_t)(layer * A + a)) * 2 * 128; }
 __host__ __device__ inline int64_t acc_bwd_doubles(int A) { return (int64_t)5 * A * 256; }
 
+// optional per-group device timing (CUDA events on the launching stream), for bench.py's roofline
+enum TimedGroup { TG_FC1_FWD = 0, TG_FC11, TG_FC1_WGRAD, TG_NARROW_FWD, TG_NARROW_BWD, TG_COUPLING, TG_WGRAD, TG_ADAM, TG_COUNT };
+void timing_begin(int group, cudaStream_t s);
+void timing_end(int group, cudaStream_t s);
+struct TimedScope {
+  int g; cudaStream_t s;
+  TimedScope(int g_, cudaStream_t s_) : g(g_), s(s_) { timing_begin(g, s); }
+  ~TimedScope() { timing_end(g, s); }
+};
+
 int compute_layout(const mvae_dims& d, mvae_layout* L);
 Work make_work(const mvae_dims& d);
 

@@ -1,6 +1,8 @@
 // layout.cu — host-side shape bookkeeping: flat parameter layout and workspace map.
 #include <stdarg.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace mvae {
@@ -13,6 +15,27 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---- per-group timing ---------------------------------------------------------------------------
+struct TimedSpan { cudaEvent_t a, b; int group; };
+static bool g_timing_on = false;
+static std::vector<TimedSpan> g_spans;
+static cudaEvent_t g_open[TG_COUNT];
+
+void timing_begin(int group, cudaStream_t s) {
+  if (!g_timing_on) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, s);
+  g_open[group] = e;
+}
+void timing_end(int group, cudaStream_t s) {
+  if (!g_timing_on) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, s);
+  g_spans.push_back({g_open[group], e, group});
 }
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -144,4 +167,23 @@ int mvae_compute_layout(const mvae_dims* dims, mvae_layout* out) {
   return mvae::compute_layout(*dims, out);
 }
 int64_t mvae_launch_count(void) { return mvae::g_launches; }
+int mvae_timing_enable(int on) {
+  for (auto& sp : mvae::g_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  mvae::g_spans.clear();
+  mvae::g_timing_on = on != 0;
+  return 0;
+}
+int mvae_timing_read(float* ms_out, int32_t* count_out, int32_t n_groups) {
+  if (!ms_out || !count_out || n_groups < mvae::TG_COUNT) { mvae::set_error("timing_read: need %d slots", mvae::TG_COUNT); return -1; }
+  for (int i = 0; i < n_groups; ++i) { ms_out[i] = 0.f; count_out[i] = 0; }
+  for (auto& sp : mvae::g_spans) {
+    cudaError_t e = cudaEventSynchronize(sp.b);
+    if (e != cudaSuccess) { mvae::set_error("timing_read: %s", cudaGetErrorString(e)); return (int)e; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, sp.a, sp.b);
+    ms_out[sp.group] += ms;
+    count_out[sp.group] += 1;
+  }
+  return 0;
+}
 }

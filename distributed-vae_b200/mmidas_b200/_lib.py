@@ -57,7 +57,8 @@ PRECISIONS = {"tf32x3_fc1": 0, "tf32x3": 1, "tf32": 2, "fp32_simt": 3}
 
 # every symbol include/mixvae_b200.h declares
 EXPORTS = ("mvae_last_error", "mvae_abi_version", "mvae_compute_layout", "mvae_forward", "mvae_loss",
-           "mvae_backward", "mvae_adam", "mvae_train_step", "mvae_argmax", "mvae_dropout_mask", "mvae_launch_count")
+           "mvae_backward", "mvae_adam", "mvae_train_step", "mvae_argmax", "mvae_dropout_mask", "mvae_launch_count",
+           "mvae_timing_enable", "mvae_timing_read")
 
 _lib = None
 
@@ -87,6 +88,10 @@ def load():
                                     C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]
     lib.mvae_argmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     lib.mvae_dropout_mask.argtypes = [P(Dims), P(HParams), P(Inputs), C.c_void_p, C.c_void_p]
+    lib.mvae_timing_enable.argtypes = [C.c_int]
+    lib.mvae_timing_enable.restype = C.c_int
+    lib.mvae_timing_read.argtypes = [P(C.c_float), P(C.c_int32), C.c_int32]
+    lib.mvae_timing_read.restype = C.c_int
     for name in ("mvae_compute_layout", "mvae_forward", "mvae_loss", "mvae_backward", "mvae_adam",
                  "mvae_train_step", "mvae_argmax", "mvae_dropout_mask"):
         getattr(lib, name).restype = C.c_int
@@ -106,6 +111,22 @@ def compute_layout(dims: Dims) -> Layout:
     lay = Layout()
     check(load().mvae_compute_layout(C.byref(dims), C.byref(lay)), "mvae_compute_layout")
     return lay
+
+
+TIMING_GROUPS = ("fc1_fwd", "fc11_loss_grad", "fc1_wgrad", "narrow_fwd", "narrow_bwd", "coupling", "narrow_wgrad", "adam")
+
+
+def timing_enable(on: bool):
+    check(load().mvae_timing_enable(int(on)), "mvae_timing_enable")
+
+
+def timing_read():
+    """{group: (total ms, spans)} of the spans recorded since timing_enable(True)."""
+    n = len(TIMING_GROUPS)
+    ms = (C.c_float * n)()
+    cnt = (C.c_int32 * n)()
+    check(load().mvae_timing_read(ms, cnt, n), "mvae_timing_read")
+    return {g: (float(ms[i]), int(cnt[i])) for i, g in enumerate(TIMING_GROUPS)}
 
 
 def launch_count() -> int:

@@ -426,10 +426,11 @@ class mixVAE_model(nn.Module):
             raise RuntimeError("backward() of a stale loss: forward() was called again before backward()")
         lib = _lib.load()
         dev = self._flat_params.device
-        g = grad_out.detach().to(dev, torch.float32).contiguous()
+        g = None if grad_out is None else grad_out.detach().to(dev, torch.float32).contiguous()
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.mvae_backward(C.byref(ctx.dims), C.byref(ctx.hp), C.byref(ctx.state), C.byref(ctx.inputs),
-                                     C.byref(ctx.outputs), g.data_ptr(), C.c_void_p(stream)), "mvae_backward")
+                                     C.byref(ctx.outputs), g.data_ptr() if g is not None else None,
+                                     C.c_void_p(stream)), "mvae_backward")
         ctx.keep.append(g)
         ctx.loss_done = False
         self.bind_grads()

@@ -160,6 +160,15 @@ int mvae_dropout_mask(const mvae_dims* dims, const mvae_hparams* hp, const mvae_
 /* Number of kernels launched by the library in this process (for bench.py's gpu_launches). */
 int64_t mvae_launch_count(void);
 
+/* Device-time accounting for bench.py's roofline: when enabled, the library brackets each kernel
+ * group with CUDA events on the launching stream.  Groups (index into ms_out / count_out):
+ *   0 fc1 forward  1 fc11 fused loss+grad  2 fc1 weight gradient  3 narrow layers forward
+ *   4 narrow layers backward  5 coupling loss  6 narrow weight gradients  7 Adam.
+ * mvae_timing_enable(on) resets the records; mvae_timing_read synchronises on the recorded events. */
+#define MVAE_TIMING_GROUPS 8
+int mvae_timing_enable(int on);
+int mvae_timing_read(float* ms_out, int32_t* count_out, int32_t n_groups);
+
 #ifdef __cplusplus
 }
 #endif
