@@ -45,6 +45,7 @@ static DropSpec make_drop(const Plan& p, const mvae_hparams& hp, const mvae_inpu
   DropSpec d;
   memset(&d, 0, sizeof(d));
   d.D = p.D;
+  d.rows = p.B;
   if (!in.training || hp.x_drop <= 0.f) {
     d.mode = 0;
     return d;

@@ -175,6 +175,7 @@ struct DropSpec {
   uint32_t thresh16;
   int mode;             // 0: no dropout, 1: injected mask, 2: in-kernel generator
   int64_t D;            // genes per row (hash index)
+  int64_t rows;         // rows of x (cells); tiles may overhang
 };
 
 }  // namespace mvae

@@ -1,13 +1,594 @@
-// gemm_tc.cu — placeholder until the tcgen05 kernels land: reports "unsupported" so that api.cu
-// takes the fp32 SIMT kernels.
+// gemm_tc.cu — the gene-dimension GEMMs of the cpl-mixVAE step on the 5th-generation tensor cores:
+// TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory -> tcgen05.mma kind::tf32 with the
+// accumulator in TMEM -> tcgen05.ld epilogue.  sm_100a only.
+//
+//   G1  fc1 forward        part[s] = dropout(x)[B,D] . W1[H,D]^T       (3xTF32, split-K)   nn_model.py:264
+//   G2  fc11 forward       pre     = h10[B,H] . W11[D,H]^T                                 nn_model.py:287
+//   G3  d h10              part[s] = dY[B,D] . W11[D,H]                (split-K)            autograd of :287
+//   G4  d fc11.weight      part[s] = dY[B,D]^T . h10[B,H]              (split-K)
+//   G5  d fc1.weight       dW1     = delta1[B,H]^T . dropout(x)[B,D]
+//
+// Every operand is read in its natural row-major layout: an operand whose reduction index is the
+// contiguous one is "K-major", the others ("MN-major") use the transposing shared-memory descriptor
+// of tcgen05 — no transposed copies are materialised.  Warp roles: warp 0 TMA producer, warp 1 MMA
+// issuer (one elected lane), warps 2-5 epilogue (TMEM lane quadrants 2,3,0,1), warps 6-9 operand
+// transform (dropout mask on the x operand and the hi/lo split of the error-compensated 3xTF32 scheme:
+// a = a_hi + a_lo with a_hi = a truncated to TF32 by the tensor core itself, a_lo = a - trunc(a);
+// a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi, fp32 accumulate).
+#include <cuda.h>
+
 #include "gemm_tc.h"
 
 namespace mvae {
-bool gemm_tc_supported(int, int, int) { return false; }
-int tc_fc1_forward(const mvae_dims&, const mvae_hparams&, const mvae_state&, const mvae_inputs&, const DropSpec&,
-                   const Work&, cudaStream_t, Fc1EpiArgs*) { set_error("tensor-core path not built"); return -3; }
-int tc_fc11_loss_grad(const mvae_dims&, const mvae_hparams&, const mvae_state&, const mvae_inputs&, const Work&, float,
-                      int, cudaStream_t) { set_error("tensor-core path not built"); return -3; }
-int tc_fc1_wgrad(const mvae_dims&, const mvae_hparams&, const mvae_state&, const mvae_inputs&, const DropSpec&,
-                 const Work&, cudaStream_t) { set_error("tensor-core path not built"); return -3; }
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M
+constexpr int BK = 32;           // floats per pipeline stage along K (= one 128-byte swizzle row)
+constexpr int UK = 8;            // K of one tcgen05.mma kind::tf32
+constexpr int TILE_BYTES = 16384;  // one operand tile: 128 x 128 B (K-major) or 4 slabs of 32 x 128 B (MN-major)
+constexpr int NUM_THREADS = 320;
+constexpr int TRANSFORM_WARP0 = 6;
+constexpr int TRANSFORM_THREADS = 128;
+
+enum : int { F_SPLIT_A = 1, F_SPLIT_B = 2, F_DROP_A = 4, F_DROP_B = 8 };
+
+struct TcArgs {
+  int M, N, K;               // logical GEMM shape (per batch entry)
+  int BN;                    // UMMA N (multiple of 16, <= 128)
+  int stages;
+  int nsplit;                // split-K factor; grid.z = batch * nsplit
+  int ktiles_per_split;      // K tiles (of BK) per split
+  int a_batched, b_batched;  // operand has a batch (arm) coordinate
+  int flags;
+  float* C; int64_t ldc, c_batch_stride, c_split_stride;
+  DropSpec drop;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (the launch fails) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("mvae tc_gemm: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start address,
+// leading / stride byte offsets (16-byte units), version 1, SWIZZLE_128B.
+// K-major operands use SWIZZLE_128B (16-byte chunks XOR row%8, 8-row atoms of 1024 B, SBO = 1024);
+// MN-major TF32 operands must use SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4, 4-row atoms of 512 B:
+// "for mn-major tf32 operands, SW128_32B is the only available smem layout", cutlass sm100_common.inl:92),
+// LBO = byte distance between 32-element MN blocks, SBO = distance between 4-row K groups.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, bool mn) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // version (Blackwell)
+  d |= (uint64_t)(mn ? 1 : 2) << 61;   // SWIZZLE_128B_BASE32B : SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4.
+__host__ __device__ inline uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_lo(float v) {
+  return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+}
+
+// One operand tile in shared memory, in place: apply the dropout mask (x operand) and/or write the
+// low part of the TF32 split to `lo`.  The tile is the TMA image: rows of 128 bytes; K-major tiles
+// (SWIZZLE_128B): 16-byte chunk p of row r holds logical chunk p ^ (r & 7); MN-major tiles
+// (SWIZZLE_128B_ATOM_32B): 32-byte chunk P of row r holds logical 32-byte chunk P ^ (r & 3).
+//   K-major tile : row r = tile row (M/N index), logical chunk c4 -> K offset 4*c4
+//   MN-major tile: slab j (32 MN elements), row r = K offset, logical chunk c4 -> MN offset 32*j + 4*c4
+template <bool MN>
+__device__ __forceinline__ void transform_tile(float* hi, float* lo, bool do_split, bool do_drop, const DropSpec& drop,
+                                               int arm, int mn0, int k0, int tid) {
+#pragma unroll 2
+  for (int q = tid; q < TILE_BYTES / 16; q += TRANSFORM_THREADS) {
+    float4 v = reinterpret_cast<float4*>(hi)[q];
+    if (do_drop) {
+      const int r = q >> 3, p = q & 7;
+      int64_t xrow, xcol;
+      if (!MN) {
+        xrow = mn0 + r;
+        xcol = k0 + 4 * (p ^ (r & 7));
+      } else {
+        const int slab = r >> 5, rr = r & 31;
+        xrow = k0 + rr;
+        xcol = mn0 + 32 * slab + 4 * (((((p >> 1) ^ (rr & 3)) << 1)) | (p & 1));   // 32-byte-chunk swizzle
+      }
+      float m[4];
+      if (drop.mode == 1) {
+        uint32_t kb = 0;
+        if (xcol < drop.D && xrow < drop.rows)   // overhanging rows/cols hold zeros from the TMA fill
+          kb = *reinterpret_cast<const uint32_t*>(drop.keep + (int64_t)arm * drop.keep_arm_stride + xrow * drop.D + xcol);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m[i] = ((kb >> (8 * i)) & 0xFF) ? drop.scale : 0.f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m[i] = drop_keep(drop.seed, arm, xrow, xcol + i, drop.D, drop.thresh16) ? drop.scale : 0.f;
+      }
+      v.x *= m[0]; v.y *= m[1]; v.z *= m[2]; v.w *= m[3];
+      reinterpret_cast<float4*>(hi)[q] = v;
+    }
+    if (do_split) {
+      float4 l;
+      l.x = tf32_lo(v.x); l.y = tf32_lo(v.y); l.z = tf32_lo(v.z); l.w = tf32_lo(v.w);
+      reinterpret_cast<float4*>(lo)[q] = l;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment of every tile is required by SWIZZLE_128B (descriptor base_offset = 0)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool splitA = args.flags & F_SPLIT_A, splitB = args.flags & F_SPLIT_B;
+  const bool dropA = args.flags & F_DROP_A, dropB = args.flags & F_DROP_B;
+  const bool need_transform = args.flags != 0;
+  const int tiles_per_stage = 2 + (splitA ? 1 : 0) + (splitB ? 1 : 0);
+  const int stage_bytes = tiles_per_stage * TILE_BYTES;
+  const int S = args.stages;
+  auto tileA = [&](int s) { return smem + (size_t)s * stage_bytes; };
+  auto tileB = [&](int s) { return smem + (size_t)s * stage_bytes + TILE_BYTES; };
+  auto tileAlo = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * TILE_BYTES; };
+  auto tileBlo = [&](int s) { return smem + (size_t)s * stage_bytes + (2 + (splitA ? 1 : 0)) * TILE_BYTES; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+  uint64_t* full = bars;            // TMA bytes landed
+  uint64_t* ready = bars + S;       // transform done (only when need_transform)
+  uint64_t* empty = bars + 2 * S;   // MMAs that read the stage have completed
+  uint64_t* tmem_full = bars + 3 * S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
+
+  const int n0 = blockIdx.x * args.BN;
+  const int m0 = blockIdx.y * BM;
+  const int batch = blockIdx.z / args.nsplit;
+  const int split = blockIdx.z - batch * args.nsplit;
+  const int ktiles_total = (args.K + BK - 1) / BK;
+  const int kt0 = split * args.ktiles_per_split;
+  const int kt1 = min(ktiles_total, kt0 + args.ktiles_per_split);
+  const int nkt = max(kt1 - kt0, 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(ready + s, TRANSFORM_THREADS);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const int ab = args.a_batched ? batch : 0, bb = args.b_batched ? batch : 0;
+      for (int i = 0; i < nkt; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (i / S) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_expect_tx(full + s, 2 * TILE_BYTES);
+        const int k0 = (kt0 + i) * BK;
+        if (!A_MN) {
+          tma_load_3d(&tmA, full + s, tileA(s), k0, m0, ab);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_3d(&tmA, full + s, tileA(s) + j * 4096, m0 + 32 * j, k0, ab);
+        }
+        if (!B_MN) {
+          tma_load_3d(&tmB, full + s, tileB(s), k0, n0, bb);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_3d(&tmB, full + s, tileB(s) + j * 4096, n0 + 32 * j, k0, bb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BM, args.BN, A_MN, B_MN);
+      const int kround = (args.K + UK - 1) / UK * UK;
+      uint32_t acc = 0;
+      for (int i = 0; i < nkt; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (i / S) & 1;
+        mbar_wait(need_transform ? ready + s : full + s, ph);
+        tc_fence_after();
+        const int k0 = (kt0 + i) * BK;
+        const uint32_t a_hi = smem_u32(tileA(s)), b_hi = smem_u32(tileB(s));
+        const uint32_t a_lo = smem_u32(tileAlo(s)), b_lo = smem_u32(tileBlo(s));
+#pragma unroll
+        for (int ks = 0; ks < BK / UK; ++ks) {
+          if (k0 + ks * UK >= kround) break;
+          const uint32_t aoff = A_MN ? ks * 1024 : ks * 32;
+          const uint32_t boff = B_MN ? ks * 1024 : ks * 32;
+          const uint32_t albo = A_MN ? 4096 : 0, blbo = B_MN ? 4096 : 0;
+          const uint32_t asbo = A_MN ? 512 : 1024, bsbo = B_MN ? 512 : 1024;
+          const uint64_t dah = make_smem_desc(a_hi + aoff, albo, asbo, A_MN);
+          const uint64_t dbh = make_smem_desc(b_hi + boff, blbo, bsbo, B_MN);
+          if (splitA) { umma_tf32(tmem_base, make_smem_desc(a_lo + aoff, albo, asbo, A_MN), dbh, idesc, acc); acc = 1; }
+          if (splitB) { umma_tf32(tmem_base, dah, make_smem_desc(b_lo + boff, blbo, bsbo, B_MN), idesc, acc); acc = 1; }
+          umma_tf32(tmem_base, dah, dbh, idesc, acc);
+          acc = 1;
+        }
+        umma_commit(empty + s);       // frees the stage once the MMAs above have read it
+      }
+      umma_commit(tmem_full);         // accumulator complete
+    }
+  } else if (warp >= TRANSFORM_WARP0) {
+    // ===== operand transform (dropout mask, TF32 hi/lo split) =====
+    if (need_transform) {
+      const int tid = threadIdx.x - TRANSFORM_WARP0 * 32;
+      for (int i = 0; i < nkt; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (i / S) & 1;
+        mbar_wait(full + s, ph);
+        const int k0 = (kt0 + i) * BK;
+        if (splitA || dropA)
+          transform_tile<A_MN>(reinterpret_cast<float*>(tileA(s)), reinterpret_cast<float*>(tileAlo(s)), splitA, dropA,
+                               args.drop, batch, m0, k0, tid);
+        if (splitB || dropB)
+          transform_tile<B_MN>(reinterpret_cast<float*>(tileB(s)), reinterpret_cast<float*>(tileBlo(s)), splitB, dropB,
+                               args.drop, batch, n0, k0, tid);
+        fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(ready + s);
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int quad = warp & 3;        // TMEM lane quadrant this warp may access
+    const int row = m0 + quad * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float* crow = args.C + (int64_t)batch * args.c_batch_stride + (int64_t)split * args.c_split_stride +
+                  (int64_t)row * args.ldc;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+    for (int c0 = 0; c0 < args.BN; c0 += 16) {
+      uint32_t r[16];
+      if (nkt > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = 0u;
+      }
+      if (row < args.M) {
+        const int col = n0 + c0;
+        if (vec_ok && col + 16 <= args.N) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(crow + col)[i] =
+                make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                            __uint_as_float(r[4 * i + 3]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (col + i < args.N) crow[col + i] = __uint_as_float(r[i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 128);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// rank-3 fp32 tensor map over a row-major matrix [outer][inner] with an optional batch dimension;
+// box = {32 floats (128 B, one swizzle row), box_outer rows, 1}.  Out-of-bounds elements read as 0.
+int make_map(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t row_pitch_floats,
+             int64_t batch, int64_t batch_stride_floats, int box_outer, bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  MVAE_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  MVAE_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  MVAE_CHECK_ARG(row_pitch_floats % 4 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  const bool batched = batch > 1 && batch_stride_floats > 0;
+  MVAE_CHECK_ARG(!batched || batch_stride_floats % 4 == 0, "TMA batch stride must be a multiple of 16 bytes");
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(batched ? batch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)row_pitch_floats * 4,
+                           (cuuint64_t)(batched ? batch_stride_floats : row_pitch_floats * outer) * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_outer, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MVAE_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return 0;
+}
+
+struct Operand {
+  const float* base;       // matrix stored row-major [outer][inner]
+  int64_t pitch;           // floats between rows
+  int64_t batch_stride;    // floats between batch entries (0: shared)
+  bool mn_major;           // true: inner index is the M/N index (K is the row index)
+};
+
+// C[batch][split] (M x N, ldc) = A . B  over K; split-K partials are summed by the caller.
+int run_tc_gemm(const Operand& A, const Operand& B, int M, int N, int K, int BN, int batch, int nsplit, int flags,
+                const DropSpec& drop, float* C, int64_t ldc, int64_t c_batch_stride, int64_t c_split_stride,
+                cudaStream_t s) {
+  CUtensorMap tmA, tmB;
+  // K-major: inner = K, outer = M (box rows = 128 / BN); MN-major: inner = M/N, outer = K (box rows = BK)
+  int rc = A.mn_major ? make_map(&tmA, A.base, M, K, A.pitch, batch, A.batch_stride, BK, true)
+                      : make_map(&tmA, A.base, K, M, A.pitch, batch, A.batch_stride, BM, false);
+  if (rc) return rc;
+  rc = B.mn_major ? make_map(&tmB, B.base, N, K, B.pitch, batch, B.batch_stride, BK, true)
+                  : make_map(&tmB, B.base, K, N, B.pitch, batch, B.batch_stride, 128, false);
+  if (rc) return rc;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M; a.N = N; a.K = K; a.BN = BN;
+  const int tiles = 2 + ((flags & F_SPLIT_A) ? 1 : 0) + ((flags & F_SPLIT_B) ? 1 : 0);
+  a.stages = tiles == 2 ? 6 : (tiles == 3 ? 4 : 3);
+  const int ktiles = (K + BK - 1) / BK;
+  if (nsplit > ktiles) nsplit = ktiles;
+  a.nsplit = nsplit;
+  a.ktiles_per_split = (ktiles + nsplit - 1) / nsplit;
+  a.a_batched = A.batch_stride > 0; a.b_batched = B.batch_stride > 0;
+  a.flags = flags;
+  a.C = C; a.ldc = ldc; a.c_batch_stride = c_batch_stride; a.c_split_stride = c_split_stride;
+  a.drop = drop;
+  const size_t smem = (size_t)a.stages * tiles * TILE_BYTES + (3 * a.stages + 2) * 8 + 1024;
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch * nsplit);
+#define TC_LAUNCH(AM, BMJ)                                                                                         \
+  do {                                                                                                             \
+    static bool attr = false;                                                                                      \
+    if (!attr) {                                                                                                   \
+      MVAE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr = true;                                                                                                 \
+    }                                                                                                              \
+    tc_gemm_kernel<AM, BMJ><<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, a);                                          \
+  } while (0)
+  if (!A.mn_major && !B.mn_major) TC_LAUNCH(false, false);
+  else if (!A.mn_major && B.mn_major) TC_LAUNCH(false, true);
+  else if (A.mn_major && !B.mn_major) TC_LAUNCH(true, false);
+  else TC_LAUNCH(true, true);
+#undef TC_LAUNCH
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[batch][m][n] = sum_s part[s][batch][m][n]
+__global__ void __launch_bounds__(256) partial_sum_kernel(const float* part, int64_t split_stride, int64_t batch_stride,
+                                                          int64_t ld, int nsplit, float* out, int64_t out_batch_stride,
+                                                          int64_t out_ld, int M, int N) {
+  const int batch = blockIdx.z;
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int m = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (m >= M || n >= N) return;
+  const float* p = part + (int64_t)batch * batch_stride + (int64_t)m * ld + n;
+  float v = 0.f;
+  for (int s = 0; s < nsplit; ++s) v += p[(int64_t)s * split_stride];
+  out[(int64_t)batch * out_batch_stride + (int64_t)m * out_ld + n] = v;
+}
+
+int round16(int x) { return (x + 15) / 16 * 16; }
+
+int choose_split(int tiles_mn, int ktiles, int max_split) {
+  // one CTA per SM (the pipeline takes most of the shared memory): pick the split whose grid fills
+  // whole waves of 148 CTAs best; ties go to the smaller split (less partial traffic)
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= max_split && s <= ktiles; ++s) {
+    const int ctas = tiles_mn * s;
+    const int waves = (ctas + 147) / 148;
+    const double eff = (double)ctas / (waves * 148.0);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(int B, int D, int H) {
+  // TMA needs 16-byte aligned row pitches: D % 4 == 0 (x, W1 rows) and H % 4 == 0 (h10, W11, delta1 rows)
+  return D % 4 == 0 && H % 4 == 0 && H <= 128 && get_encode() != nullptr;
+}
+
+int tc_part_floats(int A, int Bpad, int Dpad) {
+  int64_t a = (int64_t)4 * A * Bpad * 128, b = (int64_t)2 * A * Dpad * 128;
+  return (int)(a > b ? a : b);
+}
+
+int tc_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
+                   const DropSpec& drop, const Work& w, cudaStream_t s, Fc1EpiArgs* epi) {
+  mvae_layout L;
+  compute_layout(d, &L);
+  const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
+  const int BN = round16(H);
+  Operand x{in.x, in.x_row_stride, in.x_arm_stride, false};
+  Operand W1{st.params + L.offset[FC1_W], D, L.arm_stride, false};
+  int flags = (hp.precision == 2) ? 0 : (F_SPLIT_A | F_SPLIT_B);
+  if (drop.mode) flags |= F_DROP_A;
+  const int mt = (B + BM - 1) / BM;
+  const int nsplit = choose_split(mt * A, (D + BK - 1) / BK, w.fc1_splitk);
+  float* part = st.work + w.fc1_part;
+  const int64_t batch_stride = (int64_t)w.Bpad * 128, split_stride = (int64_t)A * batch_stride;
+  int rc = run_tc_gemm(x, W1, B, H, D, BN, A, nsplit, flags, drop, part, 128, batch_stride, split_stride, s);
+  if (rc) return rc;
+  epi->part = part; epi->split_stride = split_stride; epi->arm_stride = batch_stride; epi->ld = 128; epi->nsplit = nsplit;
+  return 0;
+}
+
+int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
+                      const Work& w, float gscale, int want_grad, cudaStream_t s) {
+  mvae_layout L;
+  compute_layout(d, &L);
+  const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
+  float* work = st.work;
+  double* acc_loss = reinterpret_cast<double*>(work + w.acc_loss);
+  const int split3 = hp.precision == 1 ? (F_SPLIT_A | F_SPLIT_B) : 0;
+  DropSpec nodrop;
+  memset(&nodrop, 0, sizeof(nodrop));
+  // G2: pre = h10 . W11^T  -> big [A][B][D]
+  Operand h10{work + w.d[4], H, (int64_t)B * H, false};
+  Operand W11{st.params + L.offset[FC11_W], H, L.arm_stride, false};
+  int rc = run_tc_gemm(h10, W11, B, D, H, 128, A, 1, split3, nodrop, work + w.big, D, (int64_t)B * D, 0, s);
+  if (rc) return rc;
+  ReconElemArgs r;
+  memset(&r, 0, sizeof(r));
+  r.pre = work + w.big; r.x = in.x; r.x_arm_stride = in.x_arm_stride; r.x_row_stride = in.x_row_stride;
+  r.params = st.params; r.p_arm_stride = L.arm_stride; r.offB = L.offset[FC11_B];
+  r.x_rec = nullptr; r.recon_acc = acc_loss; r.B = B; r.D = D; r.gscale = gscale; r.want_grad = want_grad;
+  rc = launch_recon_elem(r, A, s);
+  if (rc || !want_grad) return rc;
+  float* part = work + w.fc1_part;
+  // G3: d h10 = dY . W11   (A = dY K-major over genes; B(k=gene, n=h) = W11[gene][h]: MN-major)
+  {
+    Operand dY{work + w.big, D, (int64_t)B * D, false};
+    Operand W11t{st.params + L.offset[FC11_W], H, L.arm_stride, true};
+    const int mt = (B + BM - 1) / BM;
+    const int nsplit = choose_split(mt * A, (D + BK - 1) / BK, 4);
+    const int64_t bs = (int64_t)w.Bpad * 128, ss = (int64_t)A * bs;
+    rc = run_tc_gemm(dY, W11t, B, H, D, round16(H), A, nsplit, split3, nodrop, part, 128, bs, ss, s);
+    if (rc) return rc;
+    partial_sum_kernel<<<dim3((H + 31) / 32, (B + 7) / 8, A), 256, 0, s>>>(part, ss, bs, 128, nsplit, work + w.g_d10,
+                                                                            (int64_t)B * H, H, B, H);
+    MVAE_LAUNCH_CHECK();
+  }
+  // G4: d W11 = dY^T . h10   (A(m=gene,k=row) = dY[row][gene]: MN-major; B(k=row,n=h) = h10[row][h]: MN-major)
+  {
+    Operand dYt{work + w.big, D, (int64_t)B * D, true};
+    Operand h10t{work + w.d[4], H, (int64_t)B * H, true};
+    const int mt = (D + BM - 1) / BM;
+    const int nsplit = choose_split(mt * A, (B + BK - 1) / BK, 2);
+    const int64_t bs = (int64_t)w.Dpad * 128, ss = (int64_t)A * bs;
+    rc = run_tc_gemm(dYt, h10t, D, H, B, round16(H), A, nsplit, split3, nodrop, part, 128, bs, ss, s);
+    if (rc) return rc;
+    partial_sum_kernel<<<dim3((H + 31) / 32, (D + 7) / 8, A), 256, 0, s>>>(part, ss, bs, 128, nsplit,
+                                                                            st.grads + L.offset[FC11_W], L.arm_stride, H,
+                                                                            D, H);
+    MVAE_LAUNCH_CHECK();
+  }
+  return launch_colsum(work + w.big, (int64_t)B * D, st.grads + L.offset[FC11_B], L.arm_stride, B, D, A, s);
+}
+
+int tc_fc1_wgrad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
+                 const DropSpec& drop, const Work& w, cudaStream_t s) {
+  mvae_layout L;
+  compute_layout(d, &L);
+  const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
+  // G5: dW1[h][gene] = sum_row delta1[row][h] * xd[row][gene]: both operands MN-major
+  Operand d1{st.work + w.delta_enc[0], H, (int64_t)B * H, true};
+  Operand x{in.x, in.x_row_stride, in.x_arm_stride, true};
+  int flags = hp.precision == 1 ? (F_SPLIT_A | F_SPLIT_B) : 0;
+  if (drop.mode) flags |= F_DROP_B;
+  return run_tc_gemm(d1, x, H, D, B, 128, A, 1, flags, drop, st.grads + L.offset[FC1_W], D, L.arm_stride, 0, s);
+}
+
 }  // namespace mvae
+
+extern "C" int mvae_debug_tc_gemm(const float* A, int a_mn, int64_t a_pitch, const float* B, int b_mn, int64_t b_pitch,
+                                  int M, int N, int K, int BN, int nsplit, int flags, float* C, int64_t ldc,
+                                  int64_t c_split_stride, void* stream) {
+  using namespace mvae;
+  MVAE_CHECK_ARG(A && B && C, "null argument");
+  MVAE_CHECK_ARG(BN % 16 == 0 && BN >= 16 && BN <= 128, "BN must be a multiple of 16 in [16,128]");
+  MVAE_CHECK_ARG((flags & ~3) == 0, "only the TF32-split flags (1: A, 2: B) are accepted here");
+  Operand a{A, a_pitch, 0, a_mn != 0};
+  Operand b{B, b_pitch, 0, b_mn != 0};
+  DropSpec nodrop;
+  memset(&nodrop, 0, sizeof(nodrop));
+  return run_tc_gemm(a, b, M, N, K, BN, 1, nsplit, flags, nodrop, C, ldc, 0, c_split_stride, (cudaStream_t)stream);
+}

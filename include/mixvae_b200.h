@@ -160,6 +160,15 @@ int mvae_dropout_mask(const mvae_dims* dims, const mvae_hparams* hp, const mvae_
 /* Number of kernels launched by the library in this process (for bench.py's gpu_launches). */
 int64_t mvae_launch_count(void);
 
+/* Test hook for the tcgen05 GEMM kernel behind the gene-dimension layers:
+ * C[split] (M x N, ldc) = A . B over K with fp32 storage and TF32 (flags 0) or error-compensated
+ * 3xTF32 (flags 1|2) tensor-core math.  a_mn / b_mn: 0 = operand stored [M or N][K] (K contiguous),
+ * 1 = stored [K][M or N].  Pitches in floats (multiples of 4).  Split-K partials land
+ * c_split_stride floats apart; the caller sums them. */
+int mvae_debug_tc_gemm(const float* A, int a_mn, int64_t a_pitch, const float* B, int b_mn, int64_t b_pitch,
+                       int M, int N, int K, int BN, int nsplit, int flags, float* C, int64_t ldc,
+                       int64_t c_split_stride, void* stream);
+
 /* Device-time accounting for bench.py's roofline: when enabled, the library brackets each kernel
  * group with CUDA events on the launching stream.  Groups (index into ms_out / count_out):
  *   0 fc1 forward  1 fc11 fused loss+grad  2 fc1 weight gradient  3 narrow layers forward
