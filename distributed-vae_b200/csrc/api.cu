@@ -138,7 +138,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
     a.bn_rstd = bn_rstd + (int64_t)(l - 1) * A * 128;
     a.stats_out = training ? acc_fwd + acc_bn(l, A, 0) : nullptr;
     a.eps = hp.eps; a.relu = 1;
-    RC(launch_dense_fwd(a, A, s));
+    RC(hp.precision == 3 ? launch_dense_fwd(a, A, s) : launch_dense_fwd_mma(a, A, s));
   }
 
   // ---- categorical head, Gumbel-softmax, state head, fc6 (:269, :337-351, :278-280)
@@ -171,7 +171,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
     a.params = st.params; a.p_arm_stride = p.L.arm_stride;
     a.offW = p.L.offset[FC7_W + 2 * (l - 1)]; a.offB = p.L.offset[FC7_B + 2 * (l - 1)];
     a.B = B; a.nin = nin; a.nout = H; a.bn_mode = 0; a.eps = hp.eps; a.relu = 1;
-    RC(launch_dense_fwd(a, A, s));
+    RC(hp.precision == 3 ? launch_dense_fwd(a, A, s) : launch_dense_fwd_mma(a, A, s));
   }
   if (training)
     RC(launch_bn_update_running(st.bn_running, p.L.bn_stride, bn_off(p), st.bn_batches, acc_fwd, A, B, H, Ld,
@@ -293,7 +293,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
     a.g_in = work + w.gtmp[l & 1];
     a.params = st.params; a.p_arm_stride = p.L.arm_stride; a.offW = p.L.offset[FC7_W + 2 * (l - 1)];
     a.B = B; a.nin = nin; a.nout = H;
-    RC(launch_dense_bwd(a, A, s));
+    RC(hp.precision == 3 ? launch_dense_bwd(a, A, s) : launch_dense_bwd_mma(a, A, s));
     g_cur = a.g_in;
   }
   // g_cur = d loss / d d6, [A][B][L] in gtmp[1]
@@ -340,7 +340,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
     } else if (tc) {
       a.delta_t = work + w.delta1_t; a.delta_t_ld = w.Bpad; a.delta_t_arm_stride = (int64_t)w.Hpad * w.Bpad;
     }
-    RC(launch_dense_bwd(a, A, s));
+    RC(hp.precision == 3 ? launch_dense_bwd(a, A, s) : launch_dense_bwd_mma(a, A, s));
     g_cur = a.g_in;
   }
 
@@ -386,7 +386,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   wg.part = work + w.wg_part; wg.part_arm_stride = w.wg_floats; wg.part_split_stride = (int64_t)A * w.wg_floats;
   wg.base_off = p.L.offset[FC1_B];
   wg.grads = st.grads; wg.g_arm_stride = p.L.arm_stride;
-  RC(launch_wgrad(wg, s));
+  RC(hp.precision == 3 ? launch_wgrad(wg, s) : launch_wgrad_mma(wg, s));
   timing_end(TG_WGRAD, s);
 
   if (grad_scale) RC(launch_scale(st.grads, (int64_t)A * p.L.arm_stride, grad_scale, s));

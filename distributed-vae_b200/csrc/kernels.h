@@ -29,6 +29,8 @@ struct DenseBwdArgs {
   float* delta_t; int64_t delta_t_ld, delta_t_arm_stride;
 };
 int launch_dense_bwd(const DenseBwdArgs& a, int A, cudaStream_t s);
+int launch_dense_fwd_mma(const DenseFwdArgs& a, int A, cudaStream_t s);   // warp-MMA 3xTF32 versions (kernels_mma.cu)
+int launch_dense_bwd_mma(const DenseBwdArgs& a, int A, cudaStream_t s);
 
 struct Fc1EpiArgs {
   const float* part; int64_t split_stride, arm_stride, ld; int nsplit;
@@ -120,6 +122,7 @@ struct WgArgs {
   float* grads; int64_t g_arm_stride;
 };
 int launch_wgrad(const WgArgs& a, cudaStream_t s);
+int launch_wgrad_mma(const WgArgs& a, cudaStream_t s);
 
 // ---- optimiser / misc ------------------------------------------------------------------------
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,

@@ -1,0 +1,498 @@
+// kernels_mma.cu — the narrow (<=128-wide) layers on warp-level tensor-core MMAs.
+//
+// These layers ([B,<=128] x [<=128,<=128]) are far too small for a TMA/tcgen05 pipeline (one
+// 128-row tile has 13 K-steps) and are latency/issue-bound, not FLOP-bound: what matters is the
+// number of issued instructions per cell.  mma.sync.m16n8k8 (TF32 operands, fp32 accumulate, run as
+// the error-compensated 3xTF32 product so that results stay fp32-accurate: the categorical argmax
+// must be bit-exact) needs ~12x fewer issue slots than the scalar-FMA kernels of kernels_rows.cu,
+// which stay as the precision==3 ("fp32_simt") path.
+//
+//   dense_fwd_mma : out = act(W . bn(in) + b) + fp64 column sums for the next BatchNorm
+//   dense_bwd_mma : delta = bn_bwd(g_out) * relu'(.) ; g_in = delta . W (+ sums for the next bn_bwd)
+//   wgrad_mma     : dW = delta^T . in, db = delta^T . 1   (split over row chunks, fixed-order reduce)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mvae {
+
+namespace {
+
+constexpr int ROWS_PER_CTA = 64;   // 4 row groups of 16 rows x 2 column halves = 8 warps
+constexpr int MMA_THREADS = 256;
+
+__device__ __forceinline__ uint32_t tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+// v = hi + lo with hi = rna_tf32(v), lo = rna_tf32(v - hi)
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = tf32_rna(v);
+  lo = tf32_rna(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// d += a . b with a = a_hi + a_lo, b = b_hi + b_lo (small terms first)
+__device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                       const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+  mma_tf32(d, al, bh);
+  mma_tf32(d, ah, bl);
+  mma_tf32(d, ah, bh);
+}
+
+// pitch (floats) >= n with pitch % 32 in {8, 24}: B-fragment loads (k = tig, n = g) hit 32 banks
+__host__ __device__ inline int b_pitch(int n) {
+  int p = (n + 7) & ~7;
+  while ((p & 31) != 8 && (p & 31) != 24) p += 8;
+  return p;
+}
+// pitch (floats) >= k with pitch % 8 == 4: A-fragment loads (row = g, col = tig) hit 32 banks
+__host__ __device__ inline int a_pitch(int k) { return ((k + 7) & ~7) + 4; }
+
+// One warp: acc[NT][4] += A(16 x 8*ksteps) . B(8*ksteps x 8*NT)
+//   A element (m,k): A_T ? As[k*ap + m] : As[m*ap + k]   (m relative to the warp's 16 rows)
+//   B element (k,n): Bs[k*bp + n]
+template <int NT, bool A_T>
+__device__ __forceinline__ void warp_gemm(const float* __restrict__ As, int ap, const float* __restrict__ Bs, int bp,
+                                          int ksteps, int nt_used, float (&acc)[NT][4], int lane) {
+  const int g = lane >> 2, tig = lane & 3;
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const int k0 = ks * 8;
+    float av[4];
+    if (!A_T) {
+      av[0] = As[g * ap + k0 + tig];
+      av[1] = As[(g + 8) * ap + k0 + tig];
+      av[2] = As[g * ap + k0 + tig + 4];
+      av[3] = As[(g + 8) * ap + k0 + tig + 4];
+    } else {
+      av[0] = As[(k0 + tig) * ap + g];
+      av[1] = As[(k0 + tig) * ap + g + 8];
+      av[2] = As[(k0 + tig + 4) * ap + g];
+      av[3] = As[(k0 + tig + 4) * ap + g + 8];
+    }
+    uint32_t ah[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt < nt_used) {
+        const float b0 = Bs[(k0 + tig) * bp + nt * 8 + g];
+        const float b1 = Bs[(k0 + tig + 4) * bp + nt * 8 + g];
+        uint32_t bh[2], bl[2];
+        split_tf32(b0, bh[0], bl[0]);
+        split_tf32(b1, bh[1], bl[1]);
+        mma_3x(acc[nt], ah, al, bh, bl);
+      }
+    }
+  }
+}
+
+// fp64 sum over the 8 row groups of a warp (lanes with equal tig), result valid in lanes g == 0
+__device__ __forceinline__ double group_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+// =============================================================================================
+// forward
+// =============================================================================================
+template <int NT>
+__global__ void __launch_bounds__(MMA_THREADS) dense_fwd_mma_kernel(const DenseFwdArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  const int arm = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = (tid >> 5) & 3, wc = tid >> 7;
+  const int g = lane >> 2, tig = lane & 3;
+  const int nin = p.nin, nout = p.nout;
+  const int Kp = (nin + 7) & ~7;
+  const int ksteps = Kp / 8;
+  const int bp = b_pitch(8 * NT), ap = a_pitch(nin);
+  constexpr int NTW = NT / 2;                 // n-tiles per warp (two column halves)
+  const int nt_used = max(0, min(NTW, (nout + 7) / 8 - wc * NTW));
+  float* Wt = smem;                       // [Kp][bp]   Wt[k][n] = W[n][k]
+  float* Xs = Wt + Kp * bp;               // [64][ap]
+  float* bias = Xs + ROWS_PER_CTA * ap;   // [8*NT]
+  float* mean = bias + 8 * NT;            // [Kp]
+  float* rstd = mean + Kp;                // [Kp]
+  double* red = reinterpret_cast<double*>(smem + (((rstd + Kp) - smem + 1) & ~(ptrdiff_t)1));  // [4][2][8*NT]
+
+  const float* W = p.params + (int64_t)arm * p.p_arm_stride + p.offW;
+  const float* bsrc = p.params + (int64_t)arm * p.p_arm_stride + p.offB;
+  for (int idx = tid; idx < Kp * bp; idx += MMA_THREADS) Wt[idx] = 0.f;
+  __syncthreads();
+  for (int idx = tid; idx < nout * nin; idx += MMA_THREADS) {
+    const int n = idx / nin, k = idx - n * nin;
+    Wt[k * bp + n] = W[idx];
+  }
+  for (int j = tid; j < 8 * NT; j += MMA_THREADS) bias[j] = j < nout ? bsrc[j] : 0.f;
+  if (p.bn_mode == 1) {
+    const double* sums = p.bn_sums_in + (int64_t)arm * 256;
+    for (int i = tid; i < nin; i += MMA_THREADS) {
+      const double m = sums[i] / (double)p.B;
+      double var = sums[128 + i] / (double)p.B - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mf = (float)m, rf = (float)(1.0 / sqrt(var + (double)p.eps));
+      mean[i] = mf;
+      rstd[i] = rf;
+      if (blockIdx.x == 0) {
+        p.bn_mean[arm * 128 + i] = mf;
+        p.bn_rstd[arm * 128 + i] = rf;
+      }
+    }
+  } else if (p.bn_mode == 2) {
+    for (int i = tid; i < nin; i += MMA_THREADS) {
+      mean[i] = p.bn_mean[arm * 128 + i];
+      rstd[i] = p.bn_rstd[arm * 128 + i];
+    }
+  }
+  const float* in = p.in + (int64_t)arm * p.in_arm_stride;
+  float* out = p.out + (int64_t)arm * p.out_arm_stride;
+  const int ntiles = (p.B + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * ROWS_PER_CTA;
+    __syncthreads();   // weights/stats ready; previous tile's Xs no longer read
+    for (int idx = tid; idx < ROWS_PER_CTA * Kp; idx += MMA_THREADS) {
+      const int r = idx / Kp, k = idx - r * Kp;
+      float v = 0.f;
+      if (k < nin && row0 + r < p.B) {
+        v = in[(int64_t)(row0 + r) * nin + k];
+        if (p.bn_mode) v = (v - mean[k]) * rstd[k];
+      }
+      Xs[r * ap + k] = v;
+    }
+    __syncthreads();
+    float acc[NTW][4];
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    warp_gemm<NTW, false>(Xs + warp * 16 * ap, ap, Wt + wc * NTW * 8, bp, ksteps, nt_used, acc, lane);
+    // ---- epilogue: bias, ReLU, store, fp64 column sums
+    const int ra = row0 + warp * 16 + g, rb = ra + 8;
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      if (nt < nt_used) {
+        const int c = (wc * NTW + nt) * 8 + 2 * tig;
+        float v00 = acc[nt][0] + bias[c], v01 = acc[nt][1] + bias[c + 1];
+        float v10 = acc[nt][2] + bias[c], v11 = acc[nt][3] + bias[c + 1];
+        if (p.relu) { v00 = fmaxf(v00, 0.f); v01 = fmaxf(v01, 0.f); v10 = fmaxf(v10, 0.f); v11 = fmaxf(v11, 0.f); }
+        const bool va = ra < p.B, vb = rb < p.B;
+        if (va) { if (c < nout) out[(int64_t)ra * nout + c] = v00; if (c + 1 < nout) out[(int64_t)ra * nout + c + 1] = v01; }
+        if (vb) { if (c < nout) out[(int64_t)rb * nout + c] = v10; if (c + 1 < nout) out[(int64_t)rb * nout + c + 1] = v11; }
+        if (p.stats_out) {
+          const double a0 = va ? (double)v00 : 0.0, a1 = va ? (double)v01 : 0.0;
+          const double b0 = vb ? (double)v10 : 0.0, b1 = vb ? (double)v11 : 0.0;
+          const double s0 = group_sum(a0 + b0), s1 = group_sum(a1 + b1);
+          const double q0 = group_sum(a0 * a0 + b0 * b0), q1 = group_sum(a1 * a1 + b1 * b1);
+          if (g == 0) {
+            red[(warp * 2 + 0) * 8 * NT + c] = s0;
+            red[(warp * 2 + 0) * 8 * NT + c + 1] = s1;
+            red[(warp * 2 + 1) * 8 * NT + c] = q0;
+            red[(warp * 2 + 1) * 8 * NT + c + 1] = q1;
+          }
+        }
+      }
+    }
+    if (p.stats_out) {
+      __syncthreads();
+      for (int j = tid; j < 2 * 8 * NT; j += MMA_THREADS) {
+        const int which = j / (8 * NT), c = j - which * 8 * NT;
+        if (c < nout) {
+          double s = 0.0;
+          for (int w = 0; w < 4; ++w) s += red[(w * 2 + which) * 8 * NT + c];
+          atomicAdd(p.stats_out + (int64_t)arm * 256 + which * 128 + c, s);
+        }
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// backward (data gradient)
+// =============================================================================================
+template <int NT>
+__global__ void __launch_bounds__(MMA_THREADS) dense_bwd_mma_kernel(const DenseBwdArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  const int arm = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = (tid >> 5) & 3, wc = tid >> 7;
+  const int g = lane >> 2, tig = lane & 3;
+  const int nin = p.nin, nout = p.nout;
+  const int Kp = (nout + 7) & ~7;          // reduction over this layer's outputs
+  const int ksteps = Kp / 8;
+  const int bp = b_pitch(8 * NT), ap = a_pitch(nout);
+  constexpr int NTW = NT / 2;
+  const int nt_used = max(0, min(NTW, (nin + 7) / 8 - wc * NTW));
+  float* Ws = smem;                        // [Kp][bp]   Ws[j][i] = W[j][i]
+  float* Ds = Ws + Kp * bp;                // [64][ap]   delta tile
+  float* c1 = Ds + ROWS_PER_CTA * ap;      // [Kp]
+  float* c2 = c1 + Kp;
+  float* mo = c2 + Kp;
+  float* ro = mo + Kp;
+  float* mi = ro + Kp;                     // [8*NT]
+  float* ri = mi + 8 * NT;
+  double* red = reinterpret_cast<double*>(smem + (((ri + 8 * NT) - smem + 1) & ~(ptrdiff_t)1));   // [4][2][8*NT]
+
+  if (p.g_in) {
+    const float* W = p.params + (int64_t)arm * p.p_arm_stride + p.offW;
+    for (int idx = tid; idx < Kp * bp; idx += MMA_THREADS) Ws[idx] = 0.f;
+    __syncthreads();
+    for (int idx = tid; idx < nout * nin; idx += MMA_THREADS) {
+      const int j = idx / nin, i = idx - j * nin;
+      Ws[j * bp + i] = W[idx];
+    }
+  }
+  if (p.bn_out) {
+    const double* sums = p.bnb_sums + (int64_t)arm * 256;
+    for (int j = tid; j < nout; j += MMA_THREADS) {
+      c1[j] = (float)(sums[j] / (double)p.B);
+      c2[j] = (float)(sums[128 + j] / (double)p.B);
+      mo[j] = p.mean_out[arm * 128 + j];
+      ro[j] = p.rstd_out[arm * 128 + j];
+    }
+  }
+  if (p.bn_in) {
+    for (int i = tid; i < 8 * NT; i += MMA_THREADS) {
+      mi[i] = i < nin ? p.mean_in[arm * 128 + i] : 0.f;
+      ri[i] = i < nin ? p.rstd_in[arm * 128 + i] : 0.f;
+    }
+  }
+  const int64_t abo = (int64_t)arm * p.B;
+  const float* g_out = p.g_out + abo * nout;
+  const float* act_out = p.act_out + abo * nout;
+  float* delta = p.delta + abo * nout;
+  float* g_in = p.g_in ? p.g_in + abo * nin : nullptr;
+  const float* act_in = p.bn_in ? p.act_in + abo * nin : nullptr;
+  const int ntiles = (p.B + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * ROWS_PER_CTA;
+    __syncthreads();
+    for (int idx = tid; idx < ROWS_PER_CTA * Kp; idx += MMA_THREADS) {
+      const int r = idx / Kp, j = idx - r * Kp;
+      float d = 0.f;
+      const int row = row0 + r;
+      if (j < nout && row < p.B) {
+        float gg = g_out[(int64_t)row * nout + j];
+        const float a = act_out[(int64_t)row * nout + j];
+        if (p.bn_out) {
+          const float n = (a - mo[j]) * ro[j];
+          gg = ro[j] * (gg - c1[j] - n * c2[j]);
+        }
+        d = a > 0.f ? gg : 0.f;
+        delta[(int64_t)row * nout + j] = d;
+      }
+      Ds[r * ap + j] = d;
+    }
+    if (!g_in) continue;
+    __syncthreads();
+    float acc[NTW][4];
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    warp_gemm<NTW, false>(Ds + warp * 16 * ap, ap, Ws + wc * NTW * 8, bp, ksteps, nt_used, acc, lane);
+    const int ra = row0 + warp * 16 + g, rb = ra + 8;
+    const bool va = ra < p.B, vb = rb < p.B;
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      if (nt < nt_used) {
+        const int c = (wc * NTW + nt) * 8 + 2 * tig;
+        const bool c0ok = c < nin, c1ok = c + 1 < nin;
+        if (va) { if (c0ok) g_in[(int64_t)ra * nin + c] = acc[nt][0]; if (c1ok) g_in[(int64_t)ra * nin + c + 1] = acc[nt][1]; }
+        if (vb) { if (c0ok) g_in[(int64_t)rb * nin + c] = acc[nt][2]; if (c1ok) g_in[(int64_t)rb * nin + c + 1] = acc[nt][3]; }
+        if (p.bn_in) {
+          double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
+          if (va) {
+            if (c0ok) { const double n = (double)((act_in[(int64_t)ra * nin + c] - mi[c]) * ri[c]); s0 += (double)acc[nt][0]; q0 += (double)acc[nt][0] * n; }
+            if (c1ok) { const double n = (double)((act_in[(int64_t)ra * nin + c + 1] - mi[c + 1]) * ri[c + 1]); s1 += (double)acc[nt][1]; q1 += (double)acc[nt][1] * n; }
+          }
+          if (vb) {
+            if (c0ok) { const double n = (double)((act_in[(int64_t)rb * nin + c] - mi[c]) * ri[c]); s0 += (double)acc[nt][2]; q0 += (double)acc[nt][2] * n; }
+            if (c1ok) { const double n = (double)((act_in[(int64_t)rb * nin + c + 1] - mi[c + 1]) * ri[c + 1]); s1 += (double)acc[nt][3]; q1 += (double)acc[nt][3] * n; }
+          }
+          s0 = group_sum(s0); s1 = group_sum(s1); q0 = group_sum(q0); q1 = group_sum(q1);
+          if (g == 0) {
+            red[(warp * 2 + 0) * 8 * NT + c] = s0;
+            red[(warp * 2 + 0) * 8 * NT + c + 1] = s1;
+            red[(warp * 2 + 1) * 8 * NT + c] = q0;
+            red[(warp * 2 + 1) * 8 * NT + c + 1] = q1;
+          }
+        }
+      }
+    }
+    if (p.bn_in) {
+      __syncthreads();
+      for (int j = tid; j < 2 * 8 * NT; j += MMA_THREADS) {
+        const int which = j / (8 * NT), c = j - which * 8 * NT;
+        if (c < nin) {
+          double s = 0.0;
+          for (int w = 0; w < 4; ++w) s += red[(w * 2 + which) * 8 * NT + c];
+          atomicAdd(p.bnb_sums_next + (int64_t)arm * 256 + which * 128 + c, s);
+        }
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// weight gradients:  dW[j][i] = sum_b delta[b][j] in[b][i],  db[j] = sum_b delta[b][j] (a ones column)
+// =============================================================================================
+constexpr int WG_CHUNK = 32;
+
+__global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgArgs p) {
+  __shared__ float Ds[WG_CHUNK * 136];
+  __shared__ float Is[WG_CHUNK * 136];
+  __shared__ float bm[128], br[128];
+  const WgProblem& pr = p.prob[blockIdx.y];
+  const int arm = blockIdx.z, split = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+  const int nout = pr.nout, nin = pr.nin;
+  const int nt_used = (nin + 1 + 7) / 8;      // + the ones column that yields the bias gradient
+  const float* delta = p.work + pr.delta_off + (int64_t)arm * pr.delta_arm_stride;
+  const float* in = nin > 0 ? p.work + pr.in_off + (int64_t)arm * pr.in_arm_stride : nullptr;
+  if (pr.bn_layer >= 0) {
+    for (int i = tid; i < nin; i += 256) {
+      bm[i] = p.bn_mean[(pr.bn_layer * p.A + arm) * 128 + i];
+      br[i] = p.bn_rstd[(pr.bn_layer * p.A + arm) * 128 + i];
+    }
+  }
+  float acc[16][4];
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+  const int r0 = split * p.rows_per_split;
+  const int r1 = min(p.B, r0 + p.rows_per_split);
+  const bool active = warp * 16 < nout;
+  for (int rb = r0; rb < r1; rb += WG_CHUNK) {
+    const int nr = min(WG_CHUNK, r1 - rb);
+    __syncthreads();
+    for (int idx = tid; idx < WG_CHUNK * 128; idx += 256) {
+      const int r = idx >> 7, j = idx & 127;
+      Ds[r * 136 + j] = (r < nr && j < nout) ? delta[(int64_t)(rb + r) * nout + j] : 0.f;
+      float v = 0.f;
+      if (r < nr) {
+        if (j < nin) {
+          v = in[(int64_t)(rb + r) * pr.in_ld + j];
+          if (pr.bn_layer >= 0) v = (v - bm[j]) * br[j];
+        } else if (j == nin) {
+          v = 1.f;
+        }
+      }
+      Is[r * 136 + j] = v;
+    }
+    __syncthreads();
+    if (active) warp_gemm<16, true>(Ds + warp * 16, 136, Is, 136, WG_CHUNK / 8, nt_used, acc, lane);
+  }
+  if (!active) return;
+  float* part = p.part + (int64_t)split * p.part_split_stride + (int64_t)arm * p.part_arm_stride;
+  const int ja = warp * 16 + g, jb = ja + 8;
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+    if (nt < nt_used) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = (e & 2) ? jb : ja;
+        const int i = nt * 8 + 2 * tig + (e & 1);
+        if (j < nout) {
+          if (i < nin) part[pr.poffW - p.base_off + (int64_t)j * nin + i] = acc[nt][e];
+          else if (i == nin) part[pr.poffB - p.base_off + j] = acc[nt][e];
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce2_kernel(const WgArgs p) {
+  const WgProblem& pr = p.prob[blockIdx.y >> 1];
+  const int which = blockIdx.y & 1, arm = blockIdx.z;
+  const int64_t n = which ? pr.nout : (int64_t)pr.nout * pr.nin;
+  const int64_t poff = which ? pr.poffB : pr.poffW;
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= n) return;
+  const float* part = p.part + (int64_t)arm * p.part_arm_stride + (poff - p.base_off) + e;
+  float s = 0.f;
+  for (int sp = 0; sp < p.nsplit; ++sp) s += part[(int64_t)sp * p.part_split_stride];
+  p.grads[(int64_t)arm * p.g_arm_stride + poff + e] = s;
+}
+
+template <int NT>
+size_t fwd_smem(int nin) {
+  const int Kp = (nin + 7) & ~7;
+  size_t fl = (size_t)Kp * b_pitch(8 * NT) + (size_t)ROWS_PER_CTA * a_pitch(nin) + 8 * NT + 2 * Kp + 2;
+  return fl * 4 + (size_t)4 * 2 * 8 * NT * 8;
+}
+template <int NT>
+size_t bwd_smem(int nout) {
+  const int Kp = (nout + 7) & ~7;
+  size_t fl = (size_t)Kp * b_pitch(8 * NT) + (size_t)ROWS_PER_CTA * a_pitch(nout) + 4 * Kp + 2 * 8 * NT + 2;
+  return fl * 4 + (size_t)4 * 2 * 8 * NT * 8;
+}
+
+}  // namespace
+
+int launch_dense_fwd_mma(const DenseFwdArgs& a, int A, cudaStream_t s) {
+  const int ntiles = (a.B + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+  dim3 grid(ntiles > 592 ? 592 : ntiles, A);
+#define LAUNCH(NT)                                                                                                 \
+  do {                                                                                                             \
+    static bool attr = false;                                                                                      \
+    if (!attr) {                                                                                                   \
+      MVAE_CUDA(cudaFuncSetAttribute(dense_fwd_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
+      attr = true;                                                                                                 \
+    }                                                                                                              \
+    dense_fwd_mma_kernel<NT><<<grid, MMA_THREADS, fwd_smem<NT>(a.nin), s>>>(a);                                    \
+  } while (0)
+  if (a.nout <= 16) LAUNCH(2);
+  else if (a.nout <= 64) LAUNCH(8);
+  else if (a.nout <= 128) LAUNCH(16);
+  else { set_error("dense_fwd_mma: nout=%d too wide", a.nout); return -1; }
+#undef LAUNCH
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_dense_bwd_mma(const DenseBwdArgs& a, int A, cudaStream_t s) {
+  const int ntiles = (a.B + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+  dim3 grid(ntiles > 592 ? 592 : ntiles, A);
+  const int nin = a.g_in ? a.nin : 1;
+#define LAUNCH(NT)                                                                                                 \
+  do {                                                                                                             \
+    static bool attr = false;                                                                                      \
+    if (!attr) {                                                                                                   \
+      MVAE_CUDA(cudaFuncSetAttribute(dense_bwd_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
+      attr = true;                                                                                                 \
+    }                                                                                                              \
+    dense_bwd_mma_kernel<NT><<<grid, MMA_THREADS, bwd_smem<NT>(a.nout), s>>>(a);                                   \
+  } while (0)
+  if (nin <= 16) LAUNCH(2);
+  else if (nin <= 64) LAUNCH(8);
+  else if (nin <= 128) LAUNCH(16);
+  else { set_error("dense_bwd_mma: nin=%d too wide", a.nin); return -1; }
+#undef LAUNCH
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_wgrad_mma(const WgArgs& a, cudaStream_t s) {
+  wgrad_mma_kernel<<<dim3(a.nsplit, a.nprob, a.A), 256, 0, s>>>(a);
+  MVAE_LAUNCH_CHECK();
+  int64_t maxn = 0;
+  for (int i = 0; i < a.nprob; ++i) {
+    int64_t n = (int64_t)a.prob[i].nout * (a.prob[i].nin > 0 ? a.prob[i].nin : 0);
+    if (n > maxn) maxn = n;
+    if (a.prob[i].nout > maxn) maxn = a.prob[i].nout;
+  }
+  wgrad_reduce2_kernel<<<dim3((unsigned)((maxn + 255) / 256), a.nprob * 2, a.A), 256, 0, s>>>(a);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mvae
