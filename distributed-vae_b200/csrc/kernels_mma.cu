@@ -20,15 +20,12 @@ namespace {
 constexpr int ROWS_PER_CTA = 64;   // 4 row groups of 16 rows x 2 column halves = 8 warps
 constexpr int MMA_THREADS = 256;
 
-__device__ __forceinline__ uint32_t tf32_rna(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return r;
-}
-// v = hi + lo with hi = rna_tf32(v), lo = rna_tf32(v - hi)
+// v = hi + lo: hi is v itself (mma.sync reads the upper 19 bits of a .tf32 operand register, i.e.
+// truncates), lo = v - trunc(v) is exact in fp32 and is truncated to TF32 by the MMA in turn.
+// (cvt.rna.tf32.f32 is a ~10-instruction emulation on sm_100; truncation keeps the split at 2 ops.)
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-  hi = tf32_rna(v);
-  lo = tf32_rna(v - __uint_as_float(hi));
+  hi = __float_as_uint(v);
+  lo = __float_as_uint(v - __uint_as_float(hi & 0xFFFFE000u));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
@@ -91,6 +88,48 @@ __device__ __forceinline__ void warp_gemm(const float* __restrict__ As, int ap, 
   }
 }
 
+// Register staging of a [tile_rows x ncols] tile (row pitch ld): every load is issued before the first
+// use so that a thread has NV independent requests in flight (the kernels are latency-bound).
+template <int VEC, int NV, int NTHR>
+__device__ __forceinline__ void tile_load(float (&v)[NV][VEC], const float* __restrict__ src, int64_t ld, int rows_valid,
+                                          int ncols, int tile_rows, int tid) {
+  const int cpr = (ncols + VEC - 1) / VEC;
+  const int total = tile_rows * cpr;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const int idx = tid + u * NTHR;
+    const int r = idx / cpr, c = (idx - r * cpr) * VEC;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[u][e] = 0.f;
+    if (idx < total && r < rows_valid) {
+      if (VEC == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(src + (int64_t)r * ld + c);
+        v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w;
+      } else {
+        v[u][0] = src[(int64_t)r * ld + c];
+      }
+    }
+  }
+}
+// visit the (row, col) of every staged value: f(u, e, r, c)
+template <int VEC, int NV, int NTHR, typename F>
+__device__ __forceinline__ void tile_visit(int ncols, int tile_rows, int tid, F&& f) {
+  const int cpr = (ncols + VEC - 1) / VEC;
+  const int total = tile_rows * cpr;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const int idx = tid + u * NTHR;
+    if (idx < total) {
+      const int r = idx / cpr, c = (idx - r * cpr) * VEC;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) f(u, e, r, c + e);
+    }
+  }
+}
+__device__ __forceinline__ bool vec4_ok(const void* p, int64_t ld, int ncols) {
+  return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 3) == 0 && (ncols & 3) == 0;
+}
+
 // fp64 sum over the 8 row groups of a warp (lanes with equal tig), result valid in lanes g == 0
 __device__ __forceinline__ double group_sum(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -123,11 +162,13 @@ __global__ void __launch_bounds__(MMA_THREADS) dense_fwd_mma_kernel(const DenseF
 
   const float* W = p.params + (int64_t)arm * p.p_arm_stride + p.offW;
   const float* bsrc = p.params + (int64_t)arm * p.p_arm_stride + p.offB;
-  for (int idx = tid; idx < Kp * bp; idx += MMA_THREADS) Wt[idx] = 0.f;
+  for (int idx = tid; idx < Kp * bp + ROWS_PER_CTA * ap; idx += MMA_THREADS) Wt[idx] = 0.f;   // Wt and Xs (padding stays 0)
   __syncthreads();
+  // W[n][k] -> Wt[k][n]; consecutive threads take consecutive n: conflict-free stores, the weights are L2-resident
+#pragma unroll 8
   for (int idx = tid; idx < nout * nin; idx += MMA_THREADS) {
-    const int n = idx / nin, k = idx - n * nin;
-    Wt[k * bp + n] = W[idx];
+    const int k = idx / nout, n = idx - k * nout;
+    Wt[k * bp + n] = W[n * nin + k];
   }
   for (int j = tid; j < 8 * NT; j += MMA_THREADS) bias[j] = j < nout ? bsrc[j] : 0.f;
   if (p.bn_mode == 1) {
@@ -157,14 +198,22 @@ __global__ void __launch_bounds__(MMA_THREADS) dense_fwd_mma_kernel(const DenseF
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int row0 = tile * ROWS_PER_CTA;
     __syncthreads();   // weights/stats ready; previous tile's Xs no longer read
-    for (int idx = tid; idx < ROWS_PER_CTA * Kp; idx += MMA_THREADS) {
-      const int r = idx / Kp, k = idx - r * Kp;
-      float v = 0.f;
-      if (k < nin && row0 + r < p.B) {
-        v = in[(int64_t)(row0 + r) * nin + k];
-        if (p.bn_mode) v = (v - mean[k]) * rstd[k];
+    {
+      const float* src = in + (int64_t)row0 * nin;
+      const int rows_valid = min(ROWS_PER_CTA, p.B - row0);
+      auto put = [&](float val, int r, int c) {
+        if (p.bn_mode) val = (val - mean[c]) * rstd[c];
+        Xs[r * ap + c] = (r < rows_valid) ? val : 0.f;
+      };
+      if (vec4_ok(src, nin, nin)) {
+        float v[8][4];
+        tile_load<4, 8, MMA_THREADS>(v, src, nin, rows_valid, nin, ROWS_PER_CTA, tid);
+        tile_visit<4, 8, MMA_THREADS>(nin, ROWS_PER_CTA, tid, [&](int u, int e, int r, int c) { put(v[u][e], r, c); });
+      } else {
+        float v[32][1];
+        tile_load<1, 32, MMA_THREADS>(v, src, nin, rows_valid, nin, ROWS_PER_CTA, tid);
+        tile_visit<1, 32, MMA_THREADS>(nin, ROWS_PER_CTA, tid, [&](int u, int e, int r, int c) { put(v[u][e], r, c); });
       }
-      Xs[r * ap + k] = v;
     }
     __syncthreads();
     float acc[NTW][4];
@@ -242,11 +291,13 @@ __global__ void __launch_bounds__(MMA_THREADS) dense_bwd_mma_kernel(const DenseB
     const float* W = p.params + (int64_t)arm * p.p_arm_stride + p.offW;
     for (int idx = tid; idx < Kp * bp; idx += MMA_THREADS) Ws[idx] = 0.f;
     __syncthreads();
+#pragma unroll 8
     for (int idx = tid; idx < nout * nin; idx += MMA_THREADS) {
       const int j = idx / nin, i = idx - j * nin;
       Ws[j * bp + i] = W[idx];
     }
   }
+  for (int idx = tid; idx < ROWS_PER_CTA * ap; idx += MMA_THREADS) Ds[idx] = 0.f;
   if (p.bn_out) {
     const double* sums = p.bnb_sums + (int64_t)arm * 256;
     for (int j = tid; j < nout; j += MMA_THREADS) {
@@ -273,21 +324,34 @@ __global__ void __launch_bounds__(MMA_THREADS) dense_bwd_mma_kernel(const DenseB
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int row0 = tile * ROWS_PER_CTA;
     __syncthreads();
-    for (int idx = tid; idx < ROWS_PER_CTA * Kp; idx += MMA_THREADS) {
-      const int r = idx / Kp, j = idx - r * Kp;
-      float d = 0.f;
-      const int row = row0 + r;
-      if (j < nout && row < p.B) {
-        float gg = g_out[(int64_t)row * nout + j];
-        const float a = act_out[(int64_t)row * nout + j];
-        if (p.bn_out) {
-          const float n = (a - mo[j]) * ro[j];
-          gg = ro[j] * (gg - c1[j] - n * c2[j]);
+    {
+      const float* gsrc = g_out + (int64_t)row0 * nout;
+      const float* asrc = act_out + (int64_t)row0 * nout;
+      float* dsts = delta + (int64_t)row0 * nout;
+      const int rows_valid = min(ROWS_PER_CTA, p.B - row0);
+      auto put = [&](float gg, float a, int r, int j) {
+        float d = 0.f;
+        if (r < rows_valid) {
+          if (p.bn_out) {
+            const float n = (a - mo[j]) * ro[j];
+            gg = ro[j] * (gg - c1[j] - n * c2[j]);
+          }
+          d = a > 0.f ? gg : 0.f;
+          dsts[(int64_t)r * nout + j] = d;
         }
-        d = a > 0.f ? gg : 0.f;
-        delta[(int64_t)row * nout + j] = d;
+        Ds[r * ap + j] = d;
+      };
+      if (vec4_ok(gsrc, nout, nout) && vec4_ok(asrc, nout, nout)) {
+        float vg[8][4], va[8][4];
+        tile_load<4, 8, MMA_THREADS>(vg, gsrc, nout, rows_valid, nout, ROWS_PER_CTA, tid);
+        tile_load<4, 8, MMA_THREADS>(va, asrc, nout, rows_valid, nout, ROWS_PER_CTA, tid);
+        tile_visit<4, 8, MMA_THREADS>(nout, ROWS_PER_CTA, tid, [&](int u, int e, int r, int j) { put(vg[u][e], va[u][e], r, j); });
+      } else {
+        float vg[32][1], va[32][1];
+        tile_load<1, 32, MMA_THREADS>(vg, gsrc, nout, rows_valid, nout, ROWS_PER_CTA, tid);
+        tile_load<1, 32, MMA_THREADS>(va, asrc, nout, rows_valid, nout, ROWS_PER_CTA, tid);
+        tile_visit<1, 32, MMA_THREADS>(nout, ROWS_PER_CTA, tid, [&](int u, int e, int r, int j) { put(vg[u][e], va[u][e], r, j); });
       }
-      Ds[r * ap + j] = d;
     }
     if (!g_in) continue;
     __syncthreads();
@@ -371,24 +435,41 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgArgs p) {
   const int r0 = split * p.rows_per_split;
   const int r1 = min(p.B, r0 + p.rows_per_split);
   const bool active = warp * 16 < nout;
-  for (int rb = r0; rb < r1; rb += WG_CHUNK) {
+  for (int idx = tid; idx < WG_CHUNK * 136; idx += 256) { Ds[idx] = 0.f; Is[idx] = 0.f; }
+  const bool dv4 = vec4_ok(delta, nout, nout);
+  const bool iv4 = nin > 0 && vec4_ok(in, pr.in_ld, nin);
+  // chunk staged through registers: the loads of chunk c+1 are in flight while chunk c is multiplied
+  float vd[16][1], vi[16][1];            // scalar path: 32x128 / 256 threads
+  float vd4[4][4], vi4[4][4];            // float4 path
+  auto load_chunk = [&](int rb) {
     const int nr = min(WG_CHUNK, r1 - rb);
-    __syncthreads();
-    for (int idx = tid; idx < WG_CHUNK * 128; idx += 256) {
-      const int r = idx >> 7, j = idx & 127;
-      Ds[r * 136 + j] = (r < nr && j < nout) ? delta[(int64_t)(rb + r) * nout + j] : 0.f;
-      float v = 0.f;
-      if (r < nr) {
-        if (j < nin) {
-          v = in[(int64_t)(rb + r) * pr.in_ld + j];
-          if (pr.bn_layer >= 0) v = (v - bm[j]) * br[j];
-        } else if (j == nin) {
-          v = 1.f;
-        }
-      }
-      Is[r * 136 + j] = v;
+    if (dv4) tile_load<4, 4, 256>(vd4, delta + (int64_t)rb * nout, nout, nr, nout, WG_CHUNK, tid);
+    else tile_load<1, 16, 256>(vd, delta + (int64_t)rb * nout, nout, nr, nout, WG_CHUNK, tid);
+    if (nin > 0) {
+      if (iv4) tile_load<4, 4, 256>(vi4, in + (int64_t)rb * pr.in_ld, pr.in_ld, nr, nin, WG_CHUNK, tid);
+      else tile_load<1, 16, 256>(vi, in + (int64_t)rb * pr.in_ld, pr.in_ld, nr, nin, WG_CHUNK, tid);
     }
+  };
+  auto store_chunk = [&](int rb) {
+    const int nr = min(WG_CHUNK, r1 - rb);
+    if (dv4) tile_visit<4, 4, 256>(nout, WG_CHUNK, tid, [&](int u, int e, int r, int j) { Ds[r * 136 + j] = vd4[u][e]; });
+    else tile_visit<1, 16, 256>(nout, WG_CHUNK, tid, [&](int u, int e, int r, int j) { Ds[r * 136 + j] = vd[u][e]; });
+    auto puti = [&](float v, int r, int i) {
+      if (pr.bn_layer >= 0) v = (v - bm[i]) * br[i];
+      Is[r * 136 + i] = r < nr ? v : 0.f;
+    };
+    if (nin > 0) {
+      if (iv4) tile_visit<4, 4, 256>(nin, WG_CHUNK, tid, [&](int u, int e, int r, int i) { puti(vi4[u][e], r, i); });
+      else tile_visit<1, 16, 256>(nin, WG_CHUNK, tid, [&](int u, int e, int r, int i) { puti(vi[u][e], r, i); });
+    }
+    if (tid < WG_CHUNK) Is[tid * 136 + nin] = tid < nr ? 1.f : 0.f;   // ones column -> bias gradient
+  };
+  if (r0 < r1) load_chunk(r0);
+  for (int rb = r0; rb < r1; rb += WG_CHUNK) {
+    __syncthreads();                       // previous chunk fully consumed
+    store_chunk(rb);
     __syncthreads();
+    if (rb + WG_CHUNK < r1) load_chunk(rb + WG_CHUNK);
     if (active) warp_gemm<16, true>(Ds + warp * 16, 136, Is, 136, WG_CHUNK / 8, nt_used, acc, lane);
   }
   if (!active) return;
