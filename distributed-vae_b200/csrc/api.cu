@@ -90,6 +90,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   const int training = in.training;
   MVAE_CHECK_ARG(in.x != nullptr && in.E != nullptr, "x and E are required");
   MVAE_CHECK_ARG(!training || in.U != nullptr, "U (Gumbel uniforms) is required in training mode");
+  MVAE_CHECK_ARG(!training || B >= 2, "training needs at least 2 cells (batch statistics)");
   MVAE_CHECK_ARG(!(training && hp.s_drop > 0.f) || in.keep_s != nullptr, "keep_s is required when s_drop > 0");
   MVAE_CHECK_ARG(in.x_row_stride >= D, "x_row_stride < D");
   MVAE_CUDA(cudaMemsetAsync(acc_fwd, 0, (size_t)w.acc_fwd_floats * 4, s));
@@ -204,6 +205,7 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
   const int A = p.A, At = p.At, B = p.B, D = p.D, H = p.H, C = p.C, S = p.S;
   const Work& w = p.w;
   float* work = st.work;
+  MVAE_CHECK_ARG(B >= 2, "the loss needs at least 2 cells (unbiased batch variance in inv_var, nn_model.py:75)");
   MVAE_CHECK_ARG(At >= 2, "the coupled loss needs at least 2 arms (the reference divides by the number of arm pairs)");
   MVAE_CHECK_ARG(qc_all && csmp_all && loss_out, "null argument");
   double* acc_loss = reinterpret_cast<double*>(work + w.acc_loss);

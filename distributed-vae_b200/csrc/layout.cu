@@ -44,7 +44,7 @@ static int check_dims(const mvae_dims& d) {
   MVAE_CHECK_ARG(d.n_arm >= 1 && d.n_arm <= MVAE_MAX_ARMS, "n_arm=%d out of range [1,%d]", d.n_arm, MVAE_MAX_ARMS);
   MVAE_CHECK_ARG(d.n_arm_total >= d.n_arm && d.n_arm_total <= MVAE_MAX_ARMS, "n_arm_total=%d invalid", d.n_arm_total);
   MVAE_CHECK_ARG(d.arm_offset >= 0 && d.arm_offset + d.n_arm <= d.n_arm_total, "arm_offset=%d invalid", d.arm_offset);
-  MVAE_CHECK_ARG(d.batch >= 2, "batch=%d: the batch statistics need at least 2 cells", d.batch);
+  MVAE_CHECK_ARG(d.batch >= 1, "batch=%d", d.batch);
   MVAE_CHECK_ARG(d.input_dim >= 1, "input_dim=%d", d.input_dim);
   MVAE_CHECK_ARG(d.fc_dim >= 1 && d.fc_dim <= kMaxH, "fc_dim=%d unsupported (1..%d)", d.fc_dim, kMaxH);
   MVAE_CHECK_ARG(d.lowD_dim >= 1 && d.lowD_dim <= kMaxL, "lowD_dim=%d unsupported (1..%d)", d.lowD_dim, kMaxL);

@@ -289,8 +289,10 @@ class cpl_mixVAE:
         model.eval()
         outs = {k: [] for k in ("c_prob", "qc", "c_smp", "s_mean", "s_logvar", "s_smp", "x_low", "labels")}
         tot = []
+        # a loader with batch_size 1 means "the whole set as one batch" (the reference's convention, :722-748)
+        batches = [data_loader.dataset.tensors] if getattr(data_loader, "batch_size", None) == 1 else data_loader
         with torch.no_grad():
-            for x, _ in HostBatchFeeder(data_loader, self.device):
+            for x, _ in HostBatchFeeder(batches, self.device):
                 xs = [x for _ in range(A)]
                 x_recs, _, _, x_lows, cs, s_smps, c_smps, s_means, s_logvars, c_probs = model(x=xs, temp=self.temp, prior_c=0.0, eval=True)
                 ls = model.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0)

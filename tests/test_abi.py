@@ -50,7 +50,7 @@ def test_layout_rejects_unsupported_shapes():
     lay = lib_mod.Layout()
     for bad in (lib_mod.Dims(2, 100, 64, 200, 10, 12, 2, 2, 0),      # fc_dim > 128
                 lib_mod.Dims(2, 100, 64, 100, 10, 300, 2, 2, 0),     # too many categories
-                lib_mod.Dims(2, 1, 64, 100, 10, 12, 2, 2, 0),        # batch statistics need 2 cells
+                lib_mod.Dims(2, 0, 64, 100, 10, 12, 2, 2, 0),        # empty batch
                 lib_mod.Dims(17, 100, 64, 100, 10, 12, 2, 17, 0)):
         rc = lib_mod.load().mvae_compute_layout(C.byref(bad), C.byref(lay))
         assert rc < 0

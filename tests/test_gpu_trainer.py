@@ -1,0 +1,95 @@
+"""Trainer mirror (mmidas_b200.cpl_mixvae.cpl_mixVAE) on the GPU: the epoch loop, logged names,
+checkpoint files in the reference's layout, resume, and the sharded trainer's single-process path."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+from torch.utils.data import DataLoader, TensorDataset
+
+from oracle import mixvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+class _Run:
+    def __init__(self):
+        self.logs = []
+
+    def log(self, d):
+        self.logs.append(d)
+
+
+def _loaders(N=384, D=128, B=128):
+    gen = torch.Generator().manual_seed(546)
+    x = O.synth_x(N, D, gen)
+    idx = torch.arange(N, dtype=torch.float32)
+    train = DataLoader(TensorDataset(x[:320], idx[:320]), batch_size=B, shuffle=True, drop_last=True)
+    test = DataLoader(TensorDataset(x[320:], idx[320:]), batch_size=1)     # reference: test batch_size == 1
+    return train, test
+
+
+def test_train_loop_checkpoints_and_resume(tmp_path):
+    from mmidas_b200.cpl_mixvae import cpl_mixVAE
+    train, test = _loaders()
+    folder = str(tmp_path / "run")
+    os.makedirs(folder + "/model", exist_ok=True)
+    torch.manual_seed(546)
+    t = cpl_mixVAE(saving_folder=folder, aug_file="", device="cuda")
+    t.init_model(n_categories=9, state_dim=2, input_dim=128, x_drop=0.5, s_drop=0.0, n_arm=2, lr=1e-3)
+    run = _Run()
+    out = t.train(train, test, n_epoch=3, n_epoch_p=0, run=run, rank="cuda", good_enuf_consensus=2.0)
+    assert len(out["losses"]) == 3 and all(np.isfinite(out["losses"]))
+    assert all(0.0 <= c <= 1.0 for c in out["consensus_train"] + out["consensus_val"] + out["consensus_aug"])
+    keys = set().union(*[set(d) for d in run.logs])
+    for k in ("train/total-loss", "train/joint-loss", "train/negative-joint-entropy", "train/simplex-distance",
+              "train/l2-distance", "train/time", "train/mem", "train/consensus_aug", "train/rec-loss0", "train/rec-loss1",
+              "train/consensus", "val/total-loss", "val/rec-loss", "val/consensus"):
+        assert k in keys, k                                     # names of cpl_mixvae.py:541-560, :658-663, :768-775
+    files = sorted(glob.glob(folder + "/model/*.pth"))
+    assert any("cns_cpl_mixVAE_model_before_pruning_A2_" in f for f in files)
+    assert any(os.path.basename(f).startswith("cpl_mixVAE_model_before_pruning_A2_") for f in files)
+    ck = torch.load(files[0], map_location="cpu")
+    assert set(ck) == {"model_state_dict", "optimizer_state_dict"}
+    sd = ck["model_state_dict"]
+    assert len(sd) == 46 * 2 and sd["fc1.0.weight"].shape == (100, 128) and sd["batch_l5.1.running_var"].shape == (10,)
+    assert int(sd["batch_l1.0.num_batches_tracked"]) == 3 * 2 and int(sd["batch_s.0.num_batches_tracked"]) == 0
+    osd = ck["optimizer_state_dict"]
+    assert len(osd["state"]) == 56 and set(osd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    # a torch.optim.Adam built on an equally shaped reference-style model accepts the optimizer state
+    ref_params = [torch.nn.Parameter(torch.zeros_like(osd["state"][i]["exp_avg"])) for i in range(56)]
+    torch.optim.Adam(ref_params, lr=1e-3).load_state_dict(osd)
+    # resume: trained_model= loads model + optimizer and (like the reference, :397) skips the loop
+    t2 = cpl_mixVAE(saving_folder=folder, aug_file="", device="cuda")
+    t2.init_model(n_categories=9, state_dim=2, input_dim=128, x_drop=0.5, s_drop=0.0, n_arm=2, trained_model=files[0])
+    assert t2.init is False and t2.optimizer.step_count == 6
+    for (k, a), (_, b) in zip(t.model.state_dict().items(), t2.model.state_dict().items()):
+        assert torch.equal(a.cpu(), b.cpu()), k
+    res = t2.eval_model(test)
+    assert res["qc"].shape == (2, 64, 9) and res["labels"].shape == (2, 64) and np.isfinite(res["total_loss"])
+
+
+def test_caller_replaced_optimizer_still_trains():
+    """train.py:144-147 re-creates the optimizer with torch.optim.Adam(model.parameters()): parameters and
+    .grad are views of the flat buffers, so the stock optimizer drives the same kernels."""
+    from mmidas_b200.cpl_mixvae import cpl_mixVAE
+    torch.manual_seed(546)
+    t = cpl_mixVAE(saving_folder="", aug_file="", device="cuda", save_flag=False)
+    t.init_model(n_categories=9, state_dim=2, input_dim=128, x_drop=0.5, s_drop=0.0, n_arm=2)
+    t.optimizer = torch.optim.Adam(t.model.parameters(), lr=1e-3)
+    t.model.train()
+    gen = torch.Generator().manual_seed(1)
+    x = O.synth_x(128, 128, gen).cuda()
+    p0 = t.model.flat_parameters().clone()
+    l0 = t.train_batch(x)[0].item()
+    for _ in range(5):
+        lv = t.train_batch(x)
+    assert np.isfinite(lv[0].item()) and not torch.equal(p0, t.model.flat_parameters())
+    assert t.model.fc1[0].weight.data_ptr() == t.model.flat_parameters().data_ptr()
+
+
+def test_sharded_trainer_single_process_matches_fused_step():
+    from mmidas_b200 import FusedAdam
+    from mmidas_b200.parallel import plan_mesh
+    assert plan_mesh(1, 2).arm_ranks == 1
