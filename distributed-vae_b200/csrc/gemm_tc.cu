@@ -15,9 +15,8 @@
 // transform (dropout mask on the x operand and the hi/lo split of the error-compensated 3xTF32 scheme:
 // a = a_hi + a_lo with a_hi = a truncated to TF32 by the tensor core itself, a_lo = a - trunc(a);
 // a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi, fp32 accumulate).
-#include <cuda.h>
-
 #include "gemm_tc.h"
+#include "tc_common.cuh"
 
 namespace mvae {
 
@@ -45,104 +44,7 @@ struct TcArgs {
   DropSpec drop;
 };
 
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must trap (the launch fails) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mvae tc_gemm: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start address,
-// leading / stride byte offsets (16-byte units), version 1, SWIZZLE_128B.
-// K-major operands use SWIZZLE_128B (16-byte chunks XOR row%8, 8-row atoms of 1024 B, SBO = 1024);
-// MN-major TF32 operands must use SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4, 4-row atoms of 512 B:
-// "for mn-major tf32 operands, SW128_32B is the only available smem layout", cutlass sm100_common.inl:92),
-// LBO = byte distance between 32-element MN blocks, SBO = distance between 4-row K groups.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, bool mn) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // version (Blackwell)
-  d |= (uint64_t)(mn ? 1 : 2) << 61;   // SWIZZLE_128B_BASE32B : SWIZZLE_128B
-  return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4.
-__host__ __device__ inline uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ float tf32_lo(float v) {
-  return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-}
+using namespace tc;
 
 // One operand tile in shared memory, in place: apply the dropout mask (x operand) and/or write the
 // low part of the TF32 split to `lo`.  The tile is the TMA image: rows of 128 bytes; K-major tiles
@@ -357,46 +259,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// rank-3 fp32 tensor map over a row-major matrix [outer][inner] with an optional batch dimension;
-// box = {32 floats (128 B, one swizzle row), box_outer rows, 1}.  Out-of-bounds elements read as 0.
-int make_map(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t row_pitch_floats,
-             int64_t batch, int64_t batch_stride_floats, int box_outer, bool mn_major) {
-  EncodeTiledFn enc = get_encode();
-  MVAE_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
-  MVAE_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
-  MVAE_CHECK_ARG(row_pitch_floats % 4 == 0, "TMA row pitch must be a multiple of 16 bytes");
-  const bool batched = batch > 1 && batch_stride_floats > 0;
-  MVAE_CHECK_ARG(!batched || batch_stride_floats % 4 == 0, "TMA batch stride must be a multiple of 16 bytes");
-  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(batched ? batch : 1)};
-  cuuint64_t strides[2] = {(cuuint64_t)row_pitch_floats * 4,
-                           (cuuint64_t)(batched ? batch_stride_floats : row_pitch_floats * outer) * 4};
-  cuuint32_t box[3] = {32, (cuuint32_t)box_outer, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  MVAE_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  return 0;
-}
-
 struct Operand {
   const float* base;       // matrix stored row-major [outer][inner]
   int64_t pitch;           // floats between rows
@@ -511,7 +373,8 @@ int tc_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state&
   return 0;
 }
 
-int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
+// every gene GEMM as 3xTF32 (precision == 1): separate GEMMs around a materialised x_hat / dY
+static int tc_fc11_loss_grad_unfused(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
                       const Work& w, float gscale, int want_grad, cudaStream_t s) {
   mvae_layout L;
   compute_layout(d, &L);
@@ -547,6 +410,38 @@ int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_sta
                                                                             (int64_t)B * H, H, B, H);
     MVAE_LAUNCH_CHECK();
   }
+  // G4: d W11 = dY^T . h10   (A(m=gene,k=row) = dY[row][gene]: MN-major; B(k=row,n=h) = h10[row][h]: MN-major)
+  {
+    Operand dYt{work + w.big, D, (int64_t)B * D, true};
+    Operand h10t{work + w.d[4], H, (int64_t)B * H, true};
+    const int mt = (D + BM - 1) / BM;
+    const int nsplit = choose_split(mt * A, (B + BK - 1) / BK, 2);
+    const int64_t bs = (int64_t)w.Dpad * 128, ss = (int64_t)A * bs;
+    rc = run_tc_gemm(dYt, h10t, D, H, B, round16(H), A, nsplit, split3, nodrop, part, 128, bs, ss, s);
+    if (rc) return rc;
+    partial_sum_kernel<<<dim3((H + 31) / 32, (D + 7) / 8, A), 256, 0, s>>>(part, ss, bs, 128, nsplit,
+                                                                            st.grads + L.offset[FC11_W], L.arm_stride, H,
+                                                                            D, H);
+    MVAE_LAUNCH_CHECK();
+  }
+  return launch_colsum(work + w.big, (int64_t)B * D, st.grads + L.offset[FC11_B], L.arm_stride, B, D, A, s);
+}
+
+int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
+                      const Work& w, float gscale, int want_grad, cudaStream_t s) {
+  mvae_layout L;
+  compute_layout(d, &L);
+  const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
+  float* work = st.work;
+  double* acc_loss = reinterpret_cast<double*>(work + w.acc_loss);
+  const int split3 = hp.precision == 1 ? (F_SPLIT_A | F_SPLIT_B) : 0;
+  DropSpec nodrop;
+  memset(&nodrop, 0, sizeof(nodrop));
+  if (hp.precision == 1) return tc_fc11_loss_grad_unfused(d, hp, st, in, w, gscale, want_grad, s);
+  // fused row-owner pass: x_hat, loss sums, dY (kept in `big` for the dW11 GEMM below), d h10
+  int rc = tc_fc11_rows(d, st, in, w, gscale, want_grad, want_grad ? work + w.big : nullptr, nullptr, acc_loss, s);
+  if (rc || !want_grad) return rc;
+  float* part = work + w.fc1_part;
   // G4: d W11 = dY^T . h10   (A(m=gene,k=row) = dY[row][gene]: MN-major; B(k=row,n=h) = h10[row][h]: MN-major)
   {
     Operand dYt{work + w.big, D, (int64_t)B * D, true};

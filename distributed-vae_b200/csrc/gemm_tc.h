@@ -17,6 +17,10 @@ int tc_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state&
 int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
                       const Work& w, float gscale, int want_grad, cudaStream_t s);
 
+// fc11_fused.cu: x_hat / reconstruction loss / dY / d h10 in one pass over x (dY_out, x_rec optional)
+int tc_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale,
+                 int want_grad, float* dY_out, float* x_rec, double* recon_acc, cudaStream_t s);
+
 // d fc1.weight = delta1^T * dropout(x)
 int tc_fc1_wgrad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
                  const DropSpec& drop, const Work& w, cudaStream_t s);

@@ -123,7 +123,7 @@ Work make_work(const mvae_dims& d) {
   w.rsum = take(B * C);
   w.colc = take(A * 4 * 128);
   w.wcat = take(At * 128);
-  w.fc1_splitk = 4;
+  w.fc1_splitk = 8;
   {
     // split-K partials of the tensor-core GEMMs: fc1 / d h10 use [split<=4][A][Bpad][128], d W11 [split<=2][A][Dpad][128]
     const int64_t p1 = (int64_t)w.fc1_splitk * A * w.Bpad * 128, p2 = (int64_t)2 * A * w.Dpad * 128;
