@@ -180,7 +180,9 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   timing_end(TG_NARROW_FWD, s);
 
   // ---- optional materialised reconstruction x_rec = relu(fc11(h10)) (:287)
-  if (out.x_rec) {
+  if (out.x_rec && use_tc(p, hp) && hp.precision != 1) {
+    RC(tc_fc11_rows(p.d, st, in, w, 0.f, 0, nullptr, out.x_rec, nullptr, s));
+  } else if (out.x_rec) {
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.A = work + w.d[4]; g.sAm = H; g.sAk = 1; g.A_batch = (int64_t)B * H;

@@ -91,6 +91,7 @@ struct Work {
   int64_t colc;        // [A][4][128]  per category: w, cvar, mean, T   (coupling-gradient constants)
   int64_t wcat;        // [At][128]    w of every arm of the model
   int64_t fc1_part;    // [splitk][A][B][Hpad] split-K partials of fc1 (tensor-core path)
+  int64_t db_part;     // [8][A][Dpad]  d fc11.bias partials of the gene-owner kernel
   int64_t big;         // [A][B][D]  materialised x_hat / dY, SIMT path only (else -1)
   int64_t wg_part;     // [nsplit][A][wg_floats]  weight-gradient partials of the narrow layers
   // fp64 accumulators (offsets still in floats; 8-byte aligned)

@@ -11,6 +11,12 @@
 //     MMA2  G[128 x H]   += dY[128 x 32] . W11[32 x H]            (A = the dY tile in smem, B = W11 tile read MN-major)
 //   G (= d loss / d h10) is written as split partials and summed in a fixed order.
 //
+//   fc11_genes_kernel = the same kernel with the roles of h10 and W11 swapped ("gene owner", CTA = 128 genes x
+//   a range of cells, loop over 32-cell tiles): MMA1 X^T[128 genes x 32 cells] = W11 . h10^T, the epilogue
+//   thread owns a gene (bias and d fc11.bias are per-thread scalars), reads the x tile transposed, writes
+//   dY^T over it, MMA2 accumulates d fc11.weight[128 genes x H] += dY^T . h10 in TMEM across all cells.
+//   x_hat is recomputed instead of storing dY: one more pass over x, no [B,D] intermediate at all.
+//
 // Warp roles as in gemm_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.  Three mbarrier
 // rings: full/empty (TMA <-> MMA2), xhat_full/tmem_empty (MMA1 <-> epilogue), dy_ready (epilogue -> MMA2).
 #include "gemm_tc.h"
@@ -43,10 +49,12 @@ struct RowsArgs {
   float* x_rec; int64_t xrec_arm_stride;               // optional materialised reconstruction
   float* part; int64_t part_split_stride, part_arm_stride;   // d h10 partials [split][A][Bpad][128]
   double* recon_acc;                                   // acc_loss block
+  float* db_part; int64_t db_split_stride, db_arm_stride;    // gene owner: d fc11.bias partials [split][A][Dpad]
 };
 
+template <bool GENE>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
-fc11_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWk,
+fc11_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWk,
                  const __grid_constant__ CUtensorMap tmWm, const __grid_constant__ CUtensorMap tmX, const RowsArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -103,12 +111,17 @@ fc11_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(empty + s, ph ^ 1);
         mbar_expect_tx(full + s, STAGE_BYTES);
-        const int g0 = (t0 + i) * GN;
+        const int g0 = (t0 + i) * GN;    // first gene (row owner) / first cell (gene owner) of the tile
 #pragma unroll
         for (int j = 0; j < 4; ++j) tma_load_3d(&tmWk, full + s, wk(s) + j * 4096, 32 * j, g0, arm);
 #pragma unroll
         for (int j = 0; j < 4; ++j) tma_load_3d(&tmWm, full + s, wm(s) + j * 4096, 32 * j, g0, arm);
-        tma_load_3d(&tmX, full + s, xs(s), g0, m0, xb);
+        if (!GENE) {
+          tma_load_3d(&tmX, full + s, xs(s), g0, m0, xb);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_3d(&tmX, full + s, xs(s) + j * 4096, m0 + 32 * j, g0, xb);
+        }
       }
     }
   } else if (warp == 1) {
@@ -162,20 +175,35 @@ fc11_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
       }
       umma_commit(g_full);
     }
-  } else {
-    // ===== epilogue warps 2..5 =====
+  } else if (!GENE) {
+    // ===== epilogue warps 2..5, row owner =====
     const int quad = warp & 3;
     const int r = quad * 32 + lane;            // row within the CTA tile == TMEM lane
     const int row = m0 + r;
     const bool row_ok = row < a.B;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const float* bias = a.bias + (int64_t)arm * a.bias_arm_stride;
+    const float* __restrict__ bias = a.bias + (int64_t)arm * a.bias_arm_stride;
     float* dyrow = a.dY ? a.dY + (int64_t)arm * a.dy_arm_stride + (int64_t)row * a.D : nullptr;
     float* xrrow = a.x_rec ? a.x_rec + (int64_t)arm * a.xrec_arm_stride + (int64_t)row * a.D : nullptr;
     double sse = 0.0, mism = 0.0;
     for (int i = 0; i < nt; ++i) {
       const int s = i % STAGES, b = i & 1;
       const int g0 = (t0 + i) * GN;
+      // bias of the 32 genes of this tile: issued before the waits so that the latency overlaps them
+      // (they must not sit behind the dY global stores of the previous chunk: the compiler cannot
+      // prove that the two float* do not alias)
+      float4 bvv[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int g = g0 + 4 * c;
+        bvv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g + 3 < a.D) bvv[c] = __ldg(reinterpret_cast<const float4*>(bias + g));
+        else {
+          if (g < a.D) bvv[c].x = __ldg(bias + g);
+          if (g + 1 < a.D) bvv[c].y = __ldg(bias + g + 1);
+          if (g + 2 < a.D) bvv[c].z = __ldg(bias + g + 2);
+        }
+      }
       mbar_wait(full + s, (i / STAGES) & 1);            // x tile visible to this thread
       mbar_wait(xhat_full + b, (i >> 1) & 1);
       tc_fence_after();
@@ -191,13 +219,7 @@ fc11_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         const int p = c ^ (r & 7);                        // SWIZZLE_128B: logical chunk c lives at chunk p
         const float4 xv = xrow[p];
         const int g = g0 + 4 * c;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g + 3 < a.D) bv = *reinterpret_cast<const float4*>(bias + g);
-        else {
-          if (g < a.D) bv.x = bias[g];
-          if (g + 1 < a.D) bv.y = bias[g + 1];
-          if (g + 2 < a.D) bv.z = bias[g + 2];
-        }
+        const float4 bv = bvv[c];
         const float xin[4] = {xv.x, xv.y, xv.z, xv.w};
         const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
         float dy[4], xh[4];
@@ -257,6 +279,67 @@ fc11_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
             reinterpret_cast<float4*>(prow + c0)[e] = make_float4(__uint_as_float(rr[4 * e]), __uint_as_float(rr[4 * e + 1]),
                                                                   __uint_as_float(rr[4 * e + 2]), __uint_as_float(rr[4 * e + 3]));
         }
+      }
+    }
+    } else {
+    // ===== epilogue warps 2..5, gene owner =====
+    const int quad = warp & 3;
+    const int gl = quad * 32 + lane;           // gene within the CTA block == TMEM lane
+    const int gene = m0 + gl;
+    const bool gene_ok = gene < a.D;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const float bj = gene_ok ? __ldg(a.bias + (int64_t)arm * a.bias_arm_stride + gene) : 0.f;
+    float dbsum = 0.f;
+    for (int i = 0; i < nt; ++i) {
+      const int s = i % STAGES, b = i & 1;
+      const int r0 = (t0 + i) * GN;             // first cell of the tile
+      mbar_wait(full + s, (i / STAGES) & 1);
+      mbar_wait(xhat_full + b, (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + lane_addr + (uint32_t)(b * GN), acc);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tmem_empty + b);
+      // x tile: 4 gene slabs of [32 cells x 128 B] (SWIZZLE_128B); this thread's gene is element `lane` of slab `quad`
+      const uint8_t* xslab = xs(s) + quad * 4096;
+      float xv[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        xv[r] = *reinterpret_cast<const float*>(xslab + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // every epilogue thread has read the x tile
+      float dy[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const float xh = fmaxf(__uint_as_float(acc[r]) + bj, 0.f);
+        const bool ok = gene_ok && (r0 + r < a.B);
+        dy[r] = (ok && xh > 0.f) ? a.gscale * (xh - xv[r]) : 0.f;
+        dbsum += dy[r];
+      }
+      float4* drow = reinterpret_cast<float4*>(xs(s) + gl * 128);   // dY^T row of this gene (K-major, SWIZZLE_128B)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) drow[c ^ (gl & 7)] = make_float4(dy[4 * c], dy[4 * c + 1], dy[4 * c + 2], dy[4 * c + 3]);
+      fence_proxy_async();
+      mbar_arrive(dy_ready + s);
+    }
+    if (gene_ok) a.db_part[(int64_t)split * a.db_split_stride + (int64_t)arm * a.db_arm_stride + gene] = dbsum;
+    mbar_wait(g_full, 0);
+    tc_fence_after();
+    float* prow = a.part + (int64_t)split * a.part_split_stride + (int64_t)arm * a.part_arm_stride + (int64_t)gene * 128;
+    for (int c0 = 0; c0 < a.HN; c0 += 16) {
+      uint32_t rr[16];
+      if (nt > 0) {
+        tmem_ld16(tmem_g + lane_addr + (uint32_t)c0, rr);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) rr[e] = 0u;
+      }
+      if (gene_ok) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          reinterpret_cast<float4*>(prow + c0)[e] = make_float4(__uint_as_float(rr[4 * e]), __uint_as_float(rr[4 * e + 1]),
+                                                                __uint_as_float(rr[4 * e + 2]), __uint_as_float(rr[4 * e + 3]));
       }
     }
   }
@@ -325,16 +408,64 @@ int tc_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
   const size_t smem = H10_BYTES + (size_t)STAGES * STAGE_BYTES + 32 * 8 + 1024;
   static bool attr = false;
   if (!attr) {
-    MVAE_CUDA(cudaFuncSetAttribute(fc11_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(fc11_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  fc11_rows_kernel<<<dim3(nsplit, mt, A), FUSED_THREADS, smem, s>>>(tmH, tmWk, tmWm, tmX, a);
+  fc11_fused_kernel<false><<<dim3(nsplit, mt, A), FUSED_THREADS, smem, s>>>(tmH, tmWk, tmWm, tmX, a);
   MVAE_LAUNCH_CHECK();
   if (want_grad) {
     partial_sum2_kernel<<<dim3((H + 31) / 32, (B + 7) / 8, A), 256, 0, s>>>(a.part, a.part_split_stride, a.part_arm_stride,
                                                                             128, nsplit, work + w.g_d10, (int64_t)B * H, H, B, H);
     MVAE_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+
+// d fc11.weight and d fc11.bias by the gene-owner pass (x_hat recomputed, nothing [B,D]-sized is stored)
+int tc_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale,
+                  cudaStream_t s) {
+  mvae_layout L;
+  compute_layout(d, &L);
+  const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
+  float* work = st.work;
+  CUtensorMap tmR, tmTk, tmTm, tmX;
+  // resident operand: W11 block [128 genes x H]; tiles: h10 [32 cells x H] in both images; x: [32 cells x 32 genes] boxes
+  int rc = make_map(&tmR, st.params + L.offset[FC11_W], H, D, H, A, L.arm_stride, 128, false);
+  if (rc) return rc;
+  rc = make_map(&tmTk, work + w.d[4], H, B, H, A, (int64_t)B * H, GN, false);
+  if (rc) return rc;
+  rc = make_map(&tmTm, work + w.d[4], H, B, H, A, (int64_t)B * H, GN, true);
+  if (rc) return rc;
+  rc = make_map(&tmX, in.x, D, B, in.x_row_stride, A, in.x_arm_stride, GN, false);
+  if (rc) return rc;
+  RowsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.D = D; a.H = H; a.HN = (H + 15) / 16 * 16;
+  a.ntiles = (B + GN - 1) / GN;
+  const int mt = (D + ROWS - 1) / ROWS;
+  const int nsplit = choose_gene_split(mt * A, a.ntiles, 8);
+  a.tiles_per_split = (a.ntiles + nsplit - 1) / nsplit;
+  a.x_batched = in.x_arm_stride > 0;
+  a.gscale = gscale; a.want_grad = 1;
+  a.bias = st.params + L.offset[FC11_B]; a.bias_arm_stride = L.arm_stride;
+  a.part = work + w.fc1_part; a.part_arm_stride = (int64_t)w.Dpad * 128; a.part_split_stride = (int64_t)A * a.part_arm_stride;
+  a.db_part = work + w.db_part; a.db_arm_stride = w.Dpad; a.db_split_stride = (int64_t)A * w.Dpad;
+  const size_t smem = H10_BYTES + (size_t)STAGES * STAGE_BYTES + 32 * 8 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    MVAE_CUDA(cudaFuncSetAttribute(fc11_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  fc11_fused_kernel<true><<<dim3(nsplit, mt, A), FUSED_THREADS, smem, s>>>(tmR, tmTk, tmTm, tmX, a);
+  MVAE_LAUNCH_CHECK();
+  partial_sum2_kernel<<<dim3((H + 31) / 32, (D + 7) / 8, A), 256, 0, s>>>(a.part, a.part_split_stride, a.part_arm_stride, 128,
+                                                                          nsplit, st.grads + L.offset[FC11_W], L.arm_stride, H, D, H);
+  MVAE_LAUNCH_CHECK();
+  // d fc11.bias: [split][A][Dpad] -> grads (treated as a [1 x D] matrix per arm)
+  partial_sum2_kernel<<<dim3((D + 31) / 32, 1, A), 256, 0, s>>>(a.db_part, a.db_split_stride, a.db_arm_stride, 0, nsplit,
+                                                                st.grads + L.offset[FC11_B], L.arm_stride, 0, 1, D);
+  MVAE_LAUNCH_CHECK();
   return 0;
 }
 

@@ -438,25 +438,10 @@ int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_sta
   DropSpec nodrop;
   memset(&nodrop, 0, sizeof(nodrop));
   if (hp.precision == 1) return tc_fc11_loss_grad_unfused(d, hp, st, in, w, gscale, want_grad, s);
-  // fused row-owner pass: x_hat, loss sums, dY (kept in `big` for the dW11 GEMM below), d h10
-  int rc = tc_fc11_rows(d, st, in, w, gscale, want_grad, want_grad ? work + w.big : nullptr, nullptr, acc_loss, s);
+  // fused passes: row owner (x_hat, loss sums, d h10), then gene owner (d fc11.weight, d fc11.bias)
+  int rc = tc_fc11_rows(d, st, in, w, gscale, want_grad, nullptr, nullptr, acc_loss, s);
   if (rc || !want_grad) return rc;
-  float* part = work + w.fc1_part;
-  // G4: d W11 = dY^T . h10   (A(m=gene,k=row) = dY[row][gene]: MN-major; B(k=row,n=h) = h10[row][h]: MN-major)
-  {
-    Operand dYt{work + w.big, D, (int64_t)B * D, true};
-    Operand h10t{work + w.d[4], H, (int64_t)B * H, true};
-    const int mt = (D + BM - 1) / BM;
-    const int nsplit = choose_split(mt * A, (B + BK - 1) / BK, 2);
-    const int64_t bs = (int64_t)w.Dpad * 128, ss = (int64_t)A * bs;
-    rc = run_tc_gemm(dYt, h10t, D, H, B, round16(H), A, nsplit, split3, nodrop, part, 128, bs, ss, s);
-    if (rc) return rc;
-    partial_sum_kernel<<<dim3((H + 31) / 32, (D + 7) / 8, A), 256, 0, s>>>(part, ss, bs, 128, nsplit,
-                                                                            st.grads + L.offset[FC11_W], L.arm_stride, H,
-                                                                            D, H);
-    MVAE_LAUNCH_CHECK();
-  }
-  return launch_colsum(work + w.big, (int64_t)B * D, st.grads + L.offset[FC11_B], L.arm_stride, B, D, A, s);
+  return tc_fc11_genes(d, st, in, w, gscale, s);
 }
 
 int tc_fc1_wgrad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,

@@ -21,6 +21,9 @@ int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_sta
 int tc_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale,
                  int want_grad, float* dY_out, float* x_rec, double* recon_acc, cudaStream_t s);
 
+int tc_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale,
+                  cudaStream_t s);
+
 // d fc1.weight = delta1^T * dropout(x)
 int tc_fc1_wgrad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
                  const DropSpec& drop, const Work& w, cudaStream_t s);

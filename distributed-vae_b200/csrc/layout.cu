@@ -126,9 +126,10 @@ Work make_work(const mvae_dims& d) {
   w.fc1_splitk = 8;
   {
     // split-K partials of the tensor-core GEMMs: fc1 / d h10 use [split<=4][A][Bpad][128], d W11 [split<=2][A][Dpad][128]
-    const int64_t p1 = (int64_t)w.fc1_splitk * A * w.Bpad * 128, p2 = (int64_t)2 * A * w.Dpad * 128;
+    const int64_t p1 = (int64_t)w.fc1_splitk * A * w.Bpad * 128, p2 = (int64_t)8 * A * w.Dpad * 128;
     w.fc1_part = take(p1 > p2 ? p1 : p2);
   }
+  w.db_part = take((int64_t)8 * A * w.Dpad);
   w.big = take(A * B * D);
   // narrow-layer weight-gradient partials mirror the parameter range [offset(fc1.b), offset(fc11.w))
   mvae_layout L;
