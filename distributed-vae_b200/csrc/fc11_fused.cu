@@ -35,7 +35,8 @@ constexpr int WK_BYTES = 4 * 4096;     // W11 tile, K-major image: 4 h-slabs of 
 constexpr int WM_BYTES = 4 * 4096;     // W11 tile, MN-major image (32-byte-atom swizzle): 4 h-slabs of 32 genes x 128 B
 constexpr int X_BYTES = 16384;         // x tile / dY tile: 128 rows x 128 B
 constexpr int STAGE_BYTES = WK_BYTES + WM_BYTES + X_BYTES;
-constexpr int FUSED_THREADS = 192;
+constexpr int FUSED_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
+constexpr int EPI_THREADS = 256;
 
 struct RowsArgs {
   int B, D, H;
@@ -82,11 +83,11 @@ fc11_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, 1);
-      mbar_init(dy_ready + s, 128);
+      mbar_init(dy_ready + s, EPI_THREADS);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(xhat_full + b, 1);
-      mbar_init(tmem_empty + b, 128);
+      mbar_init(tmem_empty + b, EPI_THREADS);
     }
     mbar_init(h10_full, 1);
     mbar_init(g_full, 1);
@@ -176,75 +177,76 @@ fc11_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       umma_commit(g_full);
     }
   } else if (!GENE) {
-    // ===== epilogue warps 2..5, row owner =====
-    const int quad = warp & 3;
+    // ===== epilogue warps 2..9, row owner: thread = (cell, half of the 32 genes of a tile) =====
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;            // row within the CTA tile == TMEM lane
     const int row = m0 + r;
     const bool row_ok = row < a.B;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float* __restrict__ bias = a.bias + (int64_t)arm * a.bias_arm_stride;
-    float* dyrow = a.dY ? a.dY + (int64_t)arm * a.dy_arm_stride + (int64_t)row * a.D : nullptr;
     float* xrrow = a.x_rec ? a.x_rec + (int64_t)arm * a.xrec_arm_stride + (int64_t)row * a.D : nullptr;
     double sse = 0.0, mism = 0.0;
     for (int i = 0; i < nt; ++i) {
       const int s = i % STAGES, b = i & 1;
-      const int g0 = (t0 + i) * GN;
-      // bias of the 32 genes of this tile: issued before the waits so that the latency overlaps them
-      // (they must not sit behind the dY global stores of the previous chunk: the compiler cannot
-      // prove that the two float* do not alias)
-      float4 bvv[8];
+      const int g0 = (t0 + i) * GN + 16 * half;         // first gene of this thread's 16
+      const bool full_tile = g0 + 16 <= a.D;
+      // bias first: its latency overlaps the barrier waits
+      float4 bvv[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         const int g = g0 + 4 * c;
         bvv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g + 3 < a.D) bvv[c] = __ldg(reinterpret_cast<const float4*>(bias + g));
+        if (full_tile) bvv[c] = __ldg(reinterpret_cast<const float4*>(bias + g));
         else {
           if (g < a.D) bvv[c].x = __ldg(bias + g);
           if (g + 1 < a.D) bvv[c].y = __ldg(bias + g + 1);
           if (g + 2 < a.D) bvv[c].z = __ldg(bias + g + 2);
+          if (g + 3 < a.D) bvv[c].w = __ldg(bias + g + 3);
         }
       }
       mbar_wait(full + s, (i / STAGES) & 1);            // x tile visible to this thread
       mbar_wait(xhat_full + b, (i >> 1) & 1);
       tc_fence_after();
-      uint32_t acc[32];
-      tmem_ld32(tmem_base + lane_addr + (uint32_t)(b * GN), acc);
+      uint32_t acc[16];
+      tmem_ld16(tmem_base + lane_addr + (uint32_t)(b * GN + 16 * half), acc);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(tmem_empty + b);
       float4* xrow = reinterpret_cast<float4*>(xs(s) + r * 128);
       float fs = 0.f, fm = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int p = c ^ (r & 7);                        // SWIZZLE_128B: logical chunk c lives at chunk p
+      for (int c = 0; c < 4; ++c) {
+        const int p = (4 * half + c) ^ (r & 7);           // SWIZZLE_128B: logical chunk lives at chunk p
         const float4 xv = xrow[p];
-        const int g = g0 + 4 * c;
-        const float4 bv = bvv[c];
         const float xin[4] = {xv.x, xv.y, xv.z, xv.w};
-        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+        const float bb[4] = {bvv[c].x, bvv[c].y, bvv[c].z, bvv[c].w};
         float dy[4], xh[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           xh[e] = fmaxf(__uint_as_float(acc[4 * c + e]) + bb[e], 0.f);
           const float d = xh[e] - xin[e];
-          const bool ok = row_ok && (g + e < a.D);
-          if (ok) {
-            fs = fmaf(d, d, fs);
-            fm += ((xh[e] > 0.1f) != (xin[e] > 0.1f)) ? 1.f : 0.f;
+          fs = fmaf(d, d, fs);                            // masked below for partial tiles
+          fm += ((xh[e] > 0.1f) != (xin[e] > 0.1f)) ? 1.f : 0.f;
+          dy[e] = xh[e] > 0.f ? a.gscale * d : 0.f;
+        }
+        if (!(row_ok && full_tile)) {                     // slow path: overhanging rows / genes
+          const int g = g0 + 4 * c;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (!(row_ok && g + e < a.D)) {
+              const float d = xh[e] - xin[e];
+              fs -= d * d;
+              fm -= ((xh[e] > 0.1f) != (xin[e] > 0.1f)) ? 1.f : 0.f;
+              dy[e] = 0.f;
+            }
           }
-          dy[e] = (ok && xh[e] > 0.f) ? a.gscale * d : 0.f;
         }
         xrow[p] = make_float4(dy[0], dy[1], dy[2], dy[3]);
-        if (row_ok && g + 3 < a.D) {
-          if (dyrow) *reinterpret_cast<float4*>(dyrow + g) = make_float4(dy[0], dy[1], dy[2], dy[3]);
-          if (xrrow) *reinterpret_cast<float4*>(xrrow + g) = make_float4(xh[0], xh[1], xh[2], xh[3]);
-        } else if (row_ok) {
+        if (xrrow && row_ok) {
+          const int g = g0 + 4 * c;
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            if (g + e < a.D) {
-              if (dyrow) dyrow[g + e] = dy[e];
-              if (xrrow) xrrow[g + e] = xh[e];
-            }
+            if (g + e < a.D) xrrow[g + e] = xh[e];
         }
       }
       sse += (double)fs;
@@ -259,12 +261,12 @@ fc11_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       atomicAdd(a.recon_acc + accl_recon(arm), sse);
       atomicAdd(a.recon_acc + accl_recon(arm) + 1, mism);
     }
-    // ---- d h10 partial
+    // ---- d h10 partial: the two halves share the HN columns
     if (a.want_grad) {
       mbar_wait(g_full, 0);
       tc_fence_after();
       float* prow = a.part + (int64_t)split * a.part_split_stride + (int64_t)arm * a.part_arm_stride + (int64_t)row * 128;
-      for (int c0 = 0; c0 < a.HN; c0 += 16) {
+      for (int c0 = 64 * half; c0 < min(a.HN, 64 * half + 64); c0 += 16) {
         uint32_t rr[16];
         if (nt > 0) {
           tmem_ld16(tmem_g + lane_addr + (uint32_t)c0, rr);
@@ -281,9 +283,10 @@ fc11_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         }
       }
     }
-    } else {
-    // ===== epilogue warps 2..5, gene owner =====
-    const int quad = warp & 3;
+  } else {
+    // ===== epilogue warps 2..9, gene owner: thread = (gene, half of the 32 cells of a tile) =====
+    __shared__ float dbs[128];
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int gl = quad * 32 + lane;           // gene within the CTA block == TMEM lane
     const int gene = m0 + gl;
     const bool gene_ok = gene < a.D;
@@ -292,41 +295,49 @@ fc11_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     float dbsum = 0.f;
     for (int i = 0; i < nt; ++i) {
       const int s = i % STAGES, b = i & 1;
-      const int r0 = (t0 + i) * GN;             // first cell of the tile
+      const int r0 = (t0 + i) * GN + 16 * half;     // first cell of this thread's 16
       mbar_wait(full + s, (i / STAGES) & 1);
       mbar_wait(xhat_full + b, (i >> 1) & 1);
       tc_fence_after();
-      uint32_t acc[32];
-      tmem_ld32(tmem_base + lane_addr + (uint32_t)(b * GN), acc);
+      uint32_t acc[16];
+      tmem_ld16(tmem_base + lane_addr + (uint32_t)(b * GN + 16 * half), acc);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(tmem_empty + b);
       // x tile: 4 gene slabs of [32 cells x 128 B] (SWIZZLE_128B); this thread's gene is element `lane` of slab `quad`
       const uint8_t* xslab = xs(s) + quad * 4096;
-      float xv[32];
+      float xv[16];
 #pragma unroll
-      for (int r = 0; r < 32; ++r)
-        xv[r] = *reinterpret_cast<const float*>(xslab + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // every epilogue thread has read the x tile
-      float dy[32];
+      for (int rr = 0; rr < 16; ++rr) {
+        const int r = 16 * half + rr;
+        xv[rr] = *reinterpret_cast<const float*>(xslab + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // every epilogue thread has read the x tile
+      float dy[16];
+      const bool all_rows = gene_ok && (r0 + 16 <= a.B);
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const float xh = fmaxf(__uint_as_float(acc[r]) + bj, 0.f);
-        const bool ok = gene_ok && (r0 + r < a.B);
-        dy[r] = (ok && xh > 0.f) ? a.gscale * (xh - xv[r]) : 0.f;
-        dbsum += dy[r];
+      for (int rr = 0; rr < 16; ++rr) {
+        const float xh = fmaxf(__uint_as_float(acc[rr]) + bj, 0.f);
+        float v = xh > 0.f ? a.gscale * (xh - xv[rr]) : 0.f;
+        if (!all_rows && !(gene_ok && r0 + rr < a.B)) v = 0.f;
+        dy[rr] = v;
+        dbsum += v;
       }
       float4* drow = reinterpret_cast<float4*>(xs(s) + gl * 128);   // dY^T row of this gene (K-major, SWIZZLE_128B)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) drow[c ^ (gl & 7)] = make_float4(dy[4 * c], dy[4 * c + 1], dy[4 * c + 2], dy[4 * c + 3]);
+      for (int c = 0; c < 4; ++c)
+        drow[(4 * half + c) ^ (gl & 7)] = make_float4(dy[4 * c], dy[4 * c + 1], dy[4 * c + 2], dy[4 * c + 3]);
       fence_proxy_async();
       mbar_arrive(dy_ready + s);
     }
-    if (gene_ok) a.db_part[(int64_t)split * a.db_split_stride + (int64_t)arm * a.db_arm_stride + gene] = dbsum;
+    if (half == 1) dbs[gl] = dbsum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (half == 0 && gene_ok)
+      a.db_part[(int64_t)split * a.db_split_stride + (int64_t)arm * a.db_arm_stride + gene] = dbsum + dbs[gl];
     mbar_wait(g_full, 0);
     tc_fence_after();
     float* prow = a.part + (int64_t)split * a.part_split_stride + (int64_t)arm * a.part_arm_stride + (int64_t)gene * 128;
-    for (int c0 = 0; c0 < a.HN; c0 += 16) {
+    for (int c0 = 64 * half; c0 < min(a.HN, 64 * half + 64); c0 += 16) {
       uint32_t rr[16];
       if (nt > 0) {
         tmem_ld16(tmem_g + lane_addr + (uint32_t)c0, rr);
@@ -408,7 +419,7 @@ int tc_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
   const size_t smem = H10_BYTES + (size_t)STAGES * STAGE_BYTES + 32 * 8 + 1024;
   static bool attr = false;
   if (!attr) {
-    MVAE_CUDA(cudaFuncSetAttribute(fc11_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(fc11_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   fc11_fused_kernel<false><<<dim3(nsplit, mt, A), FUSED_THREADS, smem, s>>>(tmH, tmWk, tmWm, tmX, a);
@@ -454,7 +465,7 @@ int tc_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& i
   const size_t smem = H10_BYTES + (size_t)STAGES * STAGE_BYTES + 32 * 8 + 1024;
   static bool attr = false;
   if (!attr) {
-    MVAE_CUDA(cudaFuncSetAttribute(fc11_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(fc11_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   fc11_fused_kernel<true><<<dim3(nsplit, mt, A), FUSED_THREADS, smem, s>>>(tmR, tmTk, tmTm, tmX, a);
