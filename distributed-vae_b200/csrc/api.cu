@@ -58,7 +58,7 @@ static DropSpec make_drop(const Plan& p, const mvae_hparams& hp, const mvae_inpu
   } else {
     d.mode = 2;
     d.seed = in.seed * 0x9E3779B97F4A7C15ull + in.step * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
-    double t = (double)hp.x_drop * 65536.0;
+    double t = (double)hp.x_drop * 256.0;
     d.thresh16 = (uint32_t)(t + 0.5);
   }
   return d;

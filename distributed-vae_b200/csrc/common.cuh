@@ -151,20 +151,22 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Counter-based dropout generator: 16 random bits per element from a 32-bit mix of
-// (seed, element pair index).  keep <=> bits >= thresh16, thresh16 = round(p * 65536).
+// Counter-based dropout generator: ONE 32-bit mix per 4 consecutive elements of x (a 16-byte chunk),
+// 8 random bits per element.  keep <=> byte >= thresh, thresh = round(p * 256): exact for p = k/256
+// (the reference default p = 0.5 in particular); other rates are quantised to 1/256.
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
   return h;
 }
+__device__ __forceinline__ uint32_t drop_bits4(uint64_t seed, int arm, uint64_t chunk) {
+  return mix32((uint32_t)chunk * 0x9E3779B1u ^ (uint32_t)(chunk >> 32) * 0x7FEB352Du ^ (uint32_t)seed ^
+               ((uint32_t)(seed >> 32) * 0x846CA68Bu) ^ ((uint32_t)arm * 0x632BE5ABu));
+}
 __device__ __forceinline__ bool drop_keep(uint64_t seed, int arm, int64_t row, int64_t col, int64_t D,
-                                          uint32_t thresh16) {
-  uint64_t idx = (uint64_t)row * (uint64_t)D + (uint64_t)col;
-  uint64_t pair = idx >> 1;
-  uint32_t h = mix32((uint32_t)pair * 0x9E3779B1u ^ (uint32_t)(pair >> 32) * 0x7FEB352Du ^
-                     (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x846CA68Bu) ^ ((uint32_t)arm * 0x632BE5ABu));
-  uint32_t bits = (idx & 1) ? (h >> 16) : (h & 0xffffu);
-  return bits >= thresh16;
+                                          uint32_t thresh) {
+  const uint64_t idx = (uint64_t)row * (uint64_t)D + (uint64_t)col;
+  const uint32_t bits = (drop_bits4(seed, arm, idx >> 2) >> (8 * (uint32_t)(idx & 3))) & 0xFFu;
+  return bits >= thresh;
 }
 #endif
 
@@ -173,7 +175,7 @@ struct DropSpec {
   int64_t keep_arm_stride;
   uint64_t seed;        // used when keep == nullptr && mode == 2
   float scale;          // 1/(1-p)
-  uint32_t thresh16;
+  uint32_t thresh16;    // 8-bit threshold of the in-kernel generator (name kept): round(p * 256)
   int mode;             // 0: no dropout, 1: injected mask, 2: in-kernel generator
   int64_t D;            // genes per row (hash index)
   int64_t rows;         // rows of x (cells); tiles may overhang

@@ -26,9 +26,9 @@ constexpr int BM = 128;          // UMMA M
 constexpr int BK = 32;           // floats per pipeline stage along K (= one 128-byte swizzle row)
 constexpr int UK = 8;            // K of one tcgen05.mma kind::tf32
 constexpr int TILE_BYTES = 16384;  // one operand tile: 128 x 128 B (K-major) or 4 slabs of 32 x 128 B (MN-major)
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 448;      // TMA, MMA, 4 epilogue warps, 8 transform warps
 constexpr int TRANSFORM_WARP0 = 6;
-constexpr int TRANSFORM_THREADS = 128;
+constexpr int TRANSFORM_THREADS = 256;
 
 enum : int { F_SPLIT_A = 1, F_SPLIT_B = 2, F_DROP_A = 4, F_DROP_B = 8 };
 
@@ -54,9 +54,9 @@ using namespace tc;
 //   MN-major tile: slab j (32 MN elements), row r = K offset, logical chunk c4 -> MN offset 32*j + 4*c4
 template <bool MN>
 __device__ __forceinline__ void transform_tile(float* hi, float* lo, bool do_split, bool do_drop, const DropSpec& drop,
-                                               int arm, int mn0, int k0, int tid) {
-#pragma unroll 2
-  for (int q = tid; q < TILE_BYTES / 16; q += TRANSFORM_THREADS) {
+                                               int arm, int mn0, int k0, int tid, int nthr) {
+#pragma unroll 4
+  for (int q = tid; q < TILE_BYTES / 16; q += nthr) {
     float4 v = reinterpret_cast<float4*>(hi)[q];
     if (do_drop) {
       const int r = q >> 3, p = q & 7;
@@ -77,8 +77,10 @@ __device__ __forceinline__ void transform_tile(float* hi, float* lo, bool do_spl
 #pragma unroll
         for (int i = 0; i < 4; ++i) m[i] = ((kb >> (8 * i)) & 0xFF) ? drop.scale : 0.f;
       } else {
+        // xcol % 4 == 0 and D % 4 == 0: the 4 elements are exactly one generator chunk
+        const uint32_t bits = drop_bits4(drop.seed, arm, ((uint64_t)xrow * (uint64_t)drop.D + (uint64_t)xcol) >> 2);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) m[i] = drop_keep(drop.seed, arm, xrow, xcol + i, drop.D, drop.thresh16) ? drop.scale : 0.f;
+        for (int i = 0; i < 4; ++i) m[i] = ((bits >> (8 * i)) & 0xFFu) >= drop.thresh16 ? drop.scale : 0.f;
       }
       v.x *= m[0]; v.y *= m[1]; v.z *= m[2]; v.w *= m[3];
       reinterpret_cast<float4*>(hi)[q] = v;
@@ -207,12 +209,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (i / S) & 1;
         mbar_wait(full + s, ph);
         const int k0 = (kt0 + i) * BK;
-        if (splitA || dropA)
+        const bool doA = splitA || dropA, doB = splitB || dropB;
+        if (doA && doB) {             // 4 warps per operand
+          if (tid < 128)
+            transform_tile<A_MN>(reinterpret_cast<float*>(tileA(s)), reinterpret_cast<float*>(tileAlo(s)), splitA, dropA,
+                                 args.drop, batch, m0, k0, tid, 128);
+          else
+            transform_tile<B_MN>(reinterpret_cast<float*>(tileB(s)), reinterpret_cast<float*>(tileBlo(s)), splitB, dropB,
+                                 args.drop, batch, n0, k0, tid - 128, 128);
+        } else if (doA) {
           transform_tile<A_MN>(reinterpret_cast<float*>(tileA(s)), reinterpret_cast<float*>(tileAlo(s)), splitA, dropA,
-                               args.drop, batch, m0, k0, tid);
-        if (splitB || dropB)
+                               args.drop, batch, m0, k0, tid, TRANSFORM_THREADS);
+        } else if (doB) {
           transform_tile<B_MN>(reinterpret_cast<float*>(tileB(s)), reinterpret_cast<float*>(tileBlo(s)), splitB, dropB,
-                               args.drop, batch, n0, k0, tid);
+                               args.drop, batch, n0, k0, tid, TRANSFORM_THREADS);
+        }
         fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(ready + s);
       }
@@ -449,12 +460,23 @@ int tc_fc1_wgrad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& s
   mvae_layout L;
   compute_layout(d, &L);
   const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
-  // G5: dW1[h][gene] = sum_row delta1[row][h] * xd[row][gene]: both operands MN-major
+  // G5: dW1[h][gene] = sum_row delta1[row][h] * xd[row][gene]: both operands MN-major; split over cells
   Operand d1{st.work + w.delta_enc[0], H, (int64_t)B * H, true};
   Operand x{in.x, in.x_row_stride, in.x_arm_stride, true};
   int flags = hp.precision == 1 ? (F_SPLIT_A | F_SPLIT_B) : 0;
   if (drop.mode) flags |= F_DROP_B;
-  return run_tc_gemm(d1, x, H, D, B, 128, A, 1, flags, drop, st.grads + L.offset[FC1_W], D, L.arm_stride, 0, s);
+  const int nt = (D + 127) / 128;
+  const int nsplit = choose_split(nt * A, (B + BK - 1) / BK, 8);
+  if (nsplit == 1)
+    return run_tc_gemm(d1, x, H, D, B, 128, A, 1, flags, drop, st.grads + L.offset[FC1_W], D, L.arm_stride, 0, s);
+  float* part = st.work + w.fc1_part;                 // [split][A][128][Dpad]
+  const int64_t bs = (int64_t)128 * w.Dpad, ss = (int64_t)A * bs;
+  int rc = run_tc_gemm(d1, x, H, D, B, 128, A, nsplit, flags, drop, part, w.Dpad, bs, ss, s);
+  if (rc) return rc;
+  partial_sum_kernel<<<dim3((D + 31) / 32, (H + 7) / 8, A), 256, 0, s>>>(part, ss, bs, w.Dpad, nsplit,
+                                                                          st.grads + L.offset[FC1_W], L.arm_stride, D, H, D);
+  MVAE_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace mvae
