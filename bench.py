@@ -213,11 +213,17 @@ def main():
         trainer.model.train()
         step_fn = trainer.train_batch
         parallelism = "single GPU"
+        dp_ranks = 1
     else:
         from mmidas_b200.parallel import ShardedTrainer
         st = ShardedTrainer(model_kwargs, lr=1e-3, mode=args.mesh)
         step_fn = st.step
         parallelism = f"mesh arm{st.plan.arm_ranks} x dp{st.plan.dp_ranks}, NCCL"
+        dp_ranks = st.plan.dp_ranks          # ranks of one arm group see the SAME cells: count them once
+        if st.plan.arm_ranks > 1:
+            # every rank of an arm group must be fed the same batch
+            gen = torch.Generator(device=dev).manual_seed(546 + rank // st.plan.arm_ranks)
+            batches = [synth_x_device(B, D, w["density"], gen, dev) for _ in range(N_ROTATING_BATCHES)]
 
     def sync():
         if world > 1:
@@ -250,7 +256,7 @@ def main():
     if not (last_loss == last_loss) or abs(last_loss) == float("inf"):
         raise SystemExit(f"non-finite loss {last_loss}")
     ms_per_step = ms / args.steps
-    value = world * B * args.steps / (ms / 1e3)
+    value = dp_ranks * B * args.steps / (ms / 1e3)
 
     # ---- per-kernel-group device time (CUDA events inside the library, on the launching stream) --
     roofline = None
@@ -310,7 +316,7 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        e2e = {"value": world * B * n_e2e / dt, "unit": "cells/s", "h2d_bytes_per_step": B * D * 4,
+        e2e = {"value": dp_ranks * B * n_e2e / dt, "unit": "cells/s", "h2d_bytes_per_step": B * D * 4,
                "d2h_bytes_per_step": 4, "ms_per_step": dt / n_e2e * 1e3,
                "api": "cpl_mixVAE.train_batch via HostBatchFeeder (pinned host batch -> side-stream H2D -> fused step -> loss.item())"}
 
