@@ -163,16 +163,21 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   RC(launch_head_fwd(h, s));
 
   // ---- fc7..fc10 (:281-284)
-  for (int l = 1; l <= 4; ++l) {
-    DenseFwdArgs a;
-    memset(&a, 0, sizeof(a));
-    const int nin = l == 1 ? Ld : H;
-    a.in = work + w.d[l - 1]; a.in_arm_stride = (int64_t)B * nin;
-    a.out = work + w.d[l]; a.out_arm_stride = (int64_t)B * H;
-    a.params = st.params; a.p_arm_stride = p.L.arm_stride;
-    a.offW = p.L.offset[FC7_W + 2 * (l - 1)]; a.offB = p.L.offset[FC7_B + 2 * (l - 1)];
-    a.B = B; a.nin = nin; a.nout = H; a.bn_mode = 0; a.eps = hp.eps; a.relu = 1;
-    RC(hp.precision == 3 ? launch_dense_fwd(a, A, s) : launch_dense_fwd_mma(a, A, s));
+  if (hp.precision != 3) {
+    float* hout[4] = {work + w.d[1], work + w.d[2], work + w.d[3], work + w.d[4]};
+    RC(launch_dec_chain_fwd(st.params, p.L.arm_stride, p.L.offset, A, B, H, Ld, work + w.d[0], hout, hp.precision == 1, s));
+  } else {
+    for (int l = 1; l <= 4; ++l) {
+      DenseFwdArgs a;
+      memset(&a, 0, sizeof(a));
+      const int nin = l == 1 ? Ld : H;
+      a.in = work + w.d[l - 1]; a.in_arm_stride = (int64_t)B * nin;
+      a.out = work + w.d[l]; a.out_arm_stride = (int64_t)B * H;
+      a.params = st.params; a.p_arm_stride = p.L.arm_stride;
+      a.offW = p.L.offset[FC7_W + 2 * (l - 1)]; a.offB = p.L.offset[FC7_B + 2 * (l - 1)];
+      a.B = B; a.nin = nin; a.nout = H; a.bn_mode = 0; a.eps = hp.eps; a.relu = 1;
+      RC(launch_dense_fwd(a, A, s));
+    }
   }
   if (training)
     RC(launch_bn_update_running(st.bn_running, p.L.bn_stride, bn_off(p), st.bn_batches, acc_fwd, A, B, H, Ld,
@@ -289,16 +294,24 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   // ---- decoder fc10..fc7
   timing_begin(TG_NARROW_BWD, s);
   const float* g_cur = work + w.g_d10;
-  for (int l = 4; l >= 1; --l) {
-    DenseBwdArgs a;
-    memset(&a, 0, sizeof(a));
-    const int nin = l == 1 ? Ld : H;
-    a.g_out = g_cur; a.act_out = work + w.d[l]; a.delta = work + w.delta_dec[l];
-    a.g_in = work + w.gtmp[l & 1];
-    a.params = st.params; a.p_arm_stride = p.L.arm_stride; a.offW = p.L.offset[FC7_W + 2 * (l - 1)];
-    a.B = B; a.nin = nin; a.nout = H;
-    RC(hp.precision == 3 ? launch_dense_bwd(a, A, s) : launch_dense_bwd_mma(a, A, s));
-    g_cur = a.g_in;
+  if (hp.precision != 3) {
+    const float* act[4] = {work + w.d[1], work + w.d[2], work + w.d[3], work + w.d[4]};
+    float* dl[4] = {work + w.delta_dec[1], work + w.delta_dec[2], work + w.delta_dec[3], work + w.delta_dec[4]};
+    RC(launch_dec_chain_bwd(st.params, p.L.arm_stride, p.L.offset, A, B, H, Ld, work + w.g_d10, act, dl, work + w.gtmp[1],
+                            hp.precision == 1, s));
+    g_cur = work + w.gtmp[1];
+  } else {
+    for (int l = 4; l >= 1; --l) {
+      DenseBwdArgs a;
+      memset(&a, 0, sizeof(a));
+      const int nin = l == 1 ? Ld : H;
+      a.g_out = g_cur; a.act_out = work + w.d[l]; a.delta = work + w.delta_dec[l];
+      a.g_in = work + w.gtmp[l & 1];
+      a.params = st.params; a.p_arm_stride = p.L.arm_stride; a.offW = p.L.offset[FC7_W + 2 * (l - 1)];
+      a.B = B; a.nin = nin; a.nout = H;
+      RC(launch_dense_bwd(a, A, s));
+      g_cur = a.g_in;
+    }
   }
   // g_cur = d loss / d d6, [A][B][L] in gtmp[1]
 
@@ -344,7 +357,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
     } else if (tc) {
       a.delta_t = work + w.delta1_t; a.delta_t_ld = w.Bpad; a.delta_t_arm_stride = (int64_t)w.Hpad * w.Bpad;
     }
-    RC(hp.precision == 3 ? launch_dense_bwd(a, A, s) : launch_dense_bwd_mma(a, A, s));
+    RC(hp.precision == 3 ? launch_dense_bwd(a, A, s) : launch_dense_bwd_mma(a, A, hp.precision == 1, s));
     g_cur = a.g_in;
   }
 
@@ -390,7 +403,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   wg.part = work + w.wg_part; wg.part_arm_stride = w.wg_floats; wg.part_split_stride = (int64_t)A * w.wg_floats;
   wg.base_off = p.L.offset[FC1_B];
   wg.grads = st.grads; wg.g_arm_stride = p.L.arm_stride;
-  RC(hp.precision == 3 ? launch_wgrad(wg, s) : launch_wgrad_mma(wg, s));
+  RC(hp.precision == 3 ? launch_wgrad(wg, s) : launch_wgrad_mma(wg, hp.precision == 1, s));
   timing_end(TG_WGRAD, s);
 
   if (grad_scale) RC(launch_scale(st.grads, (int64_t)A * p.L.arm_stride, grad_scale, s));

@@ -30,7 +30,7 @@ struct DenseBwdArgs {
 };
 int launch_dense_bwd(const DenseBwdArgs& a, int A, cudaStream_t s);
 int launch_dense_fwd_mma(const DenseFwdArgs& a, int A, cudaStream_t s);   // warp-MMA 3xTF32 versions (kernels_mma.cu)
-int launch_dense_bwd_mma(const DenseBwdArgs& a, int A, cudaStream_t s);
+int launch_dense_bwd_mma(const DenseBwdArgs& a, int A, int split3, cudaStream_t s);
 
 struct Fc1EpiArgs {
   const float* part; int64_t split_stride, arm_stride, ld; int nsplit;
@@ -122,7 +122,13 @@ struct WgArgs {
   float* grads; int64_t g_arm_stride;
 };
 int launch_wgrad(const WgArgs& a, cudaStream_t s);
-int launch_wgrad_mma(const WgArgs& a, cudaStream_t s);
+int launch_wgrad_mma(const WgArgs& a, int split3, cudaStream_t s);
+// decoder stack fc7..fc10 fused per direction (kernels_chain.cu)
+int launch_dec_chain_fwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
+                         const float* h6, float* const hout[4], int split3, cudaStream_t s);
+int launch_dec_chain_bwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
+                         const float* g10, const float* const act[4], float* const delta[4], float* g6, int split3,
+                         cudaStream_t s);
 
 // ---- optimiser / misc ------------------------------------------------------------------------
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,

@@ -1,0 +1,348 @@
+// kernels_chain.cu — the decoder stack fc7..fc10 (nn_model.py:281-284) as ONE kernel per direction.
+//
+// There is no batch coupling between these four layers (no BatchNorm), so a CTA keeps its 64 cells in
+// shared memory from h6 to h10 (forward) / from d h10 to d h6 (backward) and only streams the weights:
+// the next layer's weight matrix is fetched with cp.async while the current layer is multiplied.  Same
+// warp-level 3xTF32 MMA as kernels_mma.cu; weights are used in their natural [out][in] layout in both
+// directions (forward: B(k,n) = W[n][k] with pitch = 4 mod 8; backward: B(k,n) = W[k][n], pitch = 8 mod 32).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mvae {
+
+namespace {
+
+// A CTA owns 16*MT cells (MT row groups x 2 column halves = 2*MT warps).  MT = 5 when that makes the
+// grid fit one wave of 148 CTAs (B = 5000, A = 2: 126 CTAs), else 4.  Pitches depend on H (runtime):
+//   XP  = round8(H) + 4   activation tiles and forward weights ([out][in]): pitch % 8 == 4
+//   WPB = round8(H) (+8..) backward weights read as [k][n]: pitch % 32 in {8, 24}
+
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v);
+  lo = __float_as_uint(v - __uint_as_float(hi & 0xFFFFE000u));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// copy a [rows x cols] fp32 matrix (row pitch ld) into smem (row pitch sp); 16-byte cp.async when every
+// row start is 16-byte aligned, scalar otherwise.  Rows >= rows_valid are zero-filled by the caller.
+__device__ __forceinline__ void async_tile(float* dst, int sp, const float* src, int64_t ld, int rows_valid, int cols,
+                                           int tid, int nthr) {
+  if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (ld % 4 == 0) && (cols % 4 == 0)) {
+    const int cpr = cols / 4;
+    for (int idx = tid; idx < rows_valid * cpr; idx += nthr) {
+      const int r = idx / cpr, c = (idx - r * cpr) * 4;
+      cp_async16(dst + r * sp + c, src + (int64_t)r * ld + c);
+    }
+  } else {
+    for (int idx = tid; idx < rows_valid * cols; idx += nthr) {
+      const int r = idx / cols, c = idx - r * cols;
+      dst[r * sp + c] = src[(int64_t)r * ld + c];
+    }
+  }
+}
+
+// acc[NTW][4] += A(16 x 8*ksteps) . B ; A(m,k) = As[m*ap + k];  B(k,n) = BT ? Bs[n*bp + k] : Bs[k*bp + n]
+template <int NTW, bool BT, bool SPLIT>
+__device__ __forceinline__ void warp_gemm2(const float* __restrict__ As, int ap, const float* __restrict__ Bs, int bp,
+                                           int ksteps, int nt_used, float (&acc)[NTW][4], int lane) {
+  const int g = lane >> 2, tig = lane & 3;
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const int k0 = ks * 8;
+    const float av[4] = {As[g * ap + k0 + tig], As[(g + 8) * ap + k0 + tig], As[g * ap + k0 + tig + 4],
+                         As[(g + 8) * ap + k0 + tig + 4]};
+    uint32_t ah[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      if (nt < nt_used) {
+        float b0, b1;
+        if (BT) {
+          b0 = Bs[(nt * 8 + g) * bp + k0 + tig];
+          b1 = Bs[(nt * 8 + g) * bp + k0 + tig + 4];
+        } else {
+          b0 = Bs[(k0 + tig) * bp + nt * 8 + g];
+          b1 = Bs[(k0 + tig + 4) * bp + nt * 8 + g];
+        }
+        uint32_t bh[2], bl[2];
+        if (SPLIT) {
+          split_tf32(b0, bh[0], bl[0]);
+          split_tf32(b1, bh[1], bl[1]);
+          mma_tf32(acc[nt], al, bh);
+          mma_tf32(acc[nt], ah, bl);
+        } else {
+          bh[0] = __float_as_uint(b0);
+          bh[1] = __float_as_uint(b1);
+        }
+        mma_tf32(acc[nt], ah, bh);
+      }
+    }
+  }
+}
+
+struct ChainArgs {
+  int XP, WPB, Hp;               // pitches (floats) and round8(H)
+  const float* params; int64_t p_arm_stride;
+  int64_t offW[4], offB[4];      // fc7..fc10
+  int B, H, L;
+  // forward: in = h6 [A][B][L]; out[l] = h7..h10 [A][B][H]
+  const float* h6; float* hout[4];
+  // backward: g10 = d loss / d h10 [A][B][H]; act[l] = h7..h10; delta[l] out; g6 out [A][B][L]
+  const float* g10; const float* act[4]; float* delta[4]; float* g6;
+};
+
+// =============================================================================================
+// forward chain
+// =============================================================================================
+template <int MT, bool SPLIT>
+__global__ void __launch_bounds__(64 * MT) dec_chain_fwd_kernel(const ChainArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int CR = 16 * MT, CT = 64 * MT;
+  const int XP = p.XP, WPF = p.XP, Hp = p.Hp;
+  float* Ws0 = smem;                       // [Hp][WPF]
+  float* Ws1 = Ws0 + Hp * WPF;
+  float* Xs0 = Ws1 + Hp * WPF;             // [CR][XP]
+  float* Xs1 = Xs0 + CR * XP;
+  float* bias = Xs1 + CR * XP;             // [4][128]
+  const int arm = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int warp = tid >> 5, wr = warp % MT, wc = warp / MT;
+  const int g = lane >> 2, tig = lane & 3;
+  const int H = p.H, L = p.L, B = p.B;
+  const int row0 = blockIdx.x * CR;
+  const int rows_valid = min(CR, B - row0);
+  const float* par = p.params + (int64_t)arm * p.p_arm_stride;
+
+  for (int idx = tid; idx < 2 * Hp * WPF + 2 * CR * XP; idx += CT) smem[idx] = 0.f;
+  for (int idx = tid; idx < 4 * 128; idx += CT) {
+    const int l = idx >> 7, j = idx & 127;
+    bias[idx] = j < H ? par[p.offB[l] + j] : 0.f;
+  }
+  __syncthreads();
+  // layer 0 operands (fc7: [H][L], rows of L floats: scalar path) + prefetch of fc8
+  async_tile(Ws0, WPF, par + p.offW[0], L, H, L, tid, CT);
+  async_tile(Xs0, XP, p.h6 + ((int64_t)arm * B + row0) * L, L, rows_valid, L, tid, CT);
+  cp_async_commit();
+  async_tile(Ws1, WPF, par + p.offW[1], H, H, H, tid, CT);
+  cp_async_commit();
+
+  float* Ws[2] = {Ws0, Ws1};
+  float* Xs[2] = {Xs0, Xs1};
+  const int NTW = 8;
+  for (int l = 0; l < 4; ++l) {
+    const int K = l == 0 ? L : H;
+    const int ksteps = (K + 7) / 8;
+    if (l < 3) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    float acc[NTW][4];
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    const int nt_used = max(0, min(NTW, (H + 7) / 8 - wc * NTW));
+    warp_gemm2<NTW, true, SPLIT>(Xs[l & 1] + wr * 16 * XP, XP, Ws[l & 1] + wc * NTW * 8 * WPF, WPF, ksteps, nt_used, acc, lane);
+    // epilogue: bias + ReLU -> global h_{7+l} and the next layer's operand tile
+    float* out = p.hout[l] + ((int64_t)arm * B + row0) * H;
+    float* Xn = Xs[(l + 1) & 1];
+    const int ra = wr * 16 + g, rb = ra + 8;
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      if (nt < nt_used) {
+        const int c = (wc * NTW + nt) * 8 + 2 * tig;
+        const float b0 = bias[l * 128 + c], b1 = bias[l * 128 + c + 1];
+        const float v00 = fmaxf(acc[nt][0] + b0, 0.f), v01 = fmaxf(acc[nt][1] + b1, 0.f);
+        const float v10 = fmaxf(acc[nt][2] + b0, 0.f), v11 = fmaxf(acc[nt][3] + b1, 0.f);
+        if (c < H) {      // H is even in practice; handle the odd tail element-wise
+          if (ra < rows_valid) { out[(int64_t)ra * H + c] = v00; if (c + 1 < H) out[(int64_t)ra * H + c + 1] = v01; }
+          if (rb < rows_valid) { out[(int64_t)rb * H + c] = v10; if (c + 1 < H) out[(int64_t)rb * H + c + 1] = v11; }
+          Xn[ra * XP + c] = v00; Xn[rb * XP + c] = v10;
+          if (c + 1 < H) { Xn[ra * XP + c + 1] = v01; Xn[rb * XP + c + 1] = v11; }
+        }
+      }
+    }
+    __syncthreads();                       // everyone is done with Ws[l&1] / Xs[l&1]
+    if (l + 2 < 4) {
+      async_tile(Ws[l & 1], WPF, par + p.offW[l + 2], H, H, H, tid, CT);
+      cp_async_commit();
+    }
+  }
+}
+
+// =============================================================================================
+// backward chain: delta_l = g * [h_l > 0];  g_{l-1} = delta_l . W_l
+// =============================================================================================
+template <int MT, bool SPLIT>
+__global__ void __launch_bounds__(64 * MT) dec_chain_bwd_kernel(const ChainArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int CR = 16 * MT, CT = 64 * MT;
+  const int XP = p.XP, WPB = p.WPB, Hp = p.Hp;
+  float* Ws0 = smem;                       // [Hp][WPB]  W_l natural: row j (out), col i (in)
+  float* Ws1 = Ws0 + Hp * WPB;
+  float* Gs = Ws1 + Hp * WPB;              // [CR][XP]   gradient wrt h_l, then delta_l in place
+  float* Ms0 = Gs + CR * XP;               // [CR][XP]   h_l tile (ReLU mask)
+  float* Ms1 = Ms0 + CR * XP;
+  const int arm = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int warp = tid >> 5, wr = warp % MT, wc = warp / MT;
+  const int g = lane >> 2, tig = lane & 3;
+  const int H = p.H, L = p.L, B = p.B;
+  const int row0 = blockIdx.x * CR;
+  const int rows_valid = min(CR, B - row0);
+  const float* par = p.params + (int64_t)arm * p.p_arm_stride;
+  const int64_t rbase = (int64_t)arm * B + row0;
+
+  for (int idx = tid; idx < 2 * Hp * WPB + 3 * CR * XP; idx += CT) smem[idx] = 0.f;
+  __syncthreads();
+  // group 0: g10, h10, W10 ; group 1: h9, W9
+  async_tile(Gs, XP, p.g10 + rbase * H, H, rows_valid, H, tid, CT);
+  async_tile(Ms0, XP, p.act[3] + rbase * H, H, rows_valid, H, tid, CT);
+  async_tile(Ws0, WPB, par + p.offW[3], H, H, H, tid, CT);
+  cp_async_commit();
+  async_tile(Ms1, XP, p.act[2] + rbase * H, H, rows_valid, H, tid, CT);
+  async_tile(Ws1, WPB, par + p.offW[2], H, H, H, tid, CT);
+  cp_async_commit();
+
+  float* Ws[2] = {Ws0, Ws1};
+  float* Ms[2] = {Ms0, Ms1};
+  const int NTW = 8;
+  for (int it = 0; it < 4; ++it) {
+    const int l = 3 - it;                  // layer index 3..0 = fc10..fc7
+    const int nin = l == 0 ? L : H;        // inputs of this layer
+    if (it < 3) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    // delta = g * relu'(h_l): in place in Gs, and to global for the weight-gradient kernel
+    float* dout = p.delta[l] + rbase * H;
+    const float* Mcur = Ms[it & 1];
+    for (int idx = tid; idx < CR * (H / 2 + (H & 1)); idx += CT) {
+      const int hw = H / 2 + (H & 1);
+      const int r = idx / hw, c = (idx - r * hw) * 2;
+      float d0 = Mcur[r * XP + c] > 0.f ? Gs[r * XP + c] : 0.f;
+      float d1 = (c + 1 < H && Mcur[r * XP + c + 1] > 0.f) ? Gs[r * XP + c + 1] : 0.f;
+      Gs[r * XP + c] = d0;
+      if (c + 1 < H) Gs[r * XP + c + 1] = d1;
+      if (r < rows_valid) {
+        dout[(int64_t)r * H + c] = d0;
+        if (c + 1 < H) dout[(int64_t)r * H + c + 1] = d1;
+      }
+    }
+    __syncthreads();
+    float acc[NTW][4];
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    const int nt_used = max(0, min(NTW, (nin + 7) / 8 - wc * NTW));
+    warp_gemm2<NTW, false, SPLIT>(Gs + wr * 16 * XP, XP, Ws[it & 1] + wc * NTW * 8, WPB, (H + 7) / 8, nt_used, acc, lane);
+    __syncthreads();                       // all warps have read delta before it is overwritten by the new g
+    const int ra = wr * 16 + g, rb = ra + 8;
+    float* g6 = p.g6 + rbase * L;
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      if (nt < nt_used) {
+        const int c = (wc * NTW + nt) * 8 + 2 * tig;
+        if (l > 0) {
+          Gs[ra * XP + c] = acc[nt][0]; Gs[ra * XP + c + 1] = acc[nt][1];
+          Gs[rb * XP + c] = acc[nt][2]; Gs[rb * XP + c + 1] = acc[nt][3];
+        } else {
+          if (ra < rows_valid) { if (c < L) g6[(int64_t)ra * L + c] = acc[nt][0]; if (c + 1 < L) g6[(int64_t)ra * L + c + 1] = acc[nt][1]; }
+          if (rb < rows_valid) { if (c < L) g6[(int64_t)rb * L + c] = acc[nt][2]; if (c + 1 < L) g6[(int64_t)rb * L + c + 1] = acc[nt][3]; }
+        }
+      }
+    }
+    // stage the operands of iteration it+2 into the buffers just released
+    if (it + 2 < 4) {
+      const int l2 = l - 2;
+      __syncthreads();
+      async_tile(Ms[it & 1], XP, p.act[l2] + rbase * H, H, rows_valid, H, tid, CT);
+      if (l2 == 0) {
+        for (int idx = tid; idx < Hp * WPB; idx += CT) Ws[it & 1][idx] = 0.f;   // fc7 is [H][L]: clear the wider fc9
+        __syncthreads();
+        async_tile(Ws[it & 1], WPB, par + p.offW[0], L, H, L, tid, CT);
+      } else {
+        async_tile(Ws[it & 1], WPB, par + p.offW[l2], H, H, H, tid, CT);
+      }
+      cp_async_commit();
+    }
+  }
+}
+
+}  // namespace
+
+static int b_pitch2(int n) {
+  int p = (n + 7) & ~7;
+  while ((p & 31) != 8 && (p & 31) != 24) p += 8;
+  return p;
+}
+
+static void fill_chain(ChainArgs& c, const float* params, int64_t p_arm_stride, const int64_t* off, int B, int H, int L) {
+  memset(&c, 0, sizeof(c));
+  c.params = params; c.p_arm_stride = p_arm_stride; c.B = B; c.H = H; c.L = L;
+  c.Hp = (H + 7) & ~7;
+  c.XP = c.Hp + 4;
+  c.WPB = b_pitch2(c.Hp);
+  for (int l = 0; l < 4; ++l) {
+    c.offW[l] = off[FC7_W + 2 * l];
+    c.offB[l] = off[FC7_B + 2 * l];
+  }
+}
+
+static int chain_mt(int A, int B) {
+  const int t4 = (B + 63) / 64 * A, t5 = (B + 79) / 80 * A;
+  return (t4 > 148 && t5 <= 148) ? 5 : 4;
+}
+
+int launch_dec_chain_fwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
+                         const float* h6, float* const hout[4], int split3, cudaStream_t s) {
+  ChainArgs c;
+  fill_chain(c, params, p_arm_stride, off, B, H, L);
+  c.h6 = h6;
+  for (int l = 0; l < 4; ++l) c.hout[l] = hout[l];
+  const int mt = chain_mt(A, B), cr = 16 * mt;
+  const size_t smem = (size_t)(2 * c.Hp * c.XP + 2 * cr * c.XP + 4 * 128) * 4;
+#define CHAIN_LAUNCH(MTV, SP)                                                                                        \
+  do {                                                                                                              \
+    MVAE_CUDA(cudaFuncSetAttribute(dec_chain_fwd_kernel<MTV, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    dec_chain_fwd_kernel<MTV, SP><<<dim3((B + cr - 1) / cr, A), 64 * MTV, smem, s>>>(c);                            \
+  } while (0)
+  if (mt == 5 && split3) CHAIN_LAUNCH(5, true);
+  else if (mt == 5) CHAIN_LAUNCH(5, false);
+  else if (split3) CHAIN_LAUNCH(4, true);
+  else CHAIN_LAUNCH(4, false);
+#undef CHAIN_LAUNCH
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_dec_chain_bwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
+                         const float* g10, const float* const act[4], float* const delta[4], float* g6, int split3,
+                         cudaStream_t s) {
+  ChainArgs c;
+  fill_chain(c, params, p_arm_stride, off, B, H, L);
+  c.g10 = g10; c.g6 = g6;
+  for (int l = 0; l < 4; ++l) { c.act[l] = act[l]; c.delta[l] = delta[l]; }
+  const int mt = chain_mt(A, B), cr = 16 * mt;
+  const size_t smem = (size_t)(2 * c.Hp * c.WPB + 3 * cr * c.XP) * 4;
+#define CHAIN_LAUNCH(MTV, SP)                                                                                        \
+  do {                                                                                                              \
+    MVAE_CUDA(cudaFuncSetAttribute(dec_chain_bwd_kernel<MTV, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    dec_chain_bwd_kernel<MTV, SP><<<dim3((B + cr - 1) / cr, A), 64 * MTV, smem, s>>>(c);                            \
+  } while (0)
+  if (mt == 5 && split3) CHAIN_LAUNCH(5, true);
+  else if (mt == 5) CHAIN_LAUNCH(5, false);
+  else if (split3) CHAIN_LAUNCH(4, true);
+  else CHAIN_LAUNCH(4, false);
+#undef CHAIN_LAUNCH
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mvae

@@ -53,7 +53,7 @@ __host__ __device__ inline int a_pitch(int k) { return ((k + 7) & ~7) + 4; }
 // One warp: acc[NT][4] += A(16 x 8*ksteps) . B(8*ksteps x 8*NT)
 //   A element (m,k): A_T ? As[k*ap + m] : As[m*ap + k]   (m relative to the warp's 16 rows)
 //   B element (k,n): Bs[k*bp + n]
-template <int NT, bool A_T>
+template <int NT, bool A_T, bool SPLIT = true>
 __device__ __forceinline__ void warp_gemm(const float* __restrict__ As, int ap, const float* __restrict__ Bs, int bp,
                                           int ksteps, int nt_used, float (&acc)[NT][4], int lane) {
   const int g = lane >> 2, tig = lane & 3;
@@ -80,9 +80,15 @@ __device__ __forceinline__ void warp_gemm(const float* __restrict__ As, int ap, 
         const float b0 = Bs[(k0 + tig) * bp + nt * 8 + g];
         const float b1 = Bs[(k0 + tig + 4) * bp + nt * 8 + g];
         uint32_t bh[2], bl[2];
-        split_tf32(b0, bh[0], bl[0]);
-        split_tf32(b1, bh[1], bl[1]);
-        mma_3x(acc[nt], ah, al, bh, bl);
+        if (SPLIT) {
+          split_tf32(b0, bh[0], bl[0]);
+          split_tf32(b1, bh[1], bl[1]);
+          mma_3x(acc[nt], ah, al, bh, bl);
+        } else {
+          bh[0] = __float_as_uint(b0);
+          bh[1] = __float_as_uint(b1);
+          mma_tf32(acc[nt], ah, bh);
+        }
       }
     }
   }
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(MMA_THREADS) dense_fwd_mma_kernel(const DenseF
 // =============================================================================================
 // backward (data gradient)
 // =============================================================================================
-template <int NT>
+template <int NT, bool SPLIT>
 __global__ void __launch_bounds__(MMA_THREADS) dense_bwd_mma_kernel(const DenseBwdArgs p) {
   extern __shared__ __align__(16) float smem[];
   const int arm = blockIdx.y;
@@ -360,7 +366,7 @@ __global__ void __launch_bounds__(MMA_THREADS) dense_bwd_mma_kernel(const DenseB
     for (int nt = 0; nt < NTW; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-    warp_gemm<NTW, false>(Ds + warp * 16 * ap, ap, Ws + wc * NTW * 8, bp, ksteps, nt_used, acc, lane);
+    warp_gemm<NTW, false, SPLIT>(Ds + warp * 16 * ap, ap, Ws + wc * NTW * 8, bp, ksteps, nt_used, acc, lane);
     const int ra = row0 + warp * 16 + g, rb = ra + 8;
     const bool va = ra < p.B, vb = rb < p.B;
 #pragma unroll
@@ -409,6 +415,7 @@ __global__ void __launch_bounds__(MMA_THREADS) dense_bwd_mma_kernel(const DenseB
 // =============================================================================================
 constexpr int WG_CHUNK = 32;
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgArgs p) {
   __shared__ float Ds[WG_CHUNK * 136];
   __shared__ float Is[WG_CHUNK * 136];
@@ -470,7 +477,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgArgs p) {
     store_chunk(rb);
     __syncthreads();
     if (rb + WG_CHUNK < r1) load_chunk(rb + WG_CHUNK);
-    if (active) warp_gemm<16, true>(Ds + warp * 16, 136, Is, 136, WG_CHUNK / 8, nt_used, acc, lane);
+    if (active) warp_gemm<16, true, SPLIT>(Ds + warp * 16, 136, Is, 136, WG_CHUNK / 8, nt_used, acc, lane);
   }
   if (!active) return;
   float* part = p.part + (int64_t)split * p.part_split_stride + (int64_t)arm * p.part_arm_stride;
@@ -540,30 +547,34 @@ int launch_dense_fwd_mma(const DenseFwdArgs& a, int A, cudaStream_t s) {
   return 0;
 }
 
-int launch_dense_bwd_mma(const DenseBwdArgs& a, int A, cudaStream_t s) {
+int launch_dense_bwd_mma(const DenseBwdArgs& a, int A, int split3, cudaStream_t s) {
   const int ntiles = (a.B + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
   dim3 grid(ntiles > 592 ? 592 : ntiles, A);
   const int nin = a.g_in ? a.nin : 1;
-#define LAUNCH(NT)                                                                                                 \
+#define LAUNCH(NT, SP)                                                                                             \
   do {                                                                                                             \
-    static bool attr = false;                                                                                      \
-    if (!attr) {                                                                                                   \
-      MVAE_CUDA(cudaFuncSetAttribute(dense_bwd_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
-      attr = true;                                                                                                 \
-    }                                                                                                              \
-    dense_bwd_mma_kernel<NT><<<grid, MMA_THREADS, bwd_smem<NT>(a.nout), s>>>(a);                                   \
+    MVAE_CUDA(cudaFuncSetAttribute(dense_bwd_mma_kernel<NT, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
+    dense_bwd_mma_kernel<NT, SP><<<grid, MMA_THREADS, bwd_smem<NT>(a.nout), s>>>(a);                               \
   } while (0)
-  if (nin <= 16) LAUNCH(2);
-  else if (nin <= 64) LAUNCH(8);
-  else if (nin <= 128) LAUNCH(16);
-  else { set_error("dense_bwd_mma: nin=%d too wide", a.nin); return -1; }
+  if (split3) {
+    if (nin <= 16) LAUNCH(2, true);
+    else if (nin <= 64) LAUNCH(8, true);
+    else if (nin <= 128) LAUNCH(16, true);
+    else { set_error("dense_bwd_mma: nin=%d too wide", a.nin); return -1; }
+  } else {
+    if (nin <= 16) LAUNCH(2, false);
+    else if (nin <= 64) LAUNCH(8, false);
+    else if (nin <= 128) LAUNCH(16, false);
+    else { set_error("dense_bwd_mma: nin=%d too wide", a.nin); return -1; }
+  }
 #undef LAUNCH
   MVAE_LAUNCH_CHECK();
   return 0;
 }
 
-int launch_wgrad_mma(const WgArgs& a, cudaStream_t s) {
-  wgrad_mma_kernel<<<dim3(a.nsplit, a.nprob, a.A), 256, 0, s>>>(a);
+int launch_wgrad_mma(const WgArgs& a, int split3, cudaStream_t s) {
+  if (split3) wgrad_mma_kernel<true><<<dim3(a.nsplit, a.nprob, a.A), 256, 0, s>>>(a);
+  else wgrad_mma_kernel<false><<<dim3(a.nsplit, a.nprob, a.A), 256, 0, s>>>(a);
   MVAE_LAUNCH_CHECK();
   int64_t maxn = 0;
   for (int i = 0; i < a.nprob; ++i) {

@@ -127,6 +127,8 @@ def test_multi_step_training_matches(name, precision):
     st = O.TrainState(hp, O.init_state_dict(hp, 546))
     xc = x.cuda()
     later = {"tiny": 2e-2, "a3_hard": 2e-2, "mid": 1e-3}[name]
+    if precision != "fp32_simt":
+        later *= 3          # TF32 gradients on the decoder side feed Adam's sign-like first steps
     for step, noise in enumerate(noises):
         ref = O.train_step(st, [x] * hp.n_arm, noise)
         opt.zero_grad()
