@@ -75,7 +75,7 @@ __device__ __forceinline__ void head_load_weights(const HeadArgs& p, const HeadS
 // =============================================================================================
 // forward
 // =============================================================================================
-__global__ void __launch_bounds__(kRowWarps * 32) head_fwd_kernel(const HeadArgs p) {
+__global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadArgs p) {
   extern __shared__ __align__(16) float smem[];
   const int arm = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) head_fwd_kernel(const HeadArgs
 // =============================================================================================
 // backward
 // =============================================================================================
-__global__ void __launch_bounds__(kRowWarps * 32) head_bwd_kernel(const HeadArgs p) {
+__global__ void __launch_bounds__(kRowWarps * 32, 3) head_bwd_kernel(const HeadArgs p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[kRowWarps][2][32];
   const int arm = blockIdx.y;
@@ -424,9 +424,12 @@ __global__ void __launch_bounds__(kRowWarps * 32) head_bwd_kernel(const HeadArgs
   }
 }
 
-static int head_grid(int B) {
+// persistent: at most 3 resident CTAs per SM over all arms, each warp loops over its cells (the weights
+// are loaded once per CTA)
+static int head_grid(int B, int A) {
   int gx = (B + kRowWarps - 1) / kRowWarps;
-  return gx > 592 ? 592 : gx;
+  const int cap = (148 * 3) / (A > 0 ? A : 1);
+  return gx > cap ? (cap > 0 ? cap : 1) : gx;
 }
 
 int launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
@@ -436,7 +439,7 @@ int launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
     MVAE_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
-  head_fwd_kernel<<<dim3(head_grid(a.B), a.A), kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
+  head_fwd_kernel<<<dim3(head_grid(a.B, a.A), a.A), kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -448,7 +451,7 @@ int launch_head_bwd(const HeadArgs& a, cudaStream_t s) {
     MVAE_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
-  head_bwd_kernel<<<dim3(head_grid(a.B), a.A), kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
+  head_bwd_kernel<<<dim3(head_grid(a.B, a.A), a.A), kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
   MVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -17,8 +17,9 @@ namespace mvae {
 
 namespace {
 
-constexpr int ROWS_PER_CTA = 64;   // 4 row groups of 16 rows x 2 column halves = 8 warps
-constexpr int MMA_THREADS = 256;
+constexpr int ROWS_PER_CTA = 64;   // 4 row groups of 16 rows x 4 column quarters = 16 warps
+constexpr int MMA_THREADS = 512;
+constexpr int NWC = 4;
 
 // v = hi + lo: hi is v itself (mma.sync reads the upper 19 bits of a .tf32 operand register, i.e.
 // truncates), lo = v - trunc(v) is exact in fp32 and is truncated to TF32 by the MMA in turn.
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(MMA_THREADS) dense_fwd_mma_kernel(const DenseF
   const int Kp = (nin + 7) & ~7;
   const int ksteps = Kp / 8;
   const int bp = b_pitch(8 * NT), ap = a_pitch(nin);
-  constexpr int NTW = NT / 2;                 // n-tiles per warp (two column halves)
+  constexpr int NTW = NT / NWC;               // n-tiles per warp (column quarters)
   const int nt_used = max(0, min(NTW, (nout + 7) / 8 - wc * NTW));
   float* Wt = smem;                       // [Kp][bp]   Wt[k][n] = W[n][k]
   float* Xs = Wt + Kp * bp;               // [64][ap]
@@ -212,13 +213,13 @@ __global__ void __launch_bounds__(MMA_THREADS) dense_fwd_mma_kernel(const DenseF
         Xs[r * ap + c] = (r < rows_valid) ? val : 0.f;
       };
       if (vec4_ok(src, nin, nin)) {
-        float v[8][4];
-        tile_load<4, 8, MMA_THREADS>(v, src, nin, rows_valid, nin, ROWS_PER_CTA, tid);
-        tile_visit<4, 8, MMA_THREADS>(nin, ROWS_PER_CTA, tid, [&](int u, int e, int r, int c) { put(v[u][e], r, c); });
+        float v[4][4];
+        tile_load<4, 4, MMA_THREADS>(v, src, nin, rows_valid, nin, ROWS_PER_CTA, tid);
+        tile_visit<4, 4, MMA_THREADS>(nin, ROWS_PER_CTA, tid, [&](int u, int e, int r, int c) { put(v[u][e], r, c); });
       } else {
-        float v[32][1];
-        tile_load<1, 32, MMA_THREADS>(v, src, nin, rows_valid, nin, ROWS_PER_CTA, tid);
-        tile_visit<1, 32, MMA_THREADS>(nin, ROWS_PER_CTA, tid, [&](int u, int e, int r, int c) { put(v[u][e], r, c); });
+        float v[16][1];
+        tile_load<1, 16, MMA_THREADS>(v, src, nin, rows_valid, nin, ROWS_PER_CTA, tid);
+        tile_visit<1, 16, MMA_THREADS>(nin, ROWS_PER_CTA, tid, [&](int u, int e, int r, int c) { put(v[u][e], r, c); });
       }
     }
     __syncthreads();
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(MMA_THREADS) dense_bwd_mma_kernel(const DenseB
   const int Kp = (nout + 7) & ~7;          // reduction over this layer's outputs
   const int ksteps = Kp / 8;
   const int bp = b_pitch(8 * NT), ap = a_pitch(nout);
-  constexpr int NTW = NT / 2;
+  constexpr int NTW = NT / NWC;
   const int nt_used = max(0, min(NTW, (nin + 7) / 8 - wc * NTW));
   float* Ws = smem;                        // [Kp][bp]   Ws[j][i] = W[j][i]
   float* Ds = Ws + Kp * bp;                // [64][ap]   delta tile
@@ -348,15 +349,15 @@ __global__ void __launch_bounds__(MMA_THREADS) dense_bwd_mma_kernel(const DenseB
         Ds[r * ap + j] = d;
       };
       if (vec4_ok(gsrc, nout, nout) && vec4_ok(asrc, nout, nout)) {
-        float vg[8][4], va[8][4];
-        tile_load<4, 8, MMA_THREADS>(vg, gsrc, nout, rows_valid, nout, ROWS_PER_CTA, tid);
-        tile_load<4, 8, MMA_THREADS>(va, asrc, nout, rows_valid, nout, ROWS_PER_CTA, tid);
-        tile_visit<4, 8, MMA_THREADS>(nout, ROWS_PER_CTA, tid, [&](int u, int e, int r, int j) { put(vg[u][e], va[u][e], r, j); });
+        float vg[4][4], va[4][4];
+        tile_load<4, 4, MMA_THREADS>(vg, gsrc, nout, rows_valid, nout, ROWS_PER_CTA, tid);
+        tile_load<4, 4, MMA_THREADS>(va, asrc, nout, rows_valid, nout, ROWS_PER_CTA, tid);
+        tile_visit<4, 4, MMA_THREADS>(nout, ROWS_PER_CTA, tid, [&](int u, int e, int r, int j) { put(vg[u][e], va[u][e], r, j); });
       } else {
-        float vg[32][1], va[32][1];
-        tile_load<1, 32, MMA_THREADS>(vg, gsrc, nout, rows_valid, nout, ROWS_PER_CTA, tid);
-        tile_load<1, 32, MMA_THREADS>(va, asrc, nout, rows_valid, nout, ROWS_PER_CTA, tid);
-        tile_visit<1, 32, MMA_THREADS>(nout, ROWS_PER_CTA, tid, [&](int u, int e, int r, int j) { put(vg[u][e], va[u][e], r, j); });
+        float vg[16][1], va[16][1];
+        tile_load<1, 16, MMA_THREADS>(vg, gsrc, nout, rows_valid, nout, ROWS_PER_CTA, tid);
+        tile_load<1, 16, MMA_THREADS>(va, asrc, nout, rows_valid, nout, ROWS_PER_CTA, tid);
+        tile_visit<1, 16, MMA_THREADS>(nout, ROWS_PER_CTA, tid, [&](int u, int e, int r, int j) { put(vg[u][e], va[u][e], r, j); });
       }
     }
     if (!g_in) continue;
@@ -416,58 +417,59 @@ __global__ void __launch_bounds__(MMA_THREADS) dense_bwd_mma_kernel(const DenseB
 constexpr int WG_CHUNK = 32;
 
 template <bool SPLIT>
-__global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgArgs p) {
+__global__ void __launch_bounds__(512) wgrad_mma_kernel(const WgArgs p) {
   __shared__ float Ds[WG_CHUNK * 136];
   __shared__ float Is[WG_CHUNK * 136];
   __shared__ float bm[128], br[128];
   const WgProblem& pr = p.prob[blockIdx.y];
   const int arm = blockIdx.z, split = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = (tid >> 5) & 7, wn = tid >> 8;   // m-tile, n half
   const int g = lane >> 2, tig = lane & 3;
   const int nout = pr.nout, nin = pr.nin;
-  const int nt_used = (nin + 1 + 7) / 8;      // + the ones column that yields the bias gradient
+  const int nt_all = (nin + 1 + 7) / 8;       // + the ones column that yields the bias gradient
+  const int nt_used = max(0, min(8, nt_all - wn * 8));
   const float* delta = p.work + pr.delta_off + (int64_t)arm * pr.delta_arm_stride;
   const float* in = nin > 0 ? p.work + pr.in_off + (int64_t)arm * pr.in_arm_stride : nullptr;
   if (pr.bn_layer >= 0) {
-    for (int i = tid; i < nin; i += 256) {
+    for (int i = tid; i < nin; i += 512) {
       bm[i] = p.bn_mean[(pr.bn_layer * p.A + arm) * 128 + i];
       br[i] = p.bn_rstd[(pr.bn_layer * p.A + arm) * 128 + i];
     }
   }
-  float acc[16][4];
+  float acc[8][4];
 #pragma unroll
-  for (int nt = 0; nt < 16; ++nt)
+  for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
   const int r0 = split * p.rows_per_split;
   const int r1 = min(p.B, r0 + p.rows_per_split);
-  const bool active = warp * 16 < nout;
-  for (int idx = tid; idx < WG_CHUNK * 136; idx += 256) { Ds[idx] = 0.f; Is[idx] = 0.f; }
+  const bool active = warp * 16 < nout && nt_used > 0;
+  for (int idx = tid; idx < WG_CHUNK * 136; idx += 512) { Ds[idx] = 0.f; Is[idx] = 0.f; }
   const bool dv4 = vec4_ok(delta, nout, nout);
   const bool iv4 = nin > 0 && vec4_ok(in, pr.in_ld, nin);
   // chunk staged through registers: the loads of chunk c+1 are in flight while chunk c is multiplied
-  float vd[16][1], vi[16][1];            // scalar path: 32x128 / 256 threads
-  float vd4[4][4], vi4[4][4];            // float4 path
+  float vd[8][1], vi[8][1];              // scalar path: 32x128 / 512 threads
+  float vd4[2][4], vi4[2][4];            // float4 path
   auto load_chunk = [&](int rb) {
     const int nr = min(WG_CHUNK, r1 - rb);
-    if (dv4) tile_load<4, 4, 256>(vd4, delta + (int64_t)rb * nout, nout, nr, nout, WG_CHUNK, tid);
-    else tile_load<1, 16, 256>(vd, delta + (int64_t)rb * nout, nout, nr, nout, WG_CHUNK, tid);
+    if (dv4) tile_load<4, 2, 512>(vd4, delta + (int64_t)rb * nout, nout, nr, nout, WG_CHUNK, tid);
+    else tile_load<1, 8, 512>(vd, delta + (int64_t)rb * nout, nout, nr, nout, WG_CHUNK, tid);
     if (nin > 0) {
-      if (iv4) tile_load<4, 4, 256>(vi4, in + (int64_t)rb * pr.in_ld, pr.in_ld, nr, nin, WG_CHUNK, tid);
-      else tile_load<1, 16, 256>(vi, in + (int64_t)rb * pr.in_ld, pr.in_ld, nr, nin, WG_CHUNK, tid);
+      if (iv4) tile_load<4, 2, 512>(vi4, in + (int64_t)rb * pr.in_ld, pr.in_ld, nr, nin, WG_CHUNK, tid);
+      else tile_load<1, 8, 512>(vi, in + (int64_t)rb * pr.in_ld, pr.in_ld, nr, nin, WG_CHUNK, tid);
     }
   };
   auto store_chunk = [&](int rb) {
     const int nr = min(WG_CHUNK, r1 - rb);
-    if (dv4) tile_visit<4, 4, 256>(nout, WG_CHUNK, tid, [&](int u, int e, int r, int j) { Ds[r * 136 + j] = vd4[u][e]; });
-    else tile_visit<1, 16, 256>(nout, WG_CHUNK, tid, [&](int u, int e, int r, int j) { Ds[r * 136 + j] = vd[u][e]; });
+    if (dv4) tile_visit<4, 2, 512>(nout, WG_CHUNK, tid, [&](int u, int e, int r, int j) { Ds[r * 136 + j] = vd4[u][e]; });
+    else tile_visit<1, 8, 512>(nout, WG_CHUNK, tid, [&](int u, int e, int r, int j) { Ds[r * 136 + j] = vd[u][e]; });
     auto puti = [&](float v, int r, int i) {
       if (pr.bn_layer >= 0) v = (v - bm[i]) * br[i];
       Is[r * 136 + i] = r < nr ? v : 0.f;
     };
     if (nin > 0) {
-      if (iv4) tile_visit<4, 4, 256>(nin, WG_CHUNK, tid, [&](int u, int e, int r, int i) { puti(vi4[u][e], r, i); });
-      else tile_visit<1, 16, 256>(nin, WG_CHUNK, tid, [&](int u, int e, int r, int i) { puti(vi[u][e], r, i); });
+      if (iv4) tile_visit<4, 2, 512>(nin, WG_CHUNK, tid, [&](int u, int e, int r, int i) { puti(vi4[u][e], r, i); });
+      else tile_visit<1, 8, 512>(nin, WG_CHUNK, tid, [&](int u, int e, int r, int i) { puti(vi[u][e], r, i); });
     }
     if (tid < WG_CHUNK) Is[tid * 136 + nin] = tid < nr ? 1.f : 0.f;   // ones column -> bias gradient
   };
@@ -477,18 +479,18 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgArgs p) {
     store_chunk(rb);
     __syncthreads();
     if (rb + WG_CHUNK < r1) load_chunk(rb + WG_CHUNK);
-    if (active) warp_gemm<16, true, SPLIT>(Ds + warp * 16, 136, Is, 136, WG_CHUNK / 8, nt_used, acc, lane);
+    if (active) warp_gemm<8, true, SPLIT>(Ds + warp * 16, 136, Is + wn * 64, 136, WG_CHUNK / 8, nt_used, acc, lane);
   }
   if (!active) return;
   float* part = p.part + (int64_t)split * p.part_split_stride + (int64_t)arm * p.part_arm_stride;
   const int ja = warp * 16 + g, jb = ja + 8;
 #pragma unroll
-  for (int nt = 0; nt < 16; ++nt) {
+  for (int nt = 0; nt < 8; ++nt) {
     if (nt < nt_used) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = (e & 2) ? jb : ja;
-        const int i = nt * 8 + 2 * tig + (e & 1);
+        const int i = (wn * 8 + nt) * 8 + 2 * tig + (e & 1);
         if (j < nout) {
           if (i < nin) part[pr.poffW - p.base_off + (int64_t)j * nin + i] = acc[nt][e];
           else if (i == nin) part[pr.poffB - p.base_off + j] = acc[nt][e];
@@ -538,7 +540,7 @@ int launch_dense_fwd_mma(const DenseFwdArgs& a, int A, cudaStream_t s) {
     }                                                                                                              \
     dense_fwd_mma_kernel<NT><<<grid, MMA_THREADS, fwd_smem<NT>(a.nin), s>>>(a);                                    \
   } while (0)
-  if (a.nout <= 16) LAUNCH(2);
+  if (a.nout <= 32) LAUNCH(4);
   else if (a.nout <= 64) LAUNCH(8);
   else if (a.nout <= 128) LAUNCH(16);
   else { set_error("dense_fwd_mma: nout=%d too wide", a.nout); return -1; }
@@ -557,12 +559,12 @@ int launch_dense_bwd_mma(const DenseBwdArgs& a, int A, int split3, cudaStream_t 
     dense_bwd_mma_kernel<NT, SP><<<grid, MMA_THREADS, bwd_smem<NT>(a.nout), s>>>(a);                               \
   } while (0)
   if (split3) {
-    if (nin <= 16) LAUNCH(2, true);
+    if (nin <= 32) LAUNCH(4, true);
     else if (nin <= 64) LAUNCH(8, true);
     else if (nin <= 128) LAUNCH(16, true);
     else { set_error("dense_bwd_mma: nin=%d too wide", a.nin); return -1; }
   } else {
-    if (nin <= 16) LAUNCH(2, false);
+    if (nin <= 32) LAUNCH(4, false);
     else if (nin <= 64) LAUNCH(8, false);
     else if (nin <= 128) LAUNCH(16, false);
     else { set_error("dense_bwd_mma: nin=%d too wide", a.nin); return -1; }
@@ -573,8 +575,8 @@ int launch_dense_bwd_mma(const DenseBwdArgs& a, int A, int split3, cudaStream_t 
 }
 
 int launch_wgrad_mma(const WgArgs& a, int split3, cudaStream_t s) {
-  if (split3) wgrad_mma_kernel<true><<<dim3(a.nsplit, a.nprob, a.A), 256, 0, s>>>(a);
-  else wgrad_mma_kernel<false><<<dim3(a.nsplit, a.nprob, a.A), 256, 0, s>>>(a);
+  if (split3) wgrad_mma_kernel<true><<<dim3(a.nsplit, a.nprob, a.A), 512, 0, s>>>(a);
+  else wgrad_mma_kernel<false><<<dim3(a.nsplit, a.nprob, a.A), 512, 0, s>>>(a);
   MVAE_LAUNCH_CHECK();
   int64_t maxn = 0;
   for (int i = 0; i < a.nprob; ++i) {
