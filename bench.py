@@ -122,31 +122,42 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the reference algorithm (oracle port) on the host cores
 # -------------------------------------------------------------------------------------------------
-def cpu_reference(w, steps, warmup, max_seconds=25.0):
+def cpu_reference(w, steps, warmup, max_seconds=25.0, device="cpu"):
     """Times oracle.train_step (the CPU restatement of mmidas/nn_model.py + Adam, pinned to the
-    reference by tests/test_oracle_golden.py) on a bounded sample: same shapes, full batch."""
+    reference by tests/test_oracle_golden.py) on a bounded sample: same shapes, full batch.
+    device="cuda" (--ref-device cuda, informational only) runs the same eager torch ops on the GPU:
+    the stock-PyTorch path the reference would take there, including its loss.item() sync per step."""
     from oracle import mixvae_oracle as O
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     hp = O.HP(input_dim=w["D"], n_categories=w["C"], state_dim=w["S"], n_arm=w["A"], x_drop=0.5, s_drop=0.0)
     gen = torch.Generator().manual_seed(546)
-    x = O.synth_x(w["B"], w["D"], gen, w["density"])
-    st = O.TrainState(hp, O.init_state_dict(hp, 546))
+    x = O.synth_x(w["B"], w["D"], gen, w["density"]).to(device)
+    st = O.TrainState(hp, {k: v.to(device) for k, v in O.init_state_dict(hp, 546).items()})
     xs = [x] * hp.n_arm
-    noise = O.synth_noise(hp, w["B"], gen)
+    noise = {k: (v.to(device) if torch.is_tensor(v) else [t.to(device) for t in v])
+             for k, v in O.synth_noise(hp, w["B"], gen).items()}
+    on_gpu = device != "cpu"
     for _ in range(max(1, warmup)):
         O.train_step(st, xs, noise)
+    if on_gpu:
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
-        O.train_step(st, xs, noise)
+        out = O.train_step(st, xs, noise)
+        if on_gpu:
+            float(out["loss"]["total"].item())           # cpl_mixvae.py:469
         done += 1
         if time.perf_counter() - t0 > max_seconds:
             break
+    if on_gpu:
+        torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    where = f"torch {torch.__version__} eager on {torch.cuda.get_device_name(0)}" if on_gpu else f"torch {torch.__version__} CPU"
     return {"value": w["B"] * done / dt, "unit": "cells/s", "cores": cores, "kind": "port",
             "sample": f"{done} full steps of the same workload (B={w['B']}, D={w['D']}, A={w['A']}), fp32, "
-                      f"torch {torch.__version__} CPU, {dt / done * 1e3:.1f} ms/step"}, dt / done
+                      f"{where}, {dt / done * 1e3:.1f} ms/step"}, dt / done
 
 
 def run_reference(args, w):
@@ -154,7 +165,7 @@ def run_reference(args, w):
     if rank != 0:
         return
     steps = min(args.steps, 20)
-    cb, ms = cpu_reference(w, steps, min(args.warmup, 2), max_seconds=60.0)
+    cb, ms = cpu_reference(w, steps, min(args.warmup, 2), max_seconds=60.0, device=args.ref_device)
     line = {"impl": "reference", "metric": "train cells/sec", "value": cb["value"], "unit": "cells/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": ms * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -175,6 +186,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--precision", default="tf32x3_fc1", choices=["tf32x3_fc1", "tf32x3", "tf32", "fp32_simt"])
     ap.add_argument("--mesh", default="dp", choices=["dp", "arm", "auto"])
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu (the contract) or cuda (informational: eager torch on the GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
