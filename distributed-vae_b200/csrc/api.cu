@@ -3,6 +3,7 @@
 // Step order follows mmidas/cpl_mixvae.py:434-463: zero_grad (implicit: every gradient is written,
 // never accumulated), forward, loss, backward, Adam.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_tc.h"
@@ -76,6 +77,16 @@ static BnOff bn_off(const Plan& p) {
     if (_rc) return _rc; \
   } while (0)
 
+// MVAE_LEGACY_FC1=1 keeps the round-1 split-K SS kernels for fc1 (A/B comparisons)
+static bool legacy_fc1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MVAE_LEGACY_FC1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static bool use_tc(const Plan& p, const mvae_hparams& hp) {
   return hp.precision != 3 && gemm_tc_supported(p.B, p.D, p.H);
 }
@@ -104,7 +115,10 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   Fc1EpiArgs epi;
   memset(&epi, 0, sizeof(epi));
   timing_begin(TG_FC1_FWD, s);
-  if (use_tc(p, hp)) {
+  const bool ts_path = use_tc(p, hp) && !legacy_fc1();
+  if (ts_path) {
+    RC(ts_fc1_forward(p.d, hp, st, in, drop, w, work + w.a[0], acc_fwd + acc_bn(0, A, 0), s));
+  } else if (use_tc(p, hp)) {
     RC(tc_fc1_forward(p.d, hp, st, in, drop, w, s, &epi));
   } else {
     GemmArgs g;
@@ -119,7 +133,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   }
   epi.params = st.params; epi.p_arm_stride = p.L.arm_stride; epi.offB = p.L.offset[FC1_B];
   epi.out = work + w.a[0]; epi.stats_out = acc_fwd + acc_bn(0, A, 0); epi.B = B; epi.H = H;
-  RC(launch_fc1_epilogue(epi, A, s));
+  if (!ts_path) RC(launch_fc1_epilogue(epi, A, s));
   timing_end(TG_FC1_FWD, s);
   timing_begin(TG_NARROW_FWD, s);
 
@@ -365,7 +379,9 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   // ---- d fc1.weight = delta1^T * dropout(x)
   DropSpec drop = make_drop(p, hp, in);
   timing_begin(TG_FC1_WGRAD, s);
-  if (tc) {
+  if (tc && hp.precision != 1 && !legacy_fc1()) {
+    RC(ts_fc1_wgrad(p.d, st, in, drop, w, s));
+  } else if (tc) {
     RC(tc_fc1_wgrad(p.d, hp, st, in, drop, w, s));
   } else {
     GemmArgs g;

@@ -127,7 +127,12 @@ Work make_work(const mvae_dims& d) {
   {
     // split-K partials of the tensor-core GEMMs: fc1 / d h10 use [split<=4][A][Bpad][128], d W11 [split<=2][A][Dpad][128]
     const int64_t p1 = (int64_t)w.fc1_splitk * A * w.Bpad * 128, p2 = (int64_t)8 * A * w.Dpad * 128;
-    w.fc1_part = take(p1 > p2 ? p1 : p2);
+    // stream-K partial tiles of the fc1 kernels (ts_gemm.cu): one [128][128] tile per (CTA, output tile) pair
+    const int64_t t1 = A * (w.Bpad / 128), t2 = A * (w.Dpad / 128);
+    const int64_t p3 = ((t1 > t2 ? t1 : t2) + 160) * 128 * 128;
+    int64_t pm = p1 > p2 ? p1 : p2;
+    if (p3 > pm) pm = p3;
+    w.fc1_part = take(pm);
   }
   w.db_part = take((int64_t)8 * A * w.Dpad);
   w.big = take(A * B * D);

@@ -81,6 +81,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: 8 consecutive 32-bit columns of this thread's lane (warp w may touch lanes 32*(w%4)..+31)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand (M = 128 lanes, one 32-bit column per K element) is read from
+// tensor memory ("TS" form, cute SM100_MMA_TF32_TS); A is K-major by construction.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start address,
 // leading / stride byte offsets (16-byte units), version 1, SWIZZLE_128B.
@@ -134,6 +158,29 @@ inline EncodeTiledFn get_encode() {
 
 // rank-3 fp32 tensor map over a row-major matrix [outer][inner] with an optional batch dimension;
 // box = {32 floats (128 B, one swizzle row), box_outer rows, 1}.  Out-of-bounds elements read as 0.
+// general form: box = {box_inner floats, box_outer rows, 1}; swizzle 0: none, 1: 128B, 2: 128B with 32-byte atoms
+inline int make_map_ex(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t row_pitch_floats,
+                       int64_t batch, int64_t batch_stride_floats, int box_inner, int box_outer, int swizzle) {
+  EncodeTiledFn enc = get_encode();
+  MVAE_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  MVAE_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  MVAE_CHECK_ARG(row_pitch_floats % 4 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  const bool batched = batch > 1 && batch_stride_floats > 0;
+  MVAE_CHECK_ARG(!batched || batch_stride_floats % 4 == 0, "TMA batch stride must be a multiple of 16 bytes");
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(batched ? batch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)row_pitch_floats * 4,
+                           (cuuint64_t)(batched ? batch_stride_floats : row_pitch_floats * outer) * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                : (swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MVAE_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return 0;
+}
+
 inline int make_map(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t row_pitch_floats,
              int64_t batch, int64_t batch_stride_floats, int box_outer, bool mn_major) {
   EncodeTiledFn enc = get_encode();

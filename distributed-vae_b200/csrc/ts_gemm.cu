@@ -1,0 +1,458 @@
+// ts_gemm.cu — the two passes over the gene matrix x that belong to fc1 (mmidas/nn_model.py:264):
+//
+//   FWD    a1_pre[cell][h]   = sum_gene dropout(x)[cell][gene] * W1[h][gene]      (3xTF32 or TF32)
+//   WGRAD  dW1^T[gene][h]    = sum_cell dropout(x)[cell][gene] * delta1[cell][h]  (TF32)
+//
+// Both are "x-streaming" GEMMs with a 128-wide output: HBM-bound if the per-element work on x (dropout
+// mask, TF32 hi/lo split) keeps up.  Design (sm_100a):
+//   * x tiles arrive by TMA in a deep ring of raw 16 KB tiles (they come from HBM: long latency);
+//     the small operand (W1 / delta1, L2-resident) has its own ring.
+//   * 16 transform warps read the raw tile ONCE from shared memory, apply the dropout mask and the hi/lo
+//     split in registers and write the MMA's A operand straight into TENSOR MEMORY (tcgen05.st); the
+//     MMAs are issued in the TS form (A from TMEM, B from shared memory).  No transformed tile is ever
+//     written back to shared memory, the raw slot is released as soon as it has been read, and for WGRAD the
+//     transposition of x (gene-major A operand) happens for free in the register -> TMEM step.
+//   * stream-K: the (tile, k-tile) units are cut into gridDim.x equal contiguous ranges (one CTA per SM,
+//     one wave, no tail); a CTA writes one partial tile per output tile it touches and a fix-up kernel
+//     sums the partials of each tile in a fixed order (deterministic) and applies the layer epilogue.
+//   * W1_lo = W1 - tf32(W1) is computed once per step by a tiny kernel, so the W operand needs no transform.
+#include "gemm_tc.h"
+#include "tc_common.cuh"
+
+namespace mvae {
+
+namespace {
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int BK = 32;
+constexpr int NTW = 16;                    // transform / drain warps
+constexpr int THREADS = 64 + 32 * NTW;     // warp 0: TMA, warp 1: MMA issue
+constexpr int NA = 4;                      // A-operand stages in tensor memory (64 columns each: hi | lo)
+constexpr int X_BYTES = 16384;
+constexpr int TILE_FLOATS = 128 * 128;     // one partial tile
+constexpr uint32_t ACC_COLS = 128;         // accumulator columns [0,128); A stages follow
+
+struct TsArgs {
+  int BN;                       // UMMA N (multiple of 16, <= 128)
+  int batch, mtiles, ktiles;    // arms, 128-row tiles per arm, 32-deep k tiles
+  int x_batched;                // x has an arm coordinate
+  int nx, nw;                   // ring depths
+  int w_tile_bytes;             // bytes of one W tile image
+  int split3;                   // 3xTF32 (FWD only)
+  float* part;                  // partial tiles [slot][128][128]
+  DropSpec drop;
+};
+
+__host__ __device__ inline int64_t cta_of_unit(int64_t u, int64_t U, int64_t G) { return ((u + 1) * G - 1) / U; }
+
+template <bool WGRAD>
+__global__ void __launch_bounds__(THREADS, 1)
+ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmWlo, const TsArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w_stage_bytes = a.w_tile_bytes * (a.split3 ? 2 : 1);
+  auto xs = [&](int s) { return smem + (size_t)s * X_BYTES; };
+  auto ws = [&](int s) { return smem + (size_t)a.nx * X_BYTES + (size_t)s * w_stage_bytes; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.nx * X_BYTES + (size_t)a.nw * w_stage_bytes);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = x_full + a.nx;
+  uint64_t* w_full = x_empty + a.nx;
+  uint64_t* w_empty = w_full + a.nw;
+  uint64_t* a_full = w_empty + a.nw;
+  uint64_t* a_empty = a_full + NA;
+  uint64_t* acc_full = a_empty + NA;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int KT = a.ktiles;
+  const int64_t U = (int64_t)a.batch * a.mtiles * KT, G = gridDim.x;
+  const int64_t u0 = (int64_t)blockIdx.x * U / G, u1 = ((int64_t)blockIdx.x + 1) * U / G;
+  const int nu = (int)(u1 - u0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.nx; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, NTW); }
+    for (int s = 0; s < a.nw; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
+    for (int s = 0; s < NA; ++s) { mbar_init(a_full + s, NTW); mbar_init(a_empty + s, 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < nu; ++i) {
+        const int64_t u = u0 + i;
+        const int t = (int)(u / KT), kt = (int)(u - (int64_t)t * KT);
+        const int mt = t / a.batch, arm = t - mt * a.batch;
+        const int xb = a.x_batched ? arm : 0;
+        const int sx = i % a.nx, sw = i % a.nw;
+        mbar_wait(x_empty + sx, ((i / a.nx) & 1) ^ 1);
+        mbar_expect_tx(x_full + sx, X_BYTES);
+        if (!WGRAD) tma_load_3d(&tmX, x_full + sx, xs(sx), kt * BK, mt * BM, xb);      // [128 cells][32 genes], SW128
+        else tma_load_3d(&tmX, x_full + sx, xs(sx), mt * BM, kt * BK, xb);             // [32 cells][128 genes], linear
+        mbar_wait(w_empty + sw, ((i / a.nw) & 1) ^ 1);
+        mbar_expect_tx(w_full + sw, w_stage_bytes);
+        if (!WGRAD) {
+          tma_load_3d(&tmW, w_full + sw, ws(sw), kt * BK, 0, arm);
+          if (a.split3) tma_load_3d(&tmWlo, w_full + sw, ws(sw) + a.w_tile_bytes, kt * BK, 0, arm);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_3d(&tmW, w_full + sw, ws(sw) + j * 4096, 32 * j, kt * BK, arm);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BM, a.BN, false, WGRAD);
+      uint32_t acc = 0;
+      for (int i = 0; i < nu; ++i) {
+        const int64_t u = u0 + i;
+        const int kt = (int)(u % KT);
+        const int sa = i % NA, sw = i % a.nw;
+        if (kt == 0) acc = 0;                          // a new output tile starts
+        mbar_wait(w_full + sw, (i / a.nw) & 1);
+        mbar_wait(a_full + sa, (i / NA) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = tmem_base + ACC_COLS + (uint32_t)sa * 64u, a_lo = a_hi + 32u;
+        const uint32_t wb = smem_u32(ws(sw));
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          if (!WGRAD) {
+            const uint64_t bh = make_smem_desc(wb + ks * 32, 0, 1024, false);
+            if (a.split3) {
+              umma_tf32_ts(tmem_base, a_lo + ks * 8, bh, idesc, acc);
+              acc = 1;
+              umma_tf32_ts(tmem_base, a_hi + ks * 8, make_smem_desc(wb + a.w_tile_bytes + ks * 32, 0, 1024, false), idesc, 1u);
+            }
+            umma_tf32_ts(tmem_base, a_hi + ks * 8, bh, idesc, acc);
+          } else {
+            umma_tf32_ts(tmem_base, a_hi + ks * 8, make_smem_desc(wb + ks * 1024, 4096, 512, true), idesc, acc);
+          }
+          acc = 1;
+        }
+        umma_commit(a_empty + sa);
+        umma_commit(w_empty + sw);
+        if (kt == KT - 1 || i == nu - 1) umma_commit(acc_full);      // this CTA's share of the tile is complete
+      }
+    }
+  } else {
+    // ===== transform warps: raw x tile (smem) -> masked / split A operand (TMEM); then drain the accumulator =====
+    const int quad = warp & 3, sub = (warp - 2) >> 2;     // TMEM lane quadrant, k-slice (8 of the 32 k) of a stage
+    const int r = quad * 32 + lane;                       // TMEM lane: cell (FWD) or gene (WGRAD) within the tile
+    const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
+    const DropSpec& dp = a.drop;
+    const uint64_t Dq = (uint64_t)dp.D >> 2;
+    int seg = 0;
+    for (int i = 0; i < nu; ++i) {
+      const int64_t u = u0 + i;
+      const int t = (int)(u / KT), kt = (int)(u - (int64_t)t * KT);
+      const int mt = t / a.batch, arm = t - mt * a.batch;
+      const int sx = i % a.nx, sa = i % NA;
+      mbar_wait(x_full + sx, (i / a.nx) & 1);
+      float v[8];
+      float m[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = 1.f;
+      if (!WGRAD) {
+        // thread = cell r, genes kt*32 + 8*sub .. +7: two 16-byte chunks (SWIZZLE_128B: chunk c lives at c ^ (r & 7))
+        const float4* src = reinterpret_cast<const float4*>(xs(sx) + r * 128);
+        const int c0 = 2 * sub, c1 = 2 * sub + 1;
+        const float4 v0 = src[c0 ^ (r & 7)], v1 = src[c1 ^ (r & 7)];
+        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+        if (dp.mode == 2) {
+          const uint64_t chunk = (uint64_t)(mt * BM + r) * Dq + (uint64_t)(kt * 8 + c0);
+          const uint32_t b0 = drop_bits4(dp.seed, arm, chunk), b1 = drop_bits4(dp.seed, arm, chunk + 1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            m[j] = ((b0 >> (8 * j)) & 0xFFu) >= dp.thresh16 ? dp.scale : 0.f;
+            m[4 + j] = ((b1 >> (8 * j)) & 0xFFu) >= dp.thresh16 ? dp.scale : 0.f;
+          }
+        } else if (dp.mode == 1) {
+          const int64_t xrow = mt * BM + r, xcol = (int64_t)kt * BK + 8 * sub;
+          uint32_t k0 = 0, k1 = 0;
+          if (xrow < dp.rows) {
+            const uint8_t* kp = dp.keep + (int64_t)arm * dp.keep_arm_stride + xrow * dp.D + xcol;
+            if (xcol < dp.D) k0 = *reinterpret_cast<const uint32_t*>(kp);
+            if (xcol + 4 < dp.D) k1 = *reinterpret_cast<const uint32_t*>(kp + 4);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            m[j] = ((k0 >> (8 * j)) & 0xFFu) ? dp.scale : 0.f;
+            m[4 + j] = ((k1 >> (8 * j)) & 0xFFu) ? dp.scale : 0.f;
+          }
+        }
+      } else {
+        // thread = gene r, cells kt*32 + 8*sub .. +7: column reads of the linear [32 cells][128 genes] tile
+        const float* src = reinterpret_cast<const float*>(xs(sx)) + r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = src[(8 * sub + j) * 128];
+        if (dp.mode == 2) {
+          // the warp's 8 cells x 32 genes are 64 generator chunks: two per lane, shared by shuffles
+          const uint64_t cell0 = (uint64_t)kt * BK + 8 * sub + (lane >> 3);
+          const uint64_t ccol = (uint64_t)((mt * BM + quad * 32) >> 2) + (uint64_t)(lane & 7);
+          const uint32_t hA = drop_bits4(dp.seed, arm, cell0 * Dq + ccol);
+          const uint32_t hB = drop_bits4(dp.seed, arm, (cell0 + 4) * Dq + ccol);
+          const uint32_t sh = 8u * (uint32_t)(lane & 3);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t h = __shfl_sync(0xffffffffu, j < 4 ? hA : hB, (j & 3) * 8 + (lane >> 2));
+            m[j] = ((h >> sh) & 0xFFu) >= dp.thresh16 ? dp.scale : 0.f;
+          }
+        } else if (dp.mode == 1) {
+          const int64_t gene = mt * BM + r;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int64_t cell = (int64_t)kt * BK + 8 * sub + j;
+            uint8_t kb = 0;
+            if (gene < dp.D && cell < dp.rows) kb = dp.keep[(int64_t)arm * dp.keep_arm_stride + cell * dp.D + gene];
+            m[j] = kb ? dp.scale : 0.f;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_empty + sx);            // the raw tile is in registers: hand the slot back
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float h = v[j] * m[j];
+        hi[j] = __float_as_uint(h);
+        lo[j] = __float_as_uint(tf32_lo(h));
+      }
+      mbar_wait(a_empty + sa, ((i / NA) & 1) ^ 1);         // the MMAs that read this TMEM stage have completed
+      tc_fence_after();
+      const uint32_t acol = tmem_base + lane_bits + ACC_COLS + (uint32_t)sa * 64u + 8u * (uint32_t)sub;
+      tmem_st8(acol, hi);
+      if (!WGRAD && a.split3) tmem_st8(acol + 32u, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full + sa);
+      if (kt == KT - 1 || i == nu - 1) {
+        // ---- drain this CTA's share of tile t into its partial slot (slot = cta + tile: unique, monotone)
+        mbar_wait(acc_full, seg & 1);
+        tc_fence_after();
+        float* prt = a.part + ((int64_t)blockIdx.x + t) * TILE_FLOATS;
+        for (int j = sub; j < a.BN / 16; j += 4) {
+          uint32_t rr[16];
+          tmem_ld16(tmem_base + lane_bits + (uint32_t)(j * 16), rr);
+          tmem_ld_wait();
+          if (!WGRAD) {
+            float4* dst = reinterpret_cast<float4*>(prt + r * 128 + j * 16);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              dst[e] = make_float4(__uint_as_float(rr[4 * e]), __uint_as_float(rr[4 * e + 1]), __uint_as_float(rr[4 * e + 2]),
+                                   __uint_as_float(rr[4 * e + 3]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) prt[(j * 16 + e) * 128 + r] = __uint_as_float(rr[e]);   // [h][gene]: coalesced
+          }
+        }
+        tc_fence_before();
+        ++seg;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// W1_lo = W1 - tf32(W1) for every arm (the part of fc1.weight the tensor core drops when it truncates to TF32)
+__global__ void __launch_bounds__(256) w_lo_kernel(const float* __restrict__ w, int64_t w_arm_stride, float* __restrict__ lo,
+                                                   int64_t lo_arm_stride, int64_t n4) {
+  const int arm = blockIdx.y;
+  const float4* src = reinterpret_cast<const float4*>(w + (int64_t)arm * w_arm_stride);
+  float4* dst = reinterpret_cast<float4*>(lo + (int64_t)arm * lo_arm_stride);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+  }
+}
+
+// fc1 fix-up: a1 = relu(sum of the tile's partials (fixed order) + b1), fp64 column sums for batch_l1.
+struct Fc1FixArgs {
+  const float* part; int batch, ktiles; int64_t U, G;
+  const float* params; int64_t p_arm_stride, offB;
+  float* out; double* stats_out; int B, H;
+};
+__global__ void __launch_bounds__(256) fc1_fixup_kernel(const Fc1FixArgs p) {
+  __shared__ double red[8][2][128];
+  const int arm = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* bias = p.params + (int64_t)arm * p.p_arm_stride + p.offB;
+  float* out = p.out + (int64_t)arm * p.B * p.H;
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  for (int row = blockIdx.x * 8 + warp; row < p.B; row += gridDim.x * 8) {
+    const int64_t t = (int64_t)(row >> 7) * p.batch + arm;
+    const int64_t c0 = cta_of_unit(t * p.ktiles, p.U, p.G), c1 = cta_of_unit(t * p.ktiles + p.ktiles - 1, p.U, p.G);
+    const float* base = p.part + (c0 + t) * TILE_FLOATS + (int64_t)(row & 127) * 128;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = lane + 32 * k;
+      if (j < p.H) {
+        float v = 0.f;
+        for (int64_t c = c0; c <= c1; ++c) v += base[(c - c0) * TILE_FLOATS + j];
+        v = fmaxf(v + bias[j], 0.f);
+        out[(int64_t)row * p.H + j] = v;
+        s1[k] += (double)v;
+        s2[k] += (double)v * (double)v;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    red[warp][0][lane + 32 * k] = s1[k];
+    red[warp][1][lane + 32 * k] = s2[k];
+  }
+  __syncthreads();
+  {
+    const int which = tid >> 7, j = tid & 127;
+    if (j < p.H) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += red[w][which][j];
+      atomicAdd(p.stats_out + (int64_t)arm * 256 + which * 128 + j, s);
+    }
+  }
+}
+
+// d fc1.weight fix-up: dW1[arm][h][gene] = sum of the partials [slot][h][gene in tile] in a fixed order
+__global__ void __launch_bounds__(256) wgrad_fixup_kernel(const float* part, int batch, int ktiles, int64_t U, int64_t G,
+                                                          float* grads, int64_t g_arm_stride, int D, int H) {
+  const int arm = blockIdx.z;
+  const int gene = blockIdx.x * 128 + (threadIdx.x & 127);
+  const int h = blockIdx.y * 2 + (threadIdx.x >> 7);
+  if (gene >= D || h >= H) return;
+  const int64_t t = (int64_t)blockIdx.x * batch + arm;
+  const int64_t c0 = cta_of_unit(t * ktiles, U, G), c1 = cta_of_unit(t * ktiles + ktiles - 1, U, G);
+  const float* base = part + (c0 + t) * TILE_FLOATS + (int64_t)h * 128 + (gene & 127);
+  float v = 0.f;
+  for (int64_t c = c0; c <= c1; ++c) v += base[(c - c0) * TILE_FLOATS];
+  grads[(int64_t)arm * g_arm_stride + (int64_t)h * D + gene] = v;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <bool WGRAD>
+int launch_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmWlo, TsArgs& a, int64_t* U_out,
+              int64_t* G_out, cudaStream_t s) {
+  const int64_t U = (int64_t)a.batch * a.mtiles * a.ktiles;
+  int64_t G = sm_count();
+  if (G > U) G = U;
+  const int w_stage = a.w_tile_bytes * (a.split3 ? 2 : 1);
+  // rings: the small operand gets 4-5 stages, the raw x ring the rest of the 227 KB
+  a.nw = a.split3 ? 4 : 5;
+  const int budget = 227 * 1024 - 1024 - 512 - a.nw * w_stage;
+  a.nx = budget / X_BYTES;
+  if (a.nx > 8) a.nx = 8;
+  const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * w_stage + (2 * a.nx + 2 * a.nw + 2 * NA + 2) * 8 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    MVAE_CUDA(cudaFuncSetAttribute(ts_gemm_kernel<WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  ts_gemm_kernel<WGRAD><<<dim3((unsigned)G), THREADS, smem, s>>>(tmX, tmW, tmWlo, a);
+  MVAE_LAUNCH_CHECK();
+  *U_out = U; *G_out = G;
+  return 0;
+}
+
+}  // namespace
+
+int64_t ts_part_floats(int A, int Bpad, int Dpad) {
+  const int64_t t1 = (int64_t)A * (Bpad / 128), t2 = (int64_t)A * (Dpad / 128);
+  return ((t1 > t2 ? t1 : t2) + 160) * TILE_FLOATS;
+}
+
+// fc1 forward: a1 = relu(dropout(x) . W1^T + b1) and the batch_l1 column sums (replaces GEMM + epilogue kernel)
+int ts_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
+                   const DropSpec& drop, const Work& w, float* a1_out, double* stats_out, cudaStream_t s) {
+  mvae_layout L;
+  compute_layout(d, &L);
+  const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
+  const int split3 = hp.precision != 2;
+  float* wlo = st.work + w.w11_t;                       // [A][128 * Dpad] scratch, pitch D
+  const int64_t wlo_stride = (int64_t)128 * w.Dpad;
+  if (split3) {
+    const int64_t n4 = (int64_t)H * D / 4;
+    w_lo_kernel<<<dim3(148, A), 256, 0, s>>>(st.params + L.offset[FC1_W], L.arm_stride, wlo, wlo_stride, n4);
+    MVAE_LAUNCH_CHECK();
+  }
+  TsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.BN = (H + 15) / 16 * 16;
+  a.batch = A; a.mtiles = (B + BM - 1) / BM; a.ktiles = (D + BK - 1) / BK;
+  a.x_batched = in.x_arm_stride > 0;
+  a.w_tile_bytes = a.BN * 128;
+  a.split3 = split3;
+  a.part = st.work + w.fc1_part;
+  a.drop = drop;
+  CUtensorMap tmX, tmW, tmWlo;
+  int rc = make_map_ex(&tmX, in.x, D, B, in.x_row_stride, A, in.x_arm_stride, 32, 128, 1);
+  if (rc) return rc;
+  rc = make_map_ex(&tmW, st.params + L.offset[FC1_W], D, H, D, A, L.arm_stride, 32, a.BN, 1);
+  if (rc) return rc;
+  rc = make_map_ex(&tmWlo, split3 ? wlo : st.params + L.offset[FC1_W], D, H, D, A, split3 ? wlo_stride : L.arm_stride, 32,
+                   a.BN, 1);
+  if (rc) return rc;
+  int64_t U, G;
+  rc = launch_ts<false>(tmX, tmW, tmWlo, a, &U, &G, s);
+  if (rc) return rc;
+  Fc1FixArgs f;
+  memset(&f, 0, sizeof(f));
+  f.part = a.part; f.batch = A; f.ktiles = a.ktiles; f.U = U; f.G = G;
+  f.params = st.params; f.p_arm_stride = L.arm_stride; f.offB = L.offset[FC1_B];
+  f.out = a1_out; f.stats_out = stats_out; f.B = B; f.H = H;
+  int gx = (B + 7) / 8;
+  if (gx > 296) gx = 296;
+  fc1_fixup_kernel<<<dim3(gx, A), 256, 0, s>>>(f);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// d fc1.weight = delta1^T . dropout(x), TF32
+int ts_fc1_wgrad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const DropSpec& drop, const Work& w,
+                 cudaStream_t s) {
+  mvae_layout L;
+  compute_layout(d, &L);
+  const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
+  TsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.BN = (H + 15) / 16 * 16;
+  a.batch = A; a.mtiles = (D + BM - 1) / BM; a.ktiles = (B + BK - 1) / BK;
+  a.x_batched = in.x_arm_stride > 0;
+  a.w_tile_bytes = 16384;
+  a.split3 = 0;
+  a.part = st.work + w.fc1_part;
+  a.drop = drop;
+  CUtensorMap tmX, tmW;
+  int rc = make_map_ex(&tmX, in.x, D, B, in.x_row_stride, A, in.x_arm_stride, 128, 32, 0);
+  if (rc) return rc;
+  rc = make_map_ex(&tmW, st.work + w.delta_enc[0], H, B, H, A, (int64_t)B * H, 32, 32, 2);
+  if (rc) return rc;
+  int64_t U, G;
+  rc = launch_ts<true>(tmX, tmW, tmW, a, &U, &G, s);
+  if (rc) return rc;
+  wgrad_fixup_kernel<<<dim3(a.mtiles, (H + 1) / 2, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, st.grads + L.offset[FC1_W],
+                                                                   L.arm_stride, D, H);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mvae
