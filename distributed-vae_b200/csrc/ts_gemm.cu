@@ -27,7 +27,8 @@ using namespace tc;
 constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int NTW = 16;                    // transform / drain warps
-constexpr int THREADS = 64 + 32 * NTW;     // warp 0: TMA, warp 1: MMA issue
+constexpr int CTRL_WARPS = 3;              // warp 0: TMA of x, warp 1: TMA of the small operand, warp 2: MMA issue
+constexpr int THREADS = 32 * (CTRL_WARPS + NTW);
 constexpr int NA = 4;                      // A-operand stages in tensor memory (64 columns each: hi | lo)
 constexpr int X_BYTES = 16384;
 constexpr int TILE_FLOATS = 128 * 128;     // one partial tile
@@ -78,26 +79,39 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == CTRL_WARPS) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // first unit of this CTA; every role then advances (kt, arm, mt) and its ring slots incrementally (no divisions
+  // inside the loops: the transform warps are instruction-issue bound)
+  const int t_first = (int)(u0 / KT), kt_first = (int)(u0 - (int64_t)t_first * KT);
+  const int mt_first = t_first / a.batch, arm_first = t_first - mt_first * a.batch;
+
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer of the raw x tiles (HBM): runs ahead by the whole x ring, independent of the W ring =====
     if (lane == 0) {
+      int kt = kt_first, mt = mt_first, arm = arm_first, sx = 0;
+      uint32_t phx = 1;
       for (int i = 0; i < nu; ++i) {
-        const int64_t u = u0 + i;
-        const int t = (int)(u / KT), kt = (int)(u - (int64_t)t * KT);
-        const int mt = t / a.batch, arm = t - mt * a.batch;
         const int xb = a.x_batched ? arm : 0;
-        const int sx = i % a.nx, sw = i % a.nw;
-        mbar_wait(x_empty + sx, ((i / a.nx) & 1) ^ 1);
+        mbar_wait(x_empty + sx, phx);
         mbar_expect_tx(x_full + sx, X_BYTES);
         if (!WGRAD) tma_load_3d(&tmX, x_full + sx, xs(sx), kt * BK, mt * BM, xb);      // [128 cells][32 genes], SW128
         else tma_load_3d(&tmX, x_full + sx, xs(sx), mt * BM, kt * BK, xb);             // [32 cells][128 genes], linear
-        mbar_wait(w_empty + sw, ((i / a.nw) & 1) ^ 1);
+        if (++sx == a.nx) { sx = 0; phx ^= 1; }
+        if (++kt == KT) { kt = 0; if (++arm == a.batch) { arm = 0; ++mt; } }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== TMA producer of the small operand (W1 hi/lo or delta1; L2-resident) =====
+    if (lane == 0) {
+      int kt = kt_first, arm = arm_first, sw = 0;
+      uint32_t phw = 1;
+      for (int i = 0; i < nu; ++i) {
+        mbar_wait(w_empty + sw, phw);
         mbar_expect_tx(w_full + sw, w_stage_bytes);
         if (!WGRAD) {
           tma_load_3d(&tmW, w_full + sw, ws(sw), kt * BK, 0, arm);
@@ -106,19 +120,21 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 4; ++j) tma_load_3d(&tmW, w_full + sw, ws(sw) + j * 4096, 32 * j, kt * BK, arm);
         }
+        if (++sw == a.nw) { sw = 0; phw ^= 1; }
+        if (++kt == KT) { kt = 0; if (++arm == a.batch) arm = 0; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 2) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BM, a.BN, false, WGRAD);
       uint32_t acc = 0;
+      int kt = kt_first, sw = 0;
+      uint32_t phw = 0;
       for (int i = 0; i < nu; ++i) {
-        const int64_t u = u0 + i;
-        const int kt = (int)(u % KT);
-        const int sa = i % NA, sw = i % a.nw;
+        const int sa = i & (NA - 1);
         if (kt == 0) acc = 0;                          // a new output tile starts
-        mbar_wait(w_full + sw, (i / a.nw) & 1);
+        mbar_wait(w_full + sw, phw);
         mbar_wait(a_full + sa, (i / NA) & 1);
         tc_fence_after();
         const uint32_t a_hi = tmem_base + ACC_COLS + (uint32_t)sa * 64u, a_lo = a_hi + 32u;
@@ -140,42 +156,65 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         umma_commit(a_empty + sa);
         umma_commit(w_empty + sw);
-        if (kt == KT - 1 || i == nu - 1) umma_commit(acc_full);      // this CTA's share of the tile is complete
+        if (++sw == a.nw) { sw = 0; phw ^= 1; }
+        if (++kt == KT) kt = 0;
+        if (kt == 0 || i == nu - 1) umma_commit(acc_full);      // this CTA's share of the tile is complete
       }
     }
   } else {
     // ===== transform warps: raw x tile (smem) -> masked / split A operand (TMEM); then drain the accumulator =====
-    const int quad = warp & 3, sub = (warp - 2) >> 2;     // TMEM lane quadrant, k-slice (8 of the 32 k) of a stage
+    const int quad = warp & 3, sub = (warp - CTRL_WARPS) >> 2;   // TMEM lane quadrant, k-slice (8 of the 32 k) of a stage
     const int r = quad * 32 + lane;                       // TMEM lane: cell (FWD) or gene (WGRAD) within the tile
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
     const DropSpec& dp = a.drop;
     const uint64_t Dq = (uint64_t)dp.D >> 2;
-    int seg = 0;
+    const uint32_t thr = dp.thresh16;
+    // per-thread offsets inside a raw tile
+    const uint32_t off0 = WGRAD ? (uint32_t)((8 * sub) * 512 + r * 4) : (uint32_t)(r * 128 + (((2 * sub) ^ (r & 7)) << 4));
+    const uint32_t off1 = (uint32_t)(r * 128 + (((2 * sub + 1) ^ (r & 7)) << 4));
+    const uint32_t sh = 8u * (uint32_t)(lane & 3);
+    int kt = kt_first, mt = mt_first, arm = arm_first, t = t_first, sx = 0, seg = 0;
+    uint32_t phx = 0;
     for (int i = 0; i < nu; ++i) {
-      const int64_t u = u0 + i;
-      const int t = (int)(u / KT), kt = (int)(u - (int64_t)t * KT);
-      const int mt = t / a.batch, arm = t - mt * a.batch;
-      const int sx = i % a.nx, sa = i % NA;
-      mbar_wait(x_full + sx, (i / a.nx) & 1);
-      float v[8];
-      float m[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = 1.f;
+      const int sa = i & (NA - 1);
+      mbar_wait(x_full + sx, phx);
+      const uint8_t* tile = xs(sx);
+      uint32_t v[8];
       if (!WGRAD) {
         // thread = cell r, genes kt*32 + 8*sub .. +7: two 16-byte chunks (SWIZZLE_128B: chunk c lives at c ^ (r & 7))
-        const float4* src = reinterpret_cast<const float4*>(xs(sx) + r * 128);
-        const int c0 = 2 * sub, c1 = 2 * sub + 1;
-        const float4 v0 = src[c0 ^ (r & 7)], v1 = src[c1 ^ (r & 7)];
+        const uint4 v0 = *reinterpret_cast<const uint4*>(tile + off0), v1 = *reinterpret_cast<const uint4*>(tile + off1);
         v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-        if (dp.mode == 2) {
-          const uint64_t chunk = (uint64_t)(mt * BM + r) * Dq + (uint64_t)(kt * 8 + c0);
+      } else {
+        // thread = gene r, cells kt*32 + 8*sub .. +7: column reads of the linear [32 cells][128 genes] tile
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const uint32_t*>(tile + off0 + j * 512);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_empty + sx);            // the raw tile is in registers: hand the slot back
+      // ---- dropout: zero the dropped elements (the 1/(1-p) scale is applied by the fix-up kernel)
+      if (dp.mode == 2) {
+        if (!WGRAD) {
+          const uint64_t chunk = (uint64_t)(mt * BM + r) * Dq + (uint64_t)(kt * 8 + 2 * sub);
           const uint32_t b0 = drop_bits4(dp.seed, arm, chunk), b1 = drop_bits4(dp.seed, arm, chunk + 1);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            m[j] = ((b0 >> (8 * j)) & 0xFFu) >= dp.thresh16 ? dp.scale : 0.f;
-            m[4 + j] = ((b1 >> (8 * j)) & 0xFFu) >= dp.thresh16 ? dp.scale : 0.f;
+            v[j] = ((b0 >> (8 * j)) & 0xFFu) >= thr ? v[j] : 0u;
+            v[4 + j] = ((b1 >> (8 * j)) & 0xFFu) >= thr ? v[4 + j] : 0u;
           }
-        } else if (dp.mode == 1) {
+        } else {
+          // the warp's 8 cells x 32 genes are 64 generator chunks: two per lane, shared by shuffles
+          const uint64_t cell0 = (uint64_t)(kt * BK + 8 * sub + (lane >> 3));
+          const uint64_t ccol = (uint64_t)((mt * BM + quad * 32) >> 2) + (uint64_t)(lane & 7);
+          const uint32_t hA = drop_bits4(dp.seed, arm, cell0 * Dq + ccol);
+          const uint32_t hB = drop_bits4(dp.seed, arm, (cell0 + 4) * Dq + ccol);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t h = __shfl_sync(0xffffffffu, j < 4 ? hA : hB, (j & 3) * 8 + (lane >> 2));
+            v[j] = ((h >> sh) & 0xFFu) >= thr ? v[j] : 0u;
+          }
+        }
+      } else if (dp.mode == 1) {
+        if (!WGRAD) {
           const int64_t xrow = mt * BM + r, xcol = (int64_t)kt * BK + 8 * sub;
           uint32_t k0 = 0, k1 = 0;
           if (xrow < dp.rows) {
@@ -185,57 +224,37 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            m[j] = ((k0 >> (8 * j)) & 0xFFu) ? dp.scale : 0.f;
-            m[4 + j] = ((k1 >> (8 * j)) & 0xFFu) ? dp.scale : 0.f;
+            v[j] = ((k0 >> (8 * j)) & 0xFFu) ? v[j] : 0u;
+            v[4 + j] = ((k1 >> (8 * j)) & 0xFFu) ? v[4 + j] : 0u;
           }
-        }
-      } else {
-        // thread = gene r, cells kt*32 + 8*sub .. +7: column reads of the linear [32 cells][128 genes] tile
-        const float* src = reinterpret_cast<const float*>(xs(sx)) + r;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = src[(8 * sub + j) * 128];
-        if (dp.mode == 2) {
-          // the warp's 8 cells x 32 genes are 64 generator chunks: two per lane, shared by shuffles
-          const uint64_t cell0 = (uint64_t)kt * BK + 8 * sub + (lane >> 3);
-          const uint64_t ccol = (uint64_t)((mt * BM + quad * 32) >> 2) + (uint64_t)(lane & 7);
-          const uint32_t hA = drop_bits4(dp.seed, arm, cell0 * Dq + ccol);
-          const uint32_t hB = drop_bits4(dp.seed, arm, (cell0 + 4) * Dq + ccol);
-          const uint32_t sh = 8u * (uint32_t)(lane & 3);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t h = __shfl_sync(0xffffffffu, j < 4 ? hA : hB, (j & 3) * 8 + (lane >> 2));
-            m[j] = ((h >> sh) & 0xFFu) >= dp.thresh16 ? dp.scale : 0.f;
-          }
-        } else if (dp.mode == 1) {
+        } else {
           const int64_t gene = mt * BM + r;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int64_t cell = (int64_t)kt * BK + 8 * sub + j;
             uint8_t kb = 0;
             if (gene < dp.D && cell < dp.rows) kb = dp.keep[(int64_t)arm * dp.keep_arm_stride + cell * dp.D + gene];
-            m[j] = kb ? dp.scale : 0.f;
+            v[j] = kb ? v[j] : 0u;
           }
         }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(x_empty + sx);            // the raw tile is in registers: hand the slot back
-      uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float h = v[j] * m[j];
-        hi[j] = __float_as_uint(h);
-        lo[j] = __float_as_uint(tf32_lo(h));
       }
       mbar_wait(a_empty + sa, ((i / NA) & 1) ^ 1);         // the MMAs that read this TMEM stage have completed
       tc_fence_after();
       const uint32_t acol = tmem_base + lane_bits + ACC_COLS + (uint32_t)sa * 64u + 8u * (uint32_t)sub;
-      tmem_st8(acol, hi);
-      if (!WGRAD && a.split3) tmem_st8(acol + 32u, lo);
+      tmem_st8(acol, v);                                   // "hi": the tensor core truncates to TF32 itself
+      if (!WGRAD && a.split3) {
+        uint32_t lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lo[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(v[j] & 0xFFFFE000u));
+        tmem_st8(acol + 32u, lo);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full + sa);
-      if (kt == KT - 1 || i == nu - 1) {
+      if (++sx == a.nx) { sx = 0; phx ^= 1; }
+      const bool tile_done = (kt + 1 == KT);
+      if (tile_done || i == nu - 1) {
         // ---- drain this CTA's share of tile t into its partial slot (slot = cta + tile: unique, monotone)
         mbar_wait(acc_full, seg & 1);
         tc_fence_after();
@@ -258,11 +277,12 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         tc_fence_before();
         ++seg;
       }
+      if (tile_done) { kt = 0; ++t; if (++arm == a.batch) { arm = 0; ++mt; } } else ++kt;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == CTRL_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
 // W1_lo = W1 - tf32(W1) for every arm (the part of fc1.weight the tensor core drops when it truncates to TF32)
@@ -280,6 +300,7 @@ __global__ void __launch_bounds__(256) w_lo_kernel(const float* __restrict__ w, 
 // fc1 fix-up: a1 = relu(sum of the tile's partials (fixed order) + b1), fp64 column sums for batch_l1.
 struct Fc1FixArgs {
   const float* part; int batch, ktiles; int64_t U, G;
+  float scale;                                   // 1/(1-p) of the input dropout (the GEMM ran on the unscaled mask)
   const float* params; int64_t p_arm_stride, offB;
   float* out; double* stats_out; int B, H;
 };
@@ -300,7 +321,7 @@ __global__ void __launch_bounds__(256) fc1_fixup_kernel(const Fc1FixArgs p) {
       if (j < p.H) {
         float v = 0.f;
         for (int64_t c = c0; c <= c1; ++c) v += base[(c - c0) * TILE_FLOATS + j];
-        v = fmaxf(v + bias[j], 0.f);
+        v = fmaxf(fmaf(v, p.scale, bias[j]), 0.f);
         out[(int64_t)row * p.H + j] = v;
         s1[k] += (double)v;
         s2[k] += (double)v * (double)v;
@@ -325,7 +346,7 @@ __global__ void __launch_bounds__(256) fc1_fixup_kernel(const Fc1FixArgs p) {
 
 // d fc1.weight fix-up: dW1[arm][h][gene] = sum of the partials [slot][h][gene in tile] in a fixed order
 __global__ void __launch_bounds__(256) wgrad_fixup_kernel(const float* part, int batch, int ktiles, int64_t U, int64_t G,
-                                                          float* grads, int64_t g_arm_stride, int D, int H) {
+                                                          float scale, float* grads, int64_t g_arm_stride, int D, int H) {
   const int arm = blockIdx.z;
   const int gene = blockIdx.x * 128 + (threadIdx.x & 127);
   const int h = blockIdx.y * 2 + (threadIdx.x >> 7);
@@ -335,7 +356,7 @@ __global__ void __launch_bounds__(256) wgrad_fixup_kernel(const float* part, int
   const float* base = part + (c0 + t) * TILE_FLOATS + (int64_t)h * 128 + (gene & 127);
   float v = 0.f;
   for (int64_t c = c0; c <= c1; ++c) v += base[(c - c0) * TILE_FLOATS];
-  grads[(int64_t)arm * g_arm_stride + (int64_t)h * D + gene] = v;
+  grads[(int64_t)arm * g_arm_stride + (int64_t)h * D + gene] = v * scale;
 }
 
 int sm_count() {
@@ -417,6 +438,7 @@ int ts_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state&
   Fc1FixArgs f;
   memset(&f, 0, sizeof(f));
   f.part = a.part; f.batch = A; f.ktiles = a.ktiles; f.U = U; f.G = G;
+  f.scale = drop.mode ? drop.scale : 1.f;
   f.params = st.params; f.p_arm_stride = L.arm_stride; f.offB = L.offset[FC1_B];
   f.out = a1_out; f.stats_out = stats_out; f.B = B; f.H = H;
   int gx = (B + 7) / 8;
@@ -449,8 +471,8 @@ int ts_fc1_wgrad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
   int64_t U, G;
   rc = launch_ts<true>(tmX, tmW, tmW, a, &U, &G, s);
   if (rc) return rc;
-  wgrad_fixup_kernel<<<dim3(a.mtiles, (H + 1) / 2, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, st.grads + L.offset[FC1_W],
-                                                                   L.arm_stride, D, H);
+  wgrad_fixup_kernel<<<dim3(a.mtiles, (H + 1) / 2, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, drop.mode ? drop.scale : 1.f,
+                                                                   st.grads + L.offset[FC1_W], L.arm_stride, D, H);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
