@@ -26,13 +26,14 @@ using namespace tc;
 
 constexpr int BM = 128;
 constexpr int BK = 32;
-constexpr int NTW = 16;                    // transform / drain warps
+constexpr int NG = 4;                      // transform groups: group g owns the units i = g (mod NG) of its CTA
+constexpr int NTW = 4 * NG;                // transform / drain warps: 4 per group (one per TMEM lane quadrant)
 constexpr int CTRL_WARPS = 3;              // warp 0: TMA of x, warp 1: TMA of the small operand, warp 2: MMA issue
 constexpr int THREADS = 32 * (CTRL_WARPS + NTW);
-constexpr int NA = 4;                      // A-operand stages in tensor memory (64 columns each: hi | lo)
+constexpr int NA = NG;                     // A-operand stages in tensor memory (64 columns each: hi | lo), one per group
 constexpr int X_BYTES = 16384;
 constexpr int TILE_FLOATS = 128 * 128;     // one partial tile
-constexpr uint32_t ACC_COLS = 128;         // accumulator columns [0,128); A stages follow
+constexpr uint32_t ACC_COLS = 256;         // two accumulators [0,128) and [128,256); the A stages follow
 
 struct TsArgs {
   int BN;                       // UMMA N (multiple of 16, <= 128)
@@ -64,8 +65,9 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint64_t* w_empty = w_full + a.nw;
   uint64_t* a_full = w_empty + a.nw;
   uint64_t* a_empty = a_full + NA;
-  uint64_t* acc_full = a_empty + NA;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = a_empty + NA;      // [2] MMAs of a segment complete
+  uint64_t* acc_empty = acc_full + 2;     // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int KT = a.ktiles;
   const int64_t U = (int64_t)a.batch * a.mtiles * KT, G = gridDim.x;
@@ -73,10 +75,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int nu = (int)(u1 - u0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < a.nx; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, NTW); }
+    for (int s = 0; s < a.nx; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 4); }
     for (int s = 0; s < a.nw; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
-    for (int s = 0; s < NA; ++s) { mbar_init(a_full + s, NTW); mbar_init(a_empty + s, 1); }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < NA; ++s) { mbar_init(a_full + s, 4); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
     fence_barrier_init();
   }
   if (warp == CTRL_WARPS) tmem_alloc(tmem_slot, 512);
@@ -129,11 +131,15 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BM, a.BN, false, WGRAD);
       uint32_t acc = 0;
-      int kt = kt_first, sw = 0;
+      int kt = kt_first, sw = 0, seg = 0;
       uint32_t phw = 0;
       for (int i = 0; i < nu; ++i) {
         const int sa = i & (NA - 1);
-        if (kt == 0) acc = 0;                          // a new output tile starts
+        const uint32_t dcol = tmem_base + (uint32_t)(seg & 1) * 128u;
+        if (kt == 0 || i == 0) {                       // a new segment: its accumulator must have been drained
+          acc = 0;
+          mbar_wait(acc_empty + (seg & 1), ((seg >> 1) & 1) ^ 1);
+        }
         mbar_wait(w_full + sw, phw);
         mbar_wait(a_full + sa, (i / NA) & 1);
         tc_fence_after();
@@ -144,13 +150,13 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           if (!WGRAD) {
             const uint64_t bh = make_smem_desc(wb + ks * 32, 0, 1024, false);
             if (a.split3) {
-              umma_tf32_ts(tmem_base, a_lo + ks * 8, bh, idesc, acc);
+              umma_tf32_ts(dcol, a_lo + ks * 8, bh, idesc, acc);
               acc = 1;
-              umma_tf32_ts(tmem_base, a_hi + ks * 8, make_smem_desc(wb + a.w_tile_bytes + ks * 32, 0, 1024, false), idesc, 1u);
+              umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(wb + a.w_tile_bytes + ks * 32, 0, 1024, false), idesc, 1u);
             }
-            umma_tf32_ts(tmem_base, a_hi + ks * 8, bh, idesc, acc);
+            umma_tf32_ts(dcol, a_hi + ks * 8, bh, idesc, acc);
           } else {
-            umma_tf32_ts(tmem_base, a_hi + ks * 8, make_smem_desc(wb + ks * 1024, 4096, 512, true), idesc, acc);
+            umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(wb + ks * 1024, 4096, 512, true), idesc, acc);
           }
           acc = 1;
         }
@@ -158,110 +164,128 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         umma_commit(w_empty + sw);
         if (++sw == a.nw) { sw = 0; phw ^= 1; }
         if (++kt == KT) kt = 0;
-        if (kt == 0 || i == nu - 1) umma_commit(acc_full);      // this CTA's share of the tile is complete
+        if (kt == 0 || i == nu - 1) {                  // this CTA's share of the tile is complete
+          umma_commit(acc_full + (seg & 1));
+          ++seg;
+        }
       }
     }
   } else {
-    // ===== transform warps: raw x tile (smem) -> masked / split A operand (TMEM); then drain the accumulator =====
-    const int quad = warp & 3, sub = (warp - CTRL_WARPS) >> 2;   // TMEM lane quadrant, k-slice (8 of the 32 k) of a stage
+    // ===== transform warps: raw x tile (smem) -> masked / split A operand (TMEM); the group that transforms the last
+    // unit of a segment also drains its accumulator.  Group g works on units g, g + NG, ...: NG units are in flight,
+    // which hides the per-unit latency chain (barrier -> LDS -> hash -> STTM -> fence -> barrier).
+    const int quad = warp & 3, grp = (warp - CTRL_WARPS) >> 2;
     const int r = quad * 32 + lane;                       // TMEM lane: cell (FWD) or gene (WGRAD) within the tile
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
     const DropSpec& dp = a.drop;
     const uint64_t Dq = (uint64_t)dp.D >> 2;
     const uint32_t thr = dp.thresh16;
-    // per-thread offsets inside a raw tile
-    const uint32_t off0 = WGRAD ? (uint32_t)((8 * sub) * 512 + r * 4) : (uint32_t)(r * 128 + (((2 * sub) ^ (r & 7)) << 4));
-    const uint32_t off1 = (uint32_t)(r * 128 + (((2 * sub + 1) ^ (r & 7)) << 4));
     const uint32_t sh = 8u * (uint32_t)(lane & 3);
-    int kt = kt_first, mt = mt_first, arm = arm_first, t = t_first, sx = 0, seg = 0;
-    uint32_t phx = 0;
-    for (int i = 0; i < nu; ++i) {
-      const int sa = i & (NA - 1);
+    const uint32_t acol = tmem_base + lane_bits + ACC_COLS + (uint32_t)grp * 64u;      // this group's A stage
+    // position of unit i = grp
+    int kt = kt_first + grp, t = t_first, mt = mt_first, arm = arm_first;
+    while (kt >= KT) { kt -= KT; ++t; if (++arm == a.batch) { arm = 0; ++mt; } }
+    int sx = grp % a.nx;
+    uint32_t phx = (uint32_t)((grp / a.nx) & 1);
+    uint32_t pha = 1;                                     // parity for a_empty (first use passes)
+    for (int i = grp; i < nu; i += NG) {
       mbar_wait(x_full + sx, phx);
       const uint8_t* tile = xs(sx);
-      uint32_t v[8];
-      if (!WGRAD) {
-        // thread = cell r, genes kt*32 + 8*sub .. +7: two 16-byte chunks (SWIZZLE_128B: chunk c lives at c ^ (r & 7))
-        const uint4 v0 = *reinterpret_cast<const uint4*>(tile + off0), v1 = *reinterpret_cast<const uint4*>(tile + off1);
-        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-      } else {
-        // thread = gene r, cells kt*32 + 8*sub .. +7: column reads of the linear [32 cells][128 genes] tile
+      bool waited = false;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const uint32_t*>(tile + off0 + j * 512);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(x_empty + sx);            // the raw tile is in registers: hand the slot back
-      // ---- dropout: zero the dropped elements (the 1/(1-p) scale is applied by the fix-up kernel)
-      if (dp.mode == 2) {
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[16];
         if (!WGRAD) {
-          const uint64_t chunk = (uint64_t)(mt * BM + r) * Dq + (uint64_t)(kt * 8 + 2 * sub);
-          const uint32_t b0 = drop_bits4(dp.seed, arm, chunk), b1 = drop_bits4(dp.seed, arm, chunk + 1);
+          // thread = cell r, genes kt*32 + 16*half .. +15: 16-byte chunks (SWIZZLE_128B: chunk c lives at c ^ (r & 7))
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            v[j] = ((b0 >> (8 * j)) & 0xFFu) >= thr ? v[j] : 0u;
-            v[4 + j] = ((b1 >> (8 * j)) & 0xFFu) >= thr ? v[4 + j] : 0u;
+          for (int q = 0; q < 4; ++q) {
+            const uint4 t4 = *reinterpret_cast<const uint4*>(tile + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+            v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
           }
         } else {
-          // the warp's 8 cells x 32 genes are 64 generator chunks: two per lane, shared by shuffles
-          const uint64_t cell0 = (uint64_t)(kt * BK + 8 * sub + (lane >> 3));
-          const uint64_t ccol = (uint64_t)((mt * BM + quad * 32) >> 2) + (uint64_t)(lane & 7);
-          const uint32_t hA = drop_bits4(dp.seed, arm, cell0 * Dq + ccol);
-          const uint32_t hB = drop_bits4(dp.seed, arm, (cell0 + 4) * Dq + ccol);
+          // thread = gene r, cells kt*32 + 16*half .. +15: column reads of the linear [32 cells][128 genes] tile
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t h = __shfl_sync(0xffffffffu, j < 4 ? hA : hB, (j & 3) * 8 + (lane >> 2));
-            v[j] = ((h >> sh) & 0xFFu) >= thr ? v[j] : 0u;
+          for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const uint32_t*>(tile + (16 * half + j) * 512 + r * 4);
+        }
+        if (half == 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(x_empty + sx);        // the raw tile is in registers: hand the slot back
+        }
+        // ---- dropout: zero the dropped elements (the 1/(1-p) scale is applied by the fix-up kernel)
+        if (dp.mode == 2) {
+          if (!WGRAD) {
+            const uint64_t chunk = (uint64_t)(mt * BM + r) * Dq + (uint64_t)(kt * 8 + 4 * half);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t b = drop_bits4(dp.seed, arm, chunk + q);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[4 * q + j] = ((b >> (8 * j)) & 0xFFu) >= thr ? v[4 * q + j] : 0u;
+            }
+          } else {
+            // the warp's 16 cells x 32 genes are 128 generator chunks: 4 per lane, shared by shuffles
+            const uint64_t cell0 = (uint64_t)(kt * BK + 16 * half + (lane >> 3));
+            const uint64_t ccol = (uint64_t)((mt * BM + quad * 32) >> 2) + (uint64_t)(lane & 7);
+            uint32_t hq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hq[q] = drop_bits4(dp.seed, arm, (cell0 + 4 * q) * Dq + ccol);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t h = __shfl_sync(0xffffffffu, hq[j >> 2], (j & 3) * 8 + (lane >> 2));
+              v[j] = ((h >> sh) & 0xFFu) >= thr ? v[j] : 0u;
+            }
+          }
+        } else if (dp.mode == 1) {
+          if (!WGRAD) {
+            const int64_t xrow = mt * BM + r, xcol = (int64_t)kt * BK + 16 * half;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t kw = 0;
+              if (xrow < dp.rows && xcol + 4 * q < dp.D)
+                kw = *reinterpret_cast<const uint32_t*>(dp.keep + (int64_t)arm * dp.keep_arm_stride + xrow * dp.D + xcol + 4 * q);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[4 * q + j] = ((kw >> (8 * j)) & 0xFFu) ? v[4 * q + j] : 0u;
+            }
+          } else {
+            const int64_t gene = mt * BM + r;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int64_t cell = (int64_t)kt * BK + 16 * half + j;
+              uint8_t kb = 0;
+              if (gene < dp.D && cell < dp.rows) kb = dp.keep[(int64_t)arm * dp.keep_arm_stride + cell * dp.D + gene];
+              v[j] = kb ? v[j] : 0u;
+            }
           }
         }
-      } else if (dp.mode == 1) {
-        if (!WGRAD) {
-          const int64_t xrow = mt * BM + r, xcol = (int64_t)kt * BK + 8 * sub;
-          uint32_t k0 = 0, k1 = 0;
-          if (xrow < dp.rows) {
-            const uint8_t* kp = dp.keep + (int64_t)arm * dp.keep_arm_stride + xrow * dp.D + xcol;
-            if (xcol < dp.D) k0 = *reinterpret_cast<const uint32_t*>(kp);
-            if (xcol + 4 < dp.D) k1 = *reinterpret_cast<const uint32_t*>(kp + 4);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            v[j] = ((k0 >> (8 * j)) & 0xFFu) ? v[j] : 0u;
-            v[4 + j] = ((k1 >> (8 * j)) & 0xFFu) ? v[4 + j] : 0u;
-          }
-        } else {
-          const int64_t gene = mt * BM + r;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int64_t cell = (int64_t)kt * BK + 8 * sub + j;
-            uint8_t kb = 0;
-            if (gene < dp.D && cell < dp.rows) kb = dp.keep[(int64_t)arm * dp.keep_arm_stride + cell * dp.D + gene];
-            v[j] = kb ? v[j] : 0u;
-          }
+        if (!waited) {
+          mbar_wait(a_empty + grp, pha);                   // the MMAs that read this TMEM stage have completed
+          tc_fence_after();
+          waited = true;
         }
-      }
-      mbar_wait(a_empty + sa, ((i / NA) & 1) ^ 1);         // the MMAs that read this TMEM stage have completed
-      tc_fence_after();
-      const uint32_t acol = tmem_base + lane_bits + ACC_COLS + (uint32_t)sa * 64u + 8u * (uint32_t)sub;
-      tmem_st8(acol, v);                                   // "hi": the tensor core truncates to TF32 itself
-      if (!WGRAD && a.split3) {
-        uint32_t lo[8];
+        tmem_st8(acol + 16u * half, v);                    // "hi": the tensor core truncates to TF32 itself
+        tmem_st8(acol + 16u * half + 8u, v + 8);
+        if (!WGRAD && a.split3) {
+          uint32_t lo[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) lo[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(v[j] & 0xFFFFE000u));
-        tmem_st8(acol + 32u, lo);
+          for (int j = 0; j < 16; ++j) lo[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(v[j] & 0xFFFFE000u));
+          tmem_st8(acol + 32u + 16u * half, lo);
+          tmem_st8(acol + 32u + 16u * half + 8u, lo + 8);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full + sa);
-      if (++sx == a.nx) { sx = 0; phx ^= 1; }
-      const bool tile_done = (kt + 1 == KT);
-      if (tile_done || i == nu - 1) {
+      if (lane == 0) mbar_arrive(a_full + grp);
+      pha ^= 1;
+      if (kt == KT - 1 || i == nu - 1) {
         // ---- drain this CTA's share of tile t into its partial slot (slot = cta + tile: unique, monotone)
-        mbar_wait(acc_full, seg & 1);
+        const int seg = t - t_first;
+        mbar_wait(acc_full + (seg & 1), (seg >> 1) & 1);
         tc_fence_after();
         float* prt = a.part + ((int64_t)blockIdx.x + t) * TILE_FLOATS;
-        for (int j = sub; j < a.BN / 16; j += 4) {
+        const uint32_t dcol = tmem_base + lane_bits + (uint32_t)(seg & 1) * 128u;
+        for (int j = 0; j < a.BN / 16; ++j) {
           uint32_t rr[16];
-          tmem_ld16(tmem_base + lane_bits + (uint32_t)(j * 16), rr);
+          tmem_ld16(dcol + (uint32_t)(j * 16), rr);
           tmem_ld_wait();
           if (!WGRAD) {
             float4* dst = reinterpret_cast<float4*>(prt + r * 128 + j * 16);
@@ -275,9 +299,14 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
         }
         tc_fence_before();
-        ++seg;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + (seg & 1));
       }
-      if (tile_done) { kt = 0; ++t; if (++arm == a.batch) { arm = 0; ++mt; } } else ++kt;
+      // advance to unit i + NG
+      sx += NG;
+      if (sx >= a.nx) { sx -= a.nx; phx ^= 1; }
+      kt += NG;
+      while (kt >= KT) { kt -= KT; ++t; if (++arm == a.batch) { arm = 0; ++mt; } }
     }
   }
   tc_fence_before();
@@ -382,7 +411,7 @@ int launch_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap&
   const int budget = 227 * 1024 - 1024 - 512 - a.nw * w_stage;
   a.nx = budget / X_BYTES;
   if (a.nx > 8) a.nx = 8;
-  const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * w_stage + (2 * a.nx + 2 * a.nw + 2 * NA + 2) * 8 + 1024;
+  const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * w_stage + (2 * a.nx + 2 * a.nw + 2 * NA + 6) * 8 + 1024;
   static bool attr = false;
   if (!attr) {
     MVAE_CUDA(cudaFuncSetAttribute(ts_gemm_kernel<WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
