@@ -129,7 +129,7 @@ Work make_work(const mvae_dims& d) {
     const int64_t p1 = (int64_t)w.fc1_splitk * A * w.Bpad * 128, p2 = (int64_t)8 * A * w.Dpad * 128;
     // stream-K partial tiles of the fc1 kernels (ts_gemm.cu): one [128][128] tile per (CTA, output tile) pair
     const int64_t t1 = A * (w.Bpad / 128), t2 = A * (w.Dpad / 128);
-    const int64_t p3 = ((t1 > t2 ? t1 : t2) + 160) * 128 * 128;
+    const int64_t p3 = ((t1 > t2 ? t1 : t2) + 2 * A + 320) * 128 * 128;
     int64_t pm = p1 > p2 ? p1 : p2;
     if (p3 > pm) pm = p3;
     w.fc1_part = take(pm);

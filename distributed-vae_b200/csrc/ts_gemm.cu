@@ -16,6 +16,8 @@
 //     one wave, no tail); a CTA writes one partial tile per output tile it touches and a fix-up kernel
 //     sums the partials of each tile in a fixed order (deterministic) and applies the layer epilogue.
 //   * W1_lo = W1 - tf32(W1) is computed once per step by a tiny kernel, so the W operand needs no transform.
+//   * The kernels are bound by L2 -> SM bytes (x tile + small-operand tile per unit, ~6 TB/s on the chip), so an
+//     output tile is 256 rows = two 128-row blocks that share every small-operand stage (two accumulators).
 #include "gemm_tc.h"
 #include "tc_common.cuh"
 
@@ -33,11 +35,12 @@ constexpr int THREADS = 32 * (CTRL_WARPS + NTW);
 constexpr int NA = NG;                     // A-operand stages in tensor memory (64 columns each: hi | lo), one per group
 constexpr int X_BYTES = 16384;
 constexpr int TILE_FLOATS = 128 * 128;     // one partial tile
-constexpr uint32_t ACC_COLS = 256;         // two accumulators [0,128) and [128,256); the A stages follow
+constexpr int NB = 2;                      // 128-row blocks per output tile (they share the small-operand stages)
+constexpr uint32_t ACC_COLS = 128 * NB;    // one accumulator per block: [0,128), [128,256); the A stages follow
 
 struct TsArgs {
   int BN;                       // UMMA N (multiple of 16, <= 128)
-  int batch, mtiles, ktiles;    // arms, 128-row tiles per arm, 32-deep k tiles
+  int batch, mtiles, ktiles;    // arms, 256-row tiles per arm, 32-deep k tiles
   int x_batched;                // x has an arm coordinate
   int nx, nw;                   // ring depths
   int w_tile_bytes;             // bytes of one W tile image
@@ -65,9 +68,9 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint64_t* w_empty = w_full + a.nw;
   uint64_t* a_full = w_empty + a.nw;
   uint64_t* a_empty = a_full + NA;
-  uint64_t* acc_full = a_empty + NA;      // [2] MMAs of a segment complete
-  uint64_t* acc_empty = acc_full + 2;     // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_full = a_empty + NA;      // MMAs of a segment complete (both blocks)
+  uint64_t* acc_empty = acc_full + 1;     // both accumulators drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int KT = a.ktiles;
   const int64_t U = (int64_t)a.batch * a.mtiles * KT, G = gridDim.x;
@@ -78,7 +81,8 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     for (int s = 0; s < a.nx; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 4); }
     for (int s = 0; s < a.nw; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
     for (int s = 0; s < NA; ++s) { mbar_init(a_full + s, 4); mbar_init(a_empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4 * NB);
     fence_barrier_init();
   }
   if (warp == CTRL_WARPS) tmem_alloc(tmem_slot, 512);
@@ -99,11 +103,15 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       uint32_t phx = 1;
       for (int i = 0; i < nu; ++i) {
         const int xb = a.x_batched ? arm : 0;
-        mbar_wait(x_empty + sx, phx);
-        mbar_expect_tx(x_full + sx, X_BYTES);
-        if (!WGRAD) tma_load_3d(&tmX, x_full + sx, xs(sx), kt * BK, mt * BM, xb);      // [128 cells][32 genes], SW128
-        else tma_load_3d(&tmX, x_full + sx, xs(sx), mt * BM, kt * BK, xb);             // [32 cells][128 genes], linear
-        if (++sx == a.nx) { sx = 0; phx ^= 1; }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {                 // x-unit j = NB * i + b: block b of the tile
+          const int m0 = (NB * mt + b) * BM;
+          mbar_wait(x_empty + sx, phx);
+          mbar_expect_tx(x_full + sx, X_BYTES);
+          if (!WGRAD) tma_load_3d(&tmX, x_full + sx, xs(sx), kt * BK, m0, xb);         // [128 cells][32 genes], SW128
+          else tma_load_3d(&tmX, x_full + sx, xs(sx), m0, kt * BK, xb);                // [32 cells][128 genes], linear
+          if (++sx == a.nx) { sx = 0; phx ^= 1; }
+        }
         if (++kt == KT) { kt = 0; if (++arm == a.batch) { arm = 0; ++mt; } }
       }
     }
@@ -127,48 +135,57 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
     }
   } else if (warp == 2) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, a.BN, false, WGRAD);
-      uint32_t acc = 0;
-      int kt = kt_first, sw = 0, seg = 0;
-      uint32_t phw = 0;
-      for (int i = 0; i < nu; ++i) {
-        const int sa = i & (NA - 1);
-        const uint32_t dcol = tmem_base + (uint32_t)(seg & 1) * 128u;
-        if (kt == 0 || i == 0) {                       // a new segment: its accumulator must have been drained
-          acc = 0;
-          mbar_wait(acc_empty + (seg & 1), ((seg >> 1) & 1) ^ 1);
-        }
-        mbar_wait(w_full + sw, phw);
-        mbar_wait(a_full + sa, (i / NA) & 1);
-        tc_fence_after();
-        const uint32_t a_hi = tmem_base + ACC_COLS + (uint32_t)sa * 64u, a_lo = a_hi + 32u;
-        const uint32_t wb = smem_u32(ws(sw));
-#pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {
-          if (!WGRAD) {
-            const uint64_t bh = make_smem_desc(wb + ks * 32, 0, 1024, false);
-            if (a.split3) {
-              umma_tf32_ts(dcol, a_lo + ks * 8, bh, idesc, acc);
-              acc = 1;
-              umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(wb + a.w_tile_bytes + ks * 32, 0, 1024, false), idesc, 1u);
-            }
-            umma_tf32_ts(dcol, a_hi + ks * 8, bh, idesc, acc);
-          } else {
-            umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(wb + ks * 1024, 4096, 512, true), idesc, acc);
-          }
-          acc = 1;
-        }
-        umma_commit(a_empty + sa);
-        umma_commit(w_empty + sw);
-        if (++sw == a.nw) { sw = 0; phw ^= 1; }
-        if (++kt == KT) kt = 0;
-        if (kt == 0 || i == nu - 1) {                  // this CTA's share of the tile is complete
-          umma_commit(acc_full + (seg & 1));
-          ++seg;
-        }
+    // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues =====
+    const uint32_t idesc = make_idesc(BM, a.BN, false, WGRAD);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    uint32_t acc = 0;
+    int kt = kt_first, sw = 0, seg = 0;
+    uint32_t phw = 0;
+    for (int i = 0; i < nu; ++i) {
+      if (kt == 0 || i == 0) {                       // a new segment: the accumulators must have been drained
+        acc = 0;
+        mbar_wait(acc_empty, (seg & 1) ^ 1);
       }
+      mbar_wait(w_full + sw, phw);
+      const uint32_t wb = smem_u32(ws(sw));
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const int j = NB * i + b, sa = j & (NA - 1);
+        const uint32_t dcol = tb + (uint32_t)b * 128u;
+        mbar_wait(a_full + sa, (j / NA) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = tb + ACC_COLS + (uint32_t)sa * 64u, a_lo = a_hi + 32u;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint32_t accf = (acc | (uint32_t)ks) ? 1u : 0u;
+            if (!WGRAD) {
+              const uint64_t bh = make_smem_desc(wb + ks * 32, 0, 1024, false);
+              if (a.split3) {
+                umma_tf32_ts(dcol, a_lo + ks * 8, bh, idesc, accf);
+                umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(wb + a.w_tile_bytes + ks * 32, 0, 1024, false), idesc, 1u);
+                umma_tf32_ts(dcol, a_hi + ks * 8, bh, idesc, 1u);
+              } else {
+                umma_tf32_ts(dcol, a_hi + ks * 8, bh, idesc, accf);
+              }
+            } else {
+              umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(wb + ks * 1024, 4096, 512, true), idesc, accf);
+            }
+          }
+          umma_commit(a_empty + sa);
+        }
+        __syncwarp();
+      }
+      acc = 1;
+      const bool seg_end = (kt + 1 == KT) || (i == nu - 1);
+      if (elect_one()) {
+        umma_commit(w_empty + sw);
+        if (seg_end) umma_commit(acc_full);          // this CTA's share of the tile is complete
+      }
+      __syncwarp();
+      if (++sw == a.nw) { sw = 0; phw ^= 1; }
+      if (++kt == KT) kt = 0;
+      if (seg_end) ++seg;
     }
   } else {
     // ===== transform warps: raw x tile (smem) -> masked / split A operand (TMEM); the group that transforms the last
@@ -182,13 +199,16 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const uint32_t thr = dp.thresh16;
     const uint32_t sh = 8u * (uint32_t)(lane & 3);
     const uint32_t acol = tmem_base + lane_bits + ACC_COLS + (uint32_t)grp * 64u;      // this group's A stage
-    // position of unit i = grp
-    int kt = kt_first + grp, t = t_first, mt = mt_first, arm = arm_first;
+    // group g owns the x-units j = g (mod NG), j = NB * i + b: block b = g % NB of the units i = g / NB (mod NG / NB)
+    const int blk = grp % NB;
+    constexpr int ISTEP = NG / NB;
+    int kt = kt_first + grp / NB, t = t_first, mt = mt_first, arm = arm_first;
     while (kt >= KT) { kt -= KT; ++t; if (++arm == a.batch) { arm = 0; ++mt; } }
     int sx = grp % a.nx;
     uint32_t phx = (uint32_t)((grp / a.nx) & 1);
     uint32_t pha = 1;                                     // parity for a_empty (first use passes)
-    for (int i = grp; i < nu; i += NG) {
+    for (int i = grp / NB; i < nu; i += ISTEP) {
+      const int m0 = (NB * mt + blk) * BM;                // first row (FWD: cell, WGRAD: gene) of this block
       mbar_wait(x_full + sx, phx);
       const uint8_t* tile = xs(sx);
       bool waited = false;
@@ -214,7 +234,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         // ---- dropout: zero the dropped elements (the 1/(1-p) scale is applied by the fix-up kernel)
         if (dp.mode == 2) {
           if (!WGRAD) {
-            const uint64_t chunk = (uint64_t)(mt * BM + r) * Dq + (uint64_t)(kt * 8 + 4 * half);
+            const uint64_t chunk = (uint64_t)(m0 + r) * Dq + (uint64_t)(kt * 8 + 4 * half);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint32_t b = drop_bits4(dp.seed, arm, chunk + q);
@@ -224,7 +244,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           } else {
             // the warp's 16 cells x 32 genes are 128 generator chunks: 4 per lane, shared by shuffles
             const uint64_t cell0 = (uint64_t)(kt * BK + 16 * half + (lane >> 3));
-            const uint64_t ccol = (uint64_t)((mt * BM + quad * 32) >> 2) + (uint64_t)(lane & 7);
+            const uint64_t ccol = (uint64_t)((m0 + quad * 32) >> 2) + (uint64_t)(lane & 7);
             uint32_t hq[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) hq[q] = drop_bits4(dp.seed, arm, (cell0 + 4 * q) * Dq + ccol);
@@ -236,7 +256,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
         } else if (dp.mode == 1) {
           if (!WGRAD) {
-            const int64_t xrow = mt * BM + r, xcol = (int64_t)kt * BK + 16 * half;
+            const int64_t xrow = m0 + r, xcol = (int64_t)kt * BK + 16 * half;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint32_t kw = 0;
@@ -246,7 +266,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
               for (int j = 0; j < 4; ++j) v[4 * q + j] = ((kw >> (8 * j)) & 0xFFu) ? v[4 * q + j] : 0u;
             }
           } else {
-            const int64_t gene = mt * BM + r;
+            const int64_t gene = m0 + r;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int64_t cell = (int64_t)kt * BK + 16 * half + j;
@@ -279,10 +299,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (kt == KT - 1 || i == nu - 1) {
         // ---- drain this CTA's share of tile t into its partial slot (slot = cta + tile: unique, monotone)
         const int seg = t - t_first;
-        mbar_wait(acc_full + (seg & 1), (seg >> 1) & 1);
+        mbar_wait(acc_full, seg & 1);
         tc_fence_after();
-        float* prt = a.part + ((int64_t)blockIdx.x + t) * TILE_FLOATS;
-        const uint32_t dcol = tmem_base + lane_bits + (uint32_t)(seg & 1) * 128u;
+        float* prt = a.part + (((int64_t)blockIdx.x + t) * NB + blk) * TILE_FLOATS;
+        const uint32_t dcol = tmem_base + lane_bits + (uint32_t)blk * 128u;
         for (int j = 0; j < a.BN / 16; ++j) {
           uint32_t rr[16];
           tmem_ld16(dcol + (uint32_t)(j * 16), rr);
@@ -300,12 +320,12 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty + (seg & 1));
+        if (lane == 0) mbar_arrive(acc_empty);
       }
-      // advance to unit i + NG
+      // advance to x-unit j + NG (unit i + NG / NB)
       sx += NG;
       if (sx >= a.nx) { sx -= a.nx; phx ^= 1; }
-      kt += NG;
+      kt += ISTEP;
       while (kt >= KT) { kt -= KT; ++t; if (++arm == a.batch) { arm = 0; ++mt; } }
     }
   }
@@ -341,15 +361,15 @@ __global__ void __launch_bounds__(256) fc1_fixup_kernel(const Fc1FixArgs p) {
   float* out = p.out + (int64_t)arm * p.B * p.H;
   double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
   for (int row = blockIdx.x * 8 + warp; row < p.B; row += gridDim.x * 8) {
-    const int64_t t = (int64_t)(row >> 7) * p.batch + arm;
+    const int64_t t = (int64_t)(row >> 8) * p.batch + arm;
     const int64_t c0 = cta_of_unit(t * p.ktiles, p.U, p.G), c1 = cta_of_unit(t * p.ktiles + p.ktiles - 1, p.U, p.G);
-    const float* base = p.part + (c0 + t) * TILE_FLOATS + (int64_t)(row & 127) * 128;
+    const float* base = p.part + ((c0 + t) * NB + ((row >> 7) & 1)) * TILE_FLOATS + (int64_t)(row & 127) * 128;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int j = lane + 32 * k;
       if (j < p.H) {
         float v = 0.f;
-        for (int64_t c = c0; c <= c1; ++c) v += base[(c - c0) * TILE_FLOATS + j];
+        for (int64_t c = c0; c <= c1; ++c) v += base[(c - c0) * NB * TILE_FLOATS + j];
         v = fmaxf(fmaf(v, p.scale, bias[j]), 0.f);
         out[(int64_t)row * p.H + j] = v;
         s1[k] += (double)v;
@@ -380,11 +400,11 @@ __global__ void __launch_bounds__(256) wgrad_fixup_kernel(const float* part, int
   const int gene = blockIdx.x * 128 + (threadIdx.x & 127);
   const int h = blockIdx.y * 2 + (threadIdx.x >> 7);
   if (gene >= D || h >= H) return;
-  const int64_t t = (int64_t)blockIdx.x * batch + arm;
+  const int64_t t = (int64_t)(blockIdx.x >> 1) * batch + arm;
   const int64_t c0 = cta_of_unit(t * ktiles, U, G), c1 = cta_of_unit(t * ktiles + ktiles - 1, U, G);
-  const float* base = part + (c0 + t) * TILE_FLOATS + (int64_t)h * 128 + (gene & 127);
+  const float* base = part + ((c0 + t) * NB + (blockIdx.x & 1)) * TILE_FLOATS + (int64_t)h * 128 + (gene & 127);
   float v = 0.f;
-  for (int64_t c = c0; c <= c1; ++c) v += base[(c - c0) * TILE_FLOATS];
+  for (int64_t c = c0; c <= c1; ++c) v += base[(c - c0) * NB * TILE_FLOATS];
   grads[(int64_t)arm * g_arm_stride + (int64_t)h * D + gene] = v * scale;
 }
 
@@ -427,7 +447,7 @@ int launch_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap&
 
 int64_t ts_part_floats(int A, int Bpad, int Dpad) {
   const int64_t t1 = (int64_t)A * (Bpad / 128), t2 = (int64_t)A * (Dpad / 128);
-  return ((t1 > t2 ? t1 : t2) + 160) * TILE_FLOATS;
+  return ((t1 > t2 ? t1 : t2) + 2 * A + 320) * TILE_FLOATS;
 }
 
 // fc1 forward: a1 = relu(dropout(x) . W1^T + b1) and the batch_l1 column sums (replaces GEMM + epilogue kernel)
@@ -447,7 +467,7 @@ int ts_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state&
   TsArgs a;
   memset(&a, 0, sizeof(a));
   a.BN = (H + 15) / 16 * 16;
-  a.batch = A; a.mtiles = (B + BM - 1) / BM; a.ktiles = (D + BK - 1) / BK;
+  a.batch = A; a.mtiles = (B + NB * BM - 1) / (NB * BM); a.ktiles = (D + BK - 1) / BK;
   a.x_batched = in.x_arm_stride > 0;
   a.w_tile_bytes = a.BN * 128;
   a.split3 = split3;
@@ -486,7 +506,7 @@ int ts_fc1_wgrad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
   TsArgs a;
   memset(&a, 0, sizeof(a));
   a.BN = (H + 15) / 16 * 16;
-  a.batch = A; a.mtiles = (D + BM - 1) / BM; a.ktiles = (B + BK - 1) / BK;
+  a.batch = A; a.mtiles = (D + NB * BM - 1) / (NB * BM); a.ktiles = (B + BK - 1) / BK;
   a.x_batched = in.x_arm_stride > 0;
   a.w_tile_bytes = 16384;
   a.split3 = 0;
@@ -500,7 +520,7 @@ int ts_fc1_wgrad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
   int64_t U, G;
   rc = launch_ts<true>(tmX, tmW, tmW, a, &U, &G, s);
   if (rc) return rc;
-  wgrad_fixup_kernel<<<dim3(a.mtiles, (H + 1) / 2, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, drop.mode ? drop.scale : 1.f,
+  wgrad_fixup_kernel<<<dim3((D + 127) / 128, (H + 1) / 2, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, drop.mode ? drop.scale : 1.f,
                                                                    st.grads + L.offset[FC1_W], L.arm_stride, D, H);
   MVAE_LAUNCH_CHECK();
   return 0;
