@@ -101,18 +101,21 @@ fc11_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   const uint32_t tmem_g = tmem_base + 64;          // d h10 accumulator: columns [64, 64+HN)
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      const int xb = a.x_batched ? arm : 0;
+    // ===== TMA producer (whole warp runs the uniform loop; one elected lane issues) =====
+    const int xb = a.x_batched ? arm : 0;
+    if (elect_one()) {
       mbar_expect_tx(h10_full, H10_BYTES);
 #pragma unroll
       for (int j = 0; j < 4; ++j) tma_load_3d(&tmH, h10_full, h10s + j * 16384, 32 * j, m0, arm);
-      for (int i = 0; i < nt; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(empty + s, ph ^ 1);
+    }
+    __syncwarp();
+    for (int i = 0; i < nt; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(empty + s, ph ^ 1);
+      const int g0 = (t0 + i) * GN;    // first gene (row owner) / first cell (gene owner) of the tile
+      if (elect_one()) {
         mbar_expect_tx(full + s, STAGE_BYTES);
-        const int g0 = (t0 + i) * GN;    // first gene (row owner) / first cell (gene owner) of the tile
 #pragma unroll
         for (int j = 0; j < 4; ++j) tma_load_3d(&tmWk, full + s, wk(s) + j * 4096, 32 * j, g0, arm);
 #pragma unroll
@@ -124,14 +127,17 @@ fc11_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           for (int j = 0; j < 4; ++j) tma_load_3d(&tmX, full + s, xs(s) + j * 4096, m0 + 32 * j, g0, xb);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the uniform loop, one elected lane issues (operands stay in uniform registers) =====
+    {
       const uint32_t idesc1 = make_idesc(128, GN, false, false);
       const uint32_t idesc2 = make_idesc(128, a.HN, false, true);
       const int ksteps1 = (a.H + 7) / 8;
       const uint32_t h10a = smem_u32(h10s);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t tg = tb + 64;
       mbar_wait(h10_full, 0);
       uint32_t gacc = 0;
       auto mma2 = [&](int j) {
@@ -139,13 +145,21 @@ fc11_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         mbar_wait(dy_ready + s, (j / STAGES) & 1);
         tc_fence_after();
         const uint32_t xa = smem_u32(xs(s)), wma = smem_u32(wm(s));
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < GN / 8; ++ks) {
-          umma_tf32(tmem_g, make_smem_desc(xa + ks * 32, 0, 1024, false), make_smem_desc(wma + ks * 1024, 4096, 512, true),
-                    idesc2, gacc);
-          gacc = 1;
+          for (int ks = 0; ks < GN / 8; ++ks)
+            umma_tf32(tg, make_smem_desc(xa + ks * 32, 0, 1024, false), make_smem_desc(wma + ks * 1024, 4096, 512, true),
+                      idesc2, (gacc | (uint32_t)ks) ? 1u : 0u);
+          umma_commit(empty + s);
         }
-        umma_commit(empty + s);
+        __syncwarp();
+        gacc = 1;
+      };
+      auto release = [&](int j) {          // no second MMA: the stage is free once its epilogue is done
+        const int sj = j % STAGES;
+        mbar_wait(dy_ready + sj, (j / STAGES) & 1);
+        if (elect_one()) umma_commit(empty + sj);
+        __syncwarp();
       };
       for (int i = 0; i < nt; ++i) {
         const int s = i % STAGES, b = i & 1;
@@ -153,28 +167,24 @@ fc11_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         mbar_wait(tmem_empty + b, ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t wka = smem_u32(wk(s));
-        for (int ks = 0; ks < ksteps1; ++ks) {
-          const uint32_t off = (uint32_t)(ks >> 2), sub = (uint32_t)(ks & 3) * 32;
-          umma_tf32(tmem_base + b * GN, make_smem_desc(h10a + off * 16384 + sub, 0, 1024, false),
-                    make_smem_desc(wka + off * 4096 + sub, 0, 1024, false), idesc1, ks > 0 ? 1u : 0u);
+        if (elect_one()) {
+          for (int ks = 0; ks < ksteps1; ++ks) {
+            const uint32_t off = (uint32_t)(ks >> 2), sub = (uint32_t)(ks & 3) * 32;
+            umma_tf32(tb + b * GN, make_smem_desc(h10a + off * 16384 + sub, 0, 1024, false),
+                      make_smem_desc(wka + off * 4096 + sub, 0, 1024, false), idesc1, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(xhat_full + b);
         }
-        umma_commit(xhat_full + b);
-        if (a.want_grad && i >= 1) mma2(i - 1);
-        if (!a.want_grad && i >= 1) {       // no second MMA: the stage is free once its epilogue is done
-          const int sj = (i - 1) % STAGES;
-          mbar_wait(dy_ready + sj, ((i - 1) / STAGES) & 1);
-          umma_commit(empty + sj);
+        __syncwarp();
+        if (i >= 1) {
+          if (a.want_grad) mma2(i - 1); else release(i - 1);
         }
       }
       if (nt > 0) {
-        if (a.want_grad) mma2(nt - 1);
-        else {
-          const int sj = (nt - 1) % STAGES;
-          mbar_wait(dy_ready + sj, ((nt - 1) / STAGES) & 1);
-          umma_commit(empty + sj);
-        }
+        if (a.want_grad) mma2(nt - 1); else release(nt - 1);
       }
-      umma_commit(g_full);
+      if (elect_one()) umma_commit(g_full);
+      __syncwarp();
     }
   } else if (!GENE) {
     // ===== epilogue warps 2..9, row owner: thread = (cell, half of the 32 genes of a tile) =====

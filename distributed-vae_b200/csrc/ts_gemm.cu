@@ -98,30 +98,32 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
   if (warp == 0) {
     // ===== TMA producer of the raw x tiles (HBM): runs ahead by the whole x ring, independent of the W ring =====
-    if (lane == 0) {
-      int kt = kt_first, mt = mt_first, arm = arm_first, sx = 0;
-      uint32_t phx = 1;
-      for (int i = 0; i < nu; ++i) {
-        const int xb = a.x_batched ? arm : 0;
+    // (the whole warp runs the uniform loop; one elected lane issues, so the TMA operands stay in uniform registers)
+    int kt = kt_first, mt = mt_first, arm = arm_first, sx = 0;
+    uint32_t phx = 1;
+    for (int i = 0; i < nu; ++i) {
+      const int xb = a.x_batched ? arm : 0;
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {                 // x-unit j = NB * i + b: block b of the tile
-          const int m0 = (NB * mt + b) * BM;
-          mbar_wait(x_empty + sx, phx);
+      for (int b = 0; b < NB; ++b) {                 // x-unit j = NB * i + b: block b of the tile
+        const int m0 = (NB * mt + b) * BM;
+        mbar_wait(x_empty + sx, phx);
+        if (elect_one()) {
           mbar_expect_tx(x_full + sx, X_BYTES);
           if (!WGRAD) tma_load_3d(&tmX, x_full + sx, xs(sx), kt * BK, m0, xb);         // [128 cells][32 genes], SW128
           else tma_load_3d(&tmX, x_full + sx, xs(sx), m0, kt * BK, xb);                // [32 cells][128 genes], linear
-          if (++sx == a.nx) { sx = 0; phx ^= 1; }
         }
-        if (++kt == KT) { kt = 0; if (++arm == a.batch) { arm = 0; ++mt; } }
+        __syncwarp();
+        if (++sx == a.nx) { sx = 0; phx ^= 1; }
       }
+      if (++kt == KT) { kt = 0; if (++arm == a.batch) { arm = 0; ++mt; } }
     }
   } else if (warp == 1) {
     // ===== TMA producer of the small operand (W1 hi/lo or delta1; L2-resident) =====
-    if (lane == 0) {
-      int kt = kt_first, arm = arm_first, sw = 0;
-      uint32_t phw = 1;
-      for (int i = 0; i < nu; ++i) {
-        mbar_wait(w_empty + sw, phw);
+    int kt = kt_first, arm = arm_first, sw = 0;
+    uint32_t phw = 1;
+    for (int i = 0; i < nu; ++i) {
+      mbar_wait(w_empty + sw, phw);
+      if (elect_one()) {
         mbar_expect_tx(w_full + sw, w_stage_bytes);
         if (!WGRAD) {
           tma_load_3d(&tmW, w_full + sw, ws(sw), kt * BK, 0, arm);
@@ -130,9 +132,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 4; ++j) tma_load_3d(&tmW, w_full + sw, ws(sw) + j * 4096, 32 * j, kt * BK, arm);
         }
-        if (++sw == a.nw) { sw = 0; phw ^= 1; }
-        if (++kt == KT) { kt = 0; if (++arm == a.batch) arm = 0; }
       }
+      __syncwarp();
+      if (++sw == a.nw) { sw = 0; phw ^= 1; }
+      if (++kt == KT) { kt = 0; if (++arm == a.batch) arm = 0; }
     }
   } else if (warp == 2) {
     // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues =====
