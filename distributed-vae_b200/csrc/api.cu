@@ -200,7 +200,8 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
 
   // ---- optional materialised reconstruction x_rec = relu(fc11(h10)) (:287)
   if (out.x_rec && use_tc(p, hp) && hp.precision != 1) {
-    RC(tc_fc11_rows(p.d, st, in, w, 0.f, 0, nullptr, out.x_rec, nullptr, s));
+    if (legacy_gene_kernels()) RC(tc_fc11_rows(p.d, st, in, w, 0.f, 0, nullptr, out.x_rec, nullptr, s));
+    else RC(ts_fc11_rows(p.d, st, in, w, 0.f, 0, out.x_rec, nullptr, s));
   } else if (out.x_rec) {
     GemmArgs g;
     memset(&g, 0, sizeof(g));

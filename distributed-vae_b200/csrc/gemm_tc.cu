@@ -15,6 +15,8 @@
 // transform (dropout mask on the x operand and the hi/lo split of the error-compensated 3xTF32 scheme:
 // a = a_hi + a_lo with a_hi = a truncated to TF32 by the tensor core itself, a_lo = a - trunc(a);
 // a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi, fp32 accumulate).
+#include <stdlib.h>
+
 #include "gemm_tc.h"
 #include "tc_common.cuh"
 
@@ -354,6 +356,16 @@ int choose_split(int tiles_mn, int ktiles, int max_split) {
 
 }  // namespace
 
+static bool legacy_fc11() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MVAE_LEGACY_FC11");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+bool legacy_gene_kernels() { return legacy_fc11(); }
+
 bool gemm_tc_supported(int B, int D, int H) {
   // TMA needs 16-byte aligned row pitches: D % 4 == 0 (x, W1 rows) and H % 4 == 0 (h10, W11, delta1 rows)
   return D % 4 == 0 && H % 4 == 0 && H <= 128 && get_encode() != nullptr;
@@ -450,6 +462,11 @@ int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_sta
   memset(&nodrop, 0, sizeof(nodrop));
   if (hp.precision == 1) return tc_fc11_loss_grad_unfused(d, hp, st, in, w, gscale, want_grad, s);
   // fused passes: row owner (x_hat, loss sums, d h10), then gene owner (d fc11.weight, d fc11.bias)
+  if (!legacy_fc11()) {
+    int rc = ts_fc11_rows(d, st, in, w, gscale, want_grad, nullptr, acc_loss, s);
+    if (rc || !want_grad) return rc;
+    return ts_fc11_genes(d, st, in, w, gscale, s);
+  }
   int rc = tc_fc11_rows(d, st, in, w, gscale, want_grad, nullptr, nullptr, acc_loss, s);
   if (rc || !want_grad) return rc;
   return tc_fc11_genes(d, st, in, w, gscale, s);

@@ -35,4 +35,10 @@ int ts_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state&
 int ts_fc1_wgrad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const DropSpec& drop, const Work& w,
                  cudaStream_t s);
 
+// fc11_ts.cu: second-generation fused fc11 passes (resident operand and dY in tensor memory, stream-K)
+int ts_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale, int want_grad,
+                 float* x_rec, double* recon_acc, cudaStream_t s);
+int ts_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale, cudaStream_t s);
+bool legacy_gene_kernels();   // MVAE_LEGACY_FC1=1 / MVAE_LEGACY_FC11=1: round-1 first-generation kernels (A/B comparisons)
+
 }  // namespace mvae

@@ -134,7 +134,7 @@ Work make_work(const mvae_dims& d) {
     if (p3 > pm) pm = p3;
     w.fc1_part = take(pm);
   }
-  w.db_part = take((int64_t)8 * A * w.Dpad);
+  w.db_part = take((int64_t)8 * A * w.Dpad + 160 * 512);   // also [slot][4 groups][128] of fc11_ts.cu
   w.big = take(A * B * D);
   // narrow-layer weight-gradient partials mirror the parameter range [offset(fc1.b), offset(fc11.w))
   mvae_layout L;
