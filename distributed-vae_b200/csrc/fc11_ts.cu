@@ -16,6 +16,8 @@
 //   * MMA2 (TS form) accumulates into acc2 (TMEM) over the whole segment;
 //   * stream-K over (tile, unit): one CTA per SM, one wave; partial tiles are summed in a fixed order by a fix-up kernel.
 // TMEM columns: acc2 [0,128) | acc1 4 x 32 [128,256) | dY stages 4 x 32 [256,384) | R [384,512).
+#include <stdlib.h>
+
 #include "gemm_tc.h"
 #include "tc_common.cuh"
 
@@ -39,6 +41,7 @@ struct F11Args {
   int x_batched;
   int nx, nk, nm;                   // ring depths: x, K-image, MN-image
   int want_grad;
+  int hack;
   float gscale;
   const float* R; int64_t r_arm_stride; int r_rows;     // resident operand: [arm][r_rows][H]
   const float* bias; int64_t bias_arm_stride;           // fc11.bias
@@ -119,17 +122,17 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     for (int i = 0; i < nu; ++i) {
       mbar_wait(k_empty + sk, phk);
       if (elect_one()) {
-        mbar_expect_tx(k_full + sk, IMG_BYTES);
+        mbar_expect_tx(k_full + sk, a.hack ? 4096 : IMG_BYTES);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_3d(&tmTk, k_full + sk, tk(sk) + j * 4096, 32 * j, kt * UN, arm);
+        for (int j = 0; j < 4; ++j) if (!a.hack || j == 0) tma_load_3d(&tmTk, k_full + sk, tk(sk) + j * 4096, 32 * j, kt * UN, arm);
       }
       __syncwarp();
       if (a.want_grad) {
         mbar_wait(m_empty + sm, phm);
         if (elect_one()) {
-          mbar_expect_tx(m_full + sm, IMG_BYTES);
+          mbar_expect_tx(m_full + sm, a.hack ? 4096 : IMG_BYTES);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_3d(&tmTm, m_full + sm, tm(sm) + j * 4096, 32 * j, kt * UN, arm);
+          for (int j = 0; j < 4; ++j) if (!a.hack || j == 0) tma_load_3d(&tmTm, m_full + sm, tm(sm) + j * 4096, 32 * j, kt * UN, arm);
         }
         __syncwarp();
         if (++sm == a.nm) { sm = 0; phm ^= 1; }
@@ -165,12 +168,16 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       acc2 = last ? 0u : 1u;
       if (++sm == a.nm) { sm = 0; phm ^= 1; }
     };
-    bool pending = false;
+    // MMA1 runs up to SKEW units ahead of MMA2, so that all NG epilogue groups have a unit to work on
+    constexpr int SKEW = NG - 1;
+    int next2 = 0;                                   // first unit whose MMA2 has not been issued yet
     for (int i = 0; i < nu; ++i) {
       const int g = i & (NG - 1);
       const bool new_seg = (i == 0) || (kt == 0);
       if (new_seg) {
-        if (pending) { mma2(i - 1, true); pending = false; }     // flush: the old segment must complete before R changes
+        // flush: the old segment must complete before R changes
+        if (a.want_grad)
+          while (next2 < i) { mma2(next2, next2 == i - 1); ++next2; }
         mbar_wait(r_full, seg & 1);
         ++seg;
       }
@@ -188,13 +195,12 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       __syncwarp();
       if (++sk == a.nk) { sk = 0; phk ^= 1; }
-      if (a.want_grad) {
-        if (pending) mma2(i - 1, false);
-        pending = true;
-      }
+      if (a.want_grad)
+        while (i - next2 >= SKEW) { mma2(next2, false); ++next2; }
       if (++kt == KT) kt = 0;
     }
-    if (pending) mma2(nu - 1, true);
+    if (a.want_grad)
+      while (next2 < nu) { mma2(next2, next2 == nu - 1); ++next2; }
   } else {
     // ===== epilogue groups =====
     const int quad = warp & 3, grp = (warp - CTRL_WARPS) >> 2;
@@ -389,15 +395,21 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 // out[arm][row][col] = sum over the CTAs that touched tile (row / 128, arm) of their partial, in CTA order
 __global__ void __launch_bounds__(256) f11_fixup_kernel(const float* part, int batch, int ktiles, int64_t U, int64_t G, float* out,
                                                         int64_t out_arm_stride, int ld, int rows, int cols) {
+  __shared__ int cc[2];
   const int arm = blockIdx.z;
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int row = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int64_t t = (int64_t)((blockIdx.y * 8) >> 7) * batch + arm;        // the 8 rows of a block share their tile
+  if (threadIdx.x == 0) {
+    cc[0] = (int)cta_of_unit(t * ktiles, U, G);
+    cc[1] = (int)cta_of_unit(t * ktiles + ktiles - 1, U, G);
+  }
+  __syncthreads();
   if (row >= rows || col >= cols) return;
-  const int64_t t = (int64_t)(row >> 7) * batch + arm;
-  const int64_t c0 = cta_of_unit(t * ktiles, U, G), c1 = cta_of_unit(t * ktiles + ktiles - 1, U, G);
+  const int c0 = cc[0], c1 = cc[1];
   const float* base = part + (c0 + t) * TILE_FLOATS + (int64_t)(row & 127) * 128 + col;
   float v = 0.f;
-  for (int64_t c = c0; c <= c1; ++c) v += base[(c - c0) * TILE_FLOATS];
+  for (int c = c0; c <= c1; ++c) v += base[(int64_t)(c - c0) * TILE_FLOATS];
   out[(int64_t)arm * out_arm_stride + (int64_t)row * ld + col] = v;
 }
 
@@ -441,7 +453,8 @@ int launch_f11(const CUtensorMap& tmX, const CUtensorMap& tmTk, const CUtensorMa
   const int64_t U = (int64_t)a.batch * a.rtiles * a.ktiles;
   int64_t G = sm_count2();
   if (G > U) G = U;
-  a.nk = 3; a.nm = 4;
+  a.nk = 4; a.nm = 4;
+  { const char* e = getenv("MVAE_HACK_TMA"); a.hack = (e && e[0] == '1') ? 1 : 0; }
   a.nx = (227 * 1024 - 2048 - (a.nk + a.nm) * IMG_BYTES) / X_BYTES;
   if (a.nx > 8) a.nx = 8;
   const size_t smem = (size_t)a.nx * X_BYTES + (size_t)(a.nk + a.nm) * IMG_BYTES + (2 * a.nx + 2 * a.nk + 2 * a.nm + 4 * NG + 4) * 8 + 1024;

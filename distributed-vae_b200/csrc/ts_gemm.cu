@@ -399,15 +399,21 @@ __global__ void __launch_bounds__(256) fc1_fixup_kernel(const Fc1FixArgs p) {
 // d fc1.weight fix-up: dW1[arm][h][gene] = sum of the partials [slot][h][gene in tile] in a fixed order
 __global__ void __launch_bounds__(256) wgrad_fixup_kernel(const float* part, int batch, int ktiles, int64_t U, int64_t G,
                                                           float scale, float* grads, int64_t g_arm_stride, int D, int H) {
+  __shared__ int cc[2];
   const int arm = blockIdx.z;
   const int gene = blockIdx.x * 128 + (threadIdx.x & 127);
   const int h = blockIdx.y * 2 + (threadIdx.x >> 7);
-  if (gene >= D || h >= H) return;
   const int64_t t = (int64_t)(blockIdx.x >> 1) * batch + arm;
-  const int64_t c0 = cta_of_unit(t * ktiles, U, G), c1 = cta_of_unit(t * ktiles + ktiles - 1, U, G);
+  if (threadIdx.x == 0) {
+    cc[0] = (int)cta_of_unit(t * ktiles, U, G);
+    cc[1] = (int)cta_of_unit(t * ktiles + ktiles - 1, U, G);
+  }
+  __syncthreads();
+  if (gene >= D || h >= H) return;
+  const int c0 = cc[0], c1 = cc[1];
   const float* base = part + ((c0 + t) * NB + (blockIdx.x & 1)) * TILE_FLOATS + (int64_t)h * 128 + (gene & 127);
   float v = 0.f;
-  for (int64_t c = c0; c <= c1; ++c) v += base[(c - c0) * NB * TILE_FLOATS];
+  for (int c = c0; c <= c1; ++c) v += base[(int64_t)(c - c0) * NB * TILE_FLOATS];
   grads[(int64_t)arm * g_arm_stride + (int64_t)h * D + gene] = v * scale;
 }
 
