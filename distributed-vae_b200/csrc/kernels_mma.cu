@@ -418,8 +418,8 @@ constexpr int WG_CHUNK = 32;
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(512) wgrad_mma_kernel(const WgArgs p) {
-  __shared__ float Ds[WG_CHUNK * 136];
-  __shared__ float Is[WG_CHUNK * 136];
+  __shared__ __align__(16) float Ds[WG_CHUNK * 136];
+  __shared__ __align__(16) float Is[WG_CHUNK * 136];
   __shared__ float bm[128], br[128];
   const WgProblem& pr = p.prob[blockIdx.y];
   const int arm = blockIdx.z, split = blockIdx.x;
@@ -450,26 +450,85 @@ __global__ void __launch_bounds__(512) wgrad_mma_kernel(const WgArgs p) {
   // chunk staged through registers: the loads of chunk c+1 are in flight while chunk c is multiplied
   float vd[8][1], vi[8][1];              // scalar path: 32x128 / 512 threads
   float vd4[2][4], vi4[2][4];            // float4 path
+  // float4 path: the (row, column) of this thread's two float4 per operand are the same for every chunk
+  int drow[2] = {0, 0}, dcol[2] = {0, 0}, irow[2] = {0, 0}, icol[2] = {0, 0};
+  bool dok[2] = {false, false}, iok[2] = {false, false};
+  if (dv4) {
+    const int cpr = nout >> 2;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid + u * 512;
+      dok[u] = idx < WG_CHUNK * cpr;
+      drow[u] = idx / cpr;
+      dcol[u] = (idx - drow[u] * cpr) * 4;
+    }
+  }
+  if (iv4) {
+    const int cpr = nin >> 2;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid + u * 512;
+      iok[u] = idx < WG_CHUNK * cpr;
+      irow[u] = idx / cpr;
+      icol[u] = (idx - irow[u] * cpr) * 4;
+    }
+  }
   auto load_chunk = [&](int rb) {
     const int nr = min(WG_CHUNK, r1 - rb);
-    if (dv4) tile_load<4, 2, 512>(vd4, delta + (int64_t)rb * nout, nout, nr, nout, WG_CHUNK, tid);
-    else tile_load<1, 8, 512>(vd, delta + (int64_t)rb * nout, nout, nr, nout, WG_CHUNK, tid);
+    if (dv4) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dok[u] && drow[u] < nr) t4 = *reinterpret_cast<const float4*>(delta + (int64_t)(rb + drow[u]) * nout + dcol[u]);
+        vd4[u][0] = t4.x; vd4[u][1] = t4.y; vd4[u][2] = t4.z; vd4[u][3] = t4.w;
+      }
+    } else {
+      tile_load<1, 8, 512>(vd, delta + (int64_t)rb * nout, nout, nr, nout, WG_CHUNK, tid);
+    }
     if (nin > 0) {
-      if (iv4) tile_load<4, 2, 512>(vi4, in + (int64_t)rb * pr.in_ld, pr.in_ld, nr, nin, WG_CHUNK, tid);
-      else tile_load<1, 8, 512>(vi, in + (int64_t)rb * pr.in_ld, pr.in_ld, nr, nin, WG_CHUNK, tid);
+      if (iv4) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (iok[u] && irow[u] < nr) t4 = *reinterpret_cast<const float4*>(in + (int64_t)(rb + irow[u]) * pr.in_ld + icol[u]);
+          vi4[u][0] = t4.x; vi4[u][1] = t4.y; vi4[u][2] = t4.z; vi4[u][3] = t4.w;
+        }
+      } else {
+        tile_load<1, 8, 512>(vi, in + (int64_t)rb * pr.in_ld, pr.in_ld, nr, nin, WG_CHUNK, tid);
+      }
     }
   };
   auto store_chunk = [&](int rb) {
     const int nr = min(WG_CHUNK, r1 - rb);
-    if (dv4) tile_visit<4, 2, 512>(nout, WG_CHUNK, tid, [&](int u, int e, int r, int j) { Ds[r * 136 + j] = vd4[u][e]; });
-    else tile_visit<1, 8, 512>(nout, WG_CHUNK, tid, [&](int u, int e, int r, int j) { Ds[r * 136 + j] = vd[u][e]; });
+    if (dv4) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (dok[u])
+          *reinterpret_cast<float4*>(Ds + drow[u] * 136 + dcol[u]) = make_float4(vd4[u][0], vd4[u][1], vd4[u][2], vd4[u][3]);
+    } else {
+      tile_visit<1, 8, 512>(nout, WG_CHUNK, tid, [&](int u, int e, int r, int j) { Ds[r * 136 + j] = vd[u][e]; });
+    }
     auto puti = [&](float v, int r, int i) {
       if (pr.bn_layer >= 0) v = (v - bm[i]) * br[i];
       Is[r * 136 + i] = r < nr ? v : 0.f;
     };
     if (nin > 0) {
-      if (iv4) tile_visit<4, 2, 512>(nin, WG_CHUNK, tid, [&](int u, int e, int r, int i) { puti(vi4[u][e], r, i); });
-      else tile_visit<1, 8, 512>(nin, WG_CHUNK, tid, [&](int u, int e, int r, int i) { puti(vi[u][e], r, i); });
+      if (iv4) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (iok[u]) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float v = vi4[u][e];
+              if (pr.bn_layer >= 0) v = (v - bm[icol[u] + e]) * br[icol[u] + e];
+              o[e] = irow[u] < nr ? v : 0.f;
+            }
+            *reinterpret_cast<float4*>(Is + irow[u] * 136 + icol[u]) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+      } else {
+        tile_visit<1, 8, 512>(nin, WG_CHUNK, tid, [&](int u, int e, int r, int i) { puti(vi[u][e], r, i); });
+      }
     }
     if (tid < WG_CHUNK) Is[tid * 136 + nin] = tid < nr ? 1.f : 0.f;   // ones column -> bias gradient
   };
