@@ -138,7 +138,14 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   timing_begin(TG_NARROW_FWD, s);
 
   // ---- fc2..fc5 with the BatchNorm of the previous layer folded into the load (:265-268)
-  for (int l = 1; l <= 4; ++l) {
+  int chain_rc = 1;
+  if (training && hp.precision != 3 && !legacy_fc1()) {
+    float* aout[4] = {work + w.a[1], work + w.a[2], work + w.a[3], work + w.a[4]};
+    chain_rc = launch_enc_chain_fwd(st.params, p.L.arm_stride, p.L.offset, A, B, H, Ld, work + w.a[0], aout, acc_fwd, bn_mean,
+                                    bn_rstd, hp.eps, s);
+    if (chain_rc < 0 || chain_rc > 1) return chain_rc;
+  }
+  for (int l = 1; l <= 4 && chain_rc == 1; ++l) {
     DenseFwdArgs a;
     memset(&a, 0, sizeof(a));
     const int nout = l < 4 ? H : Ld;

@@ -107,7 +107,8 @@ struct Work {
 __host__ __device__ inline int64_t acc_bn(int layer, int A, int a) { return ((int64_t)(layer * A + a)) * 2 * 128; }
 __host__ __device__ inline int64_t acc_q(int A, int a) { return (int64_t)5 * A * 256 + (int64_t)a * 256; }
 __host__ __device__ inline int64_t acc_kl(int A, int a) { return (int64_t)6 * A * 256 + (int64_t)a * 16; }
-__host__ __device__ inline int64_t acc_fwd_doubles(int A) { return (int64_t)6 * A * 256 + (int64_t)A * 16; }
+__host__ __device__ inline int64_t acc_sync(int A) { return (int64_t)6 * A * 256 + (int64_t)A * 16; }   // grid-barrier counters (8 doubles)
+__host__ __device__ inline int64_t acc_fwd_doubles(int A) { return (int64_t)6 * A * 256 + (int64_t)A * 16 + 8; }
 // acc_loss block (doubles, fixed capacity MVAE_MAX_ARMS): recon[16][2] | ent[16] | pair[120][2] | T[16][128] | qs[16][2][128]
 __host__ __device__ inline int64_t accl_recon(int a) { return (int64_t)a * 2; }
 __host__ __device__ inline int64_t accl_ent(int a) { return 32 + (int64_t)a; }

@@ -130,6 +130,12 @@ int launch_dec_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
                          const float* g10, const float* const act[4], float* const delta[4], float* g6, int split3,
                          cudaStream_t s);
 
+// encoder middle fc2..fc5 (+ batch_l1..l4 folded in, column sums for batch_l2..l5) as ONE cooperative kernel; returns 1 when
+// the shape does not fit a single co-resident wave (the caller then runs the per-layer kernels)
+int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
+                         const float* a1, float* const aout[4], double* acc_fwd, float* bn_mean, float* bn_rstd, float eps,
+                         cudaStream_t s);
+
 // ---- optimiser / misc ------------------------------------------------------------------------
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                 float wd, int adamw, int64_t step, cudaStream_t s);

@@ -275,6 +275,168 @@ __global__ void __launch_bounds__(64 * MT) dec_chain_bwd_kernel(const ChainArgs 
   }
 }
 
+// =============================================================================================
+// encoder middle: fc2..fc5 with the BatchNorm of the previous layer folded into the operand (nn_model.py:264-268).
+// BatchNorm needs batch-global statistics between layers, so this is a COOPERATIVE kernel (one co-resident wave):
+// every CTA keeps its rows in shared memory from a1 to a5, adds its fp64 column sums to the global accumulators and
+// meets the other CTAs at a grid barrier before it normalises the next layer's operand.  Weights are streamed
+// with cp.async one layer ahead, as in the decoder chain.
+// =============================================================================================
+struct EncChainArgs {
+  int XP, Hp;
+  const float* params; int64_t p_arm_stride;
+  int64_t offW[4], offB[4];      // fc2..fc5
+  int A, B, H, L;
+  const float* a1;               // [A][B][H] relu(fc1), before batch_l1
+  float* aout[4];                // a2..a4 [A][B][H], a5 [A][B][L]
+  double* sums;                  // acc_fwd: column sums / sums of squares, layer l at (l * A + arm) * 256
+  float* bn_mean; float* bn_rstd;   // [5][A][128]
+  unsigned int* bar;             // grid-barrier counters (zeroed with the accumulators)
+  float eps;
+};
+
+__device__ __forceinline__ double group_sum_d(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int n) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < n);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int MT>
+__global__ void __launch_bounds__(64 * MT) enc_chain_fwd_kernel(const EncChainArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int CR = 16 * MT, CT = 64 * MT, NTW = 8;
+  const int XP = p.XP, Hp = p.Hp;
+  float* Ws0 = smem;                       // [Hp][XP]  W natural [out][in]
+  float* Ws1 = Ws0 + Hp * XP;
+  float* Xs0 = Ws1 + Hp * XP;              // [CR][XP]
+  float* Xs1 = Xs0 + CR * XP;
+  float* bias = Xs1 + CR * XP;             // [4][128]
+  float* mean = bias + 4 * 128;            // [128]
+  float* rstd = mean + 128;                // [128]
+  double* red = reinterpret_cast<double*>(rstd + 128);   // [MT][2][128]
+  const int arm = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int warp = tid >> 5, wr = warp % MT, wc = warp / MT;
+  const int g = lane >> 2, tig = lane & 3;
+  const int H = p.H, L = p.L, B = p.B;
+  const int row0 = blockIdx.x * CR;
+  const int rows_valid = min(CR, B - row0);
+  const float* par = p.params + (int64_t)arm * p.p_arm_stride;
+  const unsigned int nctas = gridDim.x * gridDim.y;
+
+  for (int idx = tid; idx < 2 * Hp * XP + 2 * CR * XP; idx += CT) smem[idx] = 0.f;
+  for (int idx = tid; idx < 4 * 128; idx += CT) {
+    const int l = idx >> 7, j = idx & 127;
+    const int nout = l < 3 ? H : L;
+    bias[idx] = j < nout ? par[p.offB[l] + j] : 0.f;
+  }
+  __syncthreads();
+  async_tile(Ws0, XP, par + p.offW[0], H, H, H, tid, CT);
+  async_tile(Xs0, XP, p.a1 + ((int64_t)arm * B + row0) * H, H, rows_valid, H, tid, CT);
+  cp_async_commit();
+  async_tile(Ws1, XP, par + p.offW[1], H, H, H, tid, CT);
+  cp_async_commit();
+
+  float* Ws[2] = {Ws0, Ws1};
+  float* Xs[2] = {Xs0, Xs1};
+  for (int l = 0; l < 4; ++l) {
+    const int nout = l < 3 ? H : L;
+    // ---- batch statistics of this layer's input (complete: previous kernel for l == 0, grid barrier otherwise)
+    if (tid < H) {
+      const double* sums = p.sums + (int64_t)(l * p.A + arm) * 256;
+      const double s1 = __ldcg(sums + tid), s2 = __ldcg(sums + 128 + tid);
+      const double m = s1 / (double)B;
+      double var = s2 / (double)B - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mf = (float)m, rf = (float)(1.0 / sqrt(var + (double)p.eps));
+      mean[tid] = mf;
+      rstd[tid] = rf;
+      if (blockIdx.x == 0) {
+        p.bn_mean[(l * p.A + arm) * 128 + tid] = mf;
+        p.bn_rstd[(l * p.A + arm) * 128 + tid] = rf;
+      }
+    }
+    if (l < 3) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    // ---- normalise the operand tile in place (rows beyond the batch stay zero)
+    float* Xc = Xs[l & 1];
+    for (int idx = tid; idx < rows_valid * H; idx += CT) {
+      const int r = idx / H, c = idx - r * H;
+      Xc[r * XP + c] = (Xc[r * XP + c] - mean[c]) * rstd[c];
+    }
+    __syncthreads();
+    float acc[NTW][4];
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    const int nt_used = max(0, min(NTW, (nout + 7) / 8 - wc * NTW));
+    warp_gemm2<NTW, true, true>(Xc + wr * 16 * XP, XP, Ws[l & 1] + wc * NTW * 8 * XP, XP, (H + 7) / 8, nt_used, acc, lane);
+    // ---- epilogue: bias + ReLU -> global a_{l+2}, the next operand tile, fp64 column sums of the valid rows
+    float* out = p.aout[l] + ((int64_t)arm * B + row0) * nout;
+    float* Xn = Xs[(l + 1) & 1];
+    const int ra = wr * 16 + g, rb = ra + 8;
+    const bool va = ra < rows_valid, vb = rb < rows_valid;
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      if (nt < nt_used) {
+        const int c = (wc * NTW + nt) * 8 + 2 * tig;
+        const float b0 = bias[l * 128 + c], b1 = bias[l * 128 + c + 1];
+        const float v00 = fmaxf(acc[nt][0] + b0, 0.f), v01 = fmaxf(acc[nt][1] + b1, 0.f);
+        const float v10 = fmaxf(acc[nt][2] + b0, 0.f), v11 = fmaxf(acc[nt][3] + b1, 0.f);
+        if (va) { if (c < nout) out[(int64_t)ra * nout + c] = v00; if (c + 1 < nout) out[(int64_t)ra * nout + c + 1] = v01; }
+        if (vb) { if (c < nout) out[(int64_t)rb * nout + c] = v10; if (c + 1 < nout) out[(int64_t)rb * nout + c + 1] = v11; }
+        if (l < 3) {
+          Xn[ra * XP + c] = (va && c < nout) ? v00 : 0.f;
+          Xn[ra * XP + c + 1] = (va && c + 1 < nout) ? v01 : 0.f;
+          Xn[rb * XP + c] = (vb && c < nout) ? v10 : 0.f;
+          Xn[rb * XP + c + 1] = (vb && c + 1 < nout) ? v11 : 0.f;
+        }
+        const double a0 = va ? (double)v00 : 0.0, a1 = va ? (double)v01 : 0.0;
+        const double c0 = vb ? (double)v10 : 0.0, c1 = vb ? (double)v11 : 0.0;
+        const double s0 = group_sum_d(a0 + c0), s1 = group_sum_d(a1 + c1);
+        const double q0 = group_sum_d(a0 * a0 + c0 * c0), q1 = group_sum_d(a1 * a1 + c1 * c1);
+        if (g == 0) {
+          red[(wr * 2 + 0) * 128 + c] = s0; red[(wr * 2 + 0) * 128 + c + 1] = s1;
+          red[(wr * 2 + 1) * 128 + c] = q0; red[(wr * 2 + 1) * 128 + c + 1] = q1;
+        }
+      }
+    }
+    __syncthreads();                       // Ws[l&1] / Xs[l&1] released, red complete
+    for (int j = tid; j < 256; j += CT) {
+      const int which = j >> 7, c = j & 127;
+      if (c < nout) {
+        double sacc = 0.0;
+        for (int w = 0; w < MT; ++w) sacc += red[(w * 2 + which) * 128 + c];
+        atomicAdd(p.sums + (int64_t)((l + 1) * p.A + arm) * 256 + which * 128 + c, sacc);
+      }
+    }
+    if (l + 2 < 4) {
+      if (l + 2 == 3) {                    // fc5 is [L][H]: the rows beyond L keep stale (finite) fc3 weights, never stored
+        async_tile(Ws[l & 1], XP, par + p.offW[3], H, L, H, tid, CT);
+      } else {
+        async_tile(Ws[l & 1], XP, par + p.offW[l + 2], H, H, H, tid, CT);
+      }
+      cp_async_commit();
+    }
+    if (l < 3) grid_barrier(p.bar + l, nctas);
+  }
+}
+
 }  // namespace
 
 static int b_pitch2(int n) {
@@ -341,6 +503,52 @@ int launch_dec_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
   else if (split3) CHAIN_LAUNCH(4, true);
   else CHAIN_LAUNCH(4, false);
 #undef CHAIN_LAUNCH
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mvae
+
+namespace mvae {
+
+int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
+                         const float* a1, float* const aout[4], double* acc_fwd, float* bn_mean, float* bn_rstd, float eps,
+                         cudaStream_t s) {
+  static int coop = -1, nsm = 0;
+  if (coop < 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (!coop || H > 128 || L > 64 || H % 4 != 0) return 1;
+  EncChainArgs c;
+  memset(&c, 0, sizeof(c));
+  c.Hp = (H + 7) & ~7;
+  c.XP = c.Hp + 4;
+  c.params = params; c.p_arm_stride = p_arm_stride;
+  for (int l = 0; l < 4; ++l) {
+    c.offW[l] = off[FC2_W + 2 * l];
+    c.offB[l] = off[FC2_B + 2 * l];
+    c.aout[l] = aout[l];
+  }
+  c.A = A; c.B = B; c.H = H; c.L = L;
+  c.a1 = a1;
+  c.sums = acc_fwd;
+  c.bn_mean = bn_mean; c.bn_rstd = bn_rstd;
+  c.bar = reinterpret_cast<unsigned int*>(acc_fwd + acc_sync(A));
+  c.eps = eps;
+  constexpr int MT = 5, CR = 16 * MT;
+  const int tiles = (B + CR - 1) / CR;
+  if ((int64_t)tiles * A > nsm) return 1;             // must be one co-resident wave (grid barrier)
+  const size_t smem = (size_t)(2 * c.Hp * c.XP + 2 * CR * c.XP + 4 * 128 + 256) * 4 + (size_t)MT * 2 * 128 * 8;
+  static bool attr = false;
+  if (!attr) {
+    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_fwd_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  void* args[] = {(void*)&c};
+  MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_fwd_kernel<MT>, dim3(tiles, A), dim3(64 * MT), args, smem, s));
   MVAE_LAUNCH_CHECK();
   return 0;
 }
