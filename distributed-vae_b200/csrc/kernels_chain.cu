@@ -106,9 +106,9 @@ struct ChainArgs {
 // forward chain
 // =============================================================================================
 template <int MT, bool SPLIT>
-__global__ void __launch_bounds__(64 * MT) dec_chain_fwd_kernel(const ChainArgs p) {
+__global__ void __launch_bounds__(128 * MT) dec_chain_fwd_kernel(const ChainArgs p) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int CR = 16 * MT, CT = 64 * MT;
+  constexpr int CR = 16 * MT, CT = 128 * MT;     // MT row groups x 4 column groups of warps (latency-bound: more warps)
   const int XP = p.XP, WPF = p.XP, Hp = p.Hp;
   float* Ws0 = smem;                       // [Hp][WPF]
   float* Ws1 = Ws0 + Hp * WPF;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(64 * MT) dec_chain_fwd_kernel(const ChainArgs 
 
   float* Ws[2] = {Ws0, Ws1};
   float* Xs[2] = {Xs0, Xs1};
-  const int NTW = 8;
+  constexpr int NTW = 4;
   for (int l = 0; l < 4; ++l) {
     const int K = l == 0 ? L : H;
     const int ksteps = (K + 7) / 8;
@@ -182,9 +182,9 @@ __global__ void __launch_bounds__(64 * MT) dec_chain_fwd_kernel(const ChainArgs 
 // backward chain: delta_l = g * [h_l > 0];  g_{l-1} = delta_l . W_l
 // =============================================================================================
 template <int MT, bool SPLIT>
-__global__ void __launch_bounds__(64 * MT) dec_chain_bwd_kernel(const ChainArgs p) {
+__global__ void __launch_bounds__(128 * MT) dec_chain_bwd_kernel(const ChainArgs p) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int CR = 16 * MT, CT = 64 * MT;
+  constexpr int CR = 16 * MT, CT = 128 * MT;
   const int XP = p.XP, WPB = p.WPB, Hp = p.Hp;
   float* Ws0 = smem;                       // [Hp][WPB]  W_l natural: row j (out), col i (in)
   float* Ws1 = Ws0 + Hp * WPB;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(64 * MT) dec_chain_bwd_kernel(const ChainArgs 
 
   float* Ws[2] = {Ws0, Ws1};
   float* Ms[2] = {Ms0, Ms1};
-  const int NTW = 8;
+  constexpr int NTW = 4;
   for (int it = 0; it < 4; ++it) {
     const int l = 3 - it;                  // layer index 3..0 = fc10..fc7
     const int nin = l == 0 ? L : H;        // inputs of this layer
@@ -316,10 +316,10 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int n) 
   __syncthreads();
 }
 
-template <int MT>
-__global__ void __launch_bounds__(64 * MT) enc_chain_fwd_kernel(const EncChainArgs p) {
+template <int MT, int NWC>
+__global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncChainArgs p) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int CR = 16 * MT, CT = 64 * MT, NTW = 8;
+  constexpr int CR = 16 * MT, CT = 32 * MT * NWC, NTW = 16 / NWC;   // MT row groups x NWC column groups of warps
   const int XP = p.XP, Hp = p.Hp;
   float* Ws0 = smem;                       // [Hp][XP]  W natural [out][in]
   float* Ws1 = Ws0 + Hp * XP;
@@ -473,7 +473,7 @@ int launch_dec_chain_fwd(const float* params, int64_t p_arm_stride, const int64_
 #define CHAIN_LAUNCH(MTV, SP)                                                                                        \
   do {                                                                                                              \
     MVAE_CUDA(cudaFuncSetAttribute(dec_chain_fwd_kernel<MTV, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    dec_chain_fwd_kernel<MTV, SP><<<dim3((B + cr - 1) / cr, A), 64 * MTV, smem, s>>>(c);                            \
+    dec_chain_fwd_kernel<MTV, SP><<<dim3((B + cr - 1) / cr, A), 128 * MTV, smem, s>>>(c);                            \
   } while (0)
   if (mt == 5 && split3) CHAIN_LAUNCH(5, true);
   else if (mt == 5) CHAIN_LAUNCH(5, false);
@@ -496,7 +496,7 @@ int launch_dec_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
 #define CHAIN_LAUNCH(MTV, SP)                                                                                        \
   do {                                                                                                              \
     MVAE_CUDA(cudaFuncSetAttribute(dec_chain_bwd_kernel<MTV, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    dec_chain_bwd_kernel<MTV, SP><<<dim3((B + cr - 1) / cr, A), 64 * MTV, smem, s>>>(c);                            \
+    dec_chain_bwd_kernel<MTV, SP><<<dim3((B + cr - 1) / cr, A), 128 * MTV, smem, s>>>(c);                            \
   } while (0)
   if (mt == 5 && split3) CHAIN_LAUNCH(5, true);
   else if (mt == 5) CHAIN_LAUNCH(5, false);
@@ -538,17 +538,17 @@ int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_
   c.bn_mean = bn_mean; c.bn_rstd = bn_rstd;
   c.bar = reinterpret_cast<unsigned int*>(acc_fwd + acc_sync(A));
   c.eps = eps;
-  constexpr int MT = 5, CR = 16 * MT;
+  constexpr int MT = 5, NWC = 4, CR = 16 * MT;
   const int tiles = (B + CR - 1) / CR;
   if ((int64_t)tiles * A > nsm) return 1;             // must be one co-resident wave (grid barrier)
   const size_t smem = (size_t)(2 * c.Hp * c.XP + 2 * CR * c.XP + 4 * 128 + 256) * 4 + (size_t)MT * 2 * 128 * 8;
   static bool attr = false;
   if (!attr) {
-    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_fwd_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_fwd_kernel<MT, NWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   void* args[] = {(void*)&c};
-  MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_fwd_kernel<MT>, dim3(tiles, A), dim3(64 * MT), args, smem, s));
+  MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_fwd_kernel<MT, NWC>, dim3(tiles, A), dim3(32 * MT * NWC), args, smem, s));
   MVAE_LAUNCH_CHECK();
   return 0;
 }
