@@ -362,7 +362,16 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
 
   // ---- encoder fc5..fc2, then the BatchNorm+ReLU backward of layer 1
   g_cur = work + w.g_xlow;
-  for (int l = 4; l >= 0; --l) {
+  int bchain_rc = 1;
+  if (hp.precision != 3 && !legacy_fc1()) {
+    const float* act[5] = {work + w.a[0], work + w.a[1], work + w.a[2], work + w.a[3], work + w.a[4]};
+    float* dl[5] = {work + w.delta_enc[0], work + w.delta_enc[1], work + w.delta_enc[2], work + w.delta_enc[3],
+                    work + w.delta_enc[4]};
+    bchain_rc = launch_enc_chain_bwd(st.params, p.L.arm_stride, p.L.offset, A, B, H, Ld, work + w.g_xlow, act, dl, acc_bwd,
+                                     bn_mean, bn_rstd, hp.precision == 1, s);
+    if (bchain_rc < 0 || bchain_rc > 1) return bchain_rc;
+  }
+  for (int l = 4; l >= 0 && bchain_rc == 1; --l) {
     DenseBwdArgs a;
     memset(&a, 0, sizeof(a));
     const int nout = l == 4 ? Ld : H;

@@ -117,7 +117,8 @@ __host__ __device__ inline int64_t accl_T(int a) { return 48 + kMaxPairs * 2 + (
 __host__ __device__ inline int64_t accl_qs(int a) { return 48 + kMaxPairs * 2 + 16 * 128 + (int64_t)a * 256; }
 __host__ __device__ inline int64_t acc_loss_doubles() { return 48 + kMaxPairs * 2 + 16 * 128 + 16 * 256; }
 __host__ __device__ inline int64_t accb_bn(int layer, int A, int a) { return ((int64_t)(layer * A + a)) * 2 * 128; }
-__host__ __device__ inline int64_t acc_bwd_doubles(int A) { return (int64_t)5 * A * 256; }
+__host__ __device__ inline int64_t accb_sync(int A) { return (int64_t)5 * A * 256; }   // grid-barrier counters (8 doubles)
+__host__ __device__ inline int64_t acc_bwd_doubles(int A) { return (int64_t)5 * A * 256 + 8; }
 
 // optional per-group device timing (CUDA events on the launching stream), for bench.py's roofline
 enum TimedGroup { TG_FC1_FWD = 0, TG_FC11, TG_FC1_WGRAD, TG_NARROW_FWD, TG_NARROW_BWD, TG_COUPLING, TG_WGRAD, TG_ADAM, TG_COUNT };

@@ -437,6 +437,153 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
   }
 }
 
+// =============================================================================================
+// encoder middle, backward: for l = 5..1 (array index 4..0)
+//   g_l (gradient wrt the BatchNorm output of layer l) -> BatchNorm backward (needs the batch means of g and g*n:
+//   grid-wide fp64 sums) -> ReLU mask -> delta_l (stored for the weight-gradient kernel) -> g_{l-1} = delta_l . W_l,
+//   whose own BatchNorm sums are accumulated in the epilogue.  The gradient tile never leaves shared memory.
+// =============================================================================================
+struct EncBwdArgs {
+  int XP, WPB, Hp;
+  const float* params; int64_t p_arm_stride;
+  int64_t offW[5];               // fc1..fc5 weights (index 0 unused)
+  int A, B, H, L;
+  const float* g_xlow;           // [A][B][L]
+  const float* act[5];           // a1..a5 (post-ReLU, pre-BN)
+  float* delta[5];               // delta1..delta5
+  double* sums;                  // acc_bwd: layer l at (l * A + arm) * 256: sum g | sum g*n
+  const float* bn_mean; const float* bn_rstd;   // [5][A][128]
+  unsigned int* bar;
+};
+
+template <int MT, int NWC, bool SPLIT>
+__global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncBwdArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int CR = 16 * MT, CT = 32 * MT * NWC, NTW = 16 / NWC;
+  const int XP = p.XP, WPB = p.WPB, Hp = p.Hp;
+  float* Ws0 = smem;                       // [Hp][WPB]  W_l natural: row j (out), col i (in)
+  float* Ws1 = Ws0 + Hp * WPB;
+  float* Gs = Ws1 + Hp * WPB;              // [CR][XP]   g_l, then delta_l in place, then g_{l-1}
+  float* As0 = Gs + CR * XP;               // [CR][XP]   activation tiles a_l / a_{l-1}
+  float* As1 = As0 + CR * XP;
+  float* c1 = As1 + CR * XP;               // [128] each: mean_b(g), mean_b(g*n), mean/rstd of layer l and of layer l-1
+  float* c2 = c1 + 128;
+  float* mo = c2 + 128;
+  float* ro = mo + 128;
+  float* mi = ro + 128;
+  float* ri = mi + 128;
+  double* red = reinterpret_cast<double*>(ri + 128);     // [MT][2][128]
+  const int arm = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int warp = tid >> 5, wr = warp % MT, wc = warp / MT;
+  const int g = lane >> 2, tig = lane & 3;
+  const int H = p.H, L = p.L, B = p.B;
+  const int row0 = blockIdx.x * CR;
+  const int rows_valid = min(CR, B - row0);
+  const float* par = p.params + (int64_t)arm * p.p_arm_stride;
+  const int64_t rbase = (int64_t)arm * B + row0;
+  const unsigned int nctas = gridDim.x * gridDim.y;
+
+  for (int idx = tid; idx < 2 * Hp * WPB + 3 * CR * XP; idx += CT) smem[idx] = 0.f;
+  __syncthreads();
+  // group P0: g_xlow, a5, W5 (fc5: [L][H]); group P1: a4, W4
+  async_tile(Gs, XP, p.g_xlow + rbase * L, L, rows_valid, L, tid, CT);
+  async_tile(As0, XP, p.act[4] + rbase * L, L, rows_valid, L, tid, CT);
+  async_tile(Ws0, WPB, par + p.offW[4], H, L, H, tid, CT);
+  cp_async_commit();
+  async_tile(As1, XP, p.act[3] + rbase * H, H, rows_valid, H, tid, CT);
+  async_tile(Ws1, WPB, par + p.offW[3], H, H, H, tid, CT);
+  cp_async_commit();
+
+  float* Ws[2] = {Ws0, Ws1};
+  float* As[2] = {As0, As1};
+  for (int it = 0; it < 5; ++it) {
+    const int l = 4 - it;
+    const int nout = l == 4 ? L : H;
+    // ---- constants of the BatchNorm backward of layer l (sums complete: head kernel for l == 4, grid barrier otherwise)
+    if (tid < nout) {
+      const double* sums = p.sums + (int64_t)(l * p.A + arm) * 256;
+      c1[tid] = (float)(__ldcg(sums + tid) / (double)B);
+      c2[tid] = (float)(__ldcg(sums + 128 + tid) / (double)B);
+      mo[tid] = p.bn_mean[(l * p.A + arm) * 128 + tid];
+      ro[tid] = p.bn_rstd[(l * p.A + arm) * 128 + tid];
+    }
+    if (l > 0 && tid < H) {
+      mi[tid] = p.bn_mean[((l - 1) * p.A + arm) * 128 + tid];
+      ri[tid] = p.bn_rstd[((l - 1) * p.A + arm) * 128 + tid];
+    }
+    if (it < 4) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    // ---- delta_l = bn_bwd(g_l) * relu'(a_l): in place in Gs and to global
+    const float* Ac = As[it & 1];
+    float* dout = p.delta[l] + rbase * nout;
+    for (int idx = tid; idx < rows_valid * nout; idx += CT) {
+      const int r = idx / nout, j = idx - r * nout;
+      const float a = Ac[r * XP + j];
+      const float n = (a - mo[j]) * ro[j];
+      const float gg = ro[j] * (Gs[r * XP + j] - c1[j] - n * c2[j]);
+      const float d = a > 0.f ? gg : 0.f;
+      Gs[r * XP + j] = d;
+      dout[(int64_t)r * nout + j] = d;
+    }
+    if (l == 0) break;
+    cp_async_wait<0>();                    // a_{l-1} (needed by the epilogue) has landed
+    __syncthreads();
+    float acc[NTW][4];
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    const int nt_used = max(0, min(NTW, (H + 7) / 8 - wc * NTW));
+    warp_gemm2<NTW, false, SPLIT>(Gs + wr * 16 * XP, XP, Ws[it & 1] + wc * NTW * 8, WPB, (nout + 7) / 8, nt_used, acc, lane);
+    __syncthreads();                       // all warps have read delta_l before g_{l-1} overwrites it
+    // ---- epilogue: g_{l-1} -> Gs; fp64 sums of g and g * n_{l-1} over the valid rows
+    const float* An = As[(it + 1) & 1];
+    const int ra = wr * 16 + g, rb = ra + 8;
+    const bool va = ra < rows_valid, vb = rb < rows_valid;
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      if (nt < nt_used) {
+        const int c = (wc * NTW + nt) * 8 + 2 * tig;
+        const bool c0ok = c < H, c1ok = c + 1 < H;
+        double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
+        if (c0ok) {
+          Gs[ra * XP + c] = va ? acc[nt][0] : 0.f;
+          Gs[rb * XP + c] = vb ? acc[nt][2] : 0.f;
+          if (va) { const double n = (double)((An[ra * XP + c] - mi[c]) * ri[c]); s0 += (double)acc[nt][0]; q0 += (double)acc[nt][0] * n; }
+          if (vb) { const double n = (double)((An[rb * XP + c] - mi[c]) * ri[c]); s0 += (double)acc[nt][2]; q0 += (double)acc[nt][2] * n; }
+        }
+        if (c1ok) {
+          Gs[ra * XP + c + 1] = va ? acc[nt][1] : 0.f;
+          Gs[rb * XP + c + 1] = vb ? acc[nt][3] : 0.f;
+          if (va) { const double n = (double)((An[ra * XP + c + 1] - mi[c + 1]) * ri[c + 1]); s1 += (double)acc[nt][1]; q1 += (double)acc[nt][1] * n; }
+          if (vb) { const double n = (double)((An[rb * XP + c + 1] - mi[c + 1]) * ri[c + 1]); s1 += (double)acc[nt][3]; q1 += (double)acc[nt][3] * n; }
+        }
+        s0 = group_sum_d(s0); s1 = group_sum_d(s1); q0 = group_sum_d(q0); q1 = group_sum_d(q1);
+        if (g == 0) {
+          red[(wr * 2 + 0) * 128 + c] = s0; red[(wr * 2 + 0) * 128 + c + 1] = s1;
+          red[(wr * 2 + 1) * 128 + c] = q0; red[(wr * 2 + 1) * 128 + c + 1] = q1;
+        }
+      }
+    }
+    __syncthreads();
+    for (int j = tid; j < 256; j += CT) {
+      const int which = j >> 7, c = j & 127;
+      if (c < H) {
+        double sacc = 0.0;
+        for (int w = 0; w < MT; ++w) sacc += red[(w * 2 + which) * 128 + c];
+        atomicAdd(p.sums + (int64_t)((l - 1) * p.A + arm) * 256 + which * 128 + c, sacc);
+      }
+    }
+    // ---- stage a_{l-2} and W_{l-2} into the buffers of this iteration (layer 0 has no data gradient: no weights)
+    if (l - 2 >= 0) {
+      async_tile(As[it & 1], XP, p.act[l - 2] + rbase * H, H, rows_valid, H, tid, CT);
+      if (l - 2 >= 1) async_tile(Ws[it & 1], WPB, par + p.offW[l - 2], H, H, H, tid, CT);
+    }
+    cp_async_commit();
+    grid_barrier(p.bar + it, nctas);
+  }
+}
+
 }  // namespace
 
 static int b_pitch2(int n) {
@@ -549,6 +696,51 @@ int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_
   }
   void* args[] = {(void*)&c};
   MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_fwd_kernel<MT, NWC>, dim3(tiles, A), dim3(32 * MT * NWC), args, smem, s));
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_enc_chain_bwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
+                         const float* g_xlow, const float* const act[5], float* const delta[5], double* acc_bwd,
+                         const float* bn_mean, const float* bn_rstd, int split3, cudaStream_t s) {
+  static int coop = -1, nsm = 0;
+  if (coop < 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (!coop || H > 128 || L > 64 || H % 4 != 0) return 1;
+  EncBwdArgs c;
+  memset(&c, 0, sizeof(c));
+  c.Hp = (H + 7) & ~7;
+  c.XP = c.Hp + 4;
+  c.WPB = b_pitch2(c.Hp);
+  c.params = params; c.p_arm_stride = p_arm_stride;
+  for (int l = 0; l < 5; ++l) {
+    c.offW[l] = off[FC1_W + 2 * l];
+    c.act[l] = act[l];
+    c.delta[l] = delta[l];
+  }
+  c.A = A; c.B = B; c.H = H; c.L = L;
+  c.g_xlow = g_xlow;
+  c.sums = acc_bwd;
+  c.bn_mean = bn_mean; c.bn_rstd = bn_rstd;
+  c.bar = reinterpret_cast<unsigned int*>(acc_bwd + accb_sync(A));
+  constexpr int MT = 5, NWC = 4, CR = 16 * MT;
+  const int tiles = (B + CR - 1) / CR;
+  if ((int64_t)tiles * A > nsm) return 1;             // must be one co-resident wave (grid barrier)
+  const size_t smem = (size_t)(2 * c.Hp * c.WPB + 3 * CR * c.XP + 6 * 128) * 4 + (size_t)MT * 2 * 128 * 8;
+  void* args[] = {(void*)&c};
+  if (split3) {
+    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_bwd_kernel<MT, NWC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_bwd_kernel<MT, NWC, true>, dim3(tiles, A), dim3(32 * MT * NWC), args,
+                                          smem, s));
+  } else {
+    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_bwd_kernel<MT, NWC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_bwd_kernel<MT, NWC, false>, dim3(tiles, A), dim3(32 * MT * NWC), args,
+                                          smem, s));
+  }
   MVAE_LAUNCH_CHECK();
   return 0;
 }
