@@ -16,8 +16,6 @@
 //   * MMA2 (TS form) accumulates into acc2 (TMEM) over the whole segment;
 //   * stream-K over (tile, unit): one CTA per SM, one wave; partial tiles are summed in a fixed order by a fix-up kernel.
 // TMEM columns: acc2 [0,128) | acc1 4 x 32 [128,256) | dY stages 4 x 32 [256,384) | R [384,512).
-#include <stdlib.h>
-
 #include "gemm_tc.h"
 #include "tc_common.cuh"
 
@@ -41,7 +39,6 @@ struct F11Args {
   int x_batched;
   int nx, nk, nm;                   // ring depths: x, K-image, MN-image
   int want_grad;
-  int hack;
   float gscale;
   const float* R; int64_t r_arm_stride; int r_rows;     // resident operand: [arm][r_rows][H]
   const float* bias; int64_t bias_arm_stride;           // fc11.bias
@@ -70,8 +67,10 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint64_t* acc1_full = m_empty + a.nm;    uint64_t* acc1_empty = acc1_full + NG;
   uint64_t* a2_full = acc1_empty + NG;     uint64_t* a2_empty = a2_full + NG;
   uint64_t* r_full = a2_empty + NG;        // R of the current segment is in TMEM (and acc2 of the previous one drained)
+  // segment s complete: barrier s % NG.  An epilogue group can be up to NG units -- hence NG segments when a CTA's share
+  // of a tile is a single unit -- ahead of the tensor pipe; one parity bit cannot tell those apart, NG barriers can.
   uint64_t* acc2_full = r_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + NG);
 
   const int KT = a.ktiles;
   const int64_t U = (int64_t)a.batch * a.rtiles * KT, G = gridDim.x;
@@ -87,7 +86,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_init(a2_full + s, 4);   mbar_init(a2_empty + s, 1);
     }
     mbar_init(r_full, 4);
-    mbar_init(acc2_full, 1);
+    for (int s = 0; s < NG; ++s) mbar_init(acc2_full + s, 1);
     fence_barrier_init();
   }
   if (warp == CTRL_WARPS) tmem_alloc(tmem_slot, 512);
@@ -122,17 +121,17 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     for (int i = 0; i < nu; ++i) {
       mbar_wait(k_empty + sk, phk);
       if (elect_one()) {
-        mbar_expect_tx(k_full + sk, a.hack ? 4096 : IMG_BYTES);
+        mbar_expect_tx(k_full + sk, IMG_BYTES);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (!a.hack || j == 0) tma_load_3d(&tmTk, k_full + sk, tk(sk) + j * 4096, 32 * j, kt * UN, arm);
+        for (int j = 0; j < 4; ++j) tma_load_3d(&tmTk, k_full + sk, tk(sk) + j * 4096, 32 * j, kt * UN, arm);
       }
       __syncwarp();
       if (a.want_grad) {
         mbar_wait(m_empty + sm, phm);
         if (elect_one()) {
-          mbar_expect_tx(m_full + sm, a.hack ? 4096 : IMG_BYTES);
+          mbar_expect_tx(m_full + sm, IMG_BYTES);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (!a.hack || j == 0) tma_load_3d(&tmTm, m_full + sm, tm(sm) + j * 4096, 32 * j, kt * UN, arm);
+          for (int j = 0; j < 4; ++j) tma_load_3d(&tmTm, m_full + sm, tm(sm) + j * 4096, 32 * j, kt * UN, arm);
         }
         __syncwarp();
         if (++sm == a.nm) { sm = 0; phm ^= 1; }
@@ -162,7 +161,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                        idesc2, (acc2 | (uint32_t)ks) ? 1u : 0u);
         umma_commit(a2_empty + g);
         umma_commit(m_empty + sm);
-        if (last) umma_commit(acc2_full);
+        if (last) umma_commit(acc2_full + ((seg - 1) & (NG - 1)));
       }
       __syncwarp();
       acc2 = last ? 0u : 1u;
@@ -191,7 +190,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                        make_smem_desc(tka + (ks >> 2) * 4096 + (ks & 3) * 32, 0, 1024, false), idesc1, ks > 0 ? 1u : 0u);
         umma_commit(acc1_full + g);
         umma_commit(k_empty + sk);
-        if (!a.want_grad && ((kt + 1 == KT) || (i == nu - 1))) umma_commit(acc2_full);   // loss-only: segment end marker
+        if (!a.want_grad && ((kt + 1 == KT) || (i == nu - 1))) umma_commit(acc2_full + ((seg - 1) & (NG - 1)));   // loss-only: segment end marker
       }
       __syncwarp();
       if (++sk == a.nk) { sk = 0; phk ^= 1; }
@@ -360,7 +359,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       if (seg_end) {
         // ---- drain acc2 (this CTA's share of tile t), then bring in R of the next tile
-        mbar_wait(acc2_full, (t - t_first) & 1);
+        mbar_wait(acc2_full + ((t - t_first) & (NG - 1)), ((t - t_first) / NG) & 1);
         tc_fence_after();
         if (a.want_grad) {
           float* prt = a.part + ((int64_t)blockIdx.x + t) * TILE_FLOATS + r * 128;
@@ -454,10 +453,9 @@ int launch_f11(const CUtensorMap& tmX, const CUtensorMap& tmTk, const CUtensorMa
   int64_t G = sm_count2();
   if (G > U) G = U;
   a.nk = 4; a.nm = 4;
-  { const char* e = getenv("MVAE_HACK_TMA"); a.hack = (e && e[0] == '1') ? 1 : 0; }
   a.nx = (227 * 1024 - 2048 - (a.nk + a.nm) * IMG_BYTES) / X_BYTES;
   if (a.nx > 8) a.nx = 8;
-  const size_t smem = (size_t)a.nx * X_BYTES + (size_t)(a.nk + a.nm) * IMG_BYTES + (2 * a.nx + 2 * a.nk + 2 * a.nm + 4 * NG + 4) * 8 + 1024;
+  const size_t smem = (size_t)a.nx * X_BYTES + (size_t)(a.nk + a.nm) * IMG_BYTES + (2 * a.nx + 2 * a.nk + 2 * a.nm + 5 * NG + 4) * 8 + 1024;
   static bool attr = false;
   if (!attr) {
     MVAE_CUDA(cudaFuncSetAttribute(fc11_ts_kernel<GENE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -68,8 +68,11 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint64_t* w_empty = w_full + a.nw;
   uint64_t* a_full = w_empty + a.nw;
   uint64_t* a_empty = a_full + NA;
-  uint64_t* acc_full = a_empty + NA;      // MMAs of a segment complete (both blocks)
-  uint64_t* acc_empty = acc_full + 1;     // both accumulators drained
+  // MMAs of segment s complete (both blocks): barrier s % NA.  A transform group can be up to NA units -- hence up to
+  // NA segments when a CTA's share of a tile is a single unit -- ahead of the tensor pipe, which one parity bit
+  // cannot tell apart; NA barriers can.
+  uint64_t* acc_full = a_empty + NA;
+  uint64_t* acc_empty = acc_full + NA;    // both accumulators drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int KT = a.ktiles;
@@ -81,7 +84,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     for (int s = 0; s < a.nx; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 4); }
     for (int s = 0; s < a.nw; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
     for (int s = 0; s < NA; ++s) { mbar_init(a_full + s, 4); mbar_init(a_empty + s, 1); }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < NA; ++s) mbar_init(acc_full + s, 1);
     mbar_init(acc_empty, 4 * NB);
     fence_barrier_init();
   }
@@ -183,7 +186,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const bool seg_end = (kt + 1 == KT) || (i == nu - 1);
       if (elect_one()) {
         umma_commit(w_empty + sw);
-        if (seg_end) umma_commit(acc_full);          // this CTA's share of the tile is complete
+        if (seg_end) umma_commit(acc_full + (seg & (NA - 1)));          // this CTA's share of the tile is complete
       }
       __syncwarp();
       if (++sw == a.nw) { sw = 0; phw ^= 1; }
@@ -302,7 +305,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (kt == KT - 1 || i == nu - 1) {
         // ---- drain this CTA's share of tile t into its partial slot (slot = cta + tile: unique, monotone)
         const int seg = t - t_first;
-        mbar_wait(acc_full, seg & 1);
+        mbar_wait(acc_full + (seg & (NA - 1)), (seg / NA) & 1);
         tc_fence_after();
         float* prt = a.part + (((int64_t)blockIdx.x + t) * NB + blk) * TILE_FLOATS;
         const uint32_t dcol = tmem_base + lane_bits + (uint32_t)blk * 128u;
@@ -440,7 +443,7 @@ int launch_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap&
   const int budget = 227 * 1024 - 1024 - 512 - a.nw * w_stage;
   a.nx = budget / X_BYTES;
   if (a.nx > 8) a.nx = 8;
-  const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * w_stage + (2 * a.nx + 2 * a.nw + 2 * NA + 6) * 8 + 1024;
+  const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * w_stage + (2 * a.nx + 2 * a.nw + 3 * NA + 6) * 8 + 1024;
   static bool attr = false;
   if (!attr) {
     MVAE_CUDA(cudaFuncSetAttribute(ts_gemm_kernel<WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
