@@ -331,6 +331,7 @@ def main():
         dt = float(tt.item())
         e2e = {"value": dp_ranks * B * n_e2e / dt, "unit": "cells/s", "h2d_bytes_per_step": B * D * 4,
                "d2h_bytes_per_step": 4, "ms_per_step": dt / n_e2e * 1e3,
+               "h2d_gbs_per_gpu": B * D * 4 / (dt / n_e2e) / 1e9,   # ~56 GB/s = the PCIe ceiling: e2e is copy-bound
                "api": "cpl_mixVAE.train_batch via HostBatchFeeder (pinned host batch -> side-stream H2D -> fused step -> loss.item())"}
 
     cpu_base = None
