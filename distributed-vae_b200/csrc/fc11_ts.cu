@@ -394,22 +394,31 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 // out[arm][row][col] = sum over the CTAs that touched tile (row / 128, arm) of their partial, in CTA order
 __global__ void __launch_bounds__(256) f11_fixup_kernel(const float* part, int batch, int ktiles, int64_t U, int64_t G, float* out,
                                                         int64_t out_arm_stride, int ld, int rows, int cols) {
+  // block = one 128-row tile; thread = (row mod 8, float4 column): 16 rows each (cols % 4 == 0 on this path)
   __shared__ int cc[2];
-  const int arm = blockIdx.z;
-  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int row = blockIdx.y * 8 + (threadIdx.x >> 5);
-  const int64_t t = (int64_t)((blockIdx.y * 8) >> 7) * batch + arm;        // the 8 rows of a block share their tile
-  if (threadIdx.x == 0) {
+  const int arm = blockIdx.y;
+  const int tid = threadIdx.x, r8 = tid >> 5, c4 = tid & 31;
+  const int row0 = (blockIdx.x >> 3) * 128, sub0 = (blockIdx.x & 7) * 16;
+  const int64_t t = (int64_t)(blockIdx.x >> 3) * batch + arm;
+  if (tid == 0) {
     cc[0] = (int)cta_of_unit(t * ktiles, U, G);
     cc[1] = (int)cta_of_unit(t * ktiles + ktiles - 1, U, G);
   }
   __syncthreads();
-  if (row >= rows || col >= cols) return;
+  if (4 * c4 >= cols) return;
   const int c0 = cc[0], c1 = cc[1];
-  const float* base = part + (c0 + t) * TILE_FLOATS + (int64_t)(row & 127) * 128 + col;
-  float v = 0.f;
-  for (int c = c0; c <= c1; ++c) v += base[(int64_t)(c - c0) * TILE_FLOATS];
-  out[(int64_t)arm * out_arm_stride + (int64_t)row * ld + col] = v;
+  const float* base = part + (int64_t)(c0 + t) * TILE_FLOATS + 4 * c4;
+  float* o = out + (int64_t)arm * out_arm_stride + 4 * c4;
+  for (int k = 0; k < 2; ++k) {
+    const int rl = sub0 + r8 + 8 * k, row = row0 + rl;
+    if (row >= rows) break;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = c0; c <= c1; ++c) {
+      const float4 q = *reinterpret_cast<const float4*>(base + (int64_t)(c - c0) * TILE_FLOATS + rl * 128);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    *reinterpret_cast<float4*>(o + (int64_t)row * ld) = v;
+  }
 }
 
 // d fc11.bias[arm][gene] = sum over CTAs and epilogue groups of the partials; a (CTA, group) pair that processed no unit
@@ -497,8 +506,7 @@ int ts_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
   int64_t U, G;
   rc = launch_f11<false>(tmX, tmTk, tmTm, a, &U, &G, s);
   if (rc || !want_grad) return rc;
-  f11_fixup_kernel<<<dim3((H + 31) / 32, (B + 7) / 8, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, work + w.g_d10, (int64_t)B * H, H,
-                                                                      B, H);
+  f11_fixup_kernel<<<dim3((B + 127) / 128 * 8, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, work + w.g_d10, (int64_t)B * H, H, B, H);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -529,8 +537,8 @@ int ts_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& i
   int64_t U, G;
   rc = launch_f11<true>(tmX, tmTk, tmTm, a, &U, &G, s);
   if (rc) return rc;
-  f11_fixup_kernel<<<dim3((H + 31) / 32, (D + 7) / 8, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, st.grads + L.offset[FC11_W],
-                                                                      L.arm_stride, H, D, H);
+  f11_fixup_kernel<<<dim3((D + 127) / 128 * 8, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, st.grads + L.offset[FC11_W], L.arm_stride,
+                                                           H, D, H);
   MVAE_LAUNCH_CHECK();
   f11_db_fixup_kernel<<<dim3((D + 127) / 128, A), 128, 0, s>>>(a.db_part, A, a.ktiles, U, G, st.grads + L.offset[FC11_B],
                                                              L.arm_stride, D);

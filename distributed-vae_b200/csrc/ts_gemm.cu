@@ -360,41 +360,54 @@ struct Fc1FixArgs {
   float* out; double* stats_out; int B, H;
 };
 __global__ void __launch_bounds__(256) fc1_fixup_kernel(const Fc1FixArgs p) {
+  // block = 16 rows of a 128-row block of an output tile; thread = (row mod 8, float4 column): 2 rows each, 512-byte rows
   __shared__ double red[8][2][128];
+  __shared__ int cc[2];
   const int arm = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* bias = p.params + (int64_t)arm * p.p_arm_stride + p.offB;
+  const int tid = threadIdx.x, r8 = tid >> 5, c4 = tid & 31;
+  const int row0 = (blockIdx.x >> 3) * 128, sub0 = (blockIdx.x & 7) * 16;
+  const int64_t t = (int64_t)(row0 >> 8) * p.batch + arm;
+  if (tid == 0) {
+    cc[0] = (int)cta_of_unit(t * p.ktiles, p.U, p.G);
+    cc[1] = (int)cta_of_unit(t * p.ktiles + p.ktiles - 1, p.U, p.G);
+  }
+  __syncthreads();
+  const int c0 = cc[0], c1 = cc[1];
+  const bool col_ok = 4 * c4 < p.H;                       // H % 4 == 0 on this path
+  float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col_ok) bj = *reinterpret_cast<const float4*>(p.params + (int64_t)arm * p.p_arm_stride + p.offB + 4 * c4);
   float* out = p.out + (int64_t)arm * p.B * p.H;
+  const float* base = p.part + ((int64_t)(c0 + t) * NB + ((row0 >> 7) & 1)) * TILE_FLOATS + 4 * c4;
   double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-  for (int row = blockIdx.x * 8 + warp; row < p.B; row += gridDim.x * 8) {
-    const int64_t t = (int64_t)(row >> 8) * p.batch + arm;
-    const int64_t c0 = cta_of_unit(t * p.ktiles, p.U, p.G), c1 = cta_of_unit(t * p.ktiles + p.ktiles - 1, p.U, p.G);
-    const float* base = p.part + ((c0 + t) * NB + ((row >> 7) & 1)) * TILE_FLOATS + (int64_t)(row & 127) * 128;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int j = lane + 32 * k;
-      if (j < p.H) {
-        float v = 0.f;
-        for (int64_t c = c0; c <= c1; ++c) v += base[(c - c0) * NB * TILE_FLOATS + j];
-        v = fmaxf(fmaf(v, p.scale, bias[j]), 0.f);
-        out[(int64_t)row * p.H + j] = v;
-        s1[k] += (double)v;
-        s2[k] += (double)v * (double)v;
+  if (col_ok) {
+    for (int k = 0; k < 2; ++k) {
+      const int rl = sub0 + r8 + 8 * k, row = row0 + rl;
+      if (row >= p.B) break;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = c0; c <= c1; ++c) {
+        const float4 q = *reinterpret_cast<const float4*>(base + (int64_t)(c - c0) * NB * TILE_FLOATS + rl * 128);
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
       }
+      v.x = fmaxf(fmaf(v.x, p.scale, bj.x), 0.f); v.y = fmaxf(fmaf(v.y, p.scale, bj.y), 0.f);
+      v.z = fmaxf(fmaf(v.z, p.scale, bj.z), 0.f); v.w = fmaxf(fmaf(v.w, p.scale, bj.w), 0.f);
+      *reinterpret_cast<float4*>(out + (int64_t)row * p.H + 4 * c4) = v;
+      s1[0] += (double)v.x; s1[1] += (double)v.y; s1[2] += (double)v.z; s1[3] += (double)v.w;
+      s2[0] += (double)v.x * (double)v.x; s2[1] += (double)v.y * (double)v.y;
+      s2[2] += (double)v.z * (double)v.z; s2[3] += (double)v.w * (double)v.w;
     }
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    red[warp][0][lane + 32 * k] = s1[k];
-    red[warp][1][lane + 32 * k] = s2[k];
+  for (int e = 0; e < 4; ++e) {
+    red[r8][0][4 * c4 + e] = s1[e];
+    red[r8][1][4 * c4 + e] = s2[e];
   }
   __syncthreads();
   {
     const int which = tid >> 7, j = tid & 127;
     if (j < p.H) {
-      double s = 0.0;
-      for (int w = 0; w < 8; ++w) s += red[w][which][j];
-      atomicAdd(p.stats_out + (int64_t)arm * 256 + which * 128 + j, s);
+      double sacc = 0.0;
+      for (int w = 0; w < 8; ++w) sacc += red[w][which][j];
+      atomicAdd(p.stats_out + (int64_t)arm * 256 + which * 128 + j, sacc);
     }
   }
 }
@@ -402,22 +415,30 @@ __global__ void __launch_bounds__(256) fc1_fixup_kernel(const Fc1FixArgs p) {
 // d fc1.weight fix-up: dW1[arm][h][gene] = sum of the partials [slot][h][gene in tile] in a fixed order
 __global__ void __launch_bounds__(256) wgrad_fixup_kernel(const float* part, int batch, int ktiles, int64_t U, int64_t G,
                                                           float scale, float* grads, int64_t g_arm_stride, int D, int H) {
+  // block = one 128-gene block (partials are [h][gene]); thread = (h mod 8, float4 of genes)
   __shared__ int cc[2];
-  const int arm = blockIdx.z;
-  const int gene = blockIdx.x * 128 + (threadIdx.x & 127);
-  const int h = blockIdx.y * 2 + (threadIdx.x >> 7);
-  const int64_t t = (int64_t)(blockIdx.x >> 1) * batch + arm;
-  if (threadIdx.x == 0) {
+  const int arm = blockIdx.y;
+  const int tid = threadIdx.x, h8 = tid >> 5, g4 = tid & 31;
+  const int gb = blockIdx.x >> 2, hq = blockIdx.x & 3;     // 128-gene block, quarter of the h rows
+  const int gene = gb * 128 + 4 * g4;
+  const int64_t t = (int64_t)(gb >> 1) * batch + arm;
+  if (tid == 0) {
     cc[0] = (int)cta_of_unit(t * ktiles, U, G);
     cc[1] = (int)cta_of_unit(t * ktiles + ktiles - 1, U, G);
   }
   __syncthreads();
-  if (gene >= D || h >= H) return;
+  if (gene >= D) return;                                  // D % 4 == 0 on this path
   const int c0 = cc[0], c1 = cc[1];
-  const float* base = part + ((c0 + t) * NB + (blockIdx.x & 1)) * TILE_FLOATS + (int64_t)h * 128 + (gene & 127);
-  float v = 0.f;
-  for (int c = c0; c <= c1; ++c) v += base[(int64_t)(c - c0) * NB * TILE_FLOATS];
-  grads[(int64_t)arm * g_arm_stride + (int64_t)h * D + gene] = v * scale;
+  const float* base = part + ((int64_t)(c0 + t) * NB + (gb & 1)) * TILE_FLOATS + 4 * g4;
+  float* out = grads + (int64_t)arm * g_arm_stride + gene;
+  for (int h = h8 + 8 * hq; h < H; h += 32) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = c0; c <= c1; ++c) {
+      const float4 q = *reinterpret_cast<const float4*>(base + (int64_t)(c - c0) * NB * TILE_FLOATS + h * 128);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    *reinterpret_cast<float4*>(out + (int64_t)h * D) = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+  }
 }
 
 int sm_count() {
@@ -502,9 +523,7 @@ int ts_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state&
   f.scale = drop.mode ? drop.scale : 1.f;
   f.params = st.params; f.p_arm_stride = L.arm_stride; f.offB = L.offset[FC1_B];
   f.out = a1_out; f.stats_out = stats_out; f.B = B; f.H = H;
-  int gx = (B + 7) / 8;
-  if (gx > 296) gx = 296;
-  fc1_fixup_kernel<<<dim3(gx, A), 256, 0, s>>>(f);
+  fc1_fixup_kernel<<<dim3((B + 127) / 128 * 8, A), 256, 0, s>>>(f);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -532,7 +551,7 @@ int ts_fc1_wgrad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
   int64_t U, G;
   rc = launch_ts<true>(tmX, tmW, tmW, a, &U, &G, s);
   if (rc) return rc;
-  wgrad_fixup_kernel<<<dim3((D + 127) / 128, (H + 1) / 2, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, drop.mode ? drop.scale : 1.f,
+  wgrad_fixup_kernel<<<dim3((D + 127) / 128 * 4, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, drop.mode ? drop.scale : 1.f,
                                                                    st.grads + L.offset[FC1_W], L.arm_stride, D, H);
   MVAE_LAUNCH_CHECK();
   return 0;
