@@ -253,31 +253,31 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int c0 = kt * UN;           // first gene (ROW) / cell (GENE) of the unit
       mbar_wait(x_full + sx, phx);
       const uint8_t* tile = xs(sx);
+      // the x tile does not depend on MMA1: read it while the accumulator is still being produced
+      float xv[32];
+      if (!GENE) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(tile + r * 128 + ((q ^ (r & 7)) << 4));
+          xv[4 * q] = t4.x; xv[4 * q + 1] = t4.y; xv[4 * q + 2] = t4.z; xv[4 * q + 3] = t4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xv[j] = *reinterpret_cast<const float*>(tile + j * 512 + r * 4);
+      }
       mbar_wait(acc1_full + grp, ph1);
       tc_fence_after();
+      uint32_t acc[32];
+      tmem_ld16(tacc1, acc);
+      tmem_ld16(tacc1 + 16u, acc + 16);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(acc1_empty + grp); mbar_arrive(x_empty + sx); }   // both are in registers now
       bool a2_waited = false;
       float fs = 0.f, fm = 0.f;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t acc[16];
-        tmem_ld16(tacc1 + 16u * half, acc);
-        float xv[16];
-        if (!GENE) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 t4 = *reinterpret_cast<const float4*>(tile + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
-            xv[4 * q] = t4.x; xv[4 * q + 1] = t4.y; xv[4 * q + 2] = t4.z; xv[4 * q + 3] = t4.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) xv[j] = *reinterpret_cast<const float*>(tile + (16 * half + j) * 512 + r * 4);
-        }
-        tmem_ld_wait();
-        if (half == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { mbar_arrive(acc1_empty + grp); mbar_arrive(x_empty + sx); }
-        }
         uint32_t dy[16];
         if (!GENE) {
           float bb[16];
@@ -295,10 +295,11 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           float xh[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            xh[j] = fmaxf(__uint_as_float(acc[j]) + bb[j], 0.f);
-            const float d = xh[j] - xv[j];
+            const float xin = xv[16 * half + j];
+            xh[j] = fmaxf(__uint_as_float(acc[16 * half + j]) + bb[j], 0.f);
+            const float d = xh[j] - xin;
             fs = fmaf(d, d, fs);
-            fm += ((xh[j] > 0.1f) != (xv[j] > 0.1f)) ? 1.f : 0.f;
+            fm += ((xh[j] > 0.1f) != (xin > 0.1f)) ? 1.f : 0.f;
             dy[j] = __float_as_uint((row_ok && xh[j] > 0.f) ? a.gscale * d : 0.f);
           }
           if (a.x_rec && row_ok) {
@@ -312,8 +313,8 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const bool all = cell0 + 16 <= a.B;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float xh = fmaxf(__uint_as_float(acc[j]) + bj, 0.f);
-            float v = xh > 0.f ? a.gscale * (xh - xv[j]) : 0.f;
+            const float xh = fmaxf(__uint_as_float(acc[16 * half + j]) + bj, 0.f);
+            float v = xh > 0.f ? a.gscale * (xh - xv[16 * half + j]) : 0.f;
             if (!all && cell0 + j >= a.B) v = 0.f;
             dbsum += v;
             dy[j] = __float_as_uint(v);
