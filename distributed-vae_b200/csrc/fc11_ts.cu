@@ -50,10 +50,14 @@ struct F11Args {
 
 __host__ __device__ inline int64_t cta_of_unit(int64_t u, int64_t U, int64_t G) { return ((u + 1) * G - 1) / U; }
 
-template <bool GENE>
+// TRAIN = true: the training-step instance (gradients wanted, no materialised reconstruction): the flags are compile-time
+// so the epilogue carries no per-element branches for them.
+template <bool GENE, bool TRAIN>
 __global__ void __launch_bounds__(THREADS, 1)
 fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmTk,
                const __grid_constant__ CUtensorMap tmTm, const F11Args a) {
+  const bool want_grad = TRAIN || a.want_grad;
+  float* const x_rec = TRAIN ? nullptr : a.x_rec;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -126,7 +130,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         for (int j = 0; j < 4; ++j) tma_load_3d(&tmTk, k_full + sk, tk(sk) + j * 4096, 32 * j, kt * UN, arm);
       }
       __syncwarp();
-      if (a.want_grad) {
+      if (want_grad) {
         mbar_wait(m_empty + sm, phm);
         if (elect_one()) {
           mbar_expect_tx(m_full + sm, IMG_BYTES);
@@ -175,7 +179,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const bool new_seg = (i == 0) || (kt == 0);
       if (new_seg) {
         // flush: the old segment must complete before R changes
-        if (a.want_grad)
+        if (want_grad)
           while (next2 < i) { mma2(next2, next2 == i - 1); ++next2; }
         mbar_wait(r_full, seg & 1);
         ++seg;
@@ -190,15 +194,15 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                        make_smem_desc(tka + (ks >> 2) * 4096 + (ks & 3) * 32, 0, 1024, false), idesc1, ks > 0 ? 1u : 0u);
         umma_commit(acc1_full + g);
         umma_commit(k_empty + sk);
-        if (!a.want_grad && ((kt + 1 == KT) || (i == nu - 1))) umma_commit(acc2_full + ((seg - 1) & (NG - 1)));   // loss-only: segment end marker
+        if (!want_grad && ((kt + 1 == KT) || (i == nu - 1))) umma_commit(acc2_full + ((seg - 1) & (NG - 1)));   // loss-only: segment end marker
       }
       __syncwarp();
       if (++sk == a.nk) { sk = 0; phk ^= 1; }
-      if (a.want_grad)
+      if (want_grad)
         while (i - next2 >= SKEW) { mma2(next2, false); ++next2; }
       if (++kt == KT) kt = 0;
     }
-    if (a.want_grad)
+    if (want_grad)
       while (next2 < nu) { mma2(next2, next2 == nu - 1); ++next2; }
   } else {
     // ===== epilogue groups =====
@@ -276,6 +280,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (lane == 0) { mbar_arrive(acc1_empty + grp); mbar_arrive(x_empty + sx); }   // both are in registers now
       bool a2_waited = false;
       float fs = 0.f, fm = 0.f;
+      const float rscale = row_ok ? a.gscale : 0.f;        // rows beyond the batch contribute no gradient
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t dy[16];
@@ -300,10 +305,10 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             const float d = xh[j] - xin;
             fs = fmaf(d, d, fs);
             fm += ((xh[j] > 0.1f) != (xin > 0.1f)) ? 1.f : 0.f;
-            dy[j] = __float_as_uint((row_ok && xh[j] > 0.f) ? a.gscale * d : 0.f);
+            dy[j] = __float_as_uint(xh[j] > 0.f ? rscale * d : 0.f);
           }
-          if (a.x_rec && row_ok) {
-            float* xr = a.x_rec + (int64_t)arm * a.xrec_arm_stride + (int64_t)(rb * 128 + r) * a.D + g0;
+          if (x_rec && row_ok) {
+            float* xr = x_rec + (int64_t)arm * a.xrec_arm_stride + (int64_t)(rb * 128 + r) * a.D + g0;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (g0 + j < a.D) xr[j] = xh[j];
@@ -320,7 +325,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             dy[j] = __float_as_uint(v);
           }
         }
-        if (a.want_grad) {
+        if (want_grad) {
           if (!a2_waited) {
             mbar_wait(a2_empty + grp, pha);
             tc_fence_after();
@@ -331,7 +336,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
       }
       if (!GENE && row_ok) { sse += (double)fs; mism += (double)fm; }
-      if (a.want_grad) {
+      if (want_grad) {
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -362,7 +367,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         // ---- drain acc2 (this CTA's share of tile t), then bring in R of the next tile
         mbar_wait(acc2_full + ((t - t_first) & (NG - 1)), ((t - t_first) / NG) & 1);
         tc_fence_after();
-        if (a.want_grad) {
+        if (want_grad) {
           float* prt = a.part + ((int64_t)blockIdx.x + t) * TILE_FLOATS + r * 128;
           for (int j = 0; j < a.HN / 16; ++j) {
             uint32_t rr[16];
@@ -456,7 +461,7 @@ int sm_count2() {
   return n;
 }
 
-template <bool GENE>
+template <bool GENE, bool TRAIN>
 int launch_f11(const CUtensorMap& tmX, const CUtensorMap& tmTk, const CUtensorMap& tmTm, F11Args& a, int64_t* U_out,
                int64_t* G_out, cudaStream_t s) {
   const int64_t U = (int64_t)a.batch * a.rtiles * a.ktiles;
@@ -468,10 +473,10 @@ int launch_f11(const CUtensorMap& tmX, const CUtensorMap& tmTk, const CUtensorMa
   const size_t smem = (size_t)a.nx * X_BYTES + (size_t)(a.nk + a.nm) * IMG_BYTES + (2 * a.nx + 2 * a.nk + 2 * a.nm + 5 * NG + 4) * 8 + 1024;
   static bool attr = false;
   if (!attr) {
-    MVAE_CUDA(cudaFuncSetAttribute(fc11_ts_kernel<GENE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(fc11_ts_kernel<GENE, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  fc11_ts_kernel<GENE><<<dim3((unsigned)G), THREADS, smem, s>>>(tmX, tmTk, tmTm, a);
+  fc11_ts_kernel<GENE, TRAIN><<<dim3((unsigned)G), THREADS, smem, s>>>(tmX, tmTk, tmTm, a);
   MVAE_LAUNCH_CHECK();
   *U_out = U; *G_out = G;
   return 0;
@@ -505,7 +510,8 @@ int ts_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
   rc = make_map_ex(&tmTm, st.params + L.offset[FC11_W], H, D, H, A, L.arm_stride, 32, UN, 2);
   if (rc) return rc;
   int64_t U, G;
-  rc = launch_f11<false>(tmX, tmTk, tmTm, a, &U, &G, s);
+  rc = (want_grad && !x_rec) ? launch_f11<false, true>(tmX, tmTk, tmTm, a, &U, &G, s)
+                             : launch_f11<false, false>(tmX, tmTk, tmTm, a, &U, &G, s);
   if (rc || !want_grad) return rc;
   f11_fixup_kernel<<<dim3((B + 127) / 128 * 8, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, work + w.g_d10, (int64_t)B * H, H, B, H);
   MVAE_LAUNCH_CHECK();
@@ -536,7 +542,7 @@ int ts_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& i
   rc = make_map_ex(&tmTm, work + w.d[4], H, B, H, A, (int64_t)B * H, 32, UN, 2);
   if (rc) return rc;
   int64_t U, G;
-  rc = launch_f11<true>(tmX, tmTk, tmTm, a, &U, &G, s);
+  rc = launch_f11<true, true>(tmX, tmTk, tmTm, a, &U, &G, s);
   if (rc) return rc;
   f11_fixup_kernel<<<dim3((D + 127) / 128 * 8, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, st.grads + L.offset[FC11_W], L.arm_stride,
                                                            H, D, H);
