@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(128) qstats_kernel(const CouplingArgs p) {
 }
 
 int launch_qstats(const CouplingArgs& a, cudaStream_t s) {
-  int gx = (a.B + 31) / 32;
-  if (gx > 148) gx = 148;
+  int gx = (a.B + 7) / 8;
+  if (gx > 592) gx = 592;
   qstats_kernel<<<dim3(gx, a.At), 128, 0, s>>>(a);
   MVAE_LAUNCH_CHECK();
   return 0;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
 
 int launch_coupling_rows(const CouplingArgs& a, cudaStream_t s) {
   int gx = (a.B + kRowWarps - 1) / kRowWarps;
-  if (gx > 296) gx = 296;
+  if (gx > 1184) gx = 1184;            // latency-bound per row: as many warps in flight as fit (8 CTAs per SM)
   coupling_rows_kernel<<<gx, kRowWarps * 32, 0, s>>>(a);
   MVAE_LAUNCH_CHECK();
   return 0;
