@@ -105,11 +105,12 @@ struct ChainArgs {
 // =============================================================================================
 // forward chain
 // =============================================================================================
-template <int MT, bool SPLIT>
+template <int MT, bool SPLIT, int HC, int LC>
 __global__ void __launch_bounds__(128 * MT) dec_chain_fwd_kernel(const ChainArgs p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int CR = 16 * MT, CT = 128 * MT;     // MT row groups x 4 column groups of warps (latency-bound: more warps)
-  const int XP = p.XP, WPF = p.XP, Hp = p.Hp;
+  constexpr bool FAST = HC > 0;
+  const int XP = FAST ? (((HC + 7) & ~7) + 4) : p.XP, WPF = XP, Hp = FAST ? ((HC + 7) & ~7) : p.Hp;
   float* Ws0 = smem;                       // [Hp][WPF]
   float* Ws1 = Ws0 + Hp * WPF;
   float* Xs0 = Ws1 + Hp * WPF;             // [CR][XP]
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(128 * MT) dec_chain_fwd_kernel(const ChainArgs
   const int arm = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const int warp = tid >> 5, wr = warp % MT, wc = warp / MT;
   const int g = lane >> 2, tig = lane & 3;
-  const int H = p.H, L = p.L, B = p.B;
+  const int H = FAST ? HC : p.H, L = FAST ? LC : p.L, B = p.B;
   const int row0 = blockIdx.x * CR;
   const int rows_valid = min(CR, B - row0);
   const float* par = p.params + (int64_t)arm * p.p_arm_stride;
@@ -139,6 +140,8 @@ __global__ void __launch_bounds__(128 * MT) dec_chain_fwd_kernel(const ChainArgs
   float* Ws[2] = {Ws0, Ws1};
   float* Xs[2] = {Xs0, Xs1};
   constexpr int NTW = 4;
+  constexpr int UNR = FAST ? 4 : 1;
+#pragma unroll UNR
   for (int l = 0; l < 4; ++l) {
     const int K = l == 0 ? L : H;
     const int ksteps = (K + 7) / 8;
@@ -150,7 +153,17 @@ __global__ void __launch_bounds__(128 * MT) dec_chain_fwd_kernel(const ChainArgs
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
     const int nt_used = max(0, min(NTW, (H + 7) / 8 - wc * NTW));
-    warp_gemm2<NTW, true, SPLIT>(Xs[l & 1] + wr * 16 * XP, XP, Ws[l & 1] + wc * NTW * 8 * WPF, WPF, ksteps, nt_used, acc, lane);
+    {
+      const float* Aw = Xs[l & 1] + wr * 16 * XP;
+      const float* Bw = Ws[l & 1] + wc * NTW * 8 * WPF;
+      if (FAST) {
+        const int nt_total = (H + 7) / 8, full = nt_total / NTW, rem = nt_total % NTW;      // constants
+        if (wc < full) warp_gemm2<NTW, true, SPLIT>(Aw, XP, Bw, WPF, ksteps, NTW, acc, lane);
+        else if (wc == full && rem > 0) warp_gemm2<NTW, true, SPLIT>(Aw, XP, Bw, WPF, ksteps, rem, acc, lane);
+      } else {
+        warp_gemm2<NTW, true, SPLIT>(Aw, XP, Bw, WPF, ksteps, nt_used, acc, lane);
+      }
+    }
     // epilogue: bias + ReLU -> global h_{7+l} and the next layer's operand tile
     float* out = p.hout[l] + ((int64_t)arm * B + row0) * H;
     float* Xn = Xs[(l + 1) & 1];
@@ -181,11 +194,14 @@ __global__ void __launch_bounds__(128 * MT) dec_chain_fwd_kernel(const ChainArgs
 // =============================================================================================
 // backward chain: delta_l = g * [h_l > 0];  g_{l-1} = delta_l . W_l
 // =============================================================================================
-template <int MT, bool SPLIT>
+template <int MT, bool SPLIT, int HC, int LC>
 __global__ void __launch_bounds__(128 * MT) dec_chain_bwd_kernel(const ChainArgs p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int CR = 16 * MT, CT = 128 * MT;
-  const int XP = p.XP, WPB = p.WPB, Hp = p.Hp;
+  constexpr bool FAST = HC > 0;
+  constexpr int HPC = (HC + 7) & ~7;
+  const int XP = FAST ? HPC + 4 : p.XP, Hp = FAST ? HPC : p.Hp;
+  const int WPB = FAST ? (((HPC & 31) == 8 || (HPC & 31) == 24) ? HPC : p.WPB) : p.WPB;
   float* Ws0 = smem;                       // [Hp][WPB]  W_l natural: row j (out), col i (in)
   float* Ws1 = Ws0 + Hp * WPB;
   float* Gs = Ws1 + Hp * WPB;              // [CR][XP]   gradient wrt h_l, then delta_l in place
@@ -194,7 +210,7 @@ __global__ void __launch_bounds__(128 * MT) dec_chain_bwd_kernel(const ChainArgs
   const int arm = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const int warp = tid >> 5, wr = warp % MT, wc = warp / MT;
   const int g = lane >> 2, tig = lane & 3;
-  const int H = p.H, L = p.L, B = p.B;
+  const int H = FAST ? HC : p.H, L = FAST ? LC : p.L, B = p.B;
   const int row0 = blockIdx.x * CR;
   const int rows_valid = min(CR, B - row0);
   const float* par = p.params + (int64_t)arm * p.p_arm_stride;
@@ -214,6 +230,8 @@ __global__ void __launch_bounds__(128 * MT) dec_chain_bwd_kernel(const ChainArgs
   float* Ws[2] = {Ws0, Ws1};
   float* Ms[2] = {Ms0, Ms1};
   constexpr int NTW = 4;
+  constexpr int UNR = FAST ? 4 : 1;
+#pragma unroll UNR
   for (int it = 0; it < 4; ++it) {
     const int l = 3 - it;                  // layer index 3..0 = fc10..fc7
     const int nin = l == 0 ? L : H;        // inputs of this layer
@@ -241,7 +259,17 @@ __global__ void __launch_bounds__(128 * MT) dec_chain_bwd_kernel(const ChainArgs
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
     const int nt_used = max(0, min(NTW, (nin + 7) / 8 - wc * NTW));
-    warp_gemm2<NTW, false, SPLIT>(Gs + wr * 16 * XP, XP, Ws[it & 1] + wc * NTW * 8, WPB, (H + 7) / 8, nt_used, acc, lane);
+    {
+      const float* Aw = Gs + wr * 16 * XP;
+      const float* Bw = Ws[it & 1] + wc * NTW * 8;
+      if (FAST) {
+        const int nt_total = (nin + 7) / 8, full = nt_total / NTW, rem = nt_total % NTW;    // constants once unrolled
+        if (wc < full) warp_gemm2<NTW, false, SPLIT>(Aw, XP, Bw, WPB, (H + 7) / 8, NTW, acc, lane);
+        else if (wc == full && rem > 0) warp_gemm2<NTW, false, SPLIT>(Aw, XP, Bw, WPB, (H + 7) / 8, rem, acc, lane);
+      } else {
+        warp_gemm2<NTW, false, SPLIT>(Aw, XP, Bw, WPB, (H + 7) / 8, nt_used, acc, lane);
+      }
+    }
     __syncthreads();                       // all warps have read delta before it is overwritten by the new g
     const int ra = wr * 16 + g, rb = ra + 8;
     float* g6 = p.g6 + rbase * L;
@@ -316,11 +344,14 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int n) 
   __syncthreads();
 }
 
-template <int MT, int NWC>
+// HC / LC > 0: fc_dim / lowD_dim known at compile time (the reference defaults 100 / 10): pitches, k-step counts and the
+// number of column tiles per warp become constants, which shrinks the MMA loop ~5x (it is issue/latency-bound).
+template <int MT, int NWC, int HC, int LC>
 __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncChainArgs p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int CR = 16 * MT, CT = 32 * MT * NWC, NTW = 16 / NWC;   // MT row groups x NWC column groups of warps
-  const int XP = p.XP, Hp = p.Hp;
+  constexpr bool FAST = HC > 0;
+  const int XP = FAST ? (((HC + 7) & ~7) + 4) : p.XP, Hp = FAST ? ((HC + 7) & ~7) : p.Hp;
   float* Ws0 = smem;                       // [Hp][XP]  W natural [out][in]
   float* Ws1 = Ws0 + Hp * XP;
   float* Xs0 = Ws1 + Hp * XP;              // [CR][XP]
@@ -332,7 +363,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
   const int arm = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const int warp = tid >> 5, wr = warp % MT, wc = warp / MT;
   const int g = lane >> 2, tig = lane & 3;
-  const int H = p.H, L = p.L, B = p.B;
+  const int H = FAST ? HC : p.H, L = FAST ? LC : p.L, B = p.B;
   const int row0 = blockIdx.x * CR;
   const int rows_valid = min(CR, B - row0);
   const float* par = p.params + (int64_t)arm * p.p_arm_stride;
@@ -353,6 +384,8 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
 
   float* Ws[2] = {Ws0, Ws1};
   float* Xs[2] = {Xs0, Xs1};
+  constexpr int UNR = FAST ? 4 : 1;
+#pragma unroll UNR
   for (int l = 0; l < 4; ++l) {
     const int nout = l < 3 ? H : L;
     // ---- batch statistics of this layer's input (complete: previous kernel for l == 0, grid barrier otherwise)
@@ -385,7 +418,17 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
     const int nt_used = max(0, min(NTW, (nout + 7) / 8 - wc * NTW));
-    warp_gemm2<NTW, true, true>(Xc + wr * 16 * XP, XP, Ws[l & 1] + wc * NTW * 8 * XP, XP, (H + 7) / 8, nt_used, acc, lane);
+    {
+      const float* Aw = Xc + wr * 16 * XP;
+      const float* Bw = Ws[l & 1] + wc * NTW * 8 * XP;
+      if (FAST) {
+        const int nt_total = (nout + 7) / 8, full = nt_total / NTW, rem = nt_total % NTW;   // constants once unrolled
+        if (wc < full) warp_gemm2<NTW, true, true>(Aw, XP, Bw, XP, (H + 7) / 8, NTW, acc, lane);
+        else if (wc == full && rem > 0) warp_gemm2<NTW, true, true>(Aw, XP, Bw, XP, (H + 7) / 8, rem, acc, lane);
+      } else {
+        warp_gemm2<NTW, true, true>(Aw, XP, Bw, XP, (H + 7) / 8, nt_used, acc, lane);
+      }
+    }
     // ---- epilogue: bias + ReLU -> global a_{l+2}, the next operand tile, fp64 column sums of the valid rows
     float* out = p.aout[l] + ((int64_t)arm * B + row0) * nout;
     float* Xn = Xs[(l + 1) & 1];
@@ -456,11 +499,14 @@ struct EncBwdArgs {
   unsigned int* bar;
 };
 
-template <int MT, int NWC, bool SPLIT>
+template <int MT, int NWC, bool SPLIT, int HC, int LC>
 __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncBwdArgs p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int CR = 16 * MT, CT = 32 * MT * NWC, NTW = 16 / NWC;
-  const int XP = p.XP, WPB = p.WPB, Hp = p.Hp;
+  constexpr bool FAST = HC > 0;
+  constexpr int HPC = (HC + 7) & ~7;
+  const int XP = FAST ? HPC + 4 : p.XP, Hp = FAST ? HPC : p.Hp;
+  const int WPB = FAST ? (((HPC & 31) == 8 || (HPC & 31) == 24) ? HPC : p.WPB) : p.WPB;
   float* Ws0 = smem;                       // [Hp][WPB]  W_l natural: row j (out), col i (in)
   float* Ws1 = Ws0 + Hp * WPB;
   float* Gs = Ws1 + Hp * WPB;              // [CR][XP]   g_l, then delta_l in place, then g_{l-1}
@@ -476,7 +522,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncB
   const int arm = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const int warp = tid >> 5, wr = warp % MT, wc = warp / MT;
   const int g = lane >> 2, tig = lane & 3;
-  const int H = p.H, L = p.L, B = p.B;
+  const int H = FAST ? HC : p.H, L = FAST ? LC : p.L, B = p.B;
   const int row0 = blockIdx.x * CR;
   const int rows_valid = min(CR, B - row0);
   const float* par = p.params + (int64_t)arm * p.p_arm_stride;
@@ -496,6 +542,8 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncB
 
   float* Ws[2] = {Ws0, Ws1};
   float* As[2] = {As0, As1};
+  constexpr int UNR = FAST ? 5 : 1;
+#pragma unroll UNR
   for (int it = 0; it < 5; ++it) {
     const int l = 4 - it;
     const int nout = l == 4 ? L : H;
@@ -534,7 +582,17 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncB
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
     const int nt_used = max(0, min(NTW, (H + 7) / 8 - wc * NTW));
-    warp_gemm2<NTW, false, SPLIT>(Gs + wr * 16 * XP, XP, Ws[it & 1] + wc * NTW * 8, WPB, (nout + 7) / 8, nt_used, acc, lane);
+    {
+      const float* Aw = Gs + wr * 16 * XP;
+      const float* Bw = Ws[it & 1] + wc * NTW * 8;
+      if (FAST) {
+        const int nt_total = (H + 7) / 8, full = nt_total / NTW, rem = nt_total % NTW;      // constants
+        if (wc < full) warp_gemm2<NTW, false, SPLIT>(Aw, XP, Bw, WPB, (nout + 7) / 8, NTW, acc, lane);
+        else if (wc == full && rem > 0) warp_gemm2<NTW, false, SPLIT>(Aw, XP, Bw, WPB, (nout + 7) / 8, rem, acc, lane);
+      } else {
+        warp_gemm2<NTW, false, SPLIT>(Aw, XP, Bw, WPB, (nout + 7) / 8, nt_used, acc, lane);
+      }
+    }
     __syncthreads();                       // all warps have read delta_l before g_{l-1} overwrites it
     // ---- epilogue: g_{l-1} -> Gs; fp64 sums of g and g * n_{l-1} over the valid rows
     const float* An = As[(it + 1) & 1];
@@ -619,8 +677,13 @@ int launch_dec_chain_fwd(const float* params, int64_t p_arm_stride, const int64_
   const size_t smem = (size_t)(2 * c.Hp * c.XP + 2 * cr * c.XP + 4 * 128) * 4;
 #define CHAIN_LAUNCH(MTV, SP)                                                                                        \
   do {                                                                                                              \
-    MVAE_CUDA(cudaFuncSetAttribute(dec_chain_fwd_kernel<MTV, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    dec_chain_fwd_kernel<MTV, SP><<<dim3((B + cr - 1) / cr, A), 128 * MTV, smem, s>>>(c);                            \
+    if (H == 100 && L == 10) {                                                                                      \
+      MVAE_CUDA(cudaFuncSetAttribute(dec_chain_fwd_kernel<MTV, SP, 100, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      dec_chain_fwd_kernel<MTV, SP, 100, 10><<<dim3((B + cr - 1) / cr, A), 128 * MTV, smem, s>>>(c);                  \
+    } else {                                                                                                        \
+      MVAE_CUDA(cudaFuncSetAttribute(dec_chain_fwd_kernel<MTV, SP, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      dec_chain_fwd_kernel<MTV, SP, 0, 0><<<dim3((B + cr - 1) / cr, A), 128 * MTV, smem, s>>>(c);                     \
+    }                                                                                                               \
   } while (0)
   if (mt == 5 && split3) CHAIN_LAUNCH(5, true);
   else if (mt == 5) CHAIN_LAUNCH(5, false);
@@ -642,8 +705,13 @@ int launch_dec_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
   const size_t smem = (size_t)(2 * c.Hp * c.WPB + 3 * cr * c.XP) * 4;
 #define CHAIN_LAUNCH(MTV, SP)                                                                                        \
   do {                                                                                                              \
-    MVAE_CUDA(cudaFuncSetAttribute(dec_chain_bwd_kernel<MTV, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    dec_chain_bwd_kernel<MTV, SP><<<dim3((B + cr - 1) / cr, A), 128 * MTV, smem, s>>>(c);                            \
+    if (H == 100 && L == 10) {                                                                                      \
+      MVAE_CUDA(cudaFuncSetAttribute(dec_chain_bwd_kernel<MTV, SP, 100, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      dec_chain_bwd_kernel<MTV, SP, 100, 10><<<dim3((B + cr - 1) / cr, A), 128 * MTV, smem, s>>>(c);                  \
+    } else {                                                                                                        \
+      MVAE_CUDA(cudaFuncSetAttribute(dec_chain_bwd_kernel<MTV, SP, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      dec_chain_bwd_kernel<MTV, SP, 0, 0><<<dim3((B + cr - 1) / cr, A), 128 * MTV, smem, s>>>(c);                     \
+    }                                                                                                               \
   } while (0)
   if (mt == 5 && split3) CHAIN_LAUNCH(5, true);
   else if (mt == 5) CHAIN_LAUNCH(5, false);
@@ -691,11 +759,15 @@ int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_
   const size_t smem = (size_t)(2 * c.Hp * c.XP + 2 * CR * c.XP + 4 * 128 + 256) * 4 + (size_t)MT * 2 * 128 * 8;
   static bool attr = false;
   if (!attr) {
-    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_fwd_kernel<MT, NWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_fwd_kernel<MT, NWC, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_fwd_kernel<MT, NWC, 100, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   void* args[] = {(void*)&c};
-  MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_fwd_kernel<MT, NWC>, dim3(tiles, A), dim3(32 * MT * NWC), args, smem, s));
+  if (H == 100 && L == 10)
+    MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_fwd_kernel<MT, NWC, 100, 10>, dim3(tiles, A), dim3(32 * MT * NWC), args, smem, s));
+  else
+    MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_fwd_kernel<MT, NWC, 0, 0>, dim3(tiles, A), dim3(32 * MT * NWC), args, smem, s));
   MVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -732,15 +804,19 @@ int launch_enc_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
   if ((int64_t)tiles * A > nsm) return 1;             // must be one co-resident wave (grid barrier)
   const size_t smem = (size_t)(2 * c.Hp * c.WPB + 3 * CR * c.XP + 6 * 128) * 4 + (size_t)MT * 2 * 128 * 8;
   void* args[] = {(void*)&c};
-  if (split3) {
-    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_bwd_kernel<MT, NWC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_bwd_kernel<MT, NWC, true>, dim3(tiles, A), dim3(32 * MT * NWC), args,
-                                          smem, s));
-  } else {
-    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_bwd_kernel<MT, NWC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_bwd_kernel<MT, NWC, false>, dim3(tiles, A), dim3(32 * MT * NWC), args,
-                                          smem, s));
-  }
+#define ENC_BWD(SP, HCV, LCV)                                                                                              \
+  do {                                                                                                                     \
+    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_bwd_kernel<MT, NWC, SP, HCV, LCV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                   (int)smem));                                                                           \
+    MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_bwd_kernel<MT, NWC, SP, HCV, LCV>, dim3(tiles, A),               \
+                                          dim3(32 * MT * NWC), args, smem, s));                                           \
+  } while (0)
+  const bool fast = (H == 100 && L == 10);
+  if (split3 && fast) ENC_BWD(true, 100, 10);
+  else if (split3) ENC_BWD(true, 0, 0);
+  else if (fast) ENC_BWD(false, 100, 10);
+  else ENC_BWD(false, 0, 0);
+#undef ENC_BWD
   MVAE_LAUNCH_CHECK();
   return 0;
 }
