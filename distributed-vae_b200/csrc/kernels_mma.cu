@@ -538,7 +538,12 @@ __global__ void __launch_bounds__(512) wgrad_mma_kernel(const WgArgs p) {
     store_chunk(rb);
     __syncthreads();
     if (rb + WG_CHUNK < r1) load_chunk(rb + WG_CHUNK);
-    if (active) warp_gemm<8, true, SPLIT>(Ds + warp * 16, 136, Is + wn * 64, 136, WG_CHUNK / 8, nt_used, acc, lane);
+    if (active) {
+      // constant tile counts for the common shapes (nin = 100: 8 + 5 tiles): the per-tile guards fold away
+      if (nt_used == 8) warp_gemm<8, true, SPLIT>(Ds + warp * 16, 136, Is + wn * 64, 136, WG_CHUNK / 8, 8, acc, lane);
+      else if (nt_used == 5) warp_gemm<8, true, SPLIT>(Ds + warp * 16, 136, Is + wn * 64, 136, WG_CHUNK / 8, 5, acc, lane);
+      else warp_gemm<8, true, SPLIT>(Ds + warp * 16, 136, Is + wn * 64, 136, WG_CHUNK / 8, nt_used, acc, lane);
+    }
   }
   if (!active) return;
   float* part = p.part + (int64_t)split * p.part_split_stride + (int64_t)arm * p.part_arm_stride;
