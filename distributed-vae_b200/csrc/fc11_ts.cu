@@ -159,10 +159,11 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_after();
       const uint32_t tma = smem_u32(tm(sm));
       if (elect_one()) {
+        const uint64_t md0 = make_smem_desc(tma, 4096, 512, true);
+        const uint32_t a2 = tb + COL_A2 + (uint32_t)g * 32u;
 #pragma unroll
         for (int ks = 0; ks < UN / 8; ++ks)
-          umma_tf32_ts(tb + COL_ACC2, tb + COL_A2 + (uint32_t)g * 32u + ks * 8, make_smem_desc(tma + ks * 1024, 4096, 512, true),
-                       idesc2, (acc2 | (uint32_t)ks) ? 1u : 0u);
+          umma_tf32_ts(tb + COL_ACC2, a2 + ks * 8, md0 + (uint64_t)((ks * 1024) >> 4), idesc2, (acc2 | (uint32_t)ks) ? 1u : 0u);
         umma_commit(a2_empty + g);
         umma_commit(m_empty + sm);
         if (last) umma_commit(acc2_full + ((seg - 1) & (NG - 1)));
@@ -189,9 +190,14 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_after();
       const uint32_t tka = smem_u32(tk(sk));
       if (elect_one()) {
-        for (int ks = 0; ks < ksteps1; ++ks)
-          umma_tf32_ts(tb + COL_ACC1 + (uint32_t)g * 32u, tb + COL_R + ks * 8,
-                       make_smem_desc(tka + (ks >> 2) * 4096 + (ks & 3) * 32, 0, 1024, false), idesc1, ks > 0 ? 1u : 0u);
+        // fully unrolled with one descriptor per unit: the k-step offsets are immediates (a rolled loop spends ~15
+        // uniform-datapath instructions per MMA on descriptor arithmetic, which made MMA issue the bottleneck)
+        const uint64_t kd0 = make_smem_desc(tka, 0, 1024, false);
+        const uint32_t dacc = tb + COL_ACC1 + (uint32_t)g * 32u, aR = tb + COL_R;
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks)
+          if (ks < ksteps1)
+            umma_tf32_ts(dacc, aR + ks * 8, kd0 + (uint64_t)(((ks >> 2) * 4096 + (ks & 3) * 32) >> 4), idesc1, ks > 0 ? 1u : 0u);
         umma_commit(acc1_full + g);
         umma_commit(k_empty + sk);
         if (!want_grad && ((kt + 1 == KT) || (i == nu - 1))) umma_commit(acc2_full + ((seg - 1) & (NG - 1)));   // loss-only: segment end marker
