@@ -26,7 +26,7 @@ using namespace tc;
 
 constexpr int UN = 32;                     // columns per unit (genes for ROW, cells for GENE)
 constexpr int NG = 4;                      // epilogue groups (4 warps each)
-constexpr int CTRL_WARPS = 3;              // x TMA, small-operand TMA, MMA issue
+constexpr int CTRL_WARPS = 4;              // x TMA, small-operand TMA, MMA1 issue, MMA2 issue
 constexpr int THREADS = 32 * (CTRL_WARPS + 4 * NG);
 constexpr int X_BYTES = 16384;
 constexpr int IMG_BYTES = 16384;           // one image of the small operand tile: 4 slabs of [32 rows x 128 B]
@@ -144,54 +144,25 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (++kt == KT) { kt = 0; if (++arm == a.batch) arm = 0; }
     }
   } else if (warp == 2) {
-    // ===== MMA issuer (uniform loop, one elected lane issues) =====
+    // ===== MMA1 issuer: acc1[g] = R . T_K^T (uniform loop, one elected lane issues).  MMA1 and MMA2 are issued by two
+    // warps: one warp doing both spent ~1900 cycles per unit in its own serial latencies (four satisfied mbarrier
+    // waits at ~170 cycles each, commits, fences) and was the bottleneck of the kernel, not the tensor pipe.
     const uint32_t idesc1 = make_idesc(128, UN, false, false);
-    const uint32_t idesc2 = make_idesc(128, a.HN, false, true);
     const int ksteps1 = (a.H + 7) / 8;
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    int kt = kt_first, sk = 0, sm = 0, seg = 0;
-    uint32_t phk = 0, phm = 0, acc2 = 0;
-    // MMA2 of unit j (its dY is in A2 stage j % NG); `last`: the segment ends with this unit
-    auto mma2 = [&](int j, bool last) {
-      const int g = j & (NG - 1);
-      mbar_wait(m_full + sm, phm);
-      mbar_wait(a2_full + g, (j / NG) & 1);
-      tc_fence_after();
-      const uint32_t tma = smem_u32(tm(sm));
-      if (elect_one()) {
-        const uint64_t md0 = make_smem_desc(tma, 4096, 512, true);
-        const uint32_t a2 = tb + COL_A2 + (uint32_t)g * 32u;
-#pragma unroll
-        for (int ks = 0; ks < UN / 8; ++ks)
-          umma_tf32_ts(tb + COL_ACC2, a2 + ks * 8, md0 + (uint64_t)((ks * 1024) >> 4), idesc2, (acc2 | (uint32_t)ks) ? 1u : 0u);
-        umma_commit(a2_empty + g);
-        umma_commit(m_empty + sm);
-        if (last) umma_commit(acc2_full + ((seg - 1) & (NG - 1)));
-      }
-      __syncwarp();
-      acc2 = last ? 0u : 1u;
-      if (++sm == a.nm) { sm = 0; phm ^= 1; }
-    };
-    // MMA1 runs up to SKEW units ahead of MMA2, so that all NG epilogue groups have a unit to work on
-    constexpr int SKEW = NG - 1;
-    int next2 = 0;                                   // first unit whose MMA2 has not been issued yet
+    int kt = kt_first, sk = 0, seg = 0;
+    uint32_t phk = 0;
     for (int i = 0; i < nu; ++i) {
       const int g = i & (NG - 1);
-      const bool new_seg = (i == 0) || (kt == 0);
-      if (new_seg) {
-        // flush: the old segment must complete before R changes
-        if (want_grad)
-          while (next2 < i) { mma2(next2, next2 == i - 1); ++next2; }
+      if ((i == 0) || (kt == 0)) {                 // new segment: R (and the drained acc2) must be in place
         mbar_wait(r_full, seg & 1);
         ++seg;
       }
-      mbar_wait(k_full + sk, phk);
-      mbar_wait(acc1_empty + g, ((i / NG) & 1) ^ 1);
+      mbar_wait2(k_full + sk, phk, acc1_empty + g, ((i / NG) & 1) ^ 1);
       tc_fence_after();
       const uint32_t tka = smem_u32(tk(sk));
       if (elect_one()) {
-        // fully unrolled with one descriptor per unit: the k-step offsets are immediates (a rolled loop spends ~15
-        // uniform-datapath instructions per MMA on descriptor arithmetic, which made MMA issue the bottleneck)
+        // fully unrolled with one descriptor per unit: the k-step offsets are immediates
         const uint64_t kd0 = make_smem_desc(tka, 0, 1024, false);
         const uint32_t dacc = tb + COL_ACC1 + (uint32_t)g * 32u, aR = tb + COL_R;
 #pragma unroll
@@ -204,12 +175,38 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       __syncwarp();
       if (++sk == a.nk) { sk = 0; phk ^= 1; }
-      if (want_grad)
-        while (i - next2 >= SKEW) { mma2(next2, false); ++next2; }
       if (++kt == KT) kt = 0;
     }
-    if (want_grad)
-      while (next2 < nu) { mma2(next2, next2 == nu - 1); ++next2; }
+  } else if (warp == 3) {
+    // ===== MMA2 issuer: acc2 += dY[g] . T_MN (dY was written to TMEM by epilogue group g) =====
+    if (want_grad) {
+      const uint32_t idesc2 = make_idesc(128, a.HN, false, true);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      int kt = kt_first, sm = 0, seg = 0;
+      uint32_t phm = 0, acc2 = 0;
+      for (int j = 0; j < nu; ++j) {
+        const int g = j & (NG - 1);
+        const bool last = (kt + 1 == KT) || (j == nu - 1);       // the segment ends with this unit
+        mbar_wait2(m_full + sm, phm, a2_full + g, (j / NG) & 1);
+        tc_fence_after();
+        const uint32_t tma = smem_u32(tm(sm));
+        if (elect_one()) {
+          const uint64_t md0 = make_smem_desc(tma, 4096, 512, true);
+          const uint32_t a2 = tb + COL_A2 + (uint32_t)g * 32u;
+#pragma unroll
+          for (int ks = 0; ks < UN / 8; ++ks)
+            umma_tf32_ts(tb + COL_ACC2, a2 + ks * 8, md0 + (uint64_t)((ks * 1024) >> 4), idesc2, (acc2 | (uint32_t)ks) ? 1u : 0u);
+          umma_commit(a2_empty + g);
+          umma_commit(m_empty + sm);
+          if (last) umma_commit(acc2_full + (seg & (NG - 1)));
+        }
+        __syncwarp();
+        acc2 = last ? 0u : 1u;
+        if (last) ++seg;
+        if (++sm == a.nm) { sm = 0; phm ^= 1; }
+        if (++kt == KT) kt = 0;
+      }
+    }
   } else {
     // ===== epilogue groups =====
     const int quad = warp & 3, grp = (warp - CTRL_WARPS) >> 2;

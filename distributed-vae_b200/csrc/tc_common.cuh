@@ -44,6 +44,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Wait for two barriers whose results are independent: both try_waits are in flight together (a satisfied try_wait
+// still costs ~150 cycles of latency, which adds up in the single-warp issue loops).
+__device__ __forceinline__ void mbar_wait2(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb) {
+  const bool ra = mbar_try_wait(a, pa), rb = mbar_try_wait(b, pb);
+  if (ra && rb) return;
+  if (!ra) mbar_wait(a, pa);
+  if (!rb) mbar_wait(b, pb);
+}
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
