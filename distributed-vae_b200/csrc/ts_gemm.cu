@@ -152,16 +152,24 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         acc = 0;
         mbar_wait(acc_empty, (seg & 1) ^ 1);
       }
-      mbar_wait(w_full + sw, phw);
+      // the three barriers of a unit are waited for together (a satisfied try_wait still costs ~150 cycles of latency)
+      {
+        const int j0 = NB * i, j1 = NB * i + 1;
+        const bool r0 = mbar_try_wait(w_full + sw, phw);
+        const bool r1 = mbar_try_wait(a_full + (j0 & (NA - 1)), (j0 / NA) & 1);
+        const bool r2 = mbar_try_wait(a_full + (j1 & (NA - 1)), (j1 / NA) & 1);
+        if (!r0) mbar_wait(w_full + sw, phw);
+        if (!r1) mbar_wait(a_full + (j0 & (NA - 1)), (j0 / NA) & 1);
+        if (!r2) mbar_wait(a_full + (j1 & (NA - 1)), (j1 / NA) & 1);
+      }
+      tc_fence_after();
       const uint32_t wb = smem_u32(ws(sw));
+      if (elect_one()) {
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        const int j = NB * i + b, sa = j & (NA - 1);
-        const uint32_t dcol = tb + (uint32_t)b * 128u;
-        mbar_wait(a_full + sa, (j / NA) & 1);
-        tc_fence_after();
-        const uint32_t a_hi = tb + ACC_COLS + (uint32_t)sa * 64u, a_lo = a_hi + 32u;
-        if (elect_one()) {
+        for (int b = 0; b < NB; ++b) {
+          const int j = NB * i + b, sa = j & (NA - 1);
+          const uint32_t dcol = tb + (uint32_t)b * 128u;
+          const uint32_t a_hi = tb + ACC_COLS + (uint32_t)sa * 64u, a_lo = a_hi + 32u;
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
             const uint32_t accf = (acc | (uint32_t)ks) ? 1u : 0u;
@@ -180,8 +188,8 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
           umma_commit(a_empty + sa);
         }
-        __syncwarp();
       }
+      __syncwarp();
       acc = 1;
       const bool seg_end = (kt + 1 == KT) || (i == nu - 1);
       if (elect_one()) {
