@@ -280,7 +280,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(acc1_empty + grp); mbar_arrive(x_empty + sx); }   // both are in registers now
+      if (lane == 0) mbar_arrive(acc1_empty + grp);        // the accumulator is in registers (tcgen05.wait::ld)
       bool a2_waited = false;
       float fs = 0.f, fm = 0.f;
       const float rscale = row_ok ? a.gscale : 0.f;        // rows beyond the batch contribute no gradient
@@ -338,6 +338,8 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           tmem_st8(ta2 + 16u * half + 8u, dy + 8);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_empty + sx);            // every value read from the x tile has been consumed by now
       if (!GENE && row_ok) { sse += (double)fs; mism += (double)fm; }
       if (want_grad) {
         tmem_st_wait();

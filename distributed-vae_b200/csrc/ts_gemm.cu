@@ -30,7 +30,7 @@ constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int NG = 4;                      // transform groups: group g owns the units i = g (mod NG) of its CTA
 constexpr int NTW = 4 * NG;                // transform / drain warps: 4 per group (one per TMEM lane quadrant)
-constexpr int CTRL_WARPS = 4;              // warp 0: TMA of x, warp 1: TMA of the small operand, warps 2-3: MMA issue (one per block)
+constexpr int CTRL_WARPS = 3;              // warp 0: TMA of x, warp 1: TMA of the small operand, warp 2: MMA issue
 constexpr int THREADS = 32 * (CTRL_WARPS + NTW);
 constexpr int NA = NG;                     // A-operand stages in tensor memory (64 columns each: hi | lo), one per group
 constexpr int X_BYTES = 16384;
@@ -82,9 +82,9 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.nx; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 4); }
-    for (int s = 0; s < a.nw; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, NB); }
+    for (int s = 0; s < a.nw; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
     for (int s = 0; s < NA; ++s) { mbar_init(a_full + s, 4); mbar_init(a_empty + s, 1); }
-    for (int s = 0; s < NA; ++s) mbar_init(acc_full + s, NB);
+    for (int s = 0; s < NA; ++s) mbar_init(acc_full + s, 1);
     mbar_init(acc_empty, 4 * NB);
     fence_barrier_init();
   }
@@ -140,13 +140,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (++sw == a.nw) { sw = 0; phw ^= 1; }
       if (++kt == KT) { kt = 0; if (++arm == a.batch) arm = 0; }
     }
-  } else if (warp == 2 || warp == 3) {
-    // ===== MMA issuers: warp 2 + b issues the MMAs of block b of every unit (uniform loop, one elected lane).  One warp
-    // for both blocks was issue-bound (in-kernel timestamps: ~2050 cycles per unit against 1620 of tensor-pipe time).
-    const int b = warp - 2;
+  } else if (warp == 2) {
+    // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues =====
     const uint32_t idesc = make_idesc(BM, a.BN, false, WGRAD);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t dcol = tb + (uint32_t)b * 128u;
     uint32_t acc = 0;
     int kt = kt_first, sw = 0, seg = 0;
     uint32_t phw = 0;
@@ -155,40 +152,51 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         acc = 0;
         mbar_wait(acc_empty, (seg & 1) ^ 1);
       }
-      const int j = NB * i + b, sa = j & (NA - 1);
-      mbar_wait2(w_full + sw, phw, a_full + sa, (j / NA) & 1);
+      // the three barriers of a unit are waited for together (a satisfied try_wait still costs ~150 cycles of latency)
+      {
+        const int j0 = NB * i, j1 = NB * i + 1;
+        const bool r0 = mbar_try_wait(w_full + sw, phw);
+        const bool r1 = mbar_try_wait(a_full + (j0 & (NA - 1)), (j0 / NA) & 1);
+        const bool r2 = mbar_try_wait(a_full + (j1 & (NA - 1)), (j1 / NA) & 1);
+        if (!r0) mbar_wait(w_full + sw, phw);
+        if (!r1) mbar_wait(a_full + (j0 & (NA - 1)), (j0 / NA) & 1);
+        if (!r2) mbar_wait(a_full + (j1 & (NA - 1)), (j1 / NA) & 1);
+      }
       tc_fence_after();
       const uint32_t wb = smem_u32(ws(sw));
-      const bool seg_end = (kt + 1 == KT) || (i == nu - 1);
       if (elect_one()) {
-        const uint32_t a_hi = tb + ACC_COLS + (uint32_t)sa * 64u, a_lo = a_hi + 32u;
-        if (!WGRAD) {
-          const uint64_t bh0 = make_smem_desc(wb, 0, 1024, false);
-          const uint64_t bl0 = make_smem_desc(wb + a.w_tile_bytes, 0, 1024, false);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const int j = NB * i + b, sa = j & (NA - 1);
+          const uint32_t dcol = tb + (uint32_t)b * 128u;
+          const uint32_t a_hi = tb + ACC_COLS + (uint32_t)sa * 64u, a_lo = a_hi + 32u;
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
             const uint32_t accf = (acc | (uint32_t)ks) ? 1u : 0u;
-            const uint64_t bh = bh0 + (uint64_t)((ks * 32) >> 4);
-            if (a.split3) {
-              umma_tf32_ts(dcol, a_lo + ks * 8, bh, idesc, accf);
-              umma_tf32_ts(dcol, a_hi + ks * 8, bl0 + (uint64_t)((ks * 32) >> 4), idesc, 1u);
-              umma_tf32_ts(dcol, a_hi + ks * 8, bh, idesc, 1u);
+            if (!WGRAD) {
+              const uint64_t bh = make_smem_desc(wb + ks * 32, 0, 1024, false);
+              if (a.split3) {
+                umma_tf32_ts(dcol, a_lo + ks * 8, bh, idesc, accf);
+                umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(wb + a.w_tile_bytes + ks * 32, 0, 1024, false), idesc, 1u);
+                umma_tf32_ts(dcol, a_hi + ks * 8, bh, idesc, 1u);
+              } else {
+                umma_tf32_ts(dcol, a_hi + ks * 8, bh, idesc, accf);
+              }
             } else {
-              umma_tf32_ts(dcol, a_hi + ks * 8, bh, idesc, accf);
+              umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(wb + ks * 1024, 4096, 512, true), idesc, accf);
             }
           }
-        } else {
-          const uint64_t bm0 = make_smem_desc(wb, 4096, 512, true);
-#pragma unroll
-          for (int ks = 0; ks < BK / 8; ++ks)
-            umma_tf32_ts(dcol, a_hi + ks * 8, bm0 + (uint64_t)((ks * 1024) >> 4), idesc, (acc | (uint32_t)ks) ? 1u : 0u);
+          umma_commit(a_empty + sa);
         }
-        umma_commit(a_empty + sa);
-        umma_commit(w_empty + sw);
-        if (seg_end) umma_commit(acc_full + (seg & (NA - 1)));          // this warp's block of the tile is complete
       }
       __syncwarp();
       acc = 1;
+      const bool seg_end = (kt + 1 == KT) || (i == nu - 1);
+      if (elect_one()) {
+        umma_commit(w_empty + sw);
+        if (seg_end) umma_commit(acc_full + (seg & (NA - 1)));          // this CTA's share of the tile is complete
+      }
+      __syncwarp();
       if (++sw == a.nw) { sw = 0; phw ^= 1; }
       if (++kt == KT) kt = 0;
       if (seg_end) ++seg;
@@ -232,10 +240,6 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           // thread = gene r, cells kt*32 + 16*half .. +15: column reads of the linear [32 cells][128 genes] tile
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const uint32_t*>(tile + (16 * half + j) * 512 + r * 4);
-        }
-        if (half == 1) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(x_empty + sx);        // the raw tile is in registers: hand the slot back
         }
         // ---- dropout: zero the dropped elements (the 1/(1-p) scale is applied by the fix-up kernel)
         if (dp.mode == 2) {
@@ -300,7 +304,9 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full + grp);
+      // the raw slot goes back only now: every value read from it has been consumed (a register dependency), so the
+      // shared-memory reads have certainly been performed before the TMA may overwrite the slot
+      if (lane == 0) { mbar_arrive(x_empty + sx); mbar_arrive(a_full + grp); }
       pha ^= 1;
       if (kt == KT - 1 || i == nu - 1) {
         // ---- drain this CTA's share of tile t into its partial slot (slot = cta + tile: unique, monotone)
