@@ -286,6 +286,12 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
           }
         }
+        if (half == 1 && dp.mode == 2) {
+          // every value read from the raw slot has been consumed by the mask selects above (register dependencies), so
+          // the shared-memory reads have been performed: hand the slot back before the TMEM stores
+          __syncwarp();
+          if (lane == 0) mbar_arrive(x_empty + sx);
+        }
         if (!waited) {
           mbar_wait(a_empty + grp, pha);                   // the MMAs that read this TMEM stage have completed
           tc_fence_after();
@@ -306,7 +312,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       __syncwarp();
       // the raw slot goes back only now: every value read from it has been consumed (a register dependency), so the
       // shared-memory reads have certainly been performed before the TMA may overwrite the slot
-      if (lane == 0) { mbar_arrive(x_empty + sx); mbar_arrive(a_full + grp); }
+      if (lane == 0) {
+        if (dp.mode != 2) mbar_arrive(x_empty + sx);       // (no consuming instruction before the stores in these modes)
+        mbar_arrive(a_full + grp);
+      }
       pha ^= 1;
       if (kt == KT - 1 || i == nu - 1) {
         // ---- drain this CTA's share of tile t into its partial slot (slot = cta + tile: unique, monotone)
