@@ -65,6 +65,10 @@ static DropSpec make_drop(const Plan& p, const mvae_hparams& hp, const mvae_inpu
   return d;
 }
 
+static uint64_t noise_seed(const mvae_inputs& in) {
+  return in.seed * 0xA24BAED4963EE407ull + in.step * 0x9FB21C651E98DF25ull + 0x632BE59BD9B4E019ull;
+}
+
 static BnOff bn_off(const Plan& p) {
   BnOff o;
   for (int i = 0; i < 6; ++i) o.off[i] = p.L.bn_offset[i];
@@ -99,8 +103,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   float* work = st.work;
   double* acc_fwd = reinterpret_cast<double*>(work + w.acc_fwd);
   const int training = in.training;
-  MVAE_CHECK_ARG(in.x != nullptr && in.E != nullptr, "x and E are required");
-  MVAE_CHECK_ARG(!training || in.U != nullptr, "U (Gumbel uniforms) is required in training mode");
+  MVAE_CHECK_ARG(in.x != nullptr, "x is required");   // U / E may be null: drawn in-kernel from (seed, step)
   MVAE_CHECK_ARG(!training || B >= 2, "training needs at least 2 cells (batch statistics)");
   MVAE_CHECK_ARG(!(training && hp.s_drop > 0.f) || in.keep_s != nullptr, "keep_s is required when s_drop > 0");
   MVAE_CHECK_ARG(in.x_row_stride >= D, "x_row_stride < D");
@@ -175,6 +178,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   h.bn_sums5 = acc_fwd + acc_bn(4, A, 0);
   h.bn_mean5 = bn_mean + (int64_t)4 * A * 128; h.bn_rstd5 = bn_rstd + (int64_t)4 * A * 128;
   h.U = in.U; h.E = in.E; h.keep_s = (training && hp.s_drop > 0.f) ? in.keep_s : nullptr;
+  h.noise_seed = noise_seed(in);
   h.tau = hp.tau; h.temp = hp.temp; h.eps = hp.eps; h.s_scale = 1.0f / (1.0f - hp.s_drop);
   h.hard = hp.hard; h.training = training;
   h.x_low = out.x_low; h.c_prob = out.c_prob; h.qc = out.qc; h.c_smp = out.c_smp;
@@ -345,6 +349,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   h.oWc = p.L.offset[FCC_W]; h.oBc = p.L.offset[FCC_B]; h.oWmu = p.L.offset[FCMU_W]; h.oBmu = p.L.offset[FCMU_B];
   h.oWsig = p.L.offset[FCSIG_W]; h.oBsig = p.L.offset[FCSIG_B]; h.oW6 = p.L.offset[FC6_W]; h.oB6 = p.L.offset[FC6_B];
   h.E = in.E; h.keep_s = hp.s_drop > 0.f ? in.keep_s : nullptr;
+  h.noise_seed = noise_seed(in);
   h.tau = hp.tau; h.temp = hp.temp; h.eps = hp.eps; h.s_scale = 1.0f / (1.0f - hp.s_drop);
   h.hard = hp.hard; h.training = 1;
   h.x_low = out.x_low; h.c_prob = out.c_prob; h.qc = out.qc; h.c_smp = out.c_smp;

@@ -164,6 +164,13 @@ __device__ __forceinline__ uint32_t drop_bits4(uint64_t seed, int arm, uint64_t 
   return mix32((uint32_t)chunk * 0x9E3779B1u ^ (uint32_t)(chunk >> 32) * 0x7FEB352Du ^ (uint32_t)seed ^
                ((uint32_t)(seed >> 32) * 0x846CA68Bu) ^ ((uint32_t)arm * 0x632BE5ABu));
 }
+// Counter-based Uniform[0,1) draw (24 random bits, like torch.rand for fp32): stream 1 = Gumbel uniforms U[arm][cell][category],
+// stream 2 = state noise E[arm][cell][s].  Used when the caller passes no noise tensors; the backward regenerates E.
+__device__ __forceinline__ float noise_uniform(uint64_t seed, uint32_t stream, uint64_t idx) {
+  const uint32_t h = mix32((uint32_t)idx * 0x9E3779B1u ^ (uint32_t)(idx >> 32) * 0x7FEB352Du ^ (uint32_t)seed ^
+                           ((uint32_t)(seed >> 32) * 0x846CA68Bu) ^ (stream * 0x68E31DA4u));
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
 __device__ __forceinline__ bool drop_keep(uint64_t seed, int arm, int64_t row, int64_t col, int64_t D,
                                           uint32_t thresh) {
   const uint64_t idx = (uint64_t)row * (uint64_t)D + (uint64_t)col;

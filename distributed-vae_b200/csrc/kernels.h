@@ -54,7 +54,8 @@ struct HeadArgs {
   int bn_mode;                // 1 batch sums, 2 given
   const double* bn_sums5;     // [A][2][128]
   float* bn_mean5; float* bn_rstd5;  // [A][128]
-  const float* U; const float* E; const uint8_t* keep_s;
+  const float* U; const float* E; const uint8_t* keep_s;   // U / E nullptr: in-kernel counter-based draws (noise_seed)
+  uint64_t noise_seed;
   float tau, temp, eps, s_scale; int hard, training;
   // forward outputs
   float *x_low, *c_prob, *qc, *c_smp, *s_mean, *s_logvar, *s_smp;

@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
       for (int k = 0; k < KC; ++k) {
         const int kk = lane + 32 * k;
         if (kk < C) {
-          const float u = p.U[r * C + kk];
+          const float u = p.U ? p.U[r * C + kk]
+                              : noise_uniform(p.noise_seed, 1u, ((uint64_t)(arm + p.arm_off) * B + row) * C + kk);
           const float g = -logf(-logf(u + p.eps) + p.eps);
           z[k] = (logf(q[k] + p.eps) + g) / p.temp;
           m = fmaxf(m, z[k]);
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
         const float lv = logf(var + p.eps);
         const float elv = expf(lv);
         const float sd = sqrtf(elv);
-        const float e = p.E[r * S + s];
+        const float e = p.E ? p.E[r * S + s] : noise_uniform(p.noise_seed, 2u, ((uint64_t)(arm + p.arm_off) * B + row) * S + s);
         const float smp = e * sd + mu;                     // uniform noise, nn_model.py:427
         float sd_in = smp;
         if (p.training && p.keep_s) sd_in = p.keep_s[r * S + s] ? smp * p.s_scale : 0.f;
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_bwd_kernel(const HeadA
         float gs = gsd[s];
         if (p.keep_s) gs = p.keep_s[r * S + s] ? gs * p.s_scale : 0.f;
         const float mu = p.s_mean[r * S + s], lv = p.s_logvar[r * S + s], var = p.svar[r * S + s];
-        const float e = p.E[r * S + s];
+        const float e = p.E ? p.E[r * S + s] : noise_uniform(p.noise_seed, 2u, ((uint64_t)(arm + p.arm_off) * B + row) * S + s);
         const float elv = expf(lv), sd = sqrtf(elv);
         const float gmu = gs + p.kl_coef * mu;
         const float glv = gs * e * 0.5f * sd + p.kl_coef * (-0.5f) * (1.f - elv);

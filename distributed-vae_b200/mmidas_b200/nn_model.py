@@ -316,8 +316,10 @@ class mixVAE_model(nn.Module):
         # draw order per arm in the reference: dropout mask, Gumbel uniforms, state noise;
         # here the streams are independent device draws (the reference has no noise-injection hook,
         # parity tests always inject).
-        U = get("U", (A, B, Cc), torch.float32, lambda: torch.rand(A, B, Cc, device=dev)) if training else None
-        E = get("E", (A, B, S), torch.float32, lambda: torch.rand(A, B, S, device=dev))
+        # U / E not injected: None -> the library draws them in-kernel (counter-based, keyed by torch.initial_seed()
+        # and the step counter; the backward regenerates the same E)
+        U = get("U", (A, B, Cc), torch.float32, lambda: None) if training else None
+        E = get("E", (A, B, S), torch.float32, lambda: None)
         keep_x = None
         if training and self.x_drop > 0 and noise.get("keep_x") is not None:
             keep_x = get("keep_x", (A, B, D), torch.uint8, None)
@@ -343,7 +345,7 @@ class mixVAE_model(nn.Module):
         st = self._state(dims)
         self._step_counter += 1
         inp = _lib.Inputs(xt.data_ptr(), x_arm_stride, x_row_stride,
-                          U.data_ptr() if U is not None else None, E.data_ptr(),
+                          U.data_ptr() if U is not None else None, E.data_ptr() if E is not None else None,
                           keep_x.data_ptr() if keep_x is not None else None,
                           keep_s.data_ptr() if keep_s is not None else None,
                           C.c_uint64(torch.initial_seed() & 0xFFFFFFFFFFFFFFFF), self._step_counter, int(training))
@@ -457,7 +459,8 @@ class mixVAE_model(nn.Module):
         m, v = optimizer.flat_state()
         st = self._state(dims, m, v)
         self._step_counter += 1
-        inp = _lib.Inputs(xt.data_ptr(), x_arm_stride, x_row_stride, U.data_ptr(), E.data_ptr(),
+        inp = _lib.Inputs(xt.data_ptr(), x_arm_stride, x_row_stride, U.data_ptr() if U is not None else None,
+                          E.data_ptr() if E is not None else None,
                           keep_x.data_ptr() if keep_x is not None else None,
                           keep_s.data_ptr() if keep_s is not None else None,
                           C.c_uint64(torch.initial_seed() & 0xFFFFFFFFFFFFFFFF), self._step_counter, 1)

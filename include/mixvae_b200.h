@@ -82,8 +82,9 @@ typedef struct mvae_inputs {
   const float* x;          /* [A or 1][B][D]                                                  */
   int64_t x_arm_stride;    /* floats between arms' inputs; 0 = all arms share x (x.expand)     */
   int64_t x_row_stride;    /* floats between rows (>= D)                                       */
-  const float* U;          /* [A][B][C] uniforms for the Gumbel noise (nn_model.py:440)        */
-  const float* E;          /* [A][B][S] uniforms for the state sample (nn_model.py:427)        */
+  const float* U;          /* [A][B][C] uniforms for the Gumbel noise (nn_model.py:440), or NULL */
+  const float* E;          /* [A][B][S] uniforms for the state sample (nn_model.py:427), or NULL */
+                           /* NULL: drawn in-kernel, counter-based on (seed, step, arm, cell, k) */
   const uint8_t* keep_x;   /* [A][B][D] input-dropout keep mask or NULL                        */
   const uint8_t* keep_s;   /* [A][B][S] state-dropout keep mask or NULL (s_drop == 0)          */
   uint64_t seed;           /* in-kernel dropout generator                                      */

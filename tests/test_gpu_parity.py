@@ -366,3 +366,39 @@ def test_ragged_shapes_match_oracle(shape, precision):
         tol = max(K * rel_l2(r32, r64), floor)
         e = rel_l2(grads[n], r64)
         assert e <= tol, (n, e, tol)
+
+
+def test_in_kernel_noise_is_uniform_and_regenerated_by_backward():
+    """Without injected noise the library draws U and E itself (counter-based).  Check the draws look uniform, are a
+    function of (seed, step), and that the backward regenerates the same E: recover the noise from the forward
+    outputs, inject it into a second model and compare the gradients."""
+    hp = O.HP(input_dim=520, n_categories=100, state_dim=2, n_arm=2, x_drop=0.0, s_drop=0.0)
+    B = 600
+    gen = torch.Generator().manual_seed(546)
+    x = O.synth_x(B, hp.input_dim, gen, 0.35).cuda()
+    m1 = build_model(hp, "tf32x3")
+    out, ls = _fwd_loss_bwd(m1, x, None, hp.temp)
+    x_recs, _, _, x_lows, cs, s_smps, c_smps, s_means, s_logvars, c_probs = out
+    torch.cuda.synchronize()
+    mu, lv, sm = torch.stack(s_means), torch.stack(s_logvars), torch.stack(s_smps)
+    E = (sm - mu) / lv.exp().sqrt()
+    assert float(E.min()) > -1e-3 and float(E.max()) < 1 + 1e-3
+    assert abs(float(E.mean()) - 0.5) < 0.03 and abs(float(E.var()) - 1 / 12) < 0.01
+    q, y = torch.stack(cs), torch.stack(c_smps)
+    # Gumbel noise up to a per-row constant (softmax-invariant): g' = temp * log y - log(q + eps)
+    g = hp.temp * torch.log(y.clamp_min(1e-30)) - torch.log(q + hp.eps)
+    g = g - g.amax(-1, keepdim=True)
+    U = torch.exp(-torch.exp(-g)).clamp(1e-7, 1 - 1e-7)
+    m2 = build_model(hp, "tf32x3")
+    noise = {"U": U, "E": E.clamp(0, 1), "keep_x": torch.ones(hp.n_arm, B, hp.input_dim, dtype=torch.bool),
+             "keep_s": torch.ones(hp.n_arm, B, hp.state_dim, dtype=torch.bool)}
+    out2, ls2 = _fwd_loss_bwd(m2, x, to_dev_noise(noise), hp.temp)
+    torch.cuda.synchronize()
+    assert abs(ls2[0].item() / ls[0].item() - 1) < 1e-3
+    g1, g2 = cuda_grads(m1), cuda_grads(m2)
+    for n in ("fc_mu.0.weight", "fc_sigma.1.weight", "fc6.0.weight", "fc11.1.bias", "fc1.0.weight"):
+        # (the recovered U is only accurate to ~1e-2 where y underflows; a backward using another E would be off by O(1))
+        assert rel_l2(g2[n], g1[n]) < 6e-2, (n, rel_l2(g2[n], g1[n]))
+    # a second step draws different noise
+    out3, _ = _fwd_loss_bwd(m1, x, None, hp.temp)
+    assert not torch.equal(torch.stack(out3[5]), sm)
