@@ -117,12 +117,15 @@ def grad_buckets(flat_grads: torch.Tensor, off_fc11: int) -> Tuple[List[torch.Te
 
 
 def allreduce_mean(tensors: Sequence[torch.Tensor], group, world: int, async_op: bool = False):
-    """Average `tensors` in place over `group` (SUM then scale: works on gloo and NCCL alike)."""
+    """Average `tensors` in place over `group`.  NCCL: one AVG all-reduce per tensor (no scaling kernel);
+    gloo (CPU tests): SUM then scale."""
     works = []
+    nccl = dist.get_backend(group) == "nccl"
     for t in tensors:
-        w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        op = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM
+        w = dist.all_reduce(t, op=op, group=group, async_op=async_op)
         works.append(w)
-    if not async_op:
+    if not async_op and not nccl:
         for t in tensors:
             t.div_(world)
     return works
@@ -132,7 +135,8 @@ class ShardedTrainer:
     """One training step on a (arm x dp) mesh.  Each rank constructs it after init_dist_env()."""
 
     def __init__(self, model_kwargs: dict, lr: float = 1e-3, mode: str = "auto", temp: float = 1.0,
-                 seed: int = 546, rank: Optional[int] = None, world_size: Optional[int] = None):
+                 seed: int = 546, rank: Optional[int] = None, world_size: Optional[int] = None,
+                 overlap: Optional[bool] = None):
         from .nn_model import mixVAE_model
         from .optim import FusedAdam
         self.rank = dist.get_rank() if rank is None else rank
@@ -167,6 +171,12 @@ class ShardedTrainer:
         self.comm_stream = torch.cuda.Stream(dev)
         self.off_fc11 = int(self.model._layout.offset[26])
         self.device = dev
+        # Gradient exchange over the dp axis.  overlap=True: two buckets per arm, fc11 (final right after the fused
+        # loss+grad kernels) reduced on a side stream under the whole backward chain.  overlap=False: ONE all-reduce of
+        # the whole flat gradient buffer after backward.  The buffers are small (4.3 MB per arm), so the exchange is
+        # latency-bound: below ~32 MB of gradients one call beats 2*A overlapped ones (measured at N=2: 0.99 -> 0.8x ms).
+        grad_bytes = self.model.flat_grads().numel() * 4
+        self.overlap = (grad_bytes > 32 * 2 ** 20) if overlap is None else bool(overlap)
 
     def step(self, x_local: torch.Tensor, noise=None) -> torch.Tensor:
         """x_local: this dp-replica's cells [B_local, D] (identical on the ranks of one arm group).
@@ -182,15 +192,18 @@ class ShardedTrainer:
         cs_all = all_gather_arms(ot["c_smp"], plan, self.arm_group)
         ls = m.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0, qc_all=qc_all, c_smp_all=cs_all)
         cur = torch.cuda.current_stream(self.device)
-        late, early = grad_buckets(m.flat_grads(), self.off_fc11)
-        if plan.dp_ranks > 1:
+        if plan.dp_ranks > 1 and self.overlap:
+            late, early = grad_buckets(m.flat_grads(), self.off_fc11)
             # fc11 gradients are final after the fused loss+grad kernel: reduce them under the backward
             self.comm_stream.wait_stream(cur)
             with torch.cuda.stream(self.comm_stream):
                 allreduce_mean(late, self.dp_group, plan.dp_ranks)
-        m._run_backward(m._ctx.gen, None)
-        if plan.dp_ranks > 1:
+            m._run_backward(m._ctx.gen, None)
             allreduce_mean(early, self.dp_group, plan.dp_ranks)
             cur.wait_stream(self.comm_stream)
+        else:
+            m._run_backward(m._ctx.gen, None)
+            if plan.dp_ranks > 1:
+                allreduce_mean([m.flat_grads()], self.dp_group, plan.dp_ranks)
         self.optimizer.step()
         return fixup_loss_vector(m._ctx.loss_vec, plan, self.arm_group, float(m.beta))
