@@ -530,4 +530,10 @@ int mvae_argmax(const float* q, int32_t* labels, int64_t rows, int32_t cols, voi
   return launch_argmax(q, labels, rows, cols, (cudaStream_t)stream);
 }
 
+int mvae_confmat(const int32_t* labels, int64_t n_cells, int32_t n_arm, int32_t n_categories, int32_t* counts, void* stream) {
+  MVAE_CHECK_ARG(labels && counts && n_arm >= 2 && n_categories >= 1 && n_cells >= 0, "bad argument");
+  RC(check_device());
+  return launch_confmat(labels, n_cells, n_arm, n_categories, counts, (cudaStream_t)stream);
+}
+
 }  // extern "C"

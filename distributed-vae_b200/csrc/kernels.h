@@ -147,6 +147,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float l
                 float wd, int adamw, int64_t step, cudaStream_t s);
 int launch_scale(float* p, int64_t n, const float* scale_dev, cudaStream_t s);
 int launch_argmax(const float* q, int32_t* labels, int64_t rows, int cols, cudaStream_t s);
+int launch_confmat(const int32_t* labels, int64_t n, int A, int K, int32_t* counts, cudaStream_t s);
 int launch_transpose(const float* src, int64_t src_ld, int64_t src_batch_stride, float* dst, int64_t dst_ld,
                      int64_t dst_batch_stride, int rows, int cols, int batch, cudaStream_t s);
 

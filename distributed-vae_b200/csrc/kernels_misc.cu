@@ -199,6 +199,27 @@ int launch_argmax(const float* q, int32_t* labels, int64_t rows, int cols, cudaS
   return 0;
 }
 
+// Confusion (co-assignment) counts of the arm pairs: counts[pair][la][lb] += 1 per cell (mmidas/_utils.py:83
+// compute_confmat, np.add.at).  labels [A][n] int32; pairs enumerate a < b in order.  Integer work: bit-exact.
+__global__ void __launch_bounds__(256) confmat_kernel(const int32_t* labels, int64_t n, int A, int K, int32_t* counts) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  int pair = 0;
+  for (int a = 0; a < A; ++a) {
+    const int la = labels[(int64_t)a * n + i];
+    for (int b = a + 1; b < A; ++b, ++pair) {
+      const int lb = labels[(int64_t)b * n + i];
+      if (la >= 0 && la < K && lb >= 0 && lb < K) atomicAdd(counts + ((int64_t)pair * K + la) * K + lb, 1);
+    }
+  }
+}
+int launch_confmat(const int32_t* labels, int64_t n, int A, int K, int32_t* counts, cudaStream_t s) {
+  if (n <= 0) return 0;
+  confmat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(labels, n, A, K, counts);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
 // dst[c][r] = src[r][c]  (batched), 32x32 tiles through shared memory
 __global__ void __launch_bounds__(256) transpose_kernel(const float* src, int64_t src_ld, int64_t src_bs, float* dst,
                                                         int64_t dst_ld, int64_t dst_bs, int rows, int cols) {

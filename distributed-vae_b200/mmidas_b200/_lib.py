@@ -58,7 +58,7 @@ PRECISIONS = {"tf32x3_fc1": 0, "tf32x3": 1, "tf32": 2, "fp32_simt": 3}
 # every symbol include/mixvae_b200.h declares
 EXPORTS = ("mvae_last_error", "mvae_abi_version", "mvae_compute_layout", "mvae_forward", "mvae_loss",
            "mvae_backward", "mvae_adam", "mvae_train_step", "mvae_argmax", "mvae_dropout_mask", "mvae_launch_count",
-           "mvae_timing_enable", "mvae_timing_read", "mvae_debug_tc_gemm")
+           "mvae_timing_enable", "mvae_timing_read", "mvae_debug_tc_gemm", "mvae_confmat")
 
 _lib = None
 
@@ -88,6 +88,8 @@ def load():
                                     C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]
     lib.mvae_argmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     lib.mvae_dropout_mask.argtypes = [P(Dims), P(HParams), P(Inputs), C.c_void_p, C.c_void_p]
+    lib.mvae_confmat.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.mvae_confmat.restype = C.c_int
     lib.mvae_debug_tc_gemm.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.mvae_debug_tc_gemm.restype = C.c_int

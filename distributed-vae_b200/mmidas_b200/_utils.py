@@ -58,6 +58,34 @@ def consensus(labels, n_categories):
     return float(np.mean(vals)) if vals else float("nan")
 
 
+def confmat_device(labels: torch.Tensor, n_categories: int, counts: torch.Tensor = None) -> torch.Tensor:
+    """Device-side ``compute_confmat`` for every arm pair (mmidas/_utils.py:83): ``labels`` int32 [A, n] on the GPU
+    (``mixVAE_model.argmax_labels``) -> int32 counts [n_pairs, K, K], pairs (a < b) in order.  ``counts`` accumulates
+    across calls (one call per batch; the labels of an epoch never leave the device)."""
+    import ctypes as C
+    from . import _lib
+    if labels.dtype != torch.int32 or labels.dim() != 2 or not labels.is_cuda:
+        raise ValueError("labels must be a CUDA int32 tensor [n_arm, n_cells]")
+    A, n = labels.shape
+    if A < 2:
+        raise ValueError("the consensus needs at least two arms")
+    n_pairs = A * (A - 1) // 2
+    if counts is None:
+        counts = torch.zeros(n_pairs, n_categories, n_categories, dtype=torch.int32, device=labels.device)
+    labels = labels.contiguous()
+    stream = torch.cuda.current_stream(labels.device).cuda_stream
+    _lib.check(_lib.load().mvae_confmat(labels.data_ptr(), n, A, n_categories, counts.data_ptr(), C.c_void_p(stream)),
+               "mvae_confmat")
+    return counts
+
+
+def consensus_from_counts(counts) -> float:
+    """Mean over arm pairs of confmat_mean(confmat_normalize(cm)) from accumulated counts [n_pairs, K, K]."""
+    cms = counts.cpu().numpy() if torch.is_tensor(counts) else np.asarray(counts)
+    vals = [confmat_mean(confmat_normalize(cm.astype(np.float64))) for cm in cms]
+    return float(np.mean(vals)) if vals else float("nan")
+
+
 def set_seeds(seed):
     """mmidas/_utils.py:34"""
     import random

@@ -20,7 +20,7 @@ from typing import Iterable, Optional
 import numpy as np
 import torch
 
-from ._utils import consensus
+from ._utils import confmat_device, consensus, consensus_from_counts
 from .nn_model import VAEConfig, mixVAE_model
 from .optim import FusedAdam
 
@@ -191,12 +191,12 @@ class cpl_mixVAE:
             t0 = time.time()
             model.train()
             loss_sum = torch.zeros(5 + 3 * A, device=dev)
-            labels_aug = []
+            cm_aug = None                     # [pairs, C, C] co-assignment counts, accumulated on the device
             nb = 0
             for x, _item in HostBatchFeeder(train_loader, dev):
                 lv = self.train_batch(x)
                 loss_sum += lv
-                labels_aug.append(model.argmax_labels(model.last_outputs()["qc"]))
+                cm_aug = confmat_device(model.argmax_labels(model.last_outputs()["qc"]), C, cm_aug)
                 nb += 1
             ls = loss_sum.cpu().numpy() / max(nb, 1)          # the only D2H of the training pass
             losses.append(float(ls[0]))
@@ -206,8 +206,7 @@ class cpl_mixVAE:
             c_l2_dists.append(float(ls[4]))
             for a in range(A):
                 loss_recs[a].append(float(ls[5 + a]) / D)
-            lab = torch.cat(labels_aug, dim=1).cpu().numpy().astype(np.int64)
-            consensus_aug.append(consensus([lab[a] for a in range(A)], C))
+            consensus_aug.append(consensus_from_counts(cm_aug) if cm_aug is not None else float("nan"))
             _time = time.time() - t0
             print(f"epoch {e} | loss: {losses[-1]:.2f} | rec: {loss_recs[0][-1]:.2f} | distance: {c_dists[-1]:.2f} | "
                   f"l2 distance: {c_l2_dists[-1]:.2f} | aug-cns: {consensus_aug[-1]:.2f} | time: {_time:.2f} | "
@@ -221,8 +220,8 @@ class cpl_mixVAE:
 
             # ---- eval-mode pass over the training set (:563-663)
             model.eval()
-            lab_noaug = self._eval_labels(train_loader if B_val > 1 else [train_loader.dataset.tensors])
-            consensus_train.append(consensus([lab_noaug[a] for a in range(A)], C))
+            cm_noaug = self._eval_confmat(train_loader if B_val > 1 else [train_loader.dataset.tensors])
+            consensus_train.append(consensus_from_counts(cm_noaug))
             if run:
                 run.log({"train/consensus": consensus_train[-1]})
 
@@ -254,6 +253,19 @@ class cpl_mixVAE:
                 "epoch_times": epoch_times}
 
     # ------------------------------------------------------------------------------------------
+    def _eval_confmat(self, batches):
+        """Eval-mode pass (cpl_mixvae.py:563-663): argmax labels and their co-assignment counts stay on the device;
+        only [pairs, C, C] integers come back."""
+        model, A = self.model, self.n_arm
+        cm = None
+        with torch.no_grad():
+            for x, _ in HostBatchFeeder(batches, self.device):
+                xs = [x for _ in range(A)]
+                model.materialize_recon = False
+                ctx = model._launch_forward(xs, self.temp, True, None, False)
+                cm = confmat_device(model.argmax_labels(ctx.out_tensors["qc"]), self.n_categories, cm)
+        return cm
+
     def _eval_labels(self, batches):
         model, A = self.model, self.n_arm
         labs = []

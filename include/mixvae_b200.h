@@ -153,6 +153,12 @@ int mvae_train_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_st
  * cpl_mixvae.py:476 + mmidas/_utils.py:78 classify). */
 int mvae_argmax(const float* q, int32_t* labels, int64_t rows, int32_t cols, void* stream);
 
+/* Device-side confusion counts between the arms' labels (mmidas/_utils.py:83 compute_confmat, used by the
+ * consensus bookkeeping cpl_mixvae.py:512-523, :640-657, :750-763): labels [n_arm][n_cells] int32 (mvae_argmax output),
+ * counts [n_pairs][K][K] int32 with pairs (a < b) in order; counts are ACCUMULATED (zero them first), so the
+ * labels of an epoch never leave the device: only n_pairs*K*K integers do. */
+int mvae_confmat(const int32_t* labels, int64_t n_cells, int32_t n_arm, int32_t n_categories, int32_t* counts, void* stream);
+
 /* The keep-mask [A][B][D] that the in-kernel dropout generator applies for (in->seed, in->step):
  * the fc1 forward and fc1 weight-gradient kernels regenerate it on the fly instead of reading it. */
 int mvae_dropout_mask(const mvae_dims* dims, const mvae_hparams* hp, const mvae_inputs* in,
