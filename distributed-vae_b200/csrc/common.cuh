@@ -66,6 +66,7 @@ enum ParamId {
 // workspace map (offsets in floats from st->work).  Everything that is per arm is laid out
 // [A_local][...]; `acc` is the fp64 accumulator block that is zeroed by memset nodes.
 // ---------------------------------------------------------------------------------------------
+constexpr int kWgMaxSplit = 32;   // row splits per narrow weight-gradient problem (capacity of Work::wg_part)
 struct Work {
   // forward activations kept for backward
   int64_t a[5];        // a1..a4 [A][B][H], a5 [A][B][L]   post-ReLU, pre-BN
@@ -146,6 +147,28 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+// N independent sums over the 32 lanes at once (N = 2, 4, 8, 16 or 32): recursive halving with the pairing order of
+// warp_sum (xor 16, 8, 4, 2, 1), so every total is bit-identical to warp_sum(v[i]).  N - 1 + log2(32/N) shuffles
+// in 5 dependent rounds instead of 5 N shuffles in N serial chains.  The total of v[i] is returned in lanes
+// (32/N) i .. (32/N) i + 32/N - 1; v is clobbered.
+template <int N>
+__device__ __forceinline__ float warp_multi_sum(float (&v)[N], int lane) {
+  int o = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, o >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < n / 2; ++j) {
+      const float send = hi ? v[j] : v[j + n / 2];
+      const float keep = hi ? v[j + n / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  float r = v[0];
+#pragma unroll
+  for (; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
 }
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

@@ -270,6 +270,229 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Grouped weight-gradient GEMM of the narrow layers (fc2..fc4, fc8..fc10: delta^T . bn(input), both operands MN-major):
+// the same pipeline as tc_gemm_kernel<true, true>, one (problem, arm, K split) per CTA.  The warp-level mma.sync path
+// (kernels_mma.cu) is bound by the legacy HMMA pipe on sm_100 (ncu: sm__pipe_tensor_subpipe_hmma_cycles_active = 78 % of
+// the kernel, ~8 cycles per m16n8k8 per SM = 128 MAC/clk/SM, the fp32 FFMA rate); tcgen05 runs the same tile 13x faster.
+// The transform warps normalise the input tile in place ((v - mean) * rstd, batch_l1..l4), write a column of ones
+// behind the last input column (row j of that accumulator column is the bias gradient sum_b delta[b][j]) and, in the
+// 3xTF32 mode, the low halves.  Partials go to the layout wgrad_reduce2_kernel sums.
+// ---------------------------------------------------------------------------------------------
+constexpr int WGTC_MAX = 8;
+struct WgTcProblem {
+  int M, N;                  // nout, nin (the ones column is column N)
+  int bn_layer;              // -1: raw input
+  int pad;
+  int64_t offW, offB;        // offsets of the partial weight / bias gradient inside one (split, arm) block
+};
+struct WgTcParams {
+  CUtensorMap tmA[WGTC_MAX], tmB[WGTC_MAX];
+  WgTcProblem prob[WGTC_MAX];
+  int A, K, stages, nsplit, ktiles_per_split, split3;
+  float* part; int64_t part_split_stride, part_arm_stride;
+  const float* bn_mean; const float* bn_rstd;
+};
+
+// B tile (MN-major image, see transform_tile): normalise, ones column, optional low half
+__device__ __forceinline__ void wg_transform_b(float* hi, float* lo, bool do_split, bool do_norm, const float* bm,
+                                               const float* br, int N, int k0, int K, int tid, int nthr) {
+#pragma unroll 4
+  for (int q = tid; q < TILE_BYTES / 16; q += nthr) {
+    const int r = q >> 3, p = q & 7;
+    const int slab = r >> 5, rr = r & 31;
+    const int col = 32 * slab + 4 * (((((p >> 1) ^ (rr & 3)) << 1)) | (p & 1));
+    if (col > N) {                               // beyond the ones column: zeros from the TMA fill stay zeros
+      if (do_split) reinterpret_cast<float4*>(lo)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    float4 v = reinterpret_cast<float4*>(hi)[q];
+    if (do_norm) {
+      const float4 m = *reinterpret_cast<const float4*>(bm + col), rs = *reinterpret_cast<const float4*>(br + col);
+      v.x = (v.x - m.x) * rs.x; v.y = (v.y - m.y) * rs.y; v.z = (v.z - m.z) * rs.z; v.w = (v.w - m.w) * rs.w;
+    }
+    if (col + 4 > N) {                           // the chunk that holds column N
+      const float one = (k0 + rr < K) ? 1.f : 0.f;
+      const int e = N - col;
+      if (e == 0) { v.x = one; v.y = 0.f; v.z = 0.f; v.w = 0.f; }
+      else if (e == 1) { v.y = one; v.z = 0.f; v.w = 0.f; }
+      else if (e == 2) { v.z = one; v.w = 0.f; }
+      else v.w = one;
+    }
+    reinterpret_cast<float4*>(hi)[q] = v;
+    if (do_split) {
+      float4 l;
+      l.x = tf32_lo(v.x); l.y = tf32_lo(v.y); l.z = tf32_lo(v.z); l.w = tf32_lo(v.w);
+      reinterpret_cast<float4*>(lo)[q] = l;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) wg_tc_kernel(const __grid_constant__ WgTcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, pi = blockIdx.y, arm = blockIdx.z;
+  const WgTcProblem& pr = P.prob[pi];
+  const bool split3 = P.split3 != 0;
+  const int tiles_per_stage = split3 ? 4 : 2;
+  const int stage_bytes = tiles_per_stage * TILE_BYTES;
+  const int S = P.stages;
+  auto tileA = [&](int s) { return smem + (size_t)s * stage_bytes; };
+  auto tileB = [&](int s) { return smem + (size_t)s * stage_bytes + TILE_BYTES; };
+  auto tileAlo = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * TILE_BYTES; };
+  auto tileBlo = [&](int s) { return smem + (size_t)s * stage_bytes + 3 * TILE_BYTES; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* ready = bars + S;
+  uint64_t* empty = bars + 2 * S;
+  uint64_t* tmem_full = bars + 3 * S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
+  float* bm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 3 * S + 2) + 15) & ~uintptr_t(15));   // [128] | [128]
+  float* br = bm + 128;
+
+  const int BNp = (pr.N + 1 + 15) / 16 * 16;                 // UMMA N: inputs + the ones column
+  const int ktiles_total = (P.K + BK - 1) / BK;
+  const int kt0 = split * P.ktiles_per_split;
+  const int kt1 = min(ktiles_total, kt0 + P.ktiles_per_split);
+  const int nkt = max(kt1 - kt0, 0);
+  const bool do_norm = pr.bn_layer >= 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(ready + s, TRANSFORM_THREADS);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 192) {
+    const int i = threadIdx.x - 64;
+    const bool have = do_norm && i < pr.N;
+    bm[i] = have ? P.bn_mean[(pr.bn_layer * P.A + arm) * 128 + i] : 0.f;
+    br[i] = have ? P.bn_rstd[(pr.bn_layer * P.A + arm) * 128 + i] : 1.f;
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const CUtensorMap* tmA = &P.tmA[pi];
+      const CUtensorMap* tmB = &P.tmB[pi];
+      for (int i = 0; i < nkt; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (i / S) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_expect_tx(full + s, 2 * TILE_BYTES);
+        const int k0 = (kt0 + i) * BK;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_3d(tmA, full + s, tileA(s) + j * 4096, 32 * j, k0, arm);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_3d(tmB, full + s, tileB(s) + j * 4096, 32 * j, k0, arm);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BM, BNp, true, true);
+      const int kround = (P.K + UK - 1) / UK * UK;
+      uint32_t acc = 0;
+      for (int i = 0; i < nkt; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (i / S) & 1;
+        mbar_wait(ready + s, ph);
+        tc_fence_after();
+        const int k0 = (kt0 + i) * BK;
+        const uint32_t a_hi = smem_u32(tileA(s)), b_hi = smem_u32(tileB(s));
+        const uint32_t a_lo = smem_u32(tileAlo(s)), b_lo = smem_u32(tileBlo(s));
+#pragma unroll
+        for (int ks = 0; ks < BK / UK; ++ks) {
+          if (k0 + ks * UK >= kround) break;
+          const uint32_t off = ks * 1024;
+          const uint64_t dah = make_smem_desc(a_hi + off, 4096, 512, true);
+          const uint64_t dbh = make_smem_desc(b_hi + off, 4096, 512, true);
+          if (split3) {
+            umma_tf32(tmem_base, make_smem_desc(a_lo + off, 4096, 512, true), dbh, idesc, acc);
+            acc = 1;
+            umma_tf32(tmem_base, dah, make_smem_desc(b_lo + off, 4096, 512, true), idesc, acc);
+          }
+          umma_tf32(tmem_base, dah, dbh, idesc, acc);
+          acc = 1;
+        }
+        umma_commit(empty + s);
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (warp >= TRANSFORM_WARP0) {
+    // ===== operand transform: 4 warps on the input tile (normalise, ones column, low half), 4 on delta (low half) =====
+    const int tid = threadIdx.x - TRANSFORM_WARP0 * 32;
+    for (int i = 0; i < nkt; ++i) {
+      const int s = i % S;
+      const uint32_t ph = (i / S) & 1;
+      mbar_wait(full + s, ph);
+      const int k0 = (kt0 + i) * BK;
+      if (split3) {
+        if (tid < 128) {
+          DropSpec nodrop;
+          nodrop.mode = 0;
+          transform_tile<true>(reinterpret_cast<float*>(tileA(s)), reinterpret_cast<float*>(tileAlo(s)), true, false, nodrop,
+                               arm, 0, k0, tid, 128);
+        } else {
+          wg_transform_b(reinterpret_cast<float*>(tileB(s)), reinterpret_cast<float*>(tileBlo(s)), true, do_norm, bm, br,
+                         pr.N, k0, P.K, tid - 128, 128);
+        }
+      } else {
+        wg_transform_b(reinterpret_cast<float*>(tileB(s)), nullptr, false, do_norm, bm, br, pr.N, k0, P.K, tid,
+                       TRANSFORM_THREADS);
+      }
+      fence_proxy_async();
+      mbar_arrive(ready + s);
+    }
+  } else {
+    // ===== epilogue: row j of the accumulator = output unit j; columns = inputs, then the bias gradient =====
+    const int quad = warp & 3;
+    const int j = quad * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float* blk = P.part + (int64_t)split * P.part_split_stride + (int64_t)arm * P.part_arm_stride;
+    float* wrow = blk + pr.offW + (int64_t)j * pr.N;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(wrow) & 15) == 0);
+    for (int c0 = 0; c0 < BNp; c0 += 16) {
+      uint32_t r[16];
+      if (nkt > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = 0u;
+      }
+      if (j < pr.M) {
+        if (vec_ok && c0 + 16 <= pr.N) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(wrow + c0)[i] =
+                make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                            __uint_as_float(r[4 * i + 3]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (c0 + i < pr.N) wrow[c0 + i] = __uint_as_float(r[i]);
+            else if (c0 + i == pr.N) blk[pr.offB + j] = __uint_as_float(r[i]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 128);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 struct Operand {
@@ -340,6 +563,17 @@ __global__ void __launch_bounds__(256) partial_sum_kernel(const float* part, int
 
 int round16(int x) { return (x + 15) / 16 * 16; }
 
+int mma_sm_count_tc() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 int choose_split(int tiles_mn, int ktiles, int max_split) {
   // one CTA per SM (the pipeline takes most of the shared memory): pick the split whose grid fills
   // whole waves of 148 CTAs best; ties go to the smaller split (less partial traffic)
@@ -355,6 +589,53 @@ int choose_split(int tiles_mn, int ktiles, int max_split) {
 }
 
 }  // namespace
+
+// Weight gradients of the wide narrow-layer problems on tcgen05 (see wg_tc_kernel).  `idx` lists the problems of `a`
+// to run (all with TMA-compatible operands, see tc_narrow_wgrad_ok); their split count is written to a.prob[].nsplit.
+bool tc_narrow_wgrad_ok(const WgArgs& a, const WgProblem& q) {
+  if (get_encode() == nullptr) return false;
+  const uintptr_t d = reinterpret_cast<uintptr_t>(a.work + q.delta_off), i = reinterpret_cast<uintptr_t>(a.work + q.in_off);
+  return q.nin > 0 && q.nout % 4 == 0 && q.nout <= 128 && q.in_ld % 4 == 0 && q.nin + 1 <= 128 && (d & 15) == 0 &&
+         (i & 15) == 0 && q.delta_arm_stride % 4 == 0 && q.in_arm_stride % 4 == 0;
+}
+
+int tc_narrow_wgrad(WgArgs& a, const int* idx, int n, int split3, cudaStream_t s) {
+  MVAE_CHECK_ARG(n >= 1 && n <= WGTC_MAX, "tc_narrow_wgrad: %d problems", n);
+  WgTcParams P;
+  memset(&P, 0, sizeof(P));
+  for (int t = 0; t < n; ++t) {
+    const WgProblem& q = a.prob[idx[t]];
+    // MN-major operands: inner = the M/N index, outer = K (cells), box = 32 x BK
+    int rc = make_map(&P.tmA[t], a.work + q.delta_off, q.nout, a.B, q.nout, a.A, q.delta_arm_stride, BK, true);
+    if (rc) return rc;
+    rc = make_map(&P.tmB[t], a.work + q.in_off, q.nin, a.B, q.in_ld, a.A, q.in_arm_stride, BK, true);
+    if (rc) return rc;
+    P.prob[t].M = q.nout; P.prob[t].N = q.nin; P.prob[t].bn_layer = q.bn_layer;
+    P.prob[t].offW = q.poffW - a.base_off; P.prob[t].offB = q.poffB - a.base_off;
+  }
+  const int ktiles = (a.B + BK - 1) / BK;
+  int nsplit = mma_sm_count_tc() / (n * a.A);
+  if (nsplit > kWgMaxSplit) nsplit = kWgMaxSplit;
+  if (nsplit > ktiles) nsplit = ktiles;
+  if (nsplit < 1) nsplit = 1;
+  P.A = a.A; P.K = a.B; P.split3 = split3 ? 1 : 0;
+  P.stages = split3 ? 3 : 6;
+  P.ktiles_per_split = (ktiles + nsplit - 1) / nsplit;
+  nsplit = (ktiles + P.ktiles_per_split - 1) / P.ktiles_per_split;
+  P.nsplit = nsplit;
+  P.part = a.part; P.part_split_stride = a.part_split_stride; P.part_arm_stride = a.part_arm_stride;
+  P.bn_mean = a.bn_mean; P.bn_rstd = a.bn_rstd;
+  for (int t = 0; t < n; ++t) a.prob[idx[t]].nsplit = nsplit;
+  const size_t smem = (size_t)P.stages * (split3 ? 4 : 2) * TILE_BYTES + (3 * P.stages + 2) * 8 + 16 + 256 * 4 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    MVAE_CUDA(cudaFuncSetAttribute(wg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  wg_tc_kernel<<<dim3(nsplit, n, a.A), NUM_THREADS, smem, s>>>(P);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
 
 static bool legacy_fc11() {
   static int v = -1;

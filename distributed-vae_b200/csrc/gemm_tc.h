@@ -39,6 +39,10 @@ int ts_fc1_wgrad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
 int ts_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale, int want_grad,
                  float* x_rec, double* recon_acc, cudaStream_t s);
 int ts_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale, cudaStream_t s);
+// gemm_tc.cu: grouped tcgen05 weight-gradient GEMM of the wide narrow-layer problems (delta^T . bn(input), bias gradient
+// through a column of ones); partials in the layout of wgrad_reduce2_kernel
+bool tc_narrow_wgrad_ok(const WgArgs& a, const WgProblem& q);
+int tc_narrow_wgrad(WgArgs& a, const int* idx, int n, int split3, cudaStream_t s);
 bool legacy_gene_kernels();   // MVAE_LEGACY_FC1=1 / MVAE_LEGACY_FC11=1: round-1 first-generation kernels (A/B comparisons)
 
 }  // namespace mvae

@@ -114,6 +114,7 @@ struct WgProblem {
   int nout, nin, in_ld;
   int bn_layer;                        // -1: raw input, else normalise the input with bn stats of that layer
   int64_t poffW, poffB;                // param offsets (grads written there)
+  int nsplit, cta_begin;               // row splits of this problem / its first CTA (filled by launch_wgrad_mma)
 };
 struct WgArgs {
   WgProblem prob[13];

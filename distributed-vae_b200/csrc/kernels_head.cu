@@ -72,9 +72,54 @@ __device__ __forceinline__ void head_load_weights(const HeadArgs& p, const HeadS
     for (int idx = tid; idx < 4 * 128; idx += nt) h.colc[idx] = p.colc[(int64_t)arm * 4 * 128 + idx];
 }
 
+// fc6 of one cell: lane i < L returns relu(W6[i,:C] . c + W6[i,C:] . s + b6[i]); c is spread over the lanes
+// (category lane + 32 k in c[k]).  Same operation order per output as a warp_sum per row of W6.
+template <int NL>
+__device__ __forceinline__ float fc6_rows(const HeadSmem& h, const float (&c)[KC], const float (&sdp)[kMaxS], int L, int C,
+                                          int S, int lane) {
+  float part[NL];
+  const int CS = C + S;
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    part[i] = 0.f;
+    if (i < L) {
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int kk = lane + 32 * k;
+        if (kk < C) part[i] = fmaf(h.W6[i * CS + kk], c[k], part[i]);
+      }
+    }
+  }
+  const float tot = warp_multi_sum<NL>(part, lane);
+  float v = __shfl_sync(0xffffffffu, tot, (lane * (32 / NL)) & 31);
+  float d6 = 0.f;
+  if (lane < L) {
+#pragma unroll
+    for (int s = 0; s < kMaxS; ++s) if (s < S) v = fmaf(h.W6[lane * CS + C + s], sdp[s], v);
+    d6 = fmaxf(v + h.b6[lane], 0.f);
+  }
+  return d6;
+}
+// fcc backward of one cell: lane i < L returns sum_k gq[k] WcT[i][k]
+template <int NL>
+__device__ __forceinline__ float fcc_bwd_rows(const HeadSmem& h, const float (&gq)[KC], int L, int lane) {
+  float part[NL];
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    part[i] = 0.f;
+    if (i < L) {
+#pragma unroll
+      for (int k = 0; k < KC; ++k) part[i] = fmaf(gq[k], h.WcT[i * CP + lane + 32 * k], part[i]);
+    }
+  }
+  const float tot = warp_multi_sum<NL>(part, lane);
+  return __shfl_sync(0xffffffffu, tot, (lane * (32 / NL)) & 31);
+}
+
 // =============================================================================================
 // forward
 // =============================================================================================
+template <int NL>   // reduction width of the L-row products: 16 (lowD_dim <= 16) or 32
 __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadArgs p) {
   extern __shared__ __align__(16) float smem[];
   const int arm = blockIdx.y;
@@ -105,9 +150,10 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
   __syncthreads();
 
   const int64_t ab = (int64_t)arm * B;
-  double klacc[kMaxS];
-#pragma unroll
-  for (int s = 0; s < kMaxS; ++s) klacc[s] = 0.0;
+  __shared__ double klacc_sm[kRowWarps][kMaxS];   // per-warp KL sums (lane 0 only): kept out of the register file
+  double* klacc = klacc_sm[warp];
+  if (lane < kMaxS) klacc[lane] = 0.0;
+  __syncwarp();
 
   for (int row = blockIdx.x * kRowWarps + warp; row < B; row += gridDim.x * kRowWarps) {
     const int64_t r = ab + row;
@@ -201,6 +247,19 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
 #pragma unroll
       for (int k = 0; k < KC; ++k) c[k] = y[k];
     }
+    // ---- category stores (here: p, q, y are dead afterwards)
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int kk = lane + 32 * k;
+      if (kk < C) {
+        p.c_prob[r * C + kk] = pk[k];
+        p.qc[r * C + kk] = q[k];
+        p.c_smp[r * C + kk] = c[k];
+        p.ysoft[r * C + kk] = y[k];
+        p.yy[r * (L + C) + L + kk] = c[k];
+        p.zc[r * (C + S) + kk] = c[k];
+      }
+    }
     // ---- state head on [x_low | c_smp] : :347-351
     float sdp[kMaxS];
 #pragma unroll
@@ -241,38 +300,14 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
         }
       }
     }
-    // ---- d6 = relu(fc6([c_smp | dropout(s)])) : :278-280
+    // ---- d6 = relu(fc6([c_smp | dropout(s)])) : :278-280   (the L dot products are reduced together)
     float d6 = 0.f;
-    for (int i = 0; i < L; ++i) {
-      float part = 0.f;
-#pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        const int kk = lane + 32 * k;
-        if (kk < C) part = fmaf(h.W6[i * (C + S) + kk], c[k], part);
-      }
-      part = warp_sum(part);
-#pragma unroll
-      for (int s = 0; s < kMaxS; ++s) if (s < S) part = fmaf(h.W6[i * (C + S) + C + s], sdp[s], part);
-      part = fmaxf(part + h.b6[i], 0.f);
-      if (lane == i) d6 = part;
-    }
+    d6 = fc6_rows<NL>(h, c, sdp, L, C, S, lane);
     // ---- stores
     if (lane < L) {
       p.x_low[r * L + lane] = xl;
       p.yy[r * (L + C) + lane] = xl;
       p.d6[r * L + lane] = d6;
-    }
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-      const int kk = lane + 32 * k;
-      if (kk < C) {
-        p.c_prob[r * C + kk] = pk[k];
-        p.qc[r * C + kk] = q[k];
-        p.c_smp[r * C + kk] = c[k];
-        p.ysoft[r * C + kk] = y[k];
-        p.yy[r * (L + C) + L + kk] = c[k];
-        p.zc[r * (C + S) + kk] = c[k];
-      }
     }
   }
   if (p.kl_sums && lane == 0) {
@@ -285,6 +320,7 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
 // =============================================================================================
 // backward
 // =============================================================================================
+template <int NL>
 __global__ void __launch_bounds__(kRowWarps * 32, 3) head_bwd_kernel(const HeadArgs p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[kRowWarps][2][32];
@@ -398,13 +434,10 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_bwd_kernel(const HeadA
       gq[k] = pk[k] * (gq[k] - dot3);                           // delta_z
       if (kk < C) p.delta_z[r * C + kk] = gq[k];
     }
-    // ---- fcc backward into x_low
-    for (int i = 0; i < L; ++i) {
-      float part = 0.f;
-#pragma unroll
-      for (int k = 0; k < KC; ++k) part = fmaf(gq[k], h.WcT[i * CP + lane + 32 * k], part);
-      part = warp_sum(part);
-      if (lane == i) gx += part;
+    // ---- fcc backward into x_low (the L dot products are reduced together)
+    {
+      const float part = fcc_bwd_rows<NL>(h, gq, L, lane);
+      if (lane < L) gx += part;
     }
     if (lane < L) {
       p.g_xlow[r * L + lane] = gx;
@@ -433,26 +466,32 @@ static int head_grid(int B, int A) {
   return gx > cap ? (cap > 0 ? cap : 1) : gx;
 }
 
-int launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
+static int head_attrs() {
   static bool attr_done = false;
   if (!attr_done) {
-    MVAE_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    MVAE_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(head_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(head_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(head_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(head_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
-  head_fwd_kernel<<<dim3(head_grid(a.B, a.A), a.A), kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
+  return 0;
+}
+
+int launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
+  if (int rc = head_attrs()) return rc;
+  const dim3 grid(head_grid(a.B, a.A), a.A);
+  if (a.L <= 16) head_fwd_kernel<16><<<grid, kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
+  else head_fwd_kernel<32><<<grid, kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_head_bwd(const HeadArgs& a, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    MVAE_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    MVAE_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_done = true;
-  }
-  head_bwd_kernel<<<dim3(head_grid(a.B, a.A), a.A), kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
+  if (int rc = head_attrs()) return rc;
+  const dim3 grid(head_grid(a.B, a.A), a.A);
+  if (a.L <= 16) head_bwd_kernel<16><<<grid, kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
+  else head_bwd_kernel<32><<<grid, kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
   MVAE_LAUNCH_CHECK();
   return 0;
 }

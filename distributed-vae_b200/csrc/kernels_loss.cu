@@ -13,29 +13,45 @@ constexpr int KC = 4;
 // ---------------------------------------------------------------------------------------------
 // column sums of q(c|x) of every arm: sum_b q, sum_b q^2  -> inv_var (nn_model.py:75-77)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) qstats_kernel(const CouplingArgs p) {
+// 4 row groups x 128 columns per CTA, one wave of CTAs: the loads of a thread's rows are independent (unrolled), the
+// row groups are combined in shared memory and each CTA issues ONE fp64 atomic per column and moment.
+__global__ void __launch_bounds__(512) qstats_kernel(const CouplingArgs p) {
+  __shared__ double red[3][2][128];
   const int arm = blockIdx.y;  // global arm index
-  const int k = threadIdx.x;
-  if (k >= p.C) return;
+  const int k = threadIdx.x & 127, rg = threadIdx.x >> 7;
   const float* q = p.qc_all + (int64_t)arm * p.B * p.C;
   const int rows_per = (p.B + gridDim.x - 1) / gridDim.x;
   const int r0 = blockIdx.x * rows_per, r1 = min(p.B, r0 + rows_per);
   double s1 = 0.0, s2 = 0.0;
-  for (int r = r0; r < r1; ++r) {
-    const double v = (double)q[(int64_t)r * p.C + k];
-    s1 += v;
-    s2 += v * v;
+  if (k < p.C) {
+#pragma unroll 4
+    for (int r = r0 + rg; r < r1; r += 4) {
+      const double v = (double)q[(int64_t)r * p.C + k];
+      s1 += v;
+      s2 += v * v;
+    }
   }
-  if (r1 > r0) {
+  if (rg > 0) {
+    red[rg - 1][0][k] = s1;
+    red[rg - 1][1][k] = s2;
+  }
+  __syncthreads();
+  if (rg == 0 && k < p.C && r1 > r0) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      s1 += red[g][0][k];
+      s2 += red[g][1][k];
+    }
     atomicAdd(p.acc + accl_qs(arm) + k, s1);
     atomicAdd(p.acc + accl_qs(arm) + 128 + k, s2);
   }
 }
 
 int launch_qstats(const CouplingArgs& a, cudaStream_t s) {
-  int gx = (a.B + 7) / 8;
-  if (gx > 592) gx = 592;
-  qstats_kernel<<<dim3(gx, a.At), 128, 0, s>>>(a);
+  int gx = (a.B + 15) / 16;
+  const int cap = (2 * 148) / (a.At > 0 ? a.At : 1);
+  if (gx > cap) gx = cap > 0 ? cap : 1;
+  qstats_kernel<<<dim3(gx, a.At), 512, 0, s>>>(a);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -47,7 +63,7 @@ int launch_qstats(const CouplingArgs& a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const CouplingArgs p) {
   __shared__ float w[MVAE_MAX_ARMS][128];
-  __shared__ double sT[MVAE_MAX_ARMS][128];
+  extern __shared__ float sTw[];            // [kRowWarps][A local arms][128]: every lane owns its categories of its warp's slice
   __shared__ double sPair[kMaxPairs][2];
   __shared__ double sEnt[MVAE_MAX_ARMS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -64,8 +80,8 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
       if (blockIdx.x == 0) p.wcat[a * 128 + k] = wv;
     }
     w[a][k] = wv;
-    if (a < p.A) sT[a][k] = 0.0;
   }
+  for (int idx = tid; idx < kRowWarps * p.A * 128; idx += blockDim.x) sTw[idx] = 0.f;
   for (int idx = tid; idx < kMaxPairs * 2; idx += blockDim.x) (&sPair[0][0])[idx] = 0.0;
   if (tid < MVAE_MAX_ARMS) sEnt[tid] = 0.0;
   __syncthreads();
@@ -112,7 +128,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
           const int la = a - p.arm_off;
           if (la >= 0 && la < p.A) {
             const float G = gcoef * ((float)At * ra[k] - rs[k]);
-            atomicAdd(&sT[la][kk], (double)(G * lq));
+            sTw[(warp * p.A + la) * 128 + kk] += G * lq;   // a handful of rows per warp: fp32 here, fp64 across warps
           }
         }
       }
@@ -146,14 +162,25 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
   if (tid < At) atomicAdd(p.acc + accl_ent(tid), sEnt[tid]);
   for (int idx = tid; idx < p.A * 128; idx += blockDim.x) {
     const int a = idx >> 7, k = idx & 127;
-    if (k < C) atomicAdd(p.acc + accl_T(a) + k, sT[a][k]);
+    if (k < C) {
+      double t = 0.0;
+#pragma unroll
+      for (int wp = 0; wp < kRowWarps; ++wp) t += (double)sTw[(wp * p.A + a) * 128 + k];
+      atomicAdd(p.acc + accl_T(a) + k, t);
+    }
   }
 }
 
 int launch_coupling_rows(const CouplingArgs& a, cudaStream_t s) {
   int gx = (a.B + kRowWarps - 1) / kRowWarps;
-  if (gx > 1184) gx = 1184;            // latency-bound per row: as many warps in flight as fit (8 CTAs per SM)
-  coupling_rows_kernel<<<gx, kRowWarps * 32, 0, s>>>(a);
+  static bool attr = false;
+  if (!attr) {
+    MVAE_CUDA(cudaFuncSetAttribute(coupling_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kRowWarps * MVAE_MAX_ARMS * 128 * (int)sizeof(float)));
+    attr = true;
+  }
+  if (gx > 444) gx = 444;              // 3 CTAs per SM: a few rows per warp, 3x fewer global fp64 atomics than one row per warp
+  coupling_rows_kernel<<<gx, kRowWarps * 32, (size_t)kRowWarps * a.A * 128 * sizeof(float), s>>>(a);
   MVAE_LAUNCH_CHECK();
   return 0;
 }

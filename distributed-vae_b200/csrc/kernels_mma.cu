@@ -12,6 +12,7 @@
 //   wgrad_mma     : dW = delta^T . in, db = delta^T . 1   (split over row chunks, fixed-order reduce)
 #include "common.cuh"
 #include "kernels.h"
+#include "gemm_tc.h"
 
 namespace mvae {
 
@@ -564,6 +565,174 @@ __global__ void __launch_bounds__(512) wgrad_mma_kernel(const WgArgs p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Second generation (default): the first kernel above staged chunks through registers with 126 registers per
+// thread (one CTA per SM), gave every problem the same 20 row splits (520 CTAs = 3.5 waves) and spent most of its
+// issue slots on index arithmetic and barrier waits (ncu: 31 M instructions for 0.75 M MMAs).  Here
+//   * chunks of 32 rows arrive through a 3-stage cp.async ring (16-byte pieces when rows are 16-byte aligned,
+//     8/4-byte pieces otherwise; rows beyond the split are zero-filled by cp.async itself), one barrier per chunk;
+//   * the BatchNorm normalisation of the input is applied in place by the thread that copied the piece;
+//   * split counts are per problem (wide problems get twice the splits of narrow ones) so that the whole grid is
+//     ONE wave of two co-resident CTAs per SM; chunks are dealt to the splits evenly.
+// Same partial layout and the same fixed-order reduce as before.
+// ---------------------------------------------------------------------------------------------
+constexpr int WG2_STAGES = 3;
+constexpr int WG2_PITCH = 136;
+constexpr int WG2_STAGE_FLOATS = 2 * WG_CHUNK * WG2_PITCH;          // Ds | Is
+constexpr int WG2_SMEM_FLOATS = 256 + WG2_STAGES * WG2_STAGE_FLOATS;  // bm | br | stages
+
+template <int PF>
+__device__ __forceinline__ void wg2_cp(float* dst, const float* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int n = valid ? PF * 4 : 0;       // src-size 0: the destination is zero-filled
+  if (PF == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+  else if (PF == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ int wg2_piece_floats(const void* p, int64_t ld, int ncols) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  if ((a & 15) == 0 && (ld & 3) == 0 && (ncols & 3) == 0) return 4;
+  if ((a & 7) == 0 && (ld & 1) == 0 && (ncols & 1) == 0) return 2;
+  return 1;
+}
+// One row of a chunk per 16 threads: thread (r, l) copies the pieces l, l + 16, ... of row r (PF floats each).  No
+// per-piece index arithmetic: the loop is unrolled, the column offsets are immediates.
+template <int PF>
+__device__ __forceinline__ void wg2_copy_row(float* srow, const float* grow, int l, int ncols, bool row_ok) {
+#pragma unroll
+  for (int j = 0; j < 128 / (16 * PF); ++j) {
+    const int c = (l + 16 * j) * PF;
+    if (c < ncols) wg2_cp<PF>(srow + c, grow + c, row_ok);
+  }
+}
+// (v - mean) * rstd on the pieces this thread copied itself
+template <int PF>
+__device__ __forceinline__ void wg2_norm_row(float* srow, const float* bm, const float* br, int l, int ncols) {
+#pragma unroll
+  for (int j = 0; j < 128 / (16 * PF); ++j) {
+    const int c = (l + 16 * j) * PF;
+    if (c < ncols) {
+      if (PF == 4) {
+        float4 v = *reinterpret_cast<float4*>(srow + c);
+        const float4 m = *reinterpret_cast<const float4*>(bm + c), rs = *reinterpret_cast<const float4*>(br + c);
+        v.x = (v.x - m.x) * rs.x; v.y = (v.y - m.y) * rs.y; v.z = (v.z - m.z) * rs.z; v.w = (v.w - m.w) * rs.w;
+        *reinterpret_cast<float4*>(srow + c) = v;
+      } else {
+#pragma unroll
+        for (int e = 0; e < PF; ++e) srow[c + e] = (srow[c + e] - bm[c + e]) * br[c + e];
+      }
+    }
+  }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(512, SPLIT ? 1 : 2) wgrad2_kernel(const WgArgs p) {
+  extern __shared__ __align__(16) float wsm[];
+  float* bm = wsm;
+  float* br = wsm + 128;
+  float* stages = wsm + 256;
+  int pi = 0;
+  while (pi + 1 < p.nprob && (int)blockIdx.x >= p.prob[pi + 1].cta_begin) ++pi;
+  const WgProblem& pr = p.prob[pi];
+  const int split = (int)blockIdx.x - pr.cta_begin, arm = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = (tid >> 5) & 7, wn = tid >> 8;   // m-tile, n half
+  const int nout = pr.nout, nin = pr.nin, in_ld = pr.in_ld;
+  const int nt_all = (nin + 1 + 7) / 8;       // + the ones column that yields the bias gradient
+  const int nt_used = max(0, min(8, nt_all - wn * 8));
+  const float* delta = p.work + pr.delta_off + (int64_t)arm * pr.delta_arm_stride;
+  const float* in = nin > 0 ? p.work + pr.in_off + (int64_t)arm * pr.in_arm_stride : nullptr;
+  const bool bn = pr.bn_layer >= 0;
+  // chunks of this split: dealt evenly (sizes differ by at most one chunk)
+  const int T = (p.B + WG_CHUNK - 1) / WG_CHUNK;
+  const int c0 = (int)((int64_t)split * T / pr.nsplit), c1 = (int)((int64_t)(split + 1) * T / pr.nsplit);
+  const int nchunks = c1 - c0;
+
+  for (int idx = tid; idx < WG2_STAGES * WG2_STAGE_FLOATS / 4; idx += 512)
+    reinterpret_cast<float4*>(stages)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid < 128) {
+    const bool have = bn && tid < nin;
+    bm[tid] = have ? p.bn_mean[(pr.bn_layer * p.A + arm) * 128 + tid] : 0.f;
+    br[tid] = have ? p.bn_rstd[(pr.bn_layer * p.A + arm) * 128 + tid] : 1.f;
+  }
+  __syncthreads();
+  if (tid < WG2_STAGES * WG_CHUNK)        // ones column -> bias gradient (rows beyond the split have delta = 0)
+    stages[(tid / WG_CHUNK) * WG2_STAGE_FLOATS + WG_CHUNK * WG2_PITCH + (tid % WG_CHUNK) * WG2_PITCH + nin] = 1.f;
+
+  const int pfd = wg2_piece_floats(delta, nout, nout);
+  const int pfi = nin > 0 ? wg2_piece_floats(in, in_ld, nin) : 4;
+  const int lr = tid >> 4, ll = tid & 15;                 // row of the chunk, piece lane
+  const float* gd = delta + (int64_t)lr * nout;           // this thread's row in chunk 0 of the matrix
+  const float* gi = nin > 0 ? in + (int64_t)lr * in_ld : nullptr;
+  float* const srow_d = stages + lr * WG2_PITCH;
+  float* const srow_i = stages + WG_CHUNK * WG2_PITCH + lr * WG2_PITCH;
+  auto issue = [&](int c) {
+    if (c < nchunks) {
+      const int so = (c % WG2_STAGES) * WG2_STAGE_FLOATS;
+      const int rb = (c0 + c) * WG_CHUNK;
+      const bool ok = rb + lr < p.B;
+      const float* d = ok ? gd + (int64_t)rb * nout : delta;   // zero-filled rows still get a valid address (row 0)
+      if (pfd == 4) wg2_copy_row<4>(srow_d + so, d, ll, nout, ok);
+      else if (pfd == 2) wg2_copy_row<2>(srow_d + so, d, ll, nout, ok);
+      else wg2_copy_row<1>(srow_d + so, d, ll, nout, ok);
+      if (nin > 0) {
+        const float* i = ok ? gi + (int64_t)rb * in_ld : in;
+        if (pfi == 4) wg2_copy_row<4>(srow_i + so, i, ll, nin, ok);
+        else if (pfi == 2) wg2_copy_row<2>(srow_i + so, i, ll, nin, ok);
+        else wg2_copy_row<1>(srow_i + so, i, ll, nin, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+  const bool active = warp * 16 < nout && nt_used > 0;
+  __syncthreads();                          // the zero fill is ordered before the first cp.async lands
+#pragma unroll 1
+  for (int c = 0; c < WG2_STAGES - 1; ++c) issue(c);
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(WG2_STAGES - 2) : "memory");   // this thread's pieces of chunk c landed
+    const int so = (c % WG2_STAGES) * WG2_STAGE_FLOATS;
+    if (bn) {
+      if (pfi == 4) wg2_norm_row<4>(srow_i + so, bm, br, ll, nin);
+      else if (pfi == 2) wg2_norm_row<2>(srow_i + so, bm, br, ll, nin);
+      else wg2_norm_row<1>(srow_i + so, bm, br, ll, nin);
+    }
+    __syncthreads();                        // chunk c visible to all warps; chunk c-1 fully consumed
+    issue(c + WG2_STAGES - 1);              // refills the stage chunk c-1 used
+    if (active) {
+      const float* Ds = stages + so;
+      const float* Is = Ds + WG_CHUNK * WG2_PITCH;
+      if (nt_used == 8) warp_gemm<8, true, SPLIT>(Ds + warp * 16, WG2_PITCH, Is + wn * 64, WG2_PITCH, WG_CHUNK / 8, 8, acc, lane);
+      else if (nt_used == 5) warp_gemm<8, true, SPLIT>(Ds + warp * 16, WG2_PITCH, Is + wn * 64, WG2_PITCH, WG_CHUNK / 8, 5, acc, lane);
+      else warp_gemm<8, true, SPLIT>(Ds + warp * 16, WG2_PITCH, Is + wn * 64, WG2_PITCH, WG_CHUNK / 8, nt_used, acc, lane);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (!active) return;
+  float* part = p.part + (int64_t)split * p.part_split_stride + (int64_t)arm * p.part_arm_stride;
+  const int g = lane >> 2, tig = lane & 3;
+  const int ja = warp * 16 + g, jb = ja + 8;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (nt < nt_used) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = (e & 2) ? jb : ja;
+        const int i = (wn * 8 + nt) * 8 + 2 * tig + (e & 1);
+        if (j < nout) {
+          if (i < nin) part[pr.poffW - p.base_off + (int64_t)j * nin + i] = acc[nt][e];
+          else if (i == nin) part[pr.poffB - p.base_off + j] = acc[nt][e];
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) wgrad_reduce2_kernel(const WgArgs p) {
   const WgProblem& pr = p.prob[blockIdx.y >> 1];
   const int which = blockIdx.y & 1, arm = blockIdx.z;
@@ -573,7 +742,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce2_kernel(const WgArgs p) {
   if (e >= n) return;
   const float* part = p.part + (int64_t)arm * p.part_arm_stride + (poff - p.base_off) + e;
   float s = 0.f;
-  for (int sp = 0; sp < p.nsplit; ++sp) s += part[(int64_t)sp * p.part_split_stride];
+  for (int sp = 0; sp < pr.nsplit; ++sp) s += part[(int64_t)sp * p.part_split_stride];
   p.grads[(int64_t)arm * p.g_arm_stride + poff + e] = s;
 }
 
@@ -657,9 +826,70 @@ int launch_dense_bwd_mma(const DenseBwdArgs& a, int A, int split3, cudaStream_t 
   return 0;
 }
 
-int launch_wgrad_mma(const WgArgs& a, int split3, cudaStream_t s) {
-  if (split3) wgrad_mma_kernel<true><<<dim3(a.nsplit, a.nprob, a.A), 512, 0, s>>>(a);
-  else wgrad_mma_kernel<false><<<dim3(a.nsplit, a.nprob, a.A), 512, 0, s>>>(a);
+static bool legacy_wgrad() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MVAE_LEGACY_WGRAD"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+static bool no_tc_wgrad() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MVAE_NO_TC_WGRAD"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+int launch_wgrad_mma(const WgArgs& a0, int split3, cudaStream_t s) {
+  WgArgs a = a0;
+  bool fits = !legacy_wgrad();
+  for (int i = 0; i < a.nprob; ++i) fits = fits && a.prob[i].nout <= 128 && a.prob[i].nin <= 127;
+  if (fits) {
+    // the wide problems (many MMA tiles per chunk of cells) run on tcgen05 when TMA can read their operands
+    int tc_idx[8], ntc = 0;
+    bool on_tc[13];
+    for (int i = 0; i < a.nprob; ++i) {
+      const int tiles = ((a.prob[i].nout + 15) / 16) * ((a.prob[i].nin + 1 + 7) / 8);
+      on_tc[i] = !no_tc_wgrad() && tiles > 40 && ntc < 8 && tc_narrow_wgrad_ok(a, a.prob[i]);
+      if (on_tc[i]) tc_idx[ntc++] = i;
+    }
+    if (ntc > 0) {
+      const int rc = tc_narrow_wgrad(a, tc_idx, ntc, split3, s);
+      if (rc) return rc;
+    }
+    // the rest: split counts for one wave of two CTAs per SM; wide problems get twice the splits of narrow ones
+    int wsum = 0, wt[13];
+    for (int i = 0; i < a.nprob; ++i) {
+      const int tiles = ((a.prob[i].nout + 15) / 16) * ((a.prob[i].nin + 1 + 7) / 8);
+      wt[i] = on_tc[i] ? 0 : (tiles > 40 ? 2 : 1);
+      wsum += wt[i];
+    }
+    const int T = (a.B + WG_CHUNK - 1) / WG_CHUNK;
+    int per = wsum > 0 ? (2 * mma_sm_count()) / (a.A * wsum) : 1;
+    if (per < 1) per = 1;
+    int ctas = 0;
+    for (int i = 0; i < a.nprob; ++i) {
+      a.prob[i].cta_begin = ctas;
+      if (on_tc[i]) continue;               // keeps the split count tc_narrow_wgrad chose; no CTA here
+      int n = per * wt[i];
+      if (n > kWgMaxSplit) n = kWgMaxSplit;
+      if (n > T) n = T;
+      a.prob[i].nsplit = n;
+      ctas += n;
+    }
+    if (ctas > 0) {
+      static bool attr = false;
+      if (!attr) {
+        MVAE_CUDA(cudaFuncSetAttribute(wgrad2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_FLOATS * 4));
+        MVAE_CUDA(cudaFuncSetAttribute(wgrad2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_FLOATS * 4));
+        attr = true;
+      }
+      if (split3) wgrad2_kernel<true><<<dim3(ctas, a.A), 512, WG2_SMEM_FLOATS * 4, s>>>(a);
+      else wgrad2_kernel<false><<<dim3(ctas, a.A), 512, WG2_SMEM_FLOATS * 4, s>>>(a);
+    }
+  } else {
+    for (int i = 0; i < a.nprob; ++i) a.prob[i].nsplit = a.nsplit;
+    if (split3) wgrad_mma_kernel<true><<<dim3(a.nsplit, a.nprob, a.A), 512, 0, s>>>(a);
+    else wgrad_mma_kernel<false><<<dim3(a.nsplit, a.nprob, a.A), 512, 0, s>>>(a);
+  }
   MVAE_LAUNCH_CHECK();
   int64_t maxn = 0;
   for (int i = 0; i < a.nprob; ++i) {

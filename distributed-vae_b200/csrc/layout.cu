@@ -153,7 +153,8 @@ Work make_work(const mvae_dims& d) {
   w.wg_floats = L.offset[FC11_W] - L.offset[FC1_B];
   w.wg_rows = 256;
   w.wg_nsplit = (int32_t)((B + w.wg_rows - 1) / w.wg_rows);
-  w.wg_part = take((int64_t)w.wg_nsplit * A * w.wg_floats);
+  // the cp.async kernel (wgrad2) picks its split counts per problem from the SM count, at most kWgMaxSplit
+  w.wg_part = take((int64_t)(w.wg_nsplit > kWgMaxSplit ? w.wg_nsplit : kWgMaxSplit) * A * w.wg_floats);
   w.acc_fwd_floats = 2 * acc_fwd_doubles((int)A);
   w.acc_fwd = take(w.acc_fwd_floats);
   w.acc_loss_floats = 2 * acc_loss_doubles();

@@ -387,8 +387,10 @@ def test_in_kernel_noise_is_uniform_and_regenerated_by_backward():
     q, y = torch.stack(cs), torch.stack(c_smps)
     # Gumbel noise up to a per-row constant (softmax-invariant): g' = temp * log y - log(q + eps)
     g = hp.temp * torch.log(y.clamp_min(1e-30)) - torch.log(q + hp.eps)
-    g = g - g.amax(-1, keepdim=True)
-    U = torch.exp(-torch.exp(-g)).clamp(1e-7, 1 - 1e-7)
+    # shift every row so that its largest draw sits at g = 8.5 (U = 1 - 2e-4): the whole Gumbel range of a row (~7 wide)
+    # then maps into (1e-7, 1 - 1e-7) where fp32 resolves U; anchoring the maximum at 0 would clamp most draws at 1e-7
+    g = g.double() - g.double().amax(-1, keepdim=True) + 8.5
+    U = torch.exp(-torch.exp(-g)).clamp(1e-7, 1 - 1e-7).float()
     m2 = build_model(hp, "tf32x3")
     noise = {"U": U, "E": E.clamp(0, 1), "keep_x": torch.ones(hp.n_arm, B, hp.input_dim, dtype=torch.bool),
              "keep_s": torch.ones(hp.n_arm, B, hp.state_dim, dtype=torch.bool)}
