@@ -536,4 +536,32 @@ int mvae_confmat(const int32_t* labels, int64_t n_cells, int32_t n_arm, int32_t 
   return launch_confmat(labels, n_cells, n_arm, n_categories, counts, (cudaStream_t)stream);
 }
 
+// ---- augmenter forward: see include/mixvae_b200.h
+int mvae_fold_affine(const float* bias, const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                     int32_t n, float* scale, float* shift, void* stream) {
+  MVAE_CHECK_ARG(scale && shift && n >= 1, "bad argument");
+  MVAE_CHECK_ARG((mean == nullptr) == (var == nullptr), "mean and var come together");
+  RC(check_device());
+  return launch_fold_affine(bias, mean, var, gamma, beta, eps, n, scale, shift, (cudaStream_t)stream);
+}
+
+int mvae_fma_rows(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, float* out, int64_t ldo,
+                  int64_t rows, int32_t n, float a_scale, void* stream) {
+  MVAE_CHECK_ARG(a && out && rows >= 0 && n >= 1, "bad argument");
+  RC(check_device());
+  return launch_fma_rows(a, lda, b, ldb, c, ldc, out, ldo, rows, n, a_scale, (cudaStream_t)stream);
+}
+
+int mvae_linear_act(const float* x, int64_t x_pitch, const float* w, int64_t w_pitch, float* y, int64_t y_pitch, int64_t rows,
+                    int32_t n_out, int32_t k, const float* scale, const float* shift, int32_t act, int32_t split3, void* stream) {
+  MVAE_CHECK_ARG(x && w && y && scale && shift, "null argument");
+  MVAE_CHECK_ARG(rows >= 1 && rows < (1ll << 31) && n_out >= 1 && k >= 1, "bad shape");
+  MVAE_CHECK_ARG(x_pitch % 4 == 0 && w_pitch % 4 == 0 && x_pitch >= k && w_pitch >= k && y_pitch >= n_out,
+                 "pitches: x and w multiples of 4 floats and >= k, y >= n_out");
+  MVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, "x and w must be 16-byte aligned");
+  MVAE_CHECK_ARG(act >= 0 && act <= 3, "act must be 0 (none), 1 (relu), 2 (elu) or 3 (sigmoid)");
+  RC(check_device());
+  return tc_linear_act(x, x_pitch, w, w_pitch, y, y_pitch, rows, n_out, k, scale, shift, act, split3, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -44,7 +44,17 @@ struct TcArgs {
   int flags;
   float* C; int64_t ldc, c_batch_stride, c_split_stride;
   DropSpec drop;
+  // optional fused epilogue (nsplit == 1): C = act(acc * ep_scale[col] + ep_shift[col]); act 0 none, 1 relu, 2 elu, 3 sigmoid
+  const float* ep_scale; const float* ep_shift; int ep_act;
 };
+
+__device__ __forceinline__ float ep_apply(float v, float sc, float sh, int act) {
+  v = fmaf(v, sc, sh);
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return v > 0.f ? v : expm1f(v);
+  if (act == 3) return 1.f / (1.f + expf(-v));
+  return v;
+}
 
 using namespace tc;
 
@@ -250,6 +260,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (row < args.M) {
         const int col = n0 + c0;
+        if (args.ep_scale) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (col + i < args.N)
+              r[i] = __float_as_uint(ep_apply(__uint_as_float(r[i]), args.ep_scale[col + i], args.ep_shift[col + i], args.ep_act));
+        }
         if (vec_ok && col + 16 <= args.N) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -505,7 +521,7 @@ struct Operand {
 // C[batch][split] (M x N, ldc) = A . B  over K; split-K partials are summed by the caller.
 int run_tc_gemm(const Operand& A, const Operand& B, int M, int N, int K, int BN, int batch, int nsplit, int flags,
                 const DropSpec& drop, float* C, int64_t ldc, int64_t c_batch_stride, int64_t c_split_stride,
-                cudaStream_t s) {
+                cudaStream_t s, const float* ep_scale = nullptr, const float* ep_shift = nullptr, int ep_act = 0) {
   CUtensorMap tmA, tmB;
   // K-major: inner = K, outer = M (box rows = 128 / BN); MN-major: inner = M/N, outer = K (box rows = BK)
   int rc = A.mn_major ? make_map(&tmA, A.base, M, K, A.pitch, batch, A.batch_stride, BK, true)
@@ -527,6 +543,8 @@ int run_tc_gemm(const Operand& A, const Operand& B, int M, int N, int K, int BN,
   a.flags = flags;
   a.C = C; a.ldc = ldc; a.c_batch_stride = c_batch_stride; a.c_split_stride = c_split_stride;
   a.drop = drop;
+  a.ep_scale = ep_scale; a.ep_shift = ep_shift; a.ep_act = ep_act;
+  MVAE_CHECK_ARG(ep_scale == nullptr || (a.nsplit == 1 && ep_shift != nullptr), "the fused epilogue needs nsplit == 1");
   const size_t smem = (size_t)a.stages * tiles * TILE_BYTES + (3 * a.stages + 2) * 8 + 1024;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch * nsplit);
 #define TC_LAUNCH(AM, BMJ)                                                                                         \
@@ -792,3 +810,63 @@ extern "C" int mvae_debug_tc_gemm(const float* A, int a_mn, int64_t a_pitch, con
   memset(&nodrop, 0, sizeof(nodrop));
   return run_tc_gemm(a, b, M, N, K, BN, 1, nsplit, flags, nodrop, C, ldc, 0, c_split_stride, (cudaStream_t)stream);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Augmenter forward (mmidas/augmentation/udagan.py:217-329, eval mode): a chain of Linear layers whose
+// BatchNorm (running statistics) / bias / activation collapse into a per-column affine + activation epilogue.
+// ---------------------------------------------------------------------------------------------
+namespace mvae {
+namespace {
+// scale = gamma / sqrt(var + eps), shift = (bias - mean) * scale + beta   (null mean/var: plain bias)
+__global__ void __launch_bounds__(256) fold_affine_kernel(const float* bias, const float* mean, const float* var,
+                                                          const float* gamma, const float* beta, float eps, int n,
+                                                          float* scale, float* shift) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float sc = 1.f, sh = bias ? bias[i] : 0.f;
+  if (var) {
+    sc = (gamma ? gamma[i] : 1.f) / sqrtf(var[i] + eps);
+    sh = (sh - mean[i]) * sc + (beta ? beta[i] : 0.f);
+  }
+  scale[i] = sc;
+  shift[i] = sh;
+}
+// out[r][c] = a[r][c] * b[r][c] + c0[r][c] on [rows x n] views with their own pitches (reparameterisation s = eps * sigma + mu)
+__global__ void __launch_bounds__(256) fma_rows_kernel(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c0,
+                                                       int64_t ldc0, float* out, int64_t ldo, int64_t rows, int n, float a_scale) {
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= rows * n) return;
+  const int64_t r = idx / n;
+  const int c = (int)(idx - r * n);
+  const float bv = b ? b[r * ldb + c] : 1.f, cv = c0 ? c0[r * ldc0 + c] : 0.f;
+  out[r * ldo + c] = fmaf(a_scale * a[r * lda + c], bv, cv);
+}
+}  // namespace
+}  // namespace mvae
+
+namespace mvae {
+int launch_fold_affine(const float* bias, const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                       int n, float* scale, float* shift, cudaStream_t s) {
+  fold_affine_kernel<<<(n + 255) / 256, 256, 0, s>>>(bias, mean, var, gamma, beta, eps, n, scale, shift);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+int launch_fma_rows(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, float* out, int64_t ldo,
+                    int64_t rows, int n, float a_scale, cudaStream_t s) {
+  if (rows == 0) return 0;
+  fma_rows_kernel<<<(unsigned)((rows * n + 255) / 256), 256, 0, s>>>(a, lda, b, ldb, c, ldc, out, ldo, rows, n, a_scale);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+// y[rows][n_out] (pitch y_pitch) = act((x[rows][k] . w[n_out][k]^T) * scale + shift)
+int tc_linear_act(const float* x, int64_t x_pitch, const float* w, int64_t w_pitch, float* y, int64_t y_pitch, int64_t rows,
+                  int n_out, int k, const float* scale, const float* shift, int act, int split3, cudaStream_t s) {
+  Operand a{x, x_pitch, 0, false};
+  Operand b{w, w_pitch, 0, false};
+  DropSpec nodrop;
+  memset(&nodrop, 0, sizeof(nodrop));
+  const int BN = n_out >= 128 ? 128 : round16(n_out);
+  return run_tc_gemm(a, b, (int)rows, n_out, k, BN, 1, 1, split3 ? (F_SPLIT_A | F_SPLIT_B) : 0, nodrop, y, y_pitch, 0, 0, s, scale,
+                     shift, act);
+}
+}  // namespace mvae

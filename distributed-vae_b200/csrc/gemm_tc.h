@@ -43,6 +43,14 @@ int ts_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& i
 // through a column of ones); partials in the layout of wgrad_reduce2_kernel
 bool tc_narrow_wgrad_ok(const WgArgs& a, const WgProblem& q);
 int tc_narrow_wgrad(WgArgs& a, const int* idx, int n, int split3, cudaStream_t s);
+// augmenter forward pieces (udagan.py:217-329, eval mode): folded BatchNorm/bias affine, Linear with fused affine + activation
+// epilogue on tcgen05, and the row-wise fma used by the reparameterisation
+int launch_fold_affine(const float* bias, const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                       int n, float* scale, float* shift, cudaStream_t s);
+int launch_fma_rows(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, float* out, int64_t ldo,
+                    int64_t rows, int n, float a_scale, cudaStream_t s);
+int tc_linear_act(const float* x, int64_t x_pitch, const float* w, int64_t w_pitch, float* y, int64_t y_pitch, int64_t rows,
+                  int n_out, int k, const float* scale, const float* shift, int act, int split3, cudaStream_t s);
 bool legacy_gene_kernels();   // MVAE_LEGACY_FC1=1 / MVAE_LEGACY_FC11=1: round-1 first-generation kernels (A/B comparisons)
 
 }  // namespace mvae

@@ -6,3 +6,4 @@ and ``mmidas._dist_utils``; everything numeric runs in ``libmixvae_b200.so``.
 """
 from .nn_model import VAEConfig, mixVAE_model, mk_vae  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from .augmentation import Augmenter_smartseq, mk_augmenter  # noqa: F401

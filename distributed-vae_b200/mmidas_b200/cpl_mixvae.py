@@ -80,10 +80,12 @@ class cpl_mixVAE:
         if device is None or device == "cpu" or device == "mps":
             raise RuntimeError("cpl_mixVAE (B200) needs a CUDA device; there is no CPU path")
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
-        if aug_file:
-            raise NotImplementedError("the pre-trained augmenter (mmidas/augmentation, cpl_mixvae.py:128-149) is the "
-                                      "next scope row (SURVEY §8 f1); train with aug_file=''")
-        self.aug_model, self.aug_param, self.netA = None, None, None
+        if aug_file:     # cpl_mixvae.py:182-186: pre-trained VAE-GAN generator, eval mode
+            from .augmentation import mk_augmenter
+            self.aug_model, self.aug_param, netA = mk_augmenter(aug_file, load_weights)
+            self.netA = netA.to(self.device).eval()
+        else:
+            self.aug_model, self.aug_param, self.netA = None, None, None
         self.precision = "tf32x3_fc1"
 
     # ------------------------------------------------------------------------------------------
@@ -143,12 +145,14 @@ class cpl_mixVAE:
     # ------------------------------------------------------------------------------------------
     # one optimiser step (cpl_mixvae.py:434-463)
     # ------------------------------------------------------------------------------------------
-    def train_batch(self, x: torch.Tensor, noise=None) -> torch.Tensor:
+    def train_batch(self, x: torch.Tensor, noise=None, aug_noise=None) -> torch.Tensor:
         """zero_grad -> forward -> loss -> backward -> Adam on one batch ``x`` [B, D] already on the device.
         Returns the device loss vector (total, joint, entropy, distance, l2, rec[A], kl[A], ll[A]); nothing
         is synchronised."""
         A = self.n_arm
         xs = x.expand(A, -1, -1)
+        if self.netA is not None:      # cpl_mixvae.py:422-423: every arm trains on its own augmented copy of the batch
+            xs = self.netA(xs, True, 0.1, noise=aug_noise)[1]
         if isinstance(self.optimizer, FusedAdam) and self.optimizer.model is self.model:
             return self.model.fused_train_step(xs, self.temp, self.optimizer, noise=noise)
         # a caller replaced .optimizer (train.py:144-147): reference-shaped sequence on the same kernels

@@ -176,6 +176,22 @@ int mvae_debug_tc_gemm(const float* A, int a_mn, int64_t a_pitch, const float* B
                        int M, int N, int K, int BN, int nsplit, int flags, float* C, int64_t ldc,
                        int64_t c_split_stride, void* stream);
 
+/* ---- Augmenter forward: mmidas/augmentation/udagan.py:217-329 (Augmenter_smartseq.forward) as called by the
+ * training loop in eval mode (cpl_mixvae.py:184, :422-423).  With running statistics every `relu(batch_fcN(fcN(x)))` is a
+ * Linear followed by a per-column affine and an activation:
+ *   mvae_fold_affine : scale = gamma / sqrt(var + eps), shift = (bias - mean) * scale + beta   (null mean/var: shift = bias)
+ *   mvae_linear_act  : y = act((x . w^T) * scale + shift) on tcgen05 (TF32, or error-compensated 3xTF32 when split3 != 0);
+ *                      x [rows][k] and w [n_out][k] row-major, pitches multiples of 4 floats (pad columns hold zeros),
+ *                      act: 0 none, 1 relu, 2 elu, 3 sigmoid
+ *   mvae_fma_rows    : out = a_scale * a * b + c on [rows][n] views (reparam_trick, aug_utils.py:51-65; b / c may be null)
+ * replacing nn.Linear / nn.BatchNorm1d(eval) / F.relu / F.elu / torch.sigmoid of the reference. */
+int mvae_fold_affine(const float* bias, const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                     int32_t n, float* scale, float* shift, void* stream);
+int mvae_linear_act(const float* x, int64_t x_pitch, const float* w, int64_t w_pitch, float* y, int64_t y_pitch, int64_t rows,
+                    int32_t n_out, int32_t k, const float* scale, const float* shift, int32_t act, int32_t split3, void* stream);
+int mvae_fma_rows(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, float* out, int64_t ldo,
+                  int64_t rows, int32_t n, float a_scale, void* stream);
+
 /* Device-time accounting for bench.py's roofline: when enabled, the library brackets each kernel
  * group with CUDA events on the launching stream.  Groups (index into ms_out / count_out):
  *   0 fc1 forward  1 fc11 fused loss+grad  2 fc1 weight gradient  3 narrow layers forward

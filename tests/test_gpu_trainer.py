@@ -93,3 +93,33 @@ def test_sharded_trainer_single_process_matches_fused_step():
     from mmidas_b200 import FusedAdam
     from mmidas_b200.parallel import plan_mesh
     assert plan_mesh(1, 2).arm_ranks == 1
+
+
+def test_training_step_on_augmented_input_matches_oracle(tmp_path):
+    """aug_file set (cpl_mixvae.py:182-186, :422-423): the step trains on netA(x.expand(A,-1,-1), True, 0.1)[1].  With the
+    augmenter's and the VAE's noise injected, the loss equals the oracle's loss on the oracle-augmented cells."""
+    from mmidas_b200.cpl_mixvae import cpl_mixVAE
+    from oracle import augmenter_oracle as AO
+    D, B, A, C = 260, 96, 2, 9
+    # mk_augmenter builds Augmenter_smartseq with its default n_dim = 500 (cpl_mixvae.py:135-139)
+    sd_aug = AO.random_state_dict(50, 10, D, 500, seed=21)
+    path = str(tmp_path / "aug.pth")
+    torch.save({"parameters": {"num_n": 50, "num_z": 10, "n_features": D}, "netA": sd_aug}, path)
+    hp = O.HP(input_dim=D, n_categories=C, state_dim=2, n_arm=A, x_drop=0.0, s_drop=0.0)
+    t = cpl_mixVAE(saving_folder="", aug_file=path, device="cuda", save_flag=False)
+    assert t.aug_param["n_features"] == D and t.netA is not None and not t.netA.training
+    t.precision = "fp32_simt"
+    t.init_model(n_categories=C, state_dim=2, input_dim=D, x_drop=0.0, s_drop=0.0, n_arm=A, lr=1e-3)
+    sd0 = O.init_state_dict(hp, 546)
+    t.model.load_state_dict(sd0)
+    t.model.train()
+    gen = torch.Generator().manual_seed(4)
+    x = O.synth_x(B, D, gen)
+    z, eps = torch.randn(A, B, 50, generator=gen), torch.randn(A, B, 10, generator=gen)
+    noise = O.synth_noise(hp, B, gen)
+    lv = t.train_batch(x.cuda(), noise={k: v.cuda() for k, v in noise.items()}, aug_noise={"z": z.cuda(), "eps": eps.cuda()})
+    torch.cuda.synchronize()
+    _, xa = AO.forward(sd_aug, x.expand(A, -1, -1), z, eps, 0.1)
+    st = O.TrainState(hp, O.cast_state_dict(sd0, torch.float32))
+    ref = O.train_step(st, [xa[a] for a in range(A)], noise)
+    assert abs(lv[0].item() / float(ref["loss"]["total"]) - 1) < 1e-4, (lv[0].item(), float(ref["loss"]["total"]))
