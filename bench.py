@@ -188,6 +188,9 @@ def main():
     ap.add_argument("--mesh", default="dp", choices=["dp", "arm", "auto"])
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cpu (the contract) or cuda (informational: eager torch on the GPU)")
+    ap.add_argument("--augment", default="off", choices=["off", "tf32x3", "tf32"],
+                    help="single GPU only: run the VAE-GAN augmenter forward (SURVEY f1, production default "
+                         "--augmentation True) in front of every step, random-init weights; adds an `augmenter` object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -227,6 +230,15 @@ def main():
         step_fn = trainer.train_batch
         parallelism = "single GPU"
         dp_ranks = 1
+        if args.augment != "off":
+            from mmidas_b200 import Augmenter_smartseq
+            torch.manual_seed(547)
+            netA = Augmenter_smartseq(noise_dim=50, latent_dim=10, input_dim=D, precision=args.augment)
+            for m in netA.modules():                       # non-trivial running statistics, as after training
+                if isinstance(m, torch.nn.BatchNorm1d):
+                    m.running_mean.normal_(0.0, 0.2)
+                    m.running_var.uniform_(0.05, 0.55)
+            trainer.netA = netA.to(dev).eval()
     else:
         from mmidas_b200.parallel import ShardedTrainer
         st = ShardedTrainer(model_kwargs, lr=1e-3, mode=args.mesh)
@@ -260,7 +272,6 @@ def main():
     sync()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n0
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -303,6 +314,31 @@ def main():
                              "frac": algorithmic_bytes(w) / (ms_per_step / 1e3) / 1e9 / peak},
                     "groups_ms_per_step": {g: round(v["ms_per_step"], 4) for g, v in groups.items()}}
 
+    # ---- the augmenter forward alone (when enabled): device time and achieved tensor throughput ----
+    aug = None
+    if world == 1 and args.augment != "off" and rank == 0:
+        netA = trainer.netA
+        F1, nd, nz, nl = D // 5, 500, 50, 10
+        enc = D * F1 + F1 * F1 + F1 * nd + nd * nd
+        dec = nz * nz + (nd + nz) * (nd // 5) + 2 * (nd // 5) * nl + nl * (nd // 5) + (nd // 5) * nd + nd * nd + nd * F1 + F1 * F1 + F1 * D
+        flops = 2.0 * (B * enc + A * B * dec)             # fc1..fc4 once per cell, the rest per (arm, cell)
+        xs = batches[0].expand(A, -1, -1)
+        for _ in range(3):
+            netA(xs, True, 0.1)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        a0.record()
+        for i in range(args.steps):
+            netA(batches[i % N_ROTATING_BATCHES].expand(A, -1, -1), True, 0.1)
+        a1.record()
+        torch.cuda.synchronize()
+        ams = a0.elapsed_time(a1) / args.steps
+        aug = {"ms_per_step": ams, "precision": args.augment, "gflop_per_step": flops / 1e9,
+               "achieved_tflops": flops / (ams / 1e3) / 1e12, "launches_per_step": (_lib.launch_count() - l0) / args.steps,
+               "note": "Augmenter_smartseq eval forward (udagan.py:285-329), x.expand over arms: fc1..fc4 evaluated once per cell; "
+                       "3xTF32 issues 3 MMAs per product (achieved_tflops counts the fp32-equivalent product once)"}
+
     # ---- end to end: pinned host batches -> H2D -> step -> loss read-back -------------------------
     e2e = None
     if not args.no_e2e:
@@ -334,6 +370,9 @@ def main():
                "h2d_gbs_per_gpu": B * D * 4 / (dt / n_e2e) / 1e9,   # ~56 GB/s = the PCIe ceiling: e2e is copy-bound
                "api": "cpl_mixVAE.train_batch via HostBatchFeeder (pinned host batch -> side-stream H2D -> fused step -> loss.item())"}
 
+    # the sampler ran from before the timed region through the per-group and end-to-end passes (the same steps, same load):
+    # a 20 ms timed region alone would see a single 200 ms sample
+    clocks = sampler.stop() if rank == 0 else None
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base, _ = cpu_reference(w, 20, 2)
@@ -350,7 +389,9 @@ def main():
                            "precision": args.precision, "dropout": "x_drop=0.5 in-kernel counter-based generator",
                            "l2": f"inputs rotate over {N_ROTATING_BATCHES} distinct batches "
                                  f"({N_ROTATING_BATCHES * B * D * 4 / 1e6:.0f} MB > 126 MB L2)",
-                           "last_total_loss": last_loss},
+                           "last_total_loss": last_loss,
+                           **({"augmenter": f"Augmenter_smartseq forward ({args.augment}) in front of every step"} if aug else {})},
+                **({"augmenter": aug} if aug else {}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_base}
         print(json.dumps(line), flush=True)

@@ -213,6 +213,15 @@ __global__ void __launch_bounds__(128) loss_finalize_kernel(const LossFinalArgs 
     p.colc[(int64_t)a * 512 + 256 + k] = mn;
     p.colc[(int64_t)a * 512 + 384 + k] = T;
   }
+  // stage every accumulator the scalar part reads in shared memory first: one round of independent loads by all threads
+  // instead of ~30 serial global loads by thread 0 (this kernel sits on the critical path between loss and backward)
+  __shared__ double sh_rec[MVAE_MAX_ARMS][2], sh_kl[MVAE_MAX_ARMS][kMaxS], sh_pair[kMaxPairs][2], sh_ent[MVAE_MAX_ARMS];
+  const int npairs_all = At * (At - 1) / 2;
+  for (int idx = tid; idx < A * 2; idx += blockDim.x) sh_rec[idx >> 1][idx & 1] = p.acc_loss[accl_recon(idx >> 1) + (idx & 1)];
+  for (int idx = tid; idx < A * p.S; idx += blockDim.x) sh_kl[idx / p.S][idx % p.S] = p.kl_sums[(int64_t)(idx / p.S) * 16 + idx % p.S];
+  for (int idx = tid; idx < npairs_all * 2; idx += blockDim.x) sh_pair[idx >> 1][idx & 1] = p.acc_loss[accl_pair(idx >> 1) + (idx & 1)];
+  for (int idx = tid; idx < At; idx += blockDim.x) sh_ent[idx] = p.acc_loss[accl_ent(idx)];
+  __syncthreads();
   if (tid == 0) {
     const double log2pi = 1.8378770664093453;
     float* out = p.loss_out;
@@ -220,24 +229,24 @@ __global__ void __launch_bounds__(128) loss_finalize_kernel(const LossFinalArgs 
     double sum_ind = 0.0;
     for (int a = 0; a < A; ++a) {
       const int ga = a + p.arm_off;
-      const double sse = p.acc_loss[accl_recon(a)], mism = p.acc_loss[accl_recon(a) + 1];
+      const double sse = sh_rec[a][0], mism = sh_rec[a][1];
       const double numel = Bd * (double)p.D;
       const float rec = (float)(0.5 * sse / Bd + 0.5 * (100.0 * mism / numel));
       const float ll = (float)(sse / numel + Bd * log2pi);
       double kl = 0.0;
-      for (int s = 0; s < p.S; ++s) kl += -0.5 * (p.kl_sums[(int64_t)a * 16 + s] / Bd);
+      for (int s = 0; s < p.S; ++s) kl += -0.5 * (sh_kl[a][s] / Bd);
       out[5 + ga] = rec;
       out[5 + At + ga] = (float)kl;
       out[5 + 2 * At + ga] = ll;
       sum_ind += (double)rec + (double)p.beta * kl;
     }
-    const int npairs = At * (At - 1) / 2;
+    const int npairs = npairs_all;
     double sum_dist = 0.0, sum_l2 = 0.0, sum_ent = 0.0;
     for (int i = 0; i < npairs; ++i) {
-      sum_dist += p.acc_loss[accl_pair(i)] / Bd;
-      sum_l2 += p.acc_loss[accl_pair(i) + 1] / Bd;
+      sum_dist += sh_pair[i][0] / Bd;
+      sum_l2 += sh_pair[i][1] / Bd;
     }
-    for (int a = 0; a < At; ++a) sum_ent += (double)(At - 1) * p.acc_loss[accl_ent(a)] / Bd;
+    for (int a = 0; a < At; ++a) sum_ent += (double)(At - 1) * sh_ent[a] / Bd;
     const double np_f = npairs > 1 ? (double)npairs : 1.0;
     const double joint = (double)p.lam * sum_dist + sum_ent +
                          np_f * (((double)C / 2.0) * log2pi - 0.5 * log(2.0 * (double)p.lam));
