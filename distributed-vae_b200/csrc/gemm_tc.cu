@@ -288,8 +288,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // Grouped weight-gradient GEMM of the narrow layers (fc2..fc4, fc8..fc10: delta^T . bn(input), both operands MN-major):
 // the same pipeline as tc_gemm_kernel<true, true>, one (problem, arm, K split) per CTA.  The warp-level mma.sync path
-// (kernels_mma.cu) is bound by the legacy HMMA pipe on sm_100 (ncu: sm__pipe_tensor_subpipe_hmma_cycles_active = 78 % of
-// the kernel, ~8 cycles per m16n8k8 per SM = 128 MAC/clk/SM, the fp32 FFMA rate); tcgen05 runs the same tile 13x faster.
+// (kernels_mma.cu) spends its issue slots on LDS.32 fragment loads and per-chunk staging (ncu: 11 M warp instructions for
+// these six problems, HMMA pipe < 20 % busy); here the tensor core reads both operands from shared memory itself.
 // The transform warps normalise the input tile in place ((v - mean) * rstd, batch_l1..l4), write a column of ones
 // behind the last input column (row j of that accumulator column is the bias gradient sum_b delta[b][j]) and, in the
 // 3xTF32 mode, the low halves.  Partials go to the layout wgrad_reduce2_kernel sums.
