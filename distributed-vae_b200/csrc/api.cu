@@ -185,6 +185,10 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   h.s_mean = out.s_mean; h.s_logvar = out.s_logvar; h.s_smp = out.s_smp;
   h.ysoft = work + w.ysoft; h.svar = work + w.svar; h.yy = work + w.yy; h.zc = work + w.zc; h.d6 = work + w.d[0];
   h.kl_sums = acc_fwd + acc_kl(A, 0);
+  if (training) {   // running statistics of batch_l1..l5 updated by the head kernel (one launch less)
+    h.bn_running = st.bn_running; h.bn_stride = p.L.bn_stride; h.bn_off = bn_off(p); h.nbt = st.bn_batches;
+    h.bn_sums_all = acc_fwd; h.momentum = hp.momentum;
+  }
   RC(launch_head_fwd(h, s));
 
   // ---- fc7..fc10 (:281-284)
@@ -204,9 +208,6 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
       RC(launch_dense_fwd(a, A, s));
     }
   }
-  if (training)
-    RC(launch_bn_update_running(st.bn_running, p.L.bn_stride, bn_off(p), st.bn_batches, acc_fwd, A, B, H, Ld,
-                                hp.momentum, s));
   timing_end(TG_NARROW_FWD, s);
 
   // ---- optional materialised reconstruction x_rec = relu(fc11(h10)) (:287)

@@ -61,6 +61,9 @@ struct HeadArgs {
   float *x_low, *c_prob, *qc, *c_smp, *s_mean, *s_logvar, *s_smp;
   float *ysoft, *svar, *yy, *zc, *d6;
   double* kl_sums;            // [A][16]: sum_b(1+lv-mu^2-e^lv) per state dim
+  // optional (training): running-statistics update of batch_l1..l5 by block 0 of every arm (nn.BatchNorm1d momentum
+  // update, unbiased variance; replaces a separate launch).  bn_running == nullptr: skipped.
+  float* bn_running; int64_t bn_stride; BnOff bn_off; int64_t* nbt; const double* bn_sums_all; float momentum;
   // backward-only
   const float* g_d6;          // [A][B][L]
   const float* rsum;          // [B][C]

@@ -119,12 +119,19 @@ __device__ __forceinline__ float fcc_bwd_rows(const HeadSmem& h, const float (&g
 // =============================================================================================
 // forward
 // =============================================================================================
-template <int NL>   // reduction width of the L-row products: 16 (lowD_dim <= 16) or 32
+// NL: reduction width of the L-row products, 16 (lowD_dim <= 16) or 32.  C96: n_categories > 96, so that only the last of
+// the four category slots of a lane (lane + 96) needs its `< C` guard -- the other three guards fold away.
+// LC / SC: compile-time lowD_dim / state_dim (0: run-time values); the reference's 10 / 2 get their own instance.
+template <int NL, bool C96, int LC, int SC>
 __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadArgs p) {
   extern __shared__ __align__(16) float smem[];
   const int arm = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int L = p.L, C = p.C, S = p.S, B = p.B;
+  const int L = LC ? LC : p.L, C = p.C, S = SC ? SC : p.S, B = p.B;
+  if (C96) {
+    __builtin_assume(C > 96);
+    __builtin_assume(C <= 128);
+  }
   const HeadSmem h = head_carve(smem, L, C, S);
   head_load_weights(p, h, arm, false);
   if (p.bn_mode == 1) {
@@ -148,6 +155,26 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
     }
   }
   __syncthreads();
+  if (p.bn_running && blockIdx.x == 0) {
+    // running = (1 - m) running + m batch (unbiased variance), num_batches_tracked += 1: the batch sums of all five
+    // BatchNorms are final when this kernel starts
+    for (int layer = 0; layer < 5; ++layer) {
+      const int n = layer < 4 ? p.H : L;
+      float* rm = p.bn_running + (int64_t)arm * p.bn_stride + p.bn_off.off[layer];
+      float* rv = rm + n;
+      const double* sums = p.bn_sums_all + acc_bn(layer, p.A, arm);
+      for (int i = tid; i < n; i += blockDim.x) {
+        const double m = sums[i] / (double)B;
+        double var = sums[128 + i] / (double)B - m * m;
+        if (var < 0.0) var = 0.0;
+        const float mean_f = (float)m;
+        const float var_u = (float)(var * (double)B / (double)(B - 1));
+        rm[i] = (1.0f - p.momentum) * rm[i] + p.momentum * mean_f;
+        rv[i] = (1.0f - p.momentum) * rv[i] + p.momentum * var_u;
+      }
+      if (tid == 0) p.nbt[arm * 6 + layer] += 1;
+    }
+  }
 
   const int64_t ab = (int64_t)arm * B;
   __shared__ double klacc_sm[kRowWarps][kMaxS];   // per-warp KL sums (lane 0 only): kept out of the register file
@@ -320,13 +347,17 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
 // =============================================================================================
 // backward
 // =============================================================================================
-template <int NL>
+template <int NL, bool C96, int LC, int SC>
 __global__ void __launch_bounds__(kRowWarps * 32, 3) head_bwd_kernel(const HeadArgs p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[kRowWarps][2][32];
   const int arm = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int L = p.L, C = p.C, S = p.S, B = p.B;
+  const int L = LC ? LC : p.L, C = p.C, S = SC ? SC : p.S, B = p.B;
+  if (C96) {
+    __builtin_assume(C > 96);
+    __builtin_assume(C <= 128);
+  }
   const HeadSmem h = head_carve(smem, L, C, S);
   head_load_weights(p, h, arm, true);
   __syncthreads();
@@ -466,23 +497,45 @@ static int head_grid(int B, int A) {
   return gx > cap ? (cap > 0 ? cap : 1) : gx;
 }
 
+template <typename F>
+static int head_set_attr(F* f) {
+  MVAE_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  return 0;
+}
 static int head_attrs() {
   static bool attr_done = false;
   if (!attr_done) {
-    MVAE_CUDA(cudaFuncSetAttribute(head_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    MVAE_CUDA(cudaFuncSetAttribute(head_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    MVAE_CUDA(cudaFuncSetAttribute(head_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    MVAE_CUDA(cudaFuncSetAttribute(head_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+#define HEAD_ATTR(...)                                                     \
+  if (int rc = head_set_attr(head_fwd_kernel<__VA_ARGS__>)) return rc;     \
+  if (int rc = head_set_attr(head_bwd_kernel<__VA_ARGS__>)) return rc;
+    HEAD_ATTR(16, false, 0, 0) HEAD_ATTR(16, true, 0, 0) HEAD_ATTR(32, false, 0, 0) HEAD_ATTR(32, true, 0, 0)
+    HEAD_ATTR(16, false, 10, 2) HEAD_ATTR(16, true, 10, 2)
+#undef HEAD_ATTR
     attr_done = true;
   }
   return 0;
 }
 
+#define HEAD_DISPATCH(KERNEL)                                                                       \
+  do {                                                                                              \
+    const size_t sm = head_smem_bytes(a.L, a.C, a.S);                                               \
+    const bool c96 = a.C > 96;                                                                      \
+    if (a.L == 10 && a.S == 2) {                                                                    \
+      if (c96) KERNEL<16, true, 10, 2><<<grid, kRowWarps * 32, sm, s>>>(a);                         \
+      else KERNEL<16, false, 10, 2><<<grid, kRowWarps * 32, sm, s>>>(a);                            \
+    } else if (a.L <= 16) {                                                                         \
+      if (c96) KERNEL<16, true, 0, 0><<<grid, kRowWarps * 32, sm, s>>>(a);                          \
+      else KERNEL<16, false, 0, 0><<<grid, kRowWarps * 32, sm, s>>>(a);                             \
+    } else {                                                                                        \
+      if (c96) KERNEL<32, true, 0, 0><<<grid, kRowWarps * 32, sm, s>>>(a);                          \
+      else KERNEL<32, false, 0, 0><<<grid, kRowWarps * 32, sm, s>>>(a);                             \
+    }                                                                                               \
+  } while (0)
+
 int launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
   if (int rc = head_attrs()) return rc;
   const dim3 grid(head_grid(a.B, a.A), a.A);
-  if (a.L <= 16) head_fwd_kernel<16><<<grid, kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
-  else head_fwd_kernel<32><<<grid, kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
+  HEAD_DISPATCH(head_fwd_kernel);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -490,10 +543,10 @@ int launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
 int launch_head_bwd(const HeadArgs& a, cudaStream_t s) {
   if (int rc = head_attrs()) return rc;
   const dim3 grid(head_grid(a.B, a.A), a.A);
-  if (a.L <= 16) head_bwd_kernel<16><<<grid, kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
-  else head_bwd_kernel<32><<<grid, kRowWarps * 32, head_smem_bytes(a.L, a.C, a.S), s>>>(a);
+  HEAD_DISPATCH(head_bwd_kernel);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
+#undef HEAD_DISPATCH
 
 }  // namespace mvae

@@ -50,7 +50,9 @@ static int check_dims(const mvae_dims& d) {
   MVAE_CHECK_ARG(d.lowD_dim >= 1 && d.lowD_dim <= kMaxL, "lowD_dim=%d unsupported (1..%d)", d.lowD_dim, kMaxL);
   MVAE_CHECK_ARG(d.n_categories >= 2 && d.n_categories <= kMaxC, "n_categories=%d unsupported (2..%d)", d.n_categories, kMaxC);
   MVAE_CHECK_ARG(d.state_dim >= 1 && d.state_dim <= kMaxS, "state_dim=%d unsupported (1..%d)", d.state_dim, kMaxS);
-  MVAE_CHECK_ARG(d.lowD_dim + d.n_categories <= 128 && d.n_categories + d.state_dim <= 128, "lowD_dim + n_categories and n_categories + state_dim must be <= 128");
+  // the narrow weight-gradient kernels carry the bias gradient as one extra input column: inputs + 1 <= 128
+  MVAE_CHECK_ARG(d.lowD_dim + d.n_categories <= 127 && d.n_categories + d.state_dim <= 127,
+                 "lowD_dim + n_categories and n_categories + state_dim must be <= 127");
   return 0;
 }
 
