@@ -86,6 +86,13 @@ def consensus_from_counts(counts) -> float:
     return float(np.mean(vals)) if vals else float("nan")
 
 
+def ecdf(labels):
+    """mmidas/_utils.py:280: empirical distribution of integer labels."""
+    labels = np.asarray(labels)
+    assert len(labels.shape) == 1
+    return np.bincount(labels) / len(labels)
+
+
 def set_seeds(seed):
     """mmidas/_utils.py:34"""
     import random

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from mmidas_b200._utils import classify, compute_confmat, confmat_mean, confmat_normalize, consensus
+from mmidas_b200._utils import classify, compute_confmat, confmat_mean, confmat_normalize, consensus, ecdf
 
 L1, L2 = np.array([1, 0, 2, 3, 0, 3]), np.array([1, 0, 2, 3, 1, 3])
 CM_ID = np.eye(4)
@@ -24,6 +24,12 @@ def test_reference_goldens_numpy_mirror():
     assert confmat_mean(compute_confmat(L1, L2)) == 1.25                                     # test_utils.py:94-103
     np.testing.assert_array_equal(classify(P3[:3]), [0, 2, 1])
     np.testing.assert_array_equal(classify(P3), [0, 2, 1, 2])
+
+
+def test_ecdf_reference_goldens():
+    # test_utils.py:39-49
+    np.testing.assert_array_equal(ecdf(np.array([1, 0, 2, 3])), [0.25, 0.25, 0.25, 0.25])
+    np.testing.assert_allclose(ecdf(np.array([1, 0, 2, 3, 0, 3])), [1 / 3, 1 / 6, 1 / 6, 1 / 3], rtol=0, atol=1e-15)
 
 
 def test_vectorised_equals_naive_loop():
