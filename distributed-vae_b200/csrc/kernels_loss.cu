@@ -61,13 +61,19 @@ int launch_qstats(const CouplingArgs& a, cudaStream_t s) {
 // R = sum_a r_a, and for the local arms T_a[k] = sum_b G_a[b,k]*log(q_a[b,k]+eps),
 // G_a = (2 lam / B) (A r_a - R)   (gradient of the distance through inv_var)
 // ---------------------------------------------------------------------------------------------
+// ATC: compile-time number of arms (0: run-time); C96: n_categories > 96 (only the last category slot of a lane is guarded)
+template <int ATC, bool C96>
 __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const CouplingArgs p) {
   __shared__ float w[MVAE_MAX_ARMS][128];
   extern __shared__ float sTw[];            // [kRowWarps][A local arms][128]: every lane owns its categories of its warp's slice
   __shared__ double sPair[kMaxPairs][2];
   __shared__ double sEnt[MVAE_MAX_ARMS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int At = p.At, B = p.B, C = p.C;
+  const int At = ATC ? ATC : p.At, B = p.B, C = p.C;
+  if (C96) {
+    __builtin_assume(C > 96);
+    __builtin_assume(C <= 128);
+  }
   for (int idx = tid; idx < At * 128; idx += blockDim.x) {
     const int a = idx >> 7, k = idx & 127;
     float wv = 0.f;
@@ -174,13 +180,24 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
 int launch_coupling_rows(const CouplingArgs& a, cudaStream_t s) {
   int gx = (a.B + kRowWarps - 1) / kRowWarps;
   static bool attr = false;
+  const int max_dyn = kRowWarps * MVAE_MAX_ARMS * 128 * (int)sizeof(float);
   if (!attr) {
-    MVAE_CUDA(cudaFuncSetAttribute(coupling_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kRowWarps * MVAE_MAX_ARMS * 128 * (int)sizeof(float)));
+    MVAE_CUDA(cudaFuncSetAttribute(coupling_rows_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    MVAE_CUDA(cudaFuncSetAttribute(coupling_rows_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    MVAE_CUDA(cudaFuncSetAttribute(coupling_rows_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    MVAE_CUDA(cudaFuncSetAttribute(coupling_rows_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
     attr = true;
   }
   if (gx > 444) gx = 444;              // 3 CTAs per SM: a few rows per warp, 3x fewer global fp64 atomics than one row per warp
-  coupling_rows_kernel<<<gx, kRowWarps * 32, (size_t)kRowWarps * a.A * 128 * sizeof(float), s>>>(a);
+  const size_t dyn = (size_t)kRowWarps * a.A * 128 * sizeof(float);
+  const bool c96 = a.C > 96;
+  if (a.At == 2) {                     // the reference default n_arm = 2 gets compile-time arm loops
+    if (c96) coupling_rows_kernel<2, true><<<gx, kRowWarps * 32, dyn, s>>>(a);
+    else coupling_rows_kernel<2, false><<<gx, kRowWarps * 32, dyn, s>>>(a);
+  } else {
+    if (c96) coupling_rows_kernel<0, true><<<gx, kRowWarps * 32, dyn, s>>>(a);
+    else coupling_rows_kernel<0, false><<<gx, kRowWarps * 32, dyn, s>>>(a);
+  }
   MVAE_LAUNCH_CHECK();
   return 0;
 }

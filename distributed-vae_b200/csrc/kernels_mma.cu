@@ -635,10 +635,15 @@ __global__ void __launch_bounds__(512, SPLIT ? 1 : 2) wgrad2_kernel(const WgArgs
   while (pi + 1 < p.nprob && (int)blockIdx.x >= p.prob[pi + 1].cta_begin) ++pi;
   const WgProblem& pr = p.prob[pi];
   const int split = (int)blockIdx.x - pr.cta_begin, arm = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = (tid >> 5) & 7, wn = tid >> 8;   // m-tile, n half
+  const int tid = threadIdx.x, lane = tid & 31;
   const int nout = pr.nout, nin = pr.nin, in_ld = pr.in_ld;
   const int nt_all = (nin + 1 + 7) / 8;       // + the ones column that yields the bias gradient
-  const int nt_used = max(0, min(8, nt_all - wn * 8));
+  // tile ownership: 8 m-tiles x 2 halves of the n-tiles, or -- one m-tile only (nout <= 16) -- one n-tile per warp, so
+  // that the k-steps of a chunk are not serialised on two warps while fourteen wait at the barrier
+  const bool thin_m = nout <= 16;
+  const int mt = thin_m ? 0 : (tid >> 5) & 7;
+  const int nt0 = thin_m ? (tid >> 5) : (tid >> 8) * 8;
+  const int nt_used = thin_m ? ((tid >> 5) < nt_all ? 1 : 0) : max(0, min(8, nt_all - nt0));
   const float* delta = p.work + pr.delta_off + (int64_t)arm * pr.delta_arm_stride;
   const float* in = nin > 0 ? p.work + pr.in_off + (int64_t)arm * pr.in_arm_stride : nullptr;
   const bool bn = pr.bn_layer >= 0;
@@ -647,8 +652,18 @@ __global__ void __launch_bounds__(512, SPLIT ? 1 : 2) wgrad2_kernel(const WgArgs
   const int c0 = (int)((int64_t)split * T / pr.nsplit), c1 = (int)((int64_t)(split + 1) * T / pr.nsplit);
   const int nchunks = c1 - c0;
 
-  for (int idx = tid; idx < WG2_STAGES * WG2_STAGE_FLOATS / 4; idx += 512)
-    reinterpret_cast<float4*>(stages)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    // cp.async fills columns [0, nout) / [0, nin) of all 32 rows of a stage (rows beyond the split as zeros); the MMA
+    // tiles also read the pad columns up to the next multiple of 16 / 8: zero exactly those (not the whole 105 KB)
+    const int r = tid >> 4, l = tid & 15;
+    const int mpad = (nout + 15) & ~15, npad = nt_all * 8;
+    for (int st = 0; st < WG2_STAGES; ++st) {
+      float* drow = stages + st * WG2_STAGE_FLOATS + r * WG2_PITCH;
+      float* irow = drow + WG_CHUNK * WG2_PITCH;
+      if (nout + l < mpad) drow[nout + l] = 0.f;
+      if (nin + 1 + l < npad) irow[nin + 1 + l] = 0.f;
+    }
+  }
   if (tid < 128) {
     const bool have = bn && tid < nin;
     bm[tid] = have ? p.bn_mean[(pr.bn_layer * p.A + arm) * 128 + tid] : 0.f;
@@ -689,7 +704,7 @@ __global__ void __launch_bounds__(512, SPLIT ? 1 : 2) wgrad2_kernel(const WgArgs
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-  const bool active = warp * 16 < nout && nt_used > 0;
+  const bool active = mt * 16 < nout && nt_used > 0;
   __syncthreads();                          // the zero fill is ordered before the first cp.async lands
 #pragma unroll 1
   for (int c = 0; c < WG2_STAGES - 1; ++c) issue(c);
@@ -707,23 +722,23 @@ __global__ void __launch_bounds__(512, SPLIT ? 1 : 2) wgrad2_kernel(const WgArgs
     if (active) {
       const float* Ds = stages + so;
       const float* Is = Ds + WG_CHUNK * WG2_PITCH;
-      if (nt_used == 8) warp_gemm<8, true, SPLIT>(Ds + warp * 16, WG2_PITCH, Is + wn * 64, WG2_PITCH, WG_CHUNK / 8, 8, acc, lane);
-      else if (nt_used == 5) warp_gemm<8, true, SPLIT>(Ds + warp * 16, WG2_PITCH, Is + wn * 64, WG2_PITCH, WG_CHUNK / 8, 5, acc, lane);
-      else warp_gemm<8, true, SPLIT>(Ds + warp * 16, WG2_PITCH, Is + wn * 64, WG2_PITCH, WG_CHUNK / 8, nt_used, acc, lane);
+      if (nt_used == 8) warp_gemm<8, true, SPLIT>(Ds + mt * 16, WG2_PITCH, Is + nt0 * 8, WG2_PITCH, WG_CHUNK / 8, 8, acc, lane);
+      else if (nt_used == 1) warp_gemm<8, true, SPLIT>(Ds + mt * 16, WG2_PITCH, Is + nt0 * 8, WG2_PITCH, WG_CHUNK / 8, 1, acc, lane);
+      else warp_gemm<8, true, SPLIT>(Ds + mt * 16, WG2_PITCH, Is + nt0 * 8, WG2_PITCH, WG_CHUNK / 8, nt_used, acc, lane);
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (!active) return;
   float* part = p.part + (int64_t)split * p.part_split_stride + (int64_t)arm * p.part_arm_stride;
   const int g = lane >> 2, tig = lane & 3;
-  const int ja = warp * 16 + g, jb = ja + 8;
+  const int ja = mt * 16 + g, jb = ja + 8;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     if (nt < nt_used) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = (e & 2) ? jb : ja;
-        const int i = (wn * 8 + nt) * 8 + 2 * tig + (e & 1);
+        const int i = (nt0 + nt) * 8 + 2 * tig + (e & 1);
         if (j < nout) {
           if (i < nin) part[pr.poffW - p.base_off + (int64_t)j * nin + i] = acc[nt][e];
           else if (i == nin) part[pr.poffB - p.base_off + j] = acc[nt][e];
