@@ -247,6 +247,18 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
   MVAE_CUDA(cudaMemsetAsync(acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
   const float gscale = (float)(At - 1 > 1 ? At - 1 : 1) / (float)B;
 
+  timing_begin(TG_COUPLING, s);
+  // ---- coupling terms over every arm of the model (:558-569): first, while q / c_smp (just written by the head kernel or
+  // gathered) are in L2 -- the fc11 passes below stream the gene matrix through it
+  CouplingArgs c;
+  memset(&c, 0, sizeof(c));
+  c.A = A; c.At = At; c.arm_off = p.d.arm_offset; c.B = B; c.C = C;
+  c.qc_all = qc_all; c.csmp_all = csmp_all; c.acc = acc_loss;
+  c.rsum = work + w.rsum; c.wcat = work + w.wcat; c.eps = hp.eps; c.lam = hp.lam;
+  RC(launch_qstats(c, s));
+  RC(launch_coupling_rows(c, s));
+  timing_end(TG_COUPLING, s);
+
   // ---- reconstruction term: fc11 GEMM fused with loss (+ its own backward)
   timing_begin(TG_FC11, s);
   if (use_tc(p, hp)) {
@@ -286,15 +298,6 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
 
   timing_end(TG_FC11, s);
   timing_begin(TG_COUPLING, s);
-  // ---- coupling terms over every arm of the model (:558-569)
-  CouplingArgs c;
-  memset(&c, 0, sizeof(c));
-  c.A = A; c.At = At; c.arm_off = p.d.arm_offset; c.B = B; c.C = C;
-  c.qc_all = qc_all; c.csmp_all = csmp_all; c.acc = acc_loss;
-  c.rsum = work + w.rsum; c.wcat = work + w.wcat; c.eps = hp.eps; c.lam = hp.lam;
-  RC(launch_qstats(c, s));
-  RC(launch_coupling_rows(c, s));
-
   LossFinalArgs f;
   memset(&f, 0, sizeof(f));
   f.A = A; f.At = At; f.arm_off = p.d.arm_offset; f.B = B; f.D = D; f.C = C; f.S = S;
@@ -399,25 +402,8 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   }
 
   timing_end(TG_NARROW_BWD, s);
-  // ---- d fc1.weight = delta1^T * dropout(x)
-  DropSpec drop = make_drop(p, hp, in);
-  timing_begin(TG_FC1_WGRAD, s);
-  if (tc && hp.precision != 1 && !legacy_fc1()) {
-    RC(ts_fc1_wgrad(p.d, st, in, drop, w, s));
-  } else if (tc) {
-    RC(tc_fc1_wgrad(p.d, hp, st, in, drop, w, s));
-  } else {
-    GemmArgs g;
-    memset(&g, 0, sizeof(g));
-    g.A = work + w.delta_enc[0]; g.sAm = 1; g.sAk = H; g.A_batch = (int64_t)B * H;
-    g.Bm = in.x; g.sBk = in.x_row_stride; g.sBn = 1; g.B_batch = in.x_arm_stride;
-    g.C = st.grads + p.L.offset[FC1_W]; g.sCm = D; g.sCn = 1; g.C_batch = p.L.arm_stride;
-    g.M = H; g.N = D; g.K = B;
-    g.drop = drop; g.drop_operand = drop.mode ? 2 : 0;
-    RC(launch_sgemm_simt(g, A, s));
-  }
-
-  timing_end(TG_FC1_WGRAD, s);
+  // Order: the narrow weight gradients run FIRST, while the activations and deltas that narrow_bwd just touched are
+  // still in L2 -- the fc1 weight gradient streams the whole gene matrix through L2 and would evict them.
   // ---- weight gradients of every narrow layer
   timing_begin(TG_WGRAD, s);
   WgArgs wg;
@@ -444,6 +430,25 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   wg.grads = st.grads; wg.g_arm_stride = p.L.arm_stride;
   RC(hp.precision == 3 ? launch_wgrad(wg, s) : launch_wgrad_mma(wg, hp.precision == 1, s));
   timing_end(TG_WGRAD, s);
+  // ---- d fc1.weight = delta1^T * dropout(x)
+  DropSpec drop = make_drop(p, hp, in);
+  timing_begin(TG_FC1_WGRAD, s);
+  if (tc && hp.precision != 1 && !legacy_fc1()) {
+    RC(ts_fc1_wgrad(p.d, st, in, drop, w, s));
+  } else if (tc) {
+    RC(tc_fc1_wgrad(p.d, hp, st, in, drop, w, s));
+  } else {
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = work + w.delta_enc[0]; g.sAm = 1; g.sAk = H; g.A_batch = (int64_t)B * H;
+    g.Bm = in.x; g.sBk = in.x_row_stride; g.sBn = 1; g.B_batch = in.x_arm_stride;
+    g.C = st.grads + p.L.offset[FC1_W]; g.sCm = D; g.sCn = 1; g.C_batch = p.L.arm_stride;
+    g.M = H; g.N = D; g.K = B;
+    g.drop = drop; g.drop_operand = drop.mode ? 2 : 0;
+    RC(launch_sgemm_simt(g, A, s));
+  }
+
+  timing_end(TG_FC1_WGRAD, s);
 
   if (grad_scale) RC(launch_scale(st.grads, (int64_t)A * p.L.arm_stride, grad_scale, s));
   return 0;

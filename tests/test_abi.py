@@ -50,6 +50,7 @@ def test_layout_rejects_unsupported_shapes():
     lay = lib_mod.Layout()
     for bad in (lib_mod.Dims(2, 100, 64, 200, 10, 12, 2, 2, 0),      # fc_dim > 128
                 lib_mod.Dims(2, 100, 64, 100, 10, 300, 2, 2, 0),     # too many categories
+                lib_mod.Dims(2, 100, 64, 100, 10, 118, 2, 2, 0),     # lowD_dim + n_categories = 128: no room for the bias column
                 lib_mod.Dims(2, 0, 64, 100, 10, 12, 2, 2, 0),        # empty batch
                 lib_mod.Dims(17, 100, 64, 100, 10, 12, 2, 17, 0)):
         rc = lib_mod.load().mvae_compute_layout(C.byref(bad), C.byref(lay))
