@@ -509,6 +509,194 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wg_tc_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent Linear + affine + activation (the augmenter layers): y = act((x . W^T) * scale + shift), both
+// operands K-major.  Same stage pipeline as tc_gemm_kernel, but a CTA walks over output tiles (tile = blockIdx.x + i *
+// gridDim.x, m fastest so that neighbouring CTAs share the weight tile in L2) with TWO accumulators in tensor memory: the
+// epilogue warps drain tile i (tcgen05.ld, affine, activation, stores) while the TMA / MMA warps are already in the
+// main loop of tile i + 1, and the barriers, the TMEM allocation and the tensor-map fetch are paid once per CTA instead
+// of once per tile.  Measured on the first (one tile per CTA) version: fc11 of the augmenter spent ~1/3 of every CTA's
+// life outside the main loop.
+// ---------------------------------------------------------------------------------------------
+struct LinArgs {
+  int M, N, K, BN, stages, split3, tiles_m, tiles_n;
+  float* C; int64_t ldc;
+  const float* scale; const float* shift; int act;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const LinArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split3 = args.split3 != 0;
+  const int tiles_per_stage = split3 ? 4 : 2;
+  const int stage_bytes = tiles_per_stage * TILE_BYTES;
+  const int S = args.stages;
+  auto tileA = [&](int s) { return smem + (size_t)s * stage_bytes; };
+  auto tileB = [&](int s) { return smem + (size_t)s * stage_bytes + TILE_BYTES; };
+  auto tileAlo = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * TILE_BYTES; };
+  auto tileBlo = [&](int s) { return smem + (size_t)s * stage_bytes + 3 * TILE_BYTES; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* ready = bars + S;
+  uint64_t* empty = bars + 2 * S;
+  uint64_t* tfull = bars + 3 * S;          // [2] accumulator complete
+  uint64_t* tempty = bars + 3 * S + 2;     // [2] accumulator drained by the 4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+
+  const int ntiles = args.tiles_m * args.tiles_n;
+  const int nkt = (args.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(ready + s, TRANSFORM_THREADS);
+      mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b, 1);
+      mbar_init(tempty + b, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m0 = (t % args.tiles_m) * BM, n0 = (t / args.tiles_m) * args.BN;
+        for (int i = 0; i < nkt; ++i, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_expect_tx(full + s, 2 * TILE_BYTES);
+          tma_load_3d(&tmA, full + s, tileA(s), i * BK, m0, 0);
+          tma_load_3d(&tmB, full + s, tileB(s), i * BK, n0, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BM, args.BN, false, false);
+      const int kround = (args.K + UK - 1) / UK * UK;
+      int it = 0, j = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+        const int buf = j & 1;
+        mbar_wait(tempty + buf, ((j >> 1) & 1) ^ 1);        // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t dacc = tmem_base + (uint32_t)buf * 128u;
+        uint32_t acc = 0;
+        for (int i = 0; i < nkt; ++i, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(split3 ? ready + s : full + s, ph);
+          tc_fence_after();
+          const int k0 = i * BK;
+          const uint32_t a_hi = smem_u32(tileA(s)), b_hi = smem_u32(tileB(s));
+          const uint32_t a_lo = smem_u32(tileAlo(s)), b_lo = smem_u32(tileBlo(s));
+#pragma unroll
+          for (int ks = 0; ks < BK / UK; ++ks) {
+            if (k0 + ks * UK >= kround) break;
+            const uint32_t off = ks * 32;
+            const uint64_t dah = make_smem_desc(a_hi + off, 0, 1024, false);
+            const uint64_t dbh = make_smem_desc(b_hi + off, 0, 1024, false);
+            if (split3) {
+              umma_tf32(dacc, make_smem_desc(a_lo + off, 0, 1024, false), dbh, idesc, acc);
+              acc = 1;
+              umma_tf32(dacc, dah, make_smem_desc(b_lo + off, 0, 1024, false), idesc, acc);
+            }
+            umma_tf32(dacc, dah, dbh, idesc, acc);
+            acc = 1;
+          }
+          umma_commit(empty + s);
+        }
+        umma_commit(tfull + buf);
+      }
+    }
+  } else if (warp >= TRANSFORM_WARP0) {
+    // ===== TF32 low halves (3xTF32 mode): 4 warps per operand =====
+    if (split3) {
+      const int tid = threadIdx.x - TRANSFORM_WARP0 * 32;
+      DropSpec nodrop;
+      nodrop.mode = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int i = 0; i < nkt; ++i, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(full + s, ph);
+          if (tid < 128)
+            transform_tile<false>(reinterpret_cast<float*>(tileA(s)), reinterpret_cast<float*>(tileAlo(s)), true, false, nodrop, 0,
+                                  0, 0, tid, 128);
+          else
+            transform_tile<false>(reinterpret_cast<float*>(tileB(s)), reinterpret_cast<float*>(tileBlo(s)), true, false, nodrop, 0,
+                                  0, 0, tid - 128, 128);
+          fence_proxy_async();
+          mbar_arrive(ready + s);
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> affine + activation -> global, one accumulator behind the MMA warp =====
+    const int quad = warp & 3;
+    int j = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+      const int buf = j & 1;
+      const int m0 = (t % args.tiles_m) * BM, n0 = (t / args.tiles_m) * args.BN;
+      const int row = m0 + quad * 32 + lane;
+      mbar_wait(tfull + buf, (j >> 1) & 1);
+      tc_fence_after();
+      float* crow = args.C + (int64_t)row * args.ldc;
+      const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+      const uint32_t tsrc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 128u;
+      for (int c0 = 0; c0 < args.BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tsrc + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (c0 + 16 >= args.BN) {                        // last read of this accumulator: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty + buf);
+        }
+        const int col = n0 + c0;
+        if (row < args.M && col < args.N) {
+          if (col + 16 <= args.N) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              r[i] = __float_as_uint(ep_apply(__uint_as_float(r[i]), __ldg(args.scale + col + i), __ldg(args.shift + col + i), args.act));
+            if (vec_ok) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(crow + col)[i] =
+                    make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                __uint_as_float(r[4 * i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) crow[col + i] = __uint_as_float(r[i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (col + i < args.N)
+                crow[col + i] = ep_apply(__uint_as_float(r[i]), __ldg(args.scale + col + i), __ldg(args.shift + col + i), args.act);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 struct Operand {
@@ -858,15 +1046,46 @@ int launch_fma_rows(const float* a, int64_t lda, const float* b, int64_t ldb, co
   MVAE_LAUNCH_CHECK();
   return 0;
 }
+static bool legacy_linear() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MVAE_LEGACY_LINEAR"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 // y[rows][n_out] (pitch y_pitch) = act((x[rows][k] . w[n_out][k]^T) * scale + shift)
 int tc_linear_act(const float* x, int64_t x_pitch, const float* w, int64_t w_pitch, float* y, int64_t y_pitch, int64_t rows,
                   int n_out, int k, const float* scale, const float* shift, int act, int split3, cudaStream_t s) {
-  Operand a{x, x_pitch, 0, false};
-  Operand b{w, w_pitch, 0, false};
-  DropSpec nodrop;
-  memset(&nodrop, 0, sizeof(nodrop));
   const int BN = n_out >= 128 ? 128 : round16(n_out);
-  return run_tc_gemm(a, b, (int)rows, n_out, k, BN, 1, 1, split3 ? (F_SPLIT_A | F_SPLIT_B) : 0, nodrop, y, y_pitch, 0, 0, s, scale,
-                     shift, act);
+  if (legacy_linear()) {          // one tile per CTA (tc_gemm_kernel with the fused epilogue), kept for A/B comparisons
+    Operand a{x, x_pitch, 0, false};
+    Operand b{w, w_pitch, 0, false};
+    DropSpec nodrop;
+    memset(&nodrop, 0, sizeof(nodrop));
+    return run_tc_gemm(a, b, (int)rows, n_out, k, BN, 1, 1, split3 ? (F_SPLIT_A | F_SPLIT_B) : 0, nodrop, y, y_pitch, 0, 0, s, scale,
+                       shift, act);
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, x, k, rows, x_pitch, 1, 0, BM, false);
+  if (rc) return rc;
+  rc = make_map(&tmB, w, k, n_out, w_pitch, 1, 0, 128, false);
+  if (rc) return rc;
+  LinArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = (int)rows; a.N = n_out; a.K = k; a.BN = BN;
+  a.split3 = split3 ? 1 : 0;
+  a.stages = split3 ? 3 : 6;
+  a.tiles_m = (int)((rows + BM - 1) / BM); a.tiles_n = (n_out + BN - 1) / BN;
+  a.C = y; a.ldc = y_pitch; a.scale = scale; a.shift = shift; a.act = act;
+  const size_t smem = (size_t)a.stages * (split3 ? 4 : 2) * TILE_BYTES + (3 * a.stages + 6) * 8 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    MVAE_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  const int ntiles = a.tiles_m * a.tiles_n;
+  const int grid = ntiles < mma_sm_count_tc() ? ntiles : mma_sm_count_tc();
+  tc_linear_kernel<<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, a);
+  MVAE_LAUNCH_CHECK();
+  return 0;
 }
 }  // namespace mvae
