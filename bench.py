@@ -334,7 +334,30 @@ def main():
         a1.record()
         torch.cuda.synchronize()
         ams = a0.elapsed_time(a1) / args.steps
-        aug = {"ms_per_step": ams, "precision": args.augment, "gflop_per_step": flops / 1e9,
+        aug_cpu = None
+        if not args.no_cpu_baseline:
+            # the reference's own path for this row on the host cores: the oracle restatement of Augmenter_smartseq.forward
+            # (eval mode, pinned to the reference class by tests/test_augmenter_oracle.py) on a bounded sample of the cells
+            from oracle import augmenter_oracle as AO
+            cores = len(os.sched_getaffinity(0))
+            torch.set_num_threads(cores)
+            Bs = min(B, 500)
+            sd_cpu = {k: v.detach().cpu() for k, v in netA.state_dict().items()}
+            xc = batches[0][:Bs].cpu().expand(A, -1, -1)
+            zc, ec = torch.randn(A, Bs, nz), torch.randn(A, Bs, nl)
+            with torch.no_grad():
+                AO.forward(sd_cpu, xc, zc, ec, 0.1)
+                t0 = time.perf_counter()
+                reps = 0
+                while reps < 5 and time.perf_counter() - t0 < 15.0:
+                    AO.forward(sd_cpu, xc, zc, ec, 0.1)
+                    reps += 1
+            dtc = (time.perf_counter() - t0) / reps
+            aug_cpu = {"value": Bs / dtc, "unit": "cells/s", "cores": cores, "kind": "port",
+                       "sample": f"{reps} forwards of {Bs} cells x {A} arms (fp32 torch CPU, {dtc * 1e3:.0f} ms each; the reference "
+                                 "evaluates fc1..fc4 per arm)"}
+        aug = {"ms_per_step": ams, "precision": args.augment, "gflop_per_step": flops / 1e9, "cells_per_s": B / (ams / 1e3),
+               "cpu_baseline": aug_cpu,
                "achieved_tflops": flops / (ams / 1e3) / 1e12, "launches_per_step": (_lib.launch_count() - l0) / args.steps,
                "note": "Augmenter_smartseq eval forward (udagan.py:285-329), x.expand over arms: fc1..fc4 evaluated once per cell; "
                        "3xTF32 issues 3 MMAs per product (achieved_tflops counts the fp32-equivalent product once)"}

@@ -529,8 +529,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool split3 = args.split3 != 0;
-  const int tiles_per_stage = split3 ? 4 : 2;
+  const bool wide = args.BN > 128;                      // 256-column tiles (single-pass TF32 only): B tile = two TMA boxes
+  const int tiles_per_stage = split3 ? 4 : (wide ? 3 : 2);
   const int stage_bytes = tiles_per_stage * TILE_BYTES;
+  const uint32_t acc_cols = wide ? 256u : 128u;
   const int S = args.stages;
   auto tileA = [&](int s) { return smem + (size_t)s * stage_bytes; };
   auto tileB = [&](int s) { return smem + (size_t)s * stage_bytes + TILE_BYTES; };
@@ -559,7 +561,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  if (warp == 2) tmem_alloc(tmem_slot, 2 * acc_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -575,9 +577,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(empty + s, ph ^ 1);
-          mbar_expect_tx(full + s, 2 * TILE_BYTES);
+          mbar_expect_tx(full + s, (wide ? 3 : 2) * TILE_BYTES);
           tma_load_3d(&tmA, full + s, tileA(s), i * BK, m0, 0);
           tma_load_3d(&tmB, full + s, tileB(s), i * BK, n0, 0);
+          if (wide) tma_load_3d(&tmB, full + s, tileB(s) + TILE_BYTES, i * BK, n0 + 128, 0);
         }
       }
     }
@@ -591,7 +594,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int buf = j & 1;
         mbar_wait(tempty + buf, ((j >> 1) & 1) ^ 1);        // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t dacc = tmem_base + (uint32_t)buf * 128u;
+        const uint32_t dacc = tmem_base + (uint32_t)buf * acc_cols;
         uint32_t acc = 0;
         for (int i = 0; i < nkt; ++i, ++it) {
           const int s = it % S;
@@ -655,7 +658,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       float* crow = args.C + (int64_t)row * args.ldc;
       const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
-      const uint32_t tsrc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 128u;
+      const uint32_t tsrc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * acc_cols;
       for (int c0 = 0; c0 < args.BN; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(tsrc + (uint32_t)c0, r);
@@ -693,7 +696,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 256);
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * acc_cols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1055,7 +1058,7 @@ static bool legacy_linear() {
 // y[rows][n_out] (pitch y_pitch) = act((x[rows][k] . w[n_out][k]^T) * scale + shift)
 int tc_linear_act(const float* x, int64_t x_pitch, const float* w, int64_t w_pitch, float* y, int64_t y_pitch, int64_t rows,
                   int n_out, int k, const float* scale, const float* shift, int act, int split3, cudaStream_t s) {
-  const int BN = n_out >= 128 ? 128 : round16(n_out);
+  int BN = n_out >= 128 ? 128 : round16(n_out);
   if (legacy_linear()) {          // one tile per CTA (tc_gemm_kernel with the fused epilogue), kept for A/B comparisons
     Operand a{x, x_pitch, 0, false};
     Operand b{w, w_pitch, 0, false};
@@ -1069,14 +1072,19 @@ int tc_linear_act(const float* x, int64_t x_pitch, const float* w, int64_t w_pit
   if (rc) return rc;
   rc = make_map(&tmB, w, k, n_out, w_pitch, 1, 0, 128, false);
   if (rc) return rc;
+  // single-pass TF32 is bound by L2 -> shared-memory operand traffic: 256-column tiles move 24 KB instead of 32 KB per
+  // 128 x 128 x 32 block of products (3xTF32 is MMA-issue-bound and its four tiles per stage leave no room for them)
+  static int wide_ok = -1;
+  if (wide_ok < 0) { const char* e = getenv("MVAE_LINEAR_BN256"); wide_ok = (e && e[0] == '0') ? 0 : 1; }
+  if (!split3 && wide_ok && n_out >= 384 && k >= 768) BN = 256;   // short-K layers are epilogue-bound: more, smaller tiles win there
   LinArgs a;
   memset(&a, 0, sizeof(a));
   a.M = (int)rows; a.N = n_out; a.K = k; a.BN = BN;
   a.split3 = split3 ? 1 : 0;
-  a.stages = split3 ? 3 : 6;
+  a.stages = split3 ? 3 : (BN > 128 ? 4 : 6);
   a.tiles_m = (int)((rows + BM - 1) / BM); a.tiles_n = (n_out + BN - 1) / BN;
   a.C = y; a.ldc = y_pitch; a.scale = scale; a.shift = shift; a.act = act;
-  const size_t smem = (size_t)a.stages * (split3 ? 4 : 2) * TILE_BYTES + (3 * a.stages + 6) * 8 + 1024;
+  const size_t smem = (size_t)a.stages * (split3 ? 4 : (BN > 128 ? 3 : 2)) * TILE_BYTES + (3 * a.stages + 6) * 8 + 1024;
   static bool attr = false;
   if (!attr) {
     MVAE_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

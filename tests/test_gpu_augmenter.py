@@ -61,20 +61,21 @@ def test_matches_reference_goldens(path, precision):
 
 
 @pytest.mark.gpu
-def test_full_size_layers_against_fp64_oracle():
+@pytest.mark.parametrize("precision,tol", [("tf32x3", 1e-4), ("tf32", 1e-2)])
+def test_full_size_layers_against_fp64_oracle(precision, tol):
     """The production shapes (5032 genes -> 1006 -> 1006 -> 500 -> 500 | 50 -> 100 -> 10 -> ... -> 5032) on 300
     cells x 2 arms: exercises the 16-byte pitch padding of the 1006- and 550-wide layers."""
     sd = AO.random_state_dict(50, 10, 5032, 500, seed=3)
     c = dict(noise_dim=50, latent_dim=10, input_dim=5032, n_dim=500)
-    net = _module(sd, c, "tf32x3").cuda().eval()
+    net = _module(sd, c, precision).cuda().eval()      # "tf32" runs the wide layers on 256-column tiles
     g = torch.Generator().manual_seed(5)
     x = AO_synth(300, 5032, g)
     z, eps = torch.randn(2, 300, 50, generator=g), torch.randn(2, 300, 10, generator=g)
     s, xa = net(x.cuda().expand(2, -1, -1), True, 0.1, noise={"z": z.cuda(), "eps": eps.cuda()})
     sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
     s64, xa64 = AO.forward(sd64, x.expand(2, -1, -1), z, eps, 0.1)
-    assert rel_l2(s.cpu().numpy(), s64.numpy()) <= 1e-4, rel_l2(s.cpu().numpy(), s64.numpy())
-    assert rel_l2(xa.cpu().numpy(), xa64.numpy()) <= 1e-4, rel_l2(xa.cpu().numpy(), xa64.numpy())
+    assert rel_l2(s.cpu().numpy(), s64.numpy()) <= tol, rel_l2(s.cpu().numpy(), s64.numpy())
+    assert rel_l2(xa.cpu().numpy(), xa64.numpy()) <= tol, rel_l2(xa.cpu().numpy(), xa64.numpy())
     # without injected noise the draws differ between calls and between arms
     s_a, xa_a = net(x.cuda().expand(2, -1, -1), True, 0.1)
     s_b, _ = net(x.cuda().expand(2, -1, -1), True, 0.1)
