@@ -530,14 +530,20 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool split3 = args.split3 != 0;
   const bool wide = args.BN > 128;                      // 256-column tiles (single-pass TF32 only): B tile = two TMA boxes
-  const int tiles_per_stage = split3 ? 4 : (wide ? 3 : 2);
+  // 3xTF32, TS form (args.split3 == 2): the hi / lo halves of the activation tile go to TENSOR MEMORY (64 columns per
+  // stage behind the two accumulators) and the MMAs take their A operand from there -- measured issue cost of
+  // tcgen05.mma kind::tf32 M128 N128 K8: 76 cycles from TMEM vs 109 from shared memory (profiles/r1_mma_issue_cost.txt).
+  const bool ts = args.split3 == 2;
+  const int tiles_per_stage = split3 ? (ts ? 3 : 4) : (wide ? 3 : 2);
   const int stage_bytes = tiles_per_stage * TILE_BYTES;
   const uint32_t acc_cols = wide ? 256u : 128u;
+  const uint32_t tmem_cols = ts ? 512u : 2 * acc_cols;
+  constexpr uint32_t COL_A = 256;                       // TS form: A stages at [256 + 64 s, +64): hi 32 | lo 32
   const int S = args.stages;
   auto tileA = [&](int s) { return smem + (size_t)s * stage_bytes; };
   auto tileB = [&](int s) { return smem + (size_t)s * stage_bytes + TILE_BYTES; };
   auto tileAlo = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * TILE_BYTES; };
-  auto tileBlo = [&](int s) { return smem + (size_t)s * stage_bytes + 3 * TILE_BYTES; };
+  auto tileBlo = [&](int s) { return smem + (size_t)s * stage_bytes + (ts ? 2 : 3) * TILE_BYTES; };
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
   uint64_t* full = bars;
   uint64_t* ready = bars + S;
@@ -561,7 +567,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 2 * acc_cols);
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -610,6 +616,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t off = ks * 32;
             const uint64_t dah = make_smem_desc(a_hi + off, 0, 1024, false);
             const uint64_t dbh = make_smem_desc(b_hi + off, 0, 1024, false);
+            if (ts) {
+              const uint32_t ta = tmem_base + COL_A + (uint32_t)s * 64u + (uint32_t)ks * 8u;     // hi; lo at +32
+              umma_tf32_ts(dacc, ta + 32u, dbh, idesc, acc);
+              umma_tf32_ts(dacc, ta, make_smem_desc(b_lo + off, 0, 1024, false), idesc, 1u);
+              umma_tf32_ts(dacc, ta, dbh, idesc, 1u);
+              acc = 1;
+              continue;
+            }
             if (split3) {
               umma_tf32(dacc, make_smem_desc(a_lo + off, 0, 1024, false), dbh, idesc, acc);
               acc = 1;
@@ -635,7 +649,27 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(full + s, ph);
-          if (tid < 128)
+          if (tid < 128 && ts) {
+            // thread = row of the activation tile (TMEM lane quad * 32 + lane): 32 K values -> hi | lo columns of stage s
+            const int quad = warp & 3, r = quad * 32 + lane;
+            const uint8_t* rowp = tileA(s) + r * 128;
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 v = *reinterpret_cast<const float4*>(rowp + ((q ^ (r & 7)) << 4));
+              hi[4 * q] = __float_as_uint(v.x); hi[4 * q + 1] = __float_as_uint(v.y);
+              hi[4 * q + 2] = __float_as_uint(v.z); hi[4 * q + 3] = __float_as_uint(v.w);
+              lo[4 * q] = __float_as_uint(tf32_lo(v.x)); lo[4 * q + 1] = __float_as_uint(tf32_lo(v.y));
+              lo[4 * q + 2] = __float_as_uint(tf32_lo(v.z)); lo[4 * q + 3] = __float_as_uint(tf32_lo(v.w));
+            }
+            const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + COL_A + (uint32_t)s * 64u;
+            tmem_st16(ta, hi);
+            tmem_st16(ta + 16u, hi + 16);
+            tmem_st16(ta + 32u, lo);
+            tmem_st16(ta + 48u, lo + 16);
+            tmem_st_wait();
+            tc_fence_before();
+          } else if (tid < 128)
             transform_tile<false>(reinterpret_cast<float*>(tileA(s)), reinterpret_cast<float*>(tileAlo(s)), true, false, nodrop, 0,
                                   0, 0, tid, 128);
           else
@@ -696,7 +730,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 2 * acc_cols);
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1080,11 +1114,13 @@ int tc_linear_act(const float* x, int64_t x_pitch, const float* w, int64_t w_pit
   LinArgs a;
   memset(&a, 0, sizeof(a));
   a.M = (int)rows; a.N = n_out; a.K = k; a.BN = BN;
-  a.split3 = split3 ? 1 : 0;
-  a.stages = split3 ? 3 : (BN > 128 ? 4 : 6);
+  static int ts_ok = -1;
+  if (ts_ok < 0) { const char* e = getenv("MVAE_LINEAR_TS"); ts_ok = (e && e[0] == '0') ? 0 : 1; }
+  a.split3 = split3 ? (ts_ok ? 2 : 1) : 0;      // 2: 3xTF32 with the activation halves in tensor memory (TS-form MMAs)
+  a.stages = split3 ? (ts_ok ? 4 : 3) : (BN > 128 ? 4 : 6);
   a.tiles_m = (int)((rows + BM - 1) / BM); a.tiles_n = (n_out + BN - 1) / BN;
   a.C = y; a.ldc = y_pitch; a.scale = scale; a.shift = shift; a.act = act;
-  const size_t smem = (size_t)a.stages * (split3 ? 4 : (BN > 128 ? 3 : 2)) * TILE_BYTES + (3 * a.stages + 6) * 8 + 1024;
+  const size_t smem = (size_t)a.stages * (split3 ? (ts_ok ? 3 : 4) : (BN > 128 ? 3 : 2)) * TILE_BYTES + (3 * a.stages + 6) * 8 + 1024;
   static bool attr = false;
   if (!attr) {
     MVAE_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
