@@ -226,8 +226,9 @@ class Augmenter_smartseq(nn.Module):
         return s_out, out
 
 
-def mk_augmenter(pretrained: str, load_weights: bool) -> tuple[Mapping[Any, Any], Mapping[Any, Any], nn.Module]:
-    """mmidas/cpl_mixvae.py:128-149: checkpoint dict with ``parameters`` (num_n, num_z, n_features) and ``netA``."""
+def mk_augmenter(pretrained: str, load_weights: bool, precision: str = "tf32x3") -> tuple[Mapping[Any, Any], Mapping[Any, Any], nn.Module]:
+    """mmidas/cpl_mixvae.py:128-149: checkpoint dict with ``parameters`` (num_n, num_z, n_features) and ``netA``.
+    ``precision`` (added): "tf32x3" (fp32-accurate, default) or "tf32" (single pass, ~1.7x faster)."""
     aug_model = torch.load(pretrained, map_location="cpu")
     aug_param = aug_model["parameters"]
     if not load_weights:
@@ -235,6 +236,6 @@ def mk_augmenter(pretrained: str, load_weights: bool) -> tuple[Mapping[Any, Any]
                                   "(cpl_mixvae.py:142-149), which the training path does not use")
     print("loading augmenter weights")
     netA = Augmenter_smartseq(noise_dim=aug_param["num_n"], latent_dim=aug_param["num_z"],
-                              input_dim=aug_param["n_features"])
+                              input_dim=aug_param["n_features"], precision=precision)
     netA.load_state_dict(aug_model["netA"])
     return aug_model, aug_param, netA

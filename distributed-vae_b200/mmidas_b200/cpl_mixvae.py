@@ -71,7 +71,8 @@ class HostBatchFeeder:
 
 
 class cpl_mixVAE:
-    def __init__(self, saving_folder="", aug_file="", device=None, eps=1e-8, save_flag=True, load_weights=True):
+    def __init__(self, saving_folder="", aug_file="", device=None, eps=1e-8, save_flag=True, load_weights=True,
+                 aug_precision="tf32x3"):
         self.eps = eps
         self.save = save_flag
         self.folder = saving_folder
@@ -82,7 +83,7 @@ class cpl_mixVAE:
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         if aug_file:     # cpl_mixvae.py:182-186: pre-trained VAE-GAN generator, eval mode
             from .augmentation import mk_augmenter
-            self.aug_model, self.aug_param, netA = mk_augmenter(aug_file, load_weights)
+            self.aug_model, self.aug_param, netA = mk_augmenter(aug_file, load_weights, precision=aug_precision)
             self.netA = netA.to(self.device).eval()
         else:
             self.aug_model, self.aug_param, self.netA = None, None, None
