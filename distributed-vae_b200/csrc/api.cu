@@ -42,7 +42,9 @@ static int check_device() {
   return ok == 1 ? 0 : -2;
 }
 
-static DropSpec make_drop(const Plan& p, const mvae_hparams& hp, const mvae_inputs& in) {
+static uint64_t* step_keys(const Plan& p, const mvae_state& st) { return reinterpret_cast<uint64_t*>(st.work + p.w.keys); }
+
+static DropSpec make_drop(const Plan& p, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in) {
   DropSpec d;
   memset(&d, 0, sizeof(d));
   d.D = p.D;
@@ -58,15 +60,11 @@ static DropSpec make_drop(const Plan& p, const mvae_hparams& hp, const mvae_inpu
     d.keep = in.keep_x;
   } else {
     d.mode = 2;
-    d.seed = in.seed * 0x9E3779B97F4A7C15ull + in.step * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
+    d.keys = step_keys(p, st) + kStreamDrop * MVAE_MAX_ARMS;   // written by step_prep_kernel at the top of the forward
     double t = (double)hp.x_drop * 256.0;
     d.thresh16 = (uint32_t)(t + 0.5);
   }
   return d;
-}
-
-static uint64_t noise_seed(const mvae_inputs& in) {
-  return in.seed * 0xA24BAED4963EE407ull + in.step * 0x9FB21C651E98DF25ull + 0x632BE59BD9B4E019ull;
 }
 
 static BnOff bn_off(const Plan& p) {
@@ -97,7 +95,7 @@ static bool use_tc(const Plan& p, const mvae_hparams& hp) {
 
 // ---------------------------------------------------------------------------------------------
 static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
-                        const mvae_outputs& out, cudaStream_t s) {
+                        const mvae_outputs& out, int bump_adam, cudaStream_t s) {
   const int A = p.A, B = p.B, D = p.D, H = p.H, Ld = p.Ld, C = p.C, S = p.S;
   const Work& w = p.w;
   float* work = st.work;
@@ -108,13 +106,14 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   MVAE_CHECK_ARG(!(training && hp.s_drop > 0.f) || in.keep_s != nullptr, "keep_s is required when s_drop > 0");
   MVAE_CHECK_ARG(in.x_row_stride >= D, "x_row_stride < D");
   MVAE_CUDA(cudaMemsetAsync(acc_fwd, 0, (size_t)w.acc_fwd_floats * 4, s));
+  RC(launch_step_prep(in.seed, in.step, in.counters, bump_adam, p.d.arm_offset, step_keys(p, st), s));
   float* bn_mean = work + w.bn_mean;
   float* bn_rstd = work + w.bn_rstd;
   if (!training)
     RC(launch_bn_eval_prep(st.bn_running, p.L.bn_stride, bn_off(p), bn_mean, bn_rstd, A, H, Ld, hp.eps, s));
 
   // ---- fc1: [B,D] x [D,H]  (nn_model.py:264)
-  DropSpec drop = make_drop(p, hp, in);
+  DropSpec drop = make_drop(p, hp, st, in);
   Fc1EpiArgs epi;
   memset(&epi, 0, sizeof(epi));
   timing_begin(TG_FC1_FWD, s);
@@ -178,7 +177,8 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   h.bn_sums5 = acc_fwd + acc_bn(4, A, 0);
   h.bn_mean5 = bn_mean + (int64_t)4 * A * 128; h.bn_rstd5 = bn_rstd + (int64_t)4 * A * 128;
   h.U = in.U; h.E = in.E; h.keep_s = (training && hp.s_drop > 0.f) ? in.keep_s : nullptr;
-  h.noise_seed = noise_seed(in);
+  h.cat_mask = in.cat_mask;
+  h.ukeys = step_keys(p, st) + kStreamU * MVAE_MAX_ARMS; h.ekeys = step_keys(p, st) + kStreamE * MVAE_MAX_ARMS;
   h.tau = hp.tau; h.temp = hp.temp; h.eps = hp.eps; h.s_scale = 1.0f / (1.0f - hp.s_drop);
   h.hard = hp.hard; h.training = training;
   h.x_low = out.x_low; h.c_prob = out.c_prob; h.qc = out.qc; h.c_smp = out.c_smp;
@@ -353,7 +353,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   h.oWc = p.L.offset[FCC_W]; h.oBc = p.L.offset[FCC_B]; h.oWmu = p.L.offset[FCMU_W]; h.oBmu = p.L.offset[FCMU_B];
   h.oWsig = p.L.offset[FCSIG_W]; h.oBsig = p.L.offset[FCSIG_B]; h.oW6 = p.L.offset[FC6_W]; h.oB6 = p.L.offset[FC6_B];
   h.E = in.E; h.keep_s = hp.s_drop > 0.f ? in.keep_s : nullptr;
-  h.noise_seed = noise_seed(in);
+  h.ukeys = step_keys(p, st) + kStreamU * MVAE_MAX_ARMS; h.ekeys = step_keys(p, st) + kStreamE * MVAE_MAX_ARMS;   // same step: the forward's keys
   h.tau = hp.tau; h.temp = hp.temp; h.eps = hp.eps; h.s_scale = 1.0f / (1.0f - hp.s_drop);
   h.hard = hp.hard; h.training = 1;
   h.x_low = out.x_low; h.c_prob = out.c_prob; h.qc = out.qc; h.c_smp = out.c_smp;
@@ -431,7 +431,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   RC(hp.precision == 3 ? launch_wgrad(wg, s) : launch_wgrad_mma(wg, hp.precision == 1, s));
   timing_end(TG_WGRAD, s);
   // ---- d fc1.weight = delta1^T * dropout(x)
-  DropSpec drop = make_drop(p, hp, in);
+  DropSpec drop = make_drop(p, hp, st, in);
   timing_begin(TG_FC1_WGRAD, s);
   if (tc && hp.precision != 1 && !legacy_fc1()) {
     RC(ts_fc1_wgrad(p.d, st, in, drop, w, s));
@@ -466,7 +466,7 @@ int mvae_forward(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state
   RC(make_plan(dims, &p));
   MVAE_CHECK_ARG(hp && st && in && out, "null argument");
   RC(check_device());
-  return forward_impl(p, *hp, *st, *in, *out, (cudaStream_t)stream);
+  return forward_impl(p, *hp, *st, *in, *out, 0, (cudaStream_t)stream);
 }
 
 int mvae_loss(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state* st, const mvae_inputs* in,
@@ -489,10 +489,12 @@ int mvae_backward(const mvae_dims* dims, const mvae_hparams* hp, const mvae_stat
 }
 
 int mvae_adam(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-              float eps, float weight_decay, int32_t adamw, int64_t step, void* stream) {
+              float eps, float weight_decay, int32_t adamw, int64_t step, uint64_t* step_counter, void* stream) {
   MVAE_CHECK_ARG(params && grads && m && v, "null argument");
   RC(check_device());
-  return launch_adam(params, grads, m, v, n, lr, beta1, beta2, eps, weight_decay, adamw, step, (cudaStream_t)stream);
+  if (step_counter) RC(launch_counter_inc(step_counter, (cudaStream_t)stream));
+  return launch_adam(params, grads, m, v, n, lr, beta1, beta2, eps, weight_decay, adamw, step, step_counter,
+                     (cudaStream_t)stream);
 }
 
 int mvae_train_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state* st, const mvae_inputs* in,
@@ -506,12 +508,12 @@ int mvae_train_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_st
   cudaStream_t s = (cudaStream_t)stream;
   mvae_outputs o = *out;
   o.x_rec = nullptr;
-  RC(forward_impl(p, *hp, *st, *in, o, s));
+  RC(forward_impl(p, *hp, *st, *in, o, 1, s));
   RC(loss_impl(p, *hp, *st, *in, o, o.qc, o.c_smp, loss_out, 1, s));
   RC(backward_impl(p, *hp, *st, *in, o, nullptr, s));
   TimedScope ts(TG_ADAM, s);
   return launch_adam(st->params, st->grads, st->adam_m, st->adam_v, (int64_t)p.A * p.L.arm_stride, lr, beta1, beta2,
-                     adam_eps, 0.f, 0, step, s);
+                     adam_eps, 0.f, 0, step, in->counters ? in->counters + 1 : nullptr, s);
 }
 
 int mvae_dropout_mask(const mvae_dims* dims, const mvae_hparams* hp, const mvae_inputs* in, uint8_t* keep_out,
@@ -523,10 +525,14 @@ int mvae_dropout_mask(const mvae_dims* dims, const mvae_hparams* hp, const mvae_
   mvae_inputs i2 = *in;
   i2.keep_x = nullptr;
   i2.training = 1;
-  DropSpec d = make_drop(p, *hp, i2);
+  mvae_state nost;
+  memset(&nost, 0, sizeof(nost));
+  DropSpec d = make_drop(p, *hp, nost, i2);
   MVAE_CHECK_ARG(d.mode == 2, "x_drop is 0: there is no mask");
+  d.keys = nullptr;    // the keys are derived here, on the host, from the same (seed, step, global arm) function
   for (int a = 0; a < p.A; ++a)
-    RC(launch_dropout_mask(d, a, p.B, keep_out + (int64_t)a * p.B * p.D, (cudaStream_t)stream));
+    RC(launch_dropout_mask(d, stream_key(in->seed, in->step, (uint32_t)(a + p.d.arm_offset), kStreamDrop), p.B,
+                           keep_out + (int64_t)a * p.B * p.D, (cudaStream_t)stream));
   return 0;
 }
 
@@ -540,6 +546,14 @@ int mvae_confmat(const int32_t* labels, int64_t n_cells, int32_t n_arm, int32_t 
   MVAE_CHECK_ARG(labels && counts && n_arm >= 2 && n_categories >= 1 && n_cells >= 0, "bad argument");
   RC(check_device());
   return launch_confmat(labels, n_cells, n_arm, n_categories, counts, (cudaStream_t)stream);
+}
+
+int mvae_unpack_rows(const uint32_t* bitmap, const float* values, const int64_t* row_ptr, int64_t rows, int32_t n_cols,
+                     float* out, int64_t out_row_stride, void* stream) {
+  MVAE_CHECK_ARG(bitmap && values && row_ptr && out, "null argument");
+  MVAE_CHECK_ARG(rows >= 0 && n_cols >= 1 && out_row_stride >= n_cols, "bad shape");
+  RC(check_device());
+  return launch_unpack_rows(bitmap, values, row_ptr, rows, n_cols, out, out_row_stride, (cudaStream_t)stream);
 }
 
 // ---- augmenter forward: see include/mixvae_b200.h

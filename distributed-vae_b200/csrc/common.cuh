@@ -99,6 +99,7 @@ struct Work {
   int64_t acc_fwd, acc_fwd_floats;   // bn_sum[5][A][2][128], (unused q block), kl_sum[A][16]
   int64_t acc_loss, acc_loss_floats; // see accl_* below
   int64_t acc_bwd, acc_bwd_floats;   // bnb_sum[5][A][2][128]
+  int64_t keys;        // uint64 [kNumStreams][MVAE_MAX_ARMS] generator keys of the current step + [2] {rng step, Adam step}
   int64_t total;
   int32_t Bpad, Dpad, Hpad, wg_nsplit, wg_rows, fc1_splitk;
   int64_t wg_floats;   // narrow-layer params per arm (contiguous range FC2_W .. FC10_B), see wgrad
@@ -133,6 +134,27 @@ struct TimedScope {
 
 int compute_layout(const mvae_dims& d, mvae_layout* L);
 Work make_work(const mvae_dims& d);
+
+// ---------------------------------------------------------------------------------------------
+// generator keys (host and device: mvae_dropout_mask derives them on the host, step_prep_kernel on the device)
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+#define MVAE_HD __host__ __device__
+#else
+#define MVAE_HD
+#endif
+MVAE_HD inline uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+constexpr uint32_t kStreamDrop = 0, kStreamU = 1, kStreamE = 2, kNumStreams = 3;
+MVAE_HD inline uint64_t stream_key(uint64_t seed, uint64_t step, uint32_t arm_global, uint32_t stream) {
+  uint64_t k = splitmix64(seed);
+  k = splitmix64(k ^ step);
+  return splitmix64(k ^ (((uint64_t)stream << 32) | (uint64_t)arm_global));
+}
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
@@ -176,28 +198,27 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Counter-based dropout generator: ONE 32-bit mix per 4 consecutive elements of x (a 16-byte chunk),
-// 8 random bits per element.  keep <=> byte >= thresh, thresh = round(p * 256): exact for p = k/256
-// (the reference default p = 0.5 in particular); other rates are quantised to 1/256.
-__device__ __forceinline__ uint32_t mix32(uint32_t h) {
-  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+// Counter-based generators.  A 64-bit KEY per (seed, step, global arm, stream) is derived by chained splitmix64
+// (stream_key below: every input has its own mixing round, so no two (seed, step, arm, stream) tuples share a key short
+// of a 64-bit collision); the per-element work is one keyed 32-bit finaliser over the element counter with the two key
+// words injected before and between its multiply rounds.
+//   stream 0: input dropout, ONE hash per 4 consecutive elements of x (a 16-byte chunk), 8 random bits per element;
+//             keep <=> byte >= thresh, thresh = round(p * 256): exact for p = k/256 (the reference default p = 0.5 in
+//             particular); other rates are quantised to 1/256.
+//   stream 1: Gumbel uniforms U[cell][category];  stream 2: state noise E[cell][s]  (24 random bits, like torch.rand).
+__device__ __forceinline__ uint32_t keyed_mix32(uint64_t key, uint64_t ctr) {
+  uint32_t h = (uint32_t)ctr * 0x9E3779B1u ^ (uint32_t)(ctr >> 32) * 0x7FEB352Du ^ (uint32_t)key;
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= (uint32_t)(key >> 32); h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
   return h;
 }
-__device__ __forceinline__ uint32_t drop_bits4(uint64_t seed, int arm, uint64_t chunk) {
-  return mix32((uint32_t)chunk * 0x9E3779B1u ^ (uint32_t)(chunk >> 32) * 0x7FEB352Du ^ (uint32_t)seed ^
-               ((uint32_t)(seed >> 32) * 0x846CA68Bu) ^ ((uint32_t)arm * 0x632BE5ABu));
+__device__ __forceinline__ uint32_t drop_bits4(uint64_t key, uint64_t chunk) { return keyed_mix32(key, chunk); }
+// Used when the caller passes no noise tensors; the backward regenerates E.
+__device__ __forceinline__ float noise_uniform(uint64_t key, uint64_t idx) {
+  return (float)(keyed_mix32(key, idx) >> 8) * (1.0f / 16777216.0f);
 }
-// Counter-based Uniform[0,1) draw (24 random bits, like torch.rand for fp32): stream 1 = Gumbel uniforms U[arm][cell][category],
-// stream 2 = state noise E[arm][cell][s].  Used when the caller passes no noise tensors; the backward regenerates E.
-__device__ __forceinline__ float noise_uniform(uint64_t seed, uint32_t stream, uint64_t idx) {
-  const uint32_t h = mix32((uint32_t)idx * 0x9E3779B1u ^ (uint32_t)(idx >> 32) * 0x7FEB352Du ^ (uint32_t)seed ^
-                           ((uint32_t)(seed >> 32) * 0x846CA68Bu) ^ (stream * 0x68E31DA4u));
-  return (float)(h >> 8) * (1.0f / 16777216.0f);
-}
-__device__ __forceinline__ bool drop_keep(uint64_t seed, int arm, int64_t row, int64_t col, int64_t D,
-                                          uint32_t thresh) {
+__device__ __forceinline__ bool drop_keep(uint64_t key, int64_t row, int64_t col, int64_t D, uint32_t thresh) {
   const uint64_t idx = (uint64_t)row * (uint64_t)D + (uint64_t)col;
-  const uint32_t bits = (drop_bits4(seed, arm, idx >> 2) >> (8 * (uint32_t)(idx & 3))) & 0xFFu;
+  const uint32_t bits = (drop_bits4(key, idx >> 2) >> (8 * (uint32_t)(idx & 3))) & 0xFFu;
   return bits >= thresh;
 }
 #endif
@@ -205,7 +226,7 @@ __device__ __forceinline__ bool drop_keep(uint64_t seed, int arm, int64_t row, i
 struct DropSpec {
   const uint8_t* keep;  // injected mask [B][D] for this launch's arm 0, or nullptr
   int64_t keep_arm_stride;
-  uint64_t seed;        // used when keep == nullptr && mode == 2
+  const uint64_t* keys; // mode == 2: device table of generator keys, one per LOCAL arm (Work::keys, stream 0)
   float scale;          // 1/(1-p)
   uint32_t thresh16;    // 8-bit threshold of the in-kernel generator (name kept): round(p * 256)
   int mode;             // 0: no dropout, 1: injected mask, 2: in-kernel generator

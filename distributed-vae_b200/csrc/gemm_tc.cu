@@ -90,7 +90,7 @@ __device__ __forceinline__ void transform_tile(float* hi, float* lo, bool do_spl
         for (int i = 0; i < 4; ++i) m[i] = ((kb >> (8 * i)) & 0xFF) ? drop.scale : 0.f;
       } else {
         // xcol % 4 == 0 and D % 4 == 0: the 4 elements are exactly one generator chunk
-        const uint32_t bits = drop_bits4(drop.seed, arm, ((uint64_t)xrow * (uint64_t)drop.D + (uint64_t)xcol) >> 2);
+        const uint32_t bits = drop_bits4(drop.keys[arm], ((uint64_t)xrow * (uint64_t)drop.D + (uint64_t)xcol) >> 2);
 #pragma unroll
         for (int i = 0; i < 4; ++i) m[i] = ((bits >> (8 * i)) & 0xFFu) >= drop.thresh16 ? drop.scale : 0.f;
       }

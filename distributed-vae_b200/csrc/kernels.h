@@ -54,8 +54,9 @@ struct HeadArgs {
   int bn_mode;                // 1 batch sums, 2 given
   const double* bn_sums5;     // [A][2][128]
   float* bn_mean5; float* bn_rstd5;  // [A][128]
-  const float* U; const float* E; const uint8_t* keep_s;   // U / E nullptr: in-kernel counter-based draws (noise_seed)
-  uint64_t noise_seed;
+  const uint8_t* cat_mask;    // [C] 1 = category kept, or nullptr (forward(mask=...), nn_model.py:332-335)
+  const float* U; const float* E; const uint8_t* keep_s;   // U / E nullptr: in-kernel counter-based draws
+  const uint64_t* ukeys; const uint64_t* ekeys;   // device tables of generator keys per LOCAL arm (Work::keys, streams 1 / 2)
   float tau, temp, eps, s_scale; int hard, training;
   // forward outputs
   float *x_low, *c_prob, *qc, *c_smp, *s_mean, *s_logvar, *s_smp;
@@ -148,8 +149,11 @@ int launch_enc_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
 
 // ---- optimiser / misc ------------------------------------------------------------------------
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
-                float wd, int adamw, int64_t step, cudaStream_t s);
+                float wd, int adamw, int64_t step, const uint64_t* step_dev, cudaStream_t s);
 int launch_scale(float* p, int64_t n, const float* scale_dev, cudaStream_t s);
+int launch_counter_inc(uint64_t* counter, cudaStream_t s);
+int launch_unpack_rows(const uint32_t* bitmap, const float* values, const int64_t* row_ptr, int64_t rows, int D, float* out,
+                       int64_t out_ld, cudaStream_t s);
 int launch_argmax(const float* q, int32_t* labels, int64_t rows, int cols, cudaStream_t s);
 int launch_confmat(const int32_t* labels, int64_t n, int A, int K, int32_t* counts, cudaStream_t s);
 int launch_transpose(const float* src, int64_t src_ld, int64_t src_batch_stride, float* dst, int64_t dst_ld,
@@ -164,6 +168,11 @@ struct GemmArgs {
   DropSpec drop; int drop_operand;             // 0 none, 1: A is x with (row,col)=(m,k), 2: B is x with (row,col)=(k,n)
 };
 int launch_sgemm_simt(const GemmArgs& a, int batch, cudaStream_t s);
-int launch_dropout_mask(const DropSpec& d, int arm, int B, uint8_t* out, cudaStream_t s);
+int launch_dropout_mask(const DropSpec& d, uint64_t key, int B, uint8_t* out, cudaStream_t s);
+// generator keys of one step -> keys[kNumStreams][MVAE_MAX_ARMS] (local arm a uses global arm a + arm_off), counters -> keys[3*16 .. +2).
+// counters (nullable): device {rng step, Adam step}; when given the kernel INCREMENTS counters[0] (and counters[1] if
+// bump_adam) and uses the new values instead of step_host -- the form a replayed CUDA graph needs.
+int launch_step_prep(uint64_t seed, uint64_t step_host, uint64_t* counters, int bump_adam, int arm_off, uint64_t* keys_out,
+                     cudaStream_t s);
 
 }  // namespace mvae

@@ -182,6 +182,14 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
   if (lane < kMaxS) klacc[lane] = 0.0;
   __syncwarp();
 
+  // category mask of the pruning path (nn_model.py:332-335): q = softmax over the kept categories only, 0 elsewhere
+  bool kq[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int kk = lane + 32 * k;
+    kq[k] = kk < C && (p.cat_mask == nullptr || p.cat_mask[kk] != 0);
+  }
+
   for (int row = blockIdx.x * kRowWarps + warp; row < B; row += gridDim.x * kRowWarps) {
     const int64_t r = ab + row;
     // ---- x_low = batch_l5(relu(fc5)) : nn_model.py:268
@@ -214,13 +222,13 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
       z[k] = pk[k] / p.tau;
-      if (lane + 32 * k < C) m = fmaxf(m, z[k]);
+      if (kq[k]) m = fmaxf(m, z[k]);
     }
     m = warp_max(m);
     sum = 0.f;
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
-      q[k] = (lane + 32 * k < C) ? expf(z[k] - m) : 0.f;
+      q[k] = kq[k] ? expf(z[k] - m) : 0.f;
       sum += q[k];
     }
     sum = warp_sum(sum);
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
         const int kk = lane + 32 * k;
         if (kk < C) {
           const float u = p.U ? p.U[r * C + kk]
-                              : noise_uniform(p.noise_seed, 1u, ((uint64_t)(arm + p.arm_off) * B + row) * C + kk);
+                              : noise_uniform(p.ukeys[arm], (uint64_t)row * C + kk);
           const float g = -logf(-logf(u + p.eps) + p.eps);
           z[k] = (logf(q[k] + p.eps) + g) / p.temp;
           m = fmaxf(m, z[k]);
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
         const float lv = logf(var + p.eps);
         const float elv = expf(lv);
         const float sd = sqrtf(elv);
-        const float e = p.E ? p.E[r * S + s] : noise_uniform(p.noise_seed, 2u, ((uint64_t)(arm + p.arm_off) * B + row) * S + s);
+        const float e = p.E ? p.E[r * S + s] : noise_uniform(p.ekeys[arm], (uint64_t)row * S + s);
         const float smp = e * sd + mu;                     // uniform noise, nn_model.py:427
         float sd_in = smp;
         if (p.training && p.keep_s) sd_in = p.keep_s[r * S + s] ? smp * p.s_scale : 0.f;
@@ -401,7 +409,7 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_bwd_kernel(const HeadA
         float gs = gsd[s];
         if (p.keep_s) gs = p.keep_s[r * S + s] ? gs * p.s_scale : 0.f;
         const float mu = p.s_mean[r * S + s], lv = p.s_logvar[r * S + s], var = p.svar[r * S + s];
-        const float e = p.E ? p.E[r * S + s] : noise_uniform(p.noise_seed, 2u, ((uint64_t)(arm + p.arm_off) * B + row) * S + s);
+        const float e = p.E ? p.E[r * S + s] : noise_uniform(p.ekeys[arm], (uint64_t)row * S + s);
         const float elv = expf(lv), sd = sqrtf(elv);
         const float gmu = gs + p.kl_coef * mu;
         const float glv = gs * e * 0.5f * sd + p.kl_coef * (-0.5f) * (1.f - elv);

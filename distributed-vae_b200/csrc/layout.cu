@@ -163,6 +163,7 @@ Work make_work(const mvae_dims& d) {
   w.acc_loss = take(w.acc_loss_floats);
   w.acc_bwd_floats = 2 * acc_bwd_doubles((int)A);
   w.acc_bwd = take(w.acc_bwd_floats);
+  w.keys = take(2 * ((int64_t)kNumStreams * MVAE_MAX_ARMS + 2));
   w.total = off;
   return w;
 }

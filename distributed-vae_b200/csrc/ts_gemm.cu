@@ -243,11 +243,12 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         // ---- dropout: zero the dropped elements (the 1/(1-p) scale is applied by the fix-up kernel)
         if (dp.mode == 2) {
+          const uint64_t dkey = dp.keys[arm];             // generator key of (seed, step, global arm): L1/L2-resident table
           if (!WGRAD) {
             const uint64_t chunk = (uint64_t)(m0 + r) * Dq + (uint64_t)(kt * 8 + 4 * half);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint32_t b = drop_bits4(dp.seed, arm, chunk + q);
+              const uint32_t b = drop_bits4(dkey, chunk + q);
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[4 * q + j] = ((b >> (8 * j)) & 0xFFu) >= thr ? v[4 * q + j] : 0u;
             }
@@ -257,7 +258,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             const uint64_t ccol = (uint64_t)((m0 + quad * 32) >> 2) + (uint64_t)(lane & 7);
             uint32_t hq[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) hq[q] = drop_bits4(dp.seed, arm, (cell0 + 4 * q) * Dq + ccol);
+            for (int q = 0; q < 4; ++q) hq[q] = drop_bits4(dkey, (cell0 + 4 * q) * Dq + ccol);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const uint32_t h = __shfl_sync(0xffffffffu, hq[j >> 2], (j & 3) * 8 + (lane >> 2));

@@ -44,8 +44,8 @@ class State(C.Structure):
 
 class Inputs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("x_arm_stride", C.c_int64), ("x_row_stride", C.c_int64),
-                ("U", C.c_void_p), ("E", C.c_void_p), ("keep_x", C.c_void_p), ("keep_s", C.c_void_p),
-                ("seed", C.c_uint64), ("step", C.c_uint64), ("training", C.c_int32)]
+                ("U", C.c_void_p), ("E", C.c_void_p), ("keep_x", C.c_void_p), ("keep_s", C.c_void_p), ("cat_mask", C.c_void_p),
+                ("seed", C.c_uint64), ("step", C.c_uint64), ("counters", C.c_void_p), ("training", C.c_int32)]
 
 
 class Outputs(C.Structure):
@@ -59,7 +59,7 @@ PRECISIONS = {"tf32x3_fc1": 0, "tf32x3": 1, "tf32": 2, "fp32_simt": 3}
 EXPORTS = ("mvae_last_error", "mvae_abi_version", "mvae_compute_layout", "mvae_forward", "mvae_loss",
            "mvae_backward", "mvae_adam", "mvae_train_step", "mvae_argmax", "mvae_dropout_mask", "mvae_launch_count",
            "mvae_timing_enable", "mvae_timing_read", "mvae_debug_tc_gemm", "mvae_confmat", "mvae_fold_affine",
-           "mvae_linear_act", "mvae_fma_rows")
+           "mvae_linear_act", "mvae_fma_rows", "mvae_unpack_rows")
 
 _lib = None
 
@@ -84,7 +84,7 @@ def load():
                               C.c_void_p, C.c_int, C.c_void_p]
     lib.mvae_backward.argtypes = [P(Dims), P(HParams), P(State), P(Inputs), P(Outputs), C.c_void_p, C.c_void_p]
     lib.mvae_adam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
-                              C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int64, C.c_void_p]
+                              C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
     lib.mvae_train_step.argtypes = [P(Dims), P(HParams), P(State), P(Inputs), P(Outputs), C.c_void_p, C.c_float,
                                     C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]
     lib.mvae_argmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
@@ -99,6 +99,8 @@ def load():
     lib.mvae_fma_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_int64, C.c_int32, C.c_float, C.c_void_p]
     lib.mvae_fma_rows.restype = C.c_int
+    lib.mvae_unpack_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.mvae_unpack_rows.restype = C.c_int
     lib.mvae_debug_tc_gemm.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.mvae_debug_tc_gemm.restype = C.c_int
@@ -109,7 +111,7 @@ def load():
     for name in ("mvae_compute_layout", "mvae_forward", "mvae_loss", "mvae_backward", "mvae_adam",
                  "mvae_train_step", "mvae_argmax", "mvae_dropout_mask"):
         getattr(lib, name).restype = C.c_int
-    if lib.mvae_abi_version() != 1:
+    if lib.mvae_abi_version() != 2:
         raise RuntimeError("libmixvae_b200.so ABI version mismatch")
     _lib = lib
     return lib

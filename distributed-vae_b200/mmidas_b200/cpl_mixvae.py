@@ -1,19 +1,23 @@
 """Trainer mirror of ``mmidas/cpl_mixvae.py`` (class cpl_mixVAE) for the B200 path.
 
 Kept: ``cpl_mixVAE(saving_folder, aug_file, device, eps, save_flag, load_weights)`` (:153-161),
-``init_model(...)`` (:193-216), ``train(...)`` signature (:323-337), ``load_model`` (:317), the loss
-names printed/logged (``train/total-loss`` ... ``val/consensus``, :536-560, :765-775) and the
-checkpoint files/dict keys (:777-788, :851-865, :947-967).  ``.model`` and ``.optimizer`` stay public
-and re-assignable (train.py:141,145 re-creates the optimizer).
+``init_model(...)`` (:193-216), ``train(...)`` signature (:323-337), ``load_model`` (:317), ``eval_model`` and the
+dictionary it returns (:1450-1619), ``save_file`` / ``load_file`` (:1621-1650), the loss names printed/logged
+(``train/total-loss`` ... ``val/consensus``, :536-560, :765-775) and the checkpoint files/dict keys (:777-788,
+:851-865, :947-967).  ``.model`` and ``.optimizer`` stay public and re-assignable (train.py:141,145 re-creates the
+optimizer).
 
-Changed: the batch-loop body (:415-478) is one fused C call per step; the per-step host
-synchronisations of the reference (``_loss.item()`` :469, ``to_np(cs[a])`` :476) are gone — losses are
-summed on the device and read once per epoch, labels are computed by a device argmax and copied once
-per epoch; the next batch's H2D copy runs on a side stream while the current step computes.
+Changed: the batch-loop body (:415-478) is one fused C call per step, replayed from a CUDA graph when the batch
+arrives in a buffer seen before; the per-step host synchronisations of the reference (``_loss.item()`` :469,
+``to_np(cs[a])`` :476) are gone — losses are summed on the device and read once per epoch, labels are computed by a
+device argmax and only arm-pair confusion counts are copied once per epoch; the next batch's H2D copy (dense, or
+row-packed and expanded on the device) runs on a side stream while the current step computes.  ``train(ws > 1)`` —
+which the reference gates off (train.py:274-275) — runs on the (arm x dp) mesh of ``mmidas_b200.parallel``.
 """
 from __future__ import annotations
 
 import os
+import pickle
 import time
 from typing import Iterable, Optional
 
@@ -21,7 +25,8 @@ import numpy as np
 import torch
 
 from ._utils import confmat_device, consensus, consensus_from_counts
-from .nn_model import VAEConfig, mixVAE_model
+from .dataloader import PackedBatch
+from .nn_model import StepGraph, VAEConfig, mixVAE_model
 from .optim import FusedAdam
 
 
@@ -30,17 +35,38 @@ def is_master(rank):
 
 
 class HostBatchFeeder:
-    """Iterates over host batches and yields device tensors, copying batch i+1 on a side stream
-    while batch i is being consumed (the reference does a blocking ``x.to(rank)`` at :416)."""
+    """Iterates over host batches and yields device tensors, copying batch i+1 on a side stream while batch i is being
+    consumed (the reference does a blocking ``x.to(rank)`` at :416).
 
-    def __init__(self, batches: Iterable, device, pin: bool = True):
+    Batches land in a small ring of device staging buffers per batch shape, so consecutive steps see the same few
+    device pointers (what lets the trainer replay a captured CUDA graph).  Items may be dense CPU tensors (pinned on the
+    fly when they are not), tuples ``(x, idx)`` as a DataLoader yields, device tensors (passed through) or
+    ``PackedBatch`` objects, which cross PCIe in row-packed form and are expanded into the staging buffer on the copy
+    stream (bit-exact).  A buffer is refilled only after the work that read it was enqueued two ``next()`` calls ago
+    has finished (event edge to the copy stream).
+    """
+
+    def __init__(self, batches: Iterable, device, pin: bool = True, depth: int = 2):
         self.it = iter(batches)
         self.device = torch.device(device)
         self.pin = pin
+        self.depth = max(2, int(depth))
         self.stream = torch.cuda.Stream(self.device)
         self.h2d_bytes = 0
+        self.batches_copied = 0
+        self._rings = {}          # shape -> [buffers], next slot
+        self._packed_staging = {}
         self._next = None
         self._preload()
+
+    def _slot(self, shape):
+        ring = self._rings.get(shape)
+        if ring is None:
+            ring = [[torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(self.depth)], 0]
+            self._rings[shape] = ring
+        buf = ring[0][ring[1]]
+        ring[1] = (ring[1] + 1) % self.depth
+        return buf
 
     def _preload(self):
         try:
@@ -49,12 +75,32 @@ class HostBatchFeeder:
             self._next = None
             return
         x = item[0] if isinstance(item, (tuple, list)) else item
-        if x.device.type == "cpu":
-            if self.pin and not x.is_pinned():
-                x = x.pin_memory()
-            self.h2d_bytes += x.numel() * x.element_size()
+        # everything enqueued on the compute stream so far (the steps that read the ring) must finish before a refill
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
-            xd = x.to(self.device, non_blocking=True)
+            if isinstance(x, PackedBatch):
+                buf = self._slot(tuple(x.shape))
+                st = self._packed_staging.get(x.shape)
+                need = (x.bitmap.numel(), x.values.numel(), x.row_ptr.numel())
+                if st is None or st[1].numel() < need[1]:
+                    st = (torch.empty(need[0], dtype=torch.int32, device=self.device),
+                          torch.empty(int(need[1] * 1.25) + 1024, dtype=torch.float32, device=self.device),
+                          torch.empty(need[2], dtype=torch.int64, device=self.device))
+                    self._packed_staging[x.shape] = st
+                xd = x.unpack(self.device, out=buf, staging=st)
+                self.h2d_bytes += x.nbytes
+                self.batches_copied += 1
+            elif x.device.type == "cpu":
+                if x.dtype != torch.float32:
+                    x = x.float()
+                if self.pin and not x.is_pinned():
+                    x = x.pin_memory()
+                xd = self._slot(tuple(x.shape))
+                xd.copy_(x, non_blocking=True)
+                self.h2d_bytes += x.numel() * x.element_size()
+                self.batches_copied += 1
+            else:
+                xd = x
         self._next = (xd, item)
 
     def __iter__(self):
@@ -65,7 +111,6 @@ class HostBatchFeeder:
             raise StopIteration
         torch.cuda.current_stream(self.device).wait_stream(self.stream)
         xd, item = self._next
-        xd.record_stream(torch.cuda.current_stream(self.device))
         self._preload()
         return xd, item
 
@@ -88,6 +133,10 @@ class cpl_mixVAE:
         else:
             self.aug_model, self.aug_param, self.netA = None, None, None
         self.precision = "tf32x3_fc1"
+        self.use_cuda_graph = True      # replay the fused step from a CUDA graph when the batch buffer repeats
+        self.mesh_mode = "dp"           # train(ws > 1): "dp", "arm" or "auto" (mmidas_b200.parallel.plan_mesh)
+        self._graphs = {}
+        self._graph_misses = 0
 
     # ------------------------------------------------------------------------------------------
     def init_model(self, n_categories, state_dim, input_dim, fc_dim=100, lowD_dim=10, x_drop=0.5, s_drop=0.2,
@@ -108,6 +157,8 @@ class cpl_mixVAE:
                                   precision=self.precision)
         self.model = self.model.to(self.device)
         self.optimizer = FusedAdam(self.model.parameters(), lr=lr, model=self.model)
+        self._graphs = {}
+        self._graph_misses = 0
         if len(trained_model) > 0:
             print("Load the pre-trained model")
             loaded_file = torch.load(trained_model, map_location="cpu")
@@ -137,11 +188,21 @@ class cpl_mixVAE:
         self.model.load_state_dict(loaded_file["model_state_dict"])
         self.current_time = time.strftime("%Y-%m-%d-%H-%M-%S")
 
-    def _save(self, path):
+    def _save(self, path, state=None):
         print(f"saving model to: {path}")
         os.makedirs(os.path.dirname(path), exist_ok=True)
-        torch.save({"model_state_dict": self.model.state_dict(),
-                    "optimizer_state_dict": self.optimizer.state_dict()}, path)
+        msd, osd = state if state is not None else (self.model.state_dict(), self.optimizer.state_dict())
+        torch.save({"model_state_dict": msd, "optimizer_state_dict": osd}, path)
+
+    def save_file(self, fname, **kwargs):
+        """cpl_mixvae.py:1621-1635: pickle the keyword arguments to ``fname + '.p'`` (protocol 4)."""
+        with open(fname + ".p", "wb") as f:
+            pickle.dump(dict(kwargs), f, protocol=4)
+
+    def load_file(self, fname):
+        """cpl_mixvae.py:1637-1650."""
+        with open(fname + ".p", "rb") as f:
+            return pickle.load(f)
 
     # ------------------------------------------------------------------------------------------
     # one optimiser step (cpl_mixvae.py:434-463)
@@ -149,40 +210,81 @@ class cpl_mixVAE:
     def train_batch(self, x: torch.Tensor, noise=None, aug_noise=None) -> torch.Tensor:
         """zero_grad -> forward -> loss -> backward -> Adam on one batch ``x`` [B, D] already on the device.
         Returns the device loss vector (total, joint, entropy, distance, l2, rec[A], kl[A], ll[A]); nothing
-        is synchronised."""
+        is synchronised.  The vector is overwritten by the next call."""
         A = self.n_arm
+        model, opt = self.model, self.optimizer
+        fused = isinstance(opt, FusedAdam) and opt.model is model
+        graphable = (fused and self.use_cuda_graph and self.netA is None and noise is None and aug_noise is None
+                     and model.s_drop == 0.0 and model.training and x.is_cuda and x.dtype == torch.float32
+                     and x.dim() == 2 and x.stride(-1) == 1 and self._graph_misses < 32)
+        if graphable:
+            g0 = opt.param_groups[0]
+            key = (x.data_ptr(), tuple(x.shape), x.stride(0), float(self.temp), float(g0["lr"]), tuple(g0["betas"]), float(g0["eps"]),
+                   id(model), id(opt))
+            g = self._graphs.get(key)
+            if g is not None:
+                self._graph_misses = 1
+                return g.replay()
+            if self._graph_misses > 0 or self._graphs:        # (the very first step runs eagerly: lazy allocations)
+                if len(self._graphs) >= 8:
+                    self._graphs.pop(next(iter(self._graphs)))
+                torch.cuda.synchronize(self.device)
+                try:
+                    g = StepGraph(model, opt, lambda: model.fused_train_step(x.expand(A, -1, -1), self.temp, opt))
+                except Exception as err:           # capture refused: stay on the eager path
+                    print(f"cpl_mixVAE: CUDA graph capture failed ({err}); continuing without graphs")
+                    self.use_cuda_graph = False
+                    g = None
+                if g is not None:
+                    self._graphs[key] = g
+                    self._graph_misses += 1
+                    return g.replay()
+            self._graph_misses += 1
         xs = x.expand(A, -1, -1)
         if self.netA is not None:      # cpl_mixvae.py:422-423: every arm trains on its own augmented copy of the batch
             xs = self.netA(xs, True, 0.1, noise=aug_noise)[1]
-        if isinstance(self.optimizer, FusedAdam) and self.optimizer.model is self.model:
-            return self.model.fused_train_step(xs, self.temp, self.optimizer, noise=noise)
+        if fused:
+            return model.fused_train_step(xs, self.temp, opt, noise=noise)
         # a caller replaced .optimizer (train.py:144-147): reference-shaped sequence on the same kernels
-        self.optimizer.zero_grad()
-        x_recs, _, _, _, cs, _, c_smps, s_means, s_logvars, _ = self.model(xs, self.temp, 0.0, noise=noise)
-        self.model.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0)[0].backward()
-        self.optimizer.step()
-        return self.model._ctx.loss_vec
+        opt.zero_grad()
+        x_recs, _, _, _, cs, _, c_smps, s_means, s_logvars, _ = model(xs, self.temp, 0.0, noise=noise)
+        model.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0)[0].backward()
+        opt.step()
+        return model._ctx.loss_vec
 
     # ------------------------------------------------------------------------------------------
     def train(self, train_loader, test_loader, n_epoch, n_epoch_p, c_p=0, c_onehot=0, min_con=0.5, max_prun_it=0,
               rank=None, run=None, ws=1, good_enuf_consensus=0.75):
         """Epoch loop with the reference's bookkeeping (cpl_mixvae.py:323-967): per epoch one training
         pass, one eval-mode pass over the training set, one validation pass; consensus between arms;
-        checkpoints every 10 epochs, at the consensus threshold and at the end.  Returns the curves."""
+        checkpoints every 10 epochs, at the consensus threshold and at the end.  Returns the curves.
+        ``ws > 1`` (one process per GPU, process group initialised by ``init_dist_env``): the step runs on the
+        (arm x dp) mesh ``self.mesh_mode``; every rank iterates ITS loader, and the epoch sums are all-reduced as
+        at :480-483."""
         if rank is None:
             rank = self.device
-        if ws > 1:
-            raise NotImplementedError("use mmidas_b200.parallel.ShardedTrainer for multi-GPU runs "
-                                      "(the reference itself raises for ws > 1, train.py:274-275)")
         if n_epoch_p > 0 or max_prun_it > 0:
             raise NotImplementedError("pruning is forcibly disabled in the reference (cpl_mixvae.py:1007-1008)")
         A, C, E, D = self.n_arm, self.n_categories, n_epoch, self.input_dim
         Bs, Bs_val = len(train_loader), len(test_loader)
         B_val = test_loader.batch_size
         self.current_time = time.strftime("%Y-%m-%d-%H-%M-%S")
-        model = self.model
-        model.materialize_recon = False
         dev = self.device
+        dist_on = ws > 1
+        st = None
+        if dist_on:
+            import torch.distributed as dist
+            from .parallel import ShardedTrainer
+            if not dist.is_initialized():
+                raise RuntimeError("train(ws > 1) needs an initialised process group (mmidas_b200._dist_utils.init_dist_env)")
+            if self.netA is not None:
+                raise NotImplementedError("the augmenter runs on the single-GPU path only")
+            st = ShardedTrainer(model=self.model, lr=self.optimizer.param_groups[0]["lr"], mode=self.mesh_mode, temp=self.temp,
+                                use_cuda_graph=self.use_cuda_graph)
+            model = st.model
+        else:
+            model = self.model
+        model.materialize_recon = False
         losses, loss_joints, c_ents, c_l2_dists, c_dists = [], [], [], [], []
         loss_recs = [[] for _ in range(A)]
         consensus_train, consensus_aug, consensus_val = [], [], []
@@ -192,6 +294,16 @@ class cpl_mixVAE:
         if not getattr(self, "init", True):
             return {"skipped": True}     # reference: a loaded model skips the loop (:397)
         print("training started")
+        master = (not dist_on) or dist.get_rank() == 0
+
+        def save(path):
+            if dist_on:
+                state = st.full_state_dicts()        # collective over the arm axis: every rank calls it
+                if master:
+                    self._save(path, state)
+            else:
+                self._save(path)
+
         for e in range(E):
             t0 = time.time()
             model.train()
@@ -199,11 +311,20 @@ class cpl_mixVAE:
             cm_aug = None                     # [pairs, C, C] co-assignment counts, accumulated on the device
             nb = 0
             for x, _item in HostBatchFeeder(train_loader, dev):
-                lv = self.train_batch(x)
+                if dist_on:
+                    lv = st.step(x)
+                    labels = st.all_labels(model.last_outputs()["qc"])
+                else:
+                    lv = self.train_batch(x)
+                    labels = model.argmax_labels(model.last_outputs()["qc"])
                 loss_sum += lv
-                cm_aug = confmat_device(model.argmax_labels(model.last_outputs()["qc"]), C, cm_aug)
+                cm_aug = confmat_device(labels, C, cm_aug)
                 nb += 1
-            ls = loss_sum.cpu().numpy() / max(nb, 1)          # the only D2H of the training pass
+            cnt = torch.tensor([float(nb)], device=dev)
+            if dist_on:      # cpl_mixvae.py:480-483 (loss carries [sum, count]; rec and distance sums ride in the same vector)
+                dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM)
+                dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+            ls = loss_sum.cpu().numpy() / max(float(cnt.item()), 1.0)          # the only D2H of the training pass
             losses.append(float(ls[0]))
             loss_joints.append(float(ls[1]))
             c_ents.append(float(ls[2]))
@@ -225,14 +346,14 @@ class cpl_mixVAE:
 
             # ---- eval-mode pass over the training set (:563-663)
             model.eval()
-            cm_noaug = self._eval_confmat(train_loader if B_val > 1 else [train_loader.dataset.tensors])
+            cm_noaug = self._eval_confmat(train_loader if B_val > 1 else [train_loader.dataset.tensors], st)
             consensus_train.append(consensus_from_counts(cm_noaug))
             if run:
                 run.log({"train/consensus": consensus_train[-1]})
 
             # ---- validation (:666-775); test batch_size==1 means "whole test set as one batch"
             val_batches = test_loader if B_val > 1 else [test_loader.dataset.tensors]
-            val_loss, val_rec, lab_val, nvb = self._eval_loss(val_batches)
+            val_loss, val_rec, lab_val, nvb = self._eval_loss(val_batches, st)
             consensus_val.append(consensus([lab_val[a] for a in range(A)], C))
             denom = Bs_val if B_val > 1 else 1
             validation_rec_loss[e] = val_rec / denom / A
@@ -242,15 +363,24 @@ class cpl_mixVAE:
                 run.log({"val/total-loss": validation_loss[e], "val/rec-loss": validation_rec_loss[e],
                          "val/consensus": consensus_val[-1]})
             if self.save and e > 0 and e % 10 == 0:
-                self._save(self.folder + f"/model/cpl_mixVAE_model_epoch_{e}.pth")
-            if consensus_train[-1] >= good_enuf_consensus or e == E - 1:
+                save(self.folder + f"/model/cpl_mixVAE_model_epoch_{e}.pth")
+            stop = consensus_train[-1] >= good_enuf_consensus or e == E - 1
+            if dist_on:      # every rank must take the same branch (the checkpoint gather is collective)
+                flag = torch.tensor([1.0 if stop else 0.0], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                stop = bool(flag.item() > 0)
+            if stop:
                 if self.save:
-                    self._save(self.folder + f"/model/cns_cpl_mixVAE_model_before_pruning_A{A}_" + self.current_time + ".pth")
+                    save(self.folder + f"/model/cns_cpl_mixVAE_model_before_pruning_A{A}_" + self.current_time + ".pth")
                 epoch_times.append(time.time() - t0)
                 break
             epoch_times.append(time.time() - t0)
         if self.save and n_epoch > 0:
-            self._save(self.folder + f"/model/cpl_mixVAE_model_before_pruning_A{A}_" + self.current_time + ".pth")
+            save(self.folder + f"/model/cpl_mixVAE_model_before_pruning_A{A}_" + self.current_time + ".pth")
+        if dist_on:      # hand the trained weights back to the public full model (every rank)
+            msd, osd = st.full_state_dicts()
+            self.model.load_state_dict(msd)
+            self.optimizer.load_state_dict(osd)
         return {"losses": losses, "loss_joints": loss_joints, "loss_recs": loss_recs, "c_ents": c_ents,
                 "c_dists": c_dists, "c_l2_dists": c_l2_dists, "consensus_aug": consensus_aug,
                 "consensus_train": consensus_train, "consensus_val": consensus_val,
@@ -258,66 +388,108 @@ class cpl_mixVAE:
                 "epoch_times": epoch_times}
 
     # ------------------------------------------------------------------------------------------
-    def _eval_confmat(self, batches):
+    def _eval_confmat(self, batches, st=None):
         """Eval-mode pass (cpl_mixvae.py:563-663): argmax labels and their co-assignment counts stay on the device;
         only [pairs, C, C] integers come back."""
-        model, A = self.model, self.n_arm
+        model, A = (st.model if st is not None else self.model), self.n_arm
         cm = None
         with torch.no_grad():
             for x, _ in HostBatchFeeder(batches, self.device):
-                xs = [x for _ in range(A)]
-                model.materialize_recon = False
-                ctx = model._launch_forward(xs, self.temp, True, None, False)
-                cm = confmat_device(model.argmax_labels(ctx.out_tensors["qc"]), self.n_categories, cm)
+                if st is not None:
+                    _, labels = st.eval_batch(x)
+                else:
+                    xs = [x for _ in range(A)]
+                    model.materialize_recon = False
+                    ctx = model._launch_forward(xs, self.temp, True, None, False)
+                    labels = model.argmax_labels(ctx.out_tensors["qc"])
+                cm = confmat_device(labels, self.n_categories, cm)
         return cm
 
-    def _eval_labels(self, batches):
-        model, A = self.model, self.n_arm
-        labs = []
-        with torch.no_grad():
-            for x, _ in HostBatchFeeder(batches, self.device):
-                xs = [x for _ in range(A)]
-                model.materialize_recon = False
-                ctx = model._launch_forward(xs, self.temp, True, None, False)
-                labs.append(model.argmax_labels(ctx.out_tensors["qc"]))
-        return torch.cat(labs, dim=1).cpu().numpy().astype(np.int64)
-
-    def _eval_loss(self, batches):
-        model, A, D = self.model, self.n_arm, self.input_dim
+    def _eval_loss(self, batches, st=None):
+        model, A, D = (st.model if st is not None else self.model), self.n_arm, self.input_dim
         tot = torch.zeros((), device=self.device)
         rec = torch.zeros((), device=self.device)
         labs = []
         n = 0
         with torch.no_grad():
             for x, _ in HostBatchFeeder(batches, self.device):
-                xs = [x for _ in range(A)]
-                x_recs, _, _, _, cs, _, c_smps, s_means, s_logvars, _ = model(x=xs, temp=self.temp, prior_c=0.0, eval=True)
-                loss, loss_rec, *_ = model.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0)
-                tot += loss
-                rec += loss_rec.sum() / D
-                labs.append(model.argmax_labels(torch.stack(cs)))
+                if st is not None:
+                    lv, labels = st.eval_batch(x)
+                    tot += lv[0]
+                    rec += lv[5:5 + A].sum() / D
+                    labs.append(labels)
+                else:
+                    xs = [x for _ in range(A)]
+                    x_recs, _, _, _, cs, _, c_smps, s_means, s_logvars, _ = model(x=xs, temp=self.temp, prior_c=0.0, eval=True)
+                    loss, loss_rec, *_ = model.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0)
+                    tot += loss
+                    rec += loss_rec.sum() / D
+                    labs.append(model.argmax_labels(torch.stack(cs)))
                 n += 1
         return tot.item(), rec.item(), torch.cat(labs, dim=1).cpu().numpy().astype(np.int64), n
 
-    def eval_model(self, data_loader, c_p=0, c_onehot=0):
-        """Inference summary (cpl_mixvae.py:1450-1619), reduced to what the hot path produces: per-arm
-        categorical posteriors, argmax labels, state means/samples, low-D representation, losses."""
-        model, A = self.model, self.n_arm
+    def eval_model(self, data_loader, c_p=0, c_onehot=0, noise=None):
+        """Inference summary with the reference's contract (cpl_mixvae.py:1450-1619): eval-mode forward with the
+        category mask taken from the non-zero entries of ``fcc[0].bias`` (:1475-1477, :1534), loss per batch, and the
+        dictionary of :1590-1619 (``predicted_label`` / ``state_cat`` 1-based, float64 arrays).  ``noise`` (not in the
+        reference): ``{"E": [n_batches, A, B, S]}`` injects the state noise that forward draws even in eval mode
+        (nn_model.py:351), for parity tests.  A loader with ``batch_size == 1`` is read as "the whole set as one batch",
+        the convention of the reference's training loop (:722-748) — per-cell batches would make ``inv_var``'s batch
+        variance (nn_model.py:75) undefined."""
+        model, A, C = self.model, self.n_arm, self.n_categories
+        N = len(data_loader.dataset)
+        D, D_low, S = self.input_dim, self.lowD_dim, self.state_dim
         model.eval()
-        outs = {k: [] for k in ("c_prob", "qc", "c_smp", "s_mean", "s_logvar", "s_smp", "x_low", "labels")}
-        tot = []
-        # a loader with batch_size 1 means "the whole set as one batch" (the reference's convention, :722-748)
-        batches = [data_loader.dataset.tensors] if getattr(data_loader, "batch_size", None) == 1 else data_loader
+        bias = model.fcc[0].bias.detach().cpu().numpy()
+        pruning_mask = np.where(bias != 0.0)[0]
+        prune_indx = np.where(bias == 0.0)[0]
+        whole = getattr(data_loader, "batch_size", None) == 1
+        batches = [data_loader.dataset.tensors] if whole else data_loader
+        keys = ("s_mean", "s_logvar", "qc", "c_smp", "x_low", "x_rec")
+        outs = {k: [] for k in keys}
+        idxs, losses, c_dists, c_l2_dists, loss_recs, lls, labels = [], [], [], [], [], [], []
+        mat = model.materialize_recon
+        model.materialize_recon = True
         with torch.no_grad():
-            for x, _ in HostBatchFeeder(batches, self.device):
+            for i, (x, item) in enumerate(HostBatchFeeder(batches, self.device)):
                 xs = [x for _ in range(A)]
-                x_recs, _, _, x_lows, cs, s_smps, c_smps, s_means, s_logvars, c_probs = model(x=xs, temp=self.temp, prior_c=0.0, eval=True)
+                nz = None if noise is None else {"E": noise["E"][i]}
+                x_recs, _, _, x_lows, cs, s_smps, c_smps, s_means, s_logvars, _ = model(
+                    xs, self.temp, prior_c=0.0, eval=True, mask=pruning_mask if len(prune_indx) else None, noise=nz)
                 ls = model.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0)
-                tot.append(ls[0])
-                for k, v in (("c_prob", c_probs), ("qc", cs), ("c_smp", c_smps), ("s_mean", s_means),
-                             ("s_logvar", s_logvars), ("s_smp", s_smps), ("x_low", x_lows)):
-                    outs[k].append(torch.stack(v))
-                outs["labels"].append(model.argmax_labels(torch.stack(cs)))
-        res = {k: torch.cat(v, dim=1).cpu().numpy() for k, v in outs.items()}
-        res["total_loss"] = float(torch.stack(tot).mean().item()) if tot else float("nan")
-        return res
+                lv = model._ctx.loss_vec
+                losses.append(lv[0:1])
+                c_dists.append(lv[3:4])
+                c_l2_dists.append(lv[4:5])
+                loss_recs.append(ls[1])
+                lls.append(torch.stack(list(ls[8])))
+                for k, v in zip(keys, (s_means, s_logvars, cs, c_smps, x_lows, x_recs)):
+                    outs[k].append(torch.stack(v).cpu())
+                labels.append(model.argmax_labels(torch.stack(cs)))
+                idx = item[1] if isinstance(item, (tuple, list)) and len(item) > 1 else torch.arange(x.shape[0])
+                idxs.append(torch.as_tensor(idx).reshape(-1).cpu().to(torch.float64))
+        model.materialize_recon = mat
+        cat = lambda k: torch.cat(outs[k], dim=1).numpy().astype(np.float64)
+        cs_np = cat("qc")
+        lab = torch.cat(labels, dim=1).cpu().numpy().astype(np.int64)
+        mean_of = lambda lst: torch.stack([t.reshape(-1) for t in lst]).double().mean(0).cpu().numpy()
+        return {
+            "state_mu": cat("s_mean"),
+            "state_var": cat("s_logvar"),
+            "state_cat": (lab + 1).astype(np.float64),
+            "prob_cat": cs_np.max(-1),
+            "total_loss_rec": mean_of(loss_recs),
+            "total_likelihood": mean_of(lls),
+            "total_dist_z": float(mean_of(c_dists)[0]),
+            "total_dist_qz": float(mean_of(c_l2_dists)[0]),
+            "mean_test_rec": np.zeros(A),
+            "predicted_label": (lab + 1).astype(np.float64),
+            "data_indx": torch.cat(idxs).numpy()[:N],
+            "z_prob": cs_np,
+            "z_sample": cat("c_smp"),
+            "x_low": cat("x_low"),
+            "recon_c": cat("x_rec"),
+            "prune_indx": prune_indx,
+            "cnss": consensus([lab[a] for a in range(A)], C),
+            "total_loss": float(mean_of(losses)[0]),
+        }

@@ -124,6 +124,7 @@ class mixVAE_model(nn.Module):
         # arm sharding (set by mmidas_b200.parallel): this rank owns arms [arm_offset, arm_offset+n_arm)
         self.n_arm_total = n_arm
         self.arm_offset = 0
+        self.seed_salt = 0      # xor-ed into the noise seed; data-parallel replicas get distinct salts
         # forward() returns the materialised reconstruction by default (reference behaviour);
         # the fused trainer switches it off: x_hat then never touches HBM.
         self.materialize_recon = True
@@ -149,11 +150,11 @@ class mixVAE_model(nn.Module):
         self._flat_bn = None
         self._flat_nbt = None
         self._work = None
-        self._work_key = None
         self._ctx = _StepContext()
         self._gen = 0
         self._step_counter = 0
         self._grad_anchor = None
+        self._graph_counters = None
         self._flatten()
 
     # ------------------------------------------------------------------------------------------
@@ -202,7 +203,6 @@ class mixVAE_model(nn.Module):
                     m._buffers["num_batches_tracked"] = t
         self._flat_params, self._flat_grads, self._flat_bn, self._flat_nbt = flat, grads, bn, nbt
         self._work = None
-        self._work_key = None
         self._grad_anchor = torch.zeros(1, device=dev, requires_grad=True)
         self._ctx = _StepContext()
 
@@ -213,6 +213,14 @@ class mixVAE_model(nn.Module):
         if p0.dtype != torch.float32:
             raise TypeError("mixVAE_model (B200) stores fp32 parameters like the reference")
         return self
+
+    def ctor_kwargs(self) -> dict:
+        """The constructor arguments of this model (mmidas_b200.parallel rebuilds arm shards from them)."""
+        return dict(input_dim=self.input_dim, fc_dim=self.fc_dim, n_categories=self.n_categories, state_dim=self.state_dim,
+                    lowD_dim=self.lowD_dim, x_drop=self.x_drop, s_drop=self.s_drop, n_arm=self.n_arm, lam=self.lam,
+                    lam_pc=self.lam_pc, tau=self.tau, beta=self.beta, hard=self.hard, variational=self.varitional,
+                    device=self.device, eps=self.eps, momentum=self.momentum, ref_prior=self.ref_prior,
+                    loss_mode=self.loss_mode, precision=self.precision)
 
     def flat_parameters(self) -> torch.Tensor:
         """[n_arm, arm_stride] fp32: every parameter of every local arm (padding is zero)."""
@@ -249,12 +257,16 @@ class mixVAE_model(nn.Module):
                          self.state_dim, self.n_arm_total, self.arm_offset)
 
     def _workspace(self, dims: _lib.Dims):
+        # one workspace per (batch, arm placement), kept for the life of the model: captured CUDA graphs hold raw
+        # pointers into it, so a workspace is never freed or resized behind their back
         key = (dims.batch, dims.n_arm_total, dims.arm_offset)
-        if self._work_key != key:
+        if self._work is None:
+            self._work = {}
+        w = self._work.get(key)
+        if w is None:
             lay = _lib.compute_layout(dims)
-            self._work = torch.zeros(lay.work_floats, dtype=torch.float32, device=self._flat_params.device)
-            self._work_key = key
-        return self._work
+            w = self._work[key] = torch.zeros(lay.work_floats, dtype=torch.float32, device=self._flat_params.device)
+        return w
 
     def _state(self, dims, adam_m=None, adam_v=None) -> _lib.State:
         work = self._workspace(dims)
@@ -262,6 +274,17 @@ class mixVAE_model(nn.Module):
                           adam_m.data_ptr() if adam_m is not None else None,
                           adam_v.data_ptr() if adam_v is not None else None,
                           self._flat_bn.data_ptr(), self._flat_nbt.data_ptr(), work.data_ptr())
+
+    def _inputs(self, xt, x_arm_stride, x_row_stride, U, E, keep_x, keep_s, training, counters=None, cat_mask=None) -> _lib.Inputs:
+        """Per-step inputs.  In-kernel noise (dropout, Gumbel, state) is keyed on (torch.initial_seed() ^ seed_salt, step
+        counter, GLOBAL arm index): ``seed_salt`` separates data-parallel replicas (mmidas_b200.parallel), the arm index
+        separates arms wherever they live.  ``counters`` (device int64[2]) moves the step counter onto the device."""
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        seed = (torch.initial_seed() ^ self.seed_salt) & 0xFFFFFFFFFFFFFFFF
+        if counters is None:
+            counters = self._graph_counters       # set while a StepGraph captures: the step index lives on the device
+        return _lib.Inputs(xt.data_ptr(), x_arm_stride, x_row_stride, ptr(U), ptr(E), ptr(keep_x), ptr(keep_s), ptr(cat_mask),
+                           C.c_uint64(seed), self._step_counter, ptr(counters), int(training))
 
     def _prep_x(self, x):
         """Accept the reference's input forms: a list of A [B,D] tensors, or an [A,B,D] tensor
@@ -329,7 +352,18 @@ class mixVAE_model(nn.Module):
                          lambda: (torch.rand(A, B, S, device=dev) >= self.s_drop).to(torch.uint8))
         return U, E, keep_x, keep_s
 
-    def _launch_forward(self, x, temp, eval, noise, materialize):
+    def _category_mask(self, mask):
+        """forward(mask=...) (nn_model.py:332-335): indices of the categories that are kept -> uint8 [C] on the device."""
+        if mask is None:
+            return None
+        idx = torch.as_tensor(mask, dtype=torch.long, device="cpu").reshape(-1)
+        if idx.numel() == 0 or int(idx.min()) < 0 or int(idx.max()) >= self.n_categories:
+            raise ValueError("mask must hold category indices in [0, n_categories)")
+        keep = torch.zeros(self.n_categories, dtype=torch.uint8)
+        keep[idx] = 1
+        return keep.to(self._flat_params.device)
+
+    def _launch_forward(self, x, temp, eval, noise, materialize, mask=None):
         dev = self._require_cuda()
         lib = _lib.load()
         training = bool(self.training and not eval)
@@ -344,11 +378,8 @@ class mixVAE_model(nn.Module):
         hp = self._hparams(temp)
         st = self._state(dims)
         self._step_counter += 1
-        inp = _lib.Inputs(xt.data_ptr(), x_arm_stride, x_row_stride,
-                          U.data_ptr() if U is not None else None, E.data_ptr() if E is not None else None,
-                          keep_x.data_ptr() if keep_x is not None else None,
-                          keep_s.data_ptr() if keep_s is not None else None,
-                          C.c_uint64(torch.initial_seed() & 0xFFFFFFFFFFFFFFFF), self._step_counter, int(training))
+        cat_mask = self._category_mask(mask)
+        inp = self._inputs(xt, x_arm_stride, x_row_stride, U, E, keep_x, keep_s, training, cat_mask=cat_mask)
         mk = lambda n: torch.empty(A, B, n, dtype=torch.float32, device=dev)
         ot = {"x_low": mk(L), "c_prob": mk(Cc), "qc": mk(Cc), "c_smp": mk(Cc), "s_mean": mk(S), "s_logvar": mk(S),
               "s_smp": mk(S), "x_rec": mk(D) if materialize else None}
@@ -361,7 +392,7 @@ class mixVAE_model(nn.Module):
         self._gen += 1
         ctx.gen = self._gen
         ctx.training = training
-        ctx.keep = [xt, U, E, keep_x, keep_s]
+        ctx.keep = [xt, U, E, keep_x, keep_s, cat_mask]
         ctx.dims, ctx.hp, ctx.state, ctx.inputs, ctx.outputs, ctx.out_tensors = dims, hp, st, inp, out, ot
         self._ctx = ctx
         return ctx
@@ -372,11 +403,10 @@ class mixVAE_model(nn.Module):
     def forward(self, x, temp, prior_c=[], eval=False, mask=None, noise=None):
         """mixVAE_model.forward (nn_model.py:297-368).  Returns
         ``(x_recs, [], [], x_lows, cs, s_smps, c_smps, s_means, s_logvars, c_probs)``, lists over arms.
+        ``mask``: indices of the categories kept by the pruning path (:332-335, eval_model passes the non-zero
+        entries of ``fcc[0].bias``): q is a softmax over those only and exactly 0 elsewhere.
         ``noise`` (not in the reference) injects {"U","E","keep_x","keep_s"} for parity tests."""
-        if mask is not None:
-            raise NotImplementedError("category masks belong to the pruning path, which the reference disables "
-                                      "(cpl_mixvae.py:1007); out of scope (SURVEY §8f4)")
-        ctx = self._launch_forward(x, temp, eval, noise, self.materialize_recon or eval)
+        ctx = self._launch_forward(x, temp, eval, noise, self.materialize_recon or eval, mask=mask)
         ot = ctx.out_tensors
         A = self.n_arm
         split = lambda t: [t[a] for a in range(A)]
@@ -459,11 +489,7 @@ class mixVAE_model(nn.Module):
         m, v = optimizer.flat_state()
         st = self._state(dims, m, v)
         self._step_counter += 1
-        inp = _lib.Inputs(xt.data_ptr(), x_arm_stride, x_row_stride, U.data_ptr() if U is not None else None,
-                          E.data_ptr() if E is not None else None,
-                          keep_x.data_ptr() if keep_x is not None else None,
-                          keep_s.data_ptr() if keep_s is not None else None,
-                          C.c_uint64(torch.initial_seed() & 0xFFFFFFFFFFFFFFFF), self._step_counter, 1)
+        inp = self._inputs(xt, x_arm_stride, x_row_stride, U, E, keep_x, keep_s, True)
         ot = self._static_outputs(B)
         out = _lib.Outputs(*[ot[k].data_ptr() for k in ("x_low", "c_prob", "qc", "c_smp", "s_mean", "s_logvar", "s_smp")],
                            None)
@@ -508,6 +534,56 @@ class mixVAE_model(nn.Module):
         _lib.check(_lib.load().mvae_argmax(q.data_ptr(), out.data_ptr(), rows, q.size(-1), C.c_void_p(stream)),
                    "mvae_argmax")
         return out
+
+
+class StepGraph:
+    """One training step captured in a CUDA graph and replayed with ONE launch.
+
+    What makes the step replayable: the library enqueues everything on the caller's stream without host
+    synchronisation or allocation, tensor maps are baked into the kernel arguments at capture time, and the two
+    per-step scalars — the noise step index and Adam's step — live on the device (``mvae_inputs.counters``), bumped by
+    the first kernel of the step.  ``step_fn`` is any closure that runs one step on the model (the fused C call, or
+    the sharded forward / all-gather / loss / backward / all-reduce / Adam sequence incl. its NCCL calls) and returns
+    the device loss vector; it must read its input from the same device buffer on every replay.
+    """
+
+    def __init__(self, model: "mixVAE_model", optimizer, step_fn):
+        dev = model._require_cuda()
+        self.model, self.optimizer = model, optimizer
+        self.counters = torch.zeros(2, dtype=torch.int64, device=dev)
+        self._sync_counters()
+        self.graph = torch.cuda.CUDAGraph()
+        model._graph_counters = self.counters
+        optimizer._graph_counters = self.counters
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss_vec = step_fn()
+        finally:
+            model._graph_counters = None
+            optimizer._graph_counters = None
+        # capture enqueues nothing: the host mirrors were advanced by step_fn's bookkeeping, undo that
+        model._step_counter = self._held[0]
+        optimizer.step_count = self._held[1]
+        self.ctx = model._ctx               # its output tensors live in the graph's pool: rewritten by every replay
+
+    def _sync_counters(self):
+        want = (self.model._step_counter, self.optimizer.step_count)
+        if getattr(self, "_held", None) != want:
+            self.counters[0].fill_(want[0])
+            self.counters[1].fill_(want[1])
+            self._held = want
+
+    def replay(self) -> torch.Tensor:
+        """Run the captured step; returns the (static) device loss vector of this replay."""
+        self._sync_counters()          # eager steps / eval forwards in between moved the host-side counters
+        self.graph.replay()
+        self.model._step_counter += 1
+        self.optimizer.step_count += 1
+        self._held = (self.model._step_counter, self.optimizer.step_count)
+        self.model._gen += 1            # outstanding forward contexts are stale now
+        self.ctx.gen, self.ctx.loss_done = -1, False
+        self.model._ctx = self.ctx      # last_outputs() = what this replay wrote
+        return self.loss_vec
 
 
 def mk_vae(C, state_dim, input_dim, device, eps=1e-8, fc_dim=100, latent_dim=10, x_drop=0.5, s_drop=0.2, lr=0.001,

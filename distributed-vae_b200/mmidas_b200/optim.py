@@ -31,6 +31,7 @@ class FusedAdam(torch.optim.Optimizer):
         if len(plist) != len(mlist) or any(a is not b for a, b in zip(plist, mlist)):
             raise ValueError("FusedAdam must be given model.parameters() of the bound model, in order")
         self.step_count = 0
+        self._graph_counters = None      # set while nn_model.StepGraph captures: Adam's step index lives on the device
         self._m = None
         self._v = None
 
@@ -59,6 +60,7 @@ class FusedAdam(torch.optim.Optimizer):
                                          flat.numel(), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
                                          float(g["eps"]), float(g["weight_decay"]),
                                          int(bool(g.get("decoupled_weight_decay", False))), self.step_count,
+                                         self._graph_counters[1:].data_ptr() if self._graph_counters is not None else None,
                                          C.c_void_p(stream)), "mvae_adam")
         return loss
 

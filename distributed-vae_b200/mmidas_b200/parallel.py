@@ -7,16 +7,18 @@ train.py:274-275): a 2-D mesh (arm axis x data-parallel axis), one process per G
   arms (remote arms are constants, exactly what autograd gives each arm).
 * data-parallel axis: the cell batch is split; replicas keep LOCAL BatchNorm / inv_var statistics
   (the semantics of the reference's FSDP wrap) and average gradients with an NCCL
-  all-reduce in two buckets: fc11 (final right after the fused loss+grad kernel, overlapping the whole
-  backward chain) and the rest.
+  all-reduce.
 
-Everything here is plumbing around torch.distributed; the arithmetic stays in libmixvae_b200.so.
-The helpers take plain tensors so that the host logic is testable with gloo on CPU.
+The whole step — forward, all-gather, loss, backward, all-reduce, Adam — is captured once per input
+buffer in a CUDA graph (nn_model.StepGraph; NCCL collectives are capturable) and replayed with one
+launch, so the Python dispatch of the six calls and the host-side tensor-map encoding disappear from
+the step.  Everything here is plumbing around torch.distributed; the arithmetic stays in
+libmixvae_b200.so.  The helpers take plain tensors so that the host logic is testable with gloo on CPU.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -67,20 +69,32 @@ def plan_mesh(world_size: int, n_arm: int, mode: str = "auto") -> MeshPlan:
     return MeshPlan(world_size, n_arm, arm_ranks, world_size // arm_ranks, ranges)
 
 
-def make_groups(plan: MeshPlan, rank: int):
-    """Create the arm-axis and dp-axis process groups (every rank must call this)."""
+def make_groups(plan: MeshPlan, rank: int, ranks: Optional[Sequence[int]] = None):
+    """Create the arm-axis and dp-axis process groups.  EVERY rank of the default group must call this (group
+    creation is collective), also ranks outside ``ranks``.  ``ranks``: the global ranks that form the mesh, in mesh
+    order (default: all of them); ``rank`` is the caller's global rank.  Returns (arm_group, dp_group, mesh_group);
+    all None on a rank outside the mesh."""
+    ranks = list(range(plan.world_size)) if ranks is None else list(ranks)
+    if len(ranks) != plan.world_size:
+        raise ValueError("len(ranks) must equal the mesh size")
     arm_group = dp_group = None
     for d in range(plan.dp_ranks):
-        ranks = [d * plan.arm_ranks + a for a in range(plan.arm_ranks)]
-        g = dist.new_group(ranks) if plan.arm_ranks > 1 else None
-        if rank in ranks:
+        members = [ranks[d * plan.arm_ranks + a] for a in range(plan.arm_ranks)]
+        g = dist.new_group(members) if plan.arm_ranks > 1 else None
+        if rank in members:
             arm_group = g
     for a in range(plan.arm_ranks):
-        ranks = [d * plan.arm_ranks + a for d in range(plan.dp_ranks)]
-        g = dist.new_group(ranks) if plan.dp_ranks > 1 else None
-        if rank in ranks:
+        members = [ranks[d * plan.arm_ranks + a] for d in range(plan.dp_ranks)]
+        g = dist.new_group(members) if plan.dp_ranks > 1 else None
+        if rank in members:
             dp_group = g
-    return arm_group, dp_group
+    mesh_group = None
+    if len(ranks) != dist.get_world_size():
+        g = dist.new_group(ranks)
+        mesh_group = g if rank in ranks else None
+    elif rank in ranks:
+        mesh_group = dist.group.WORLD
+    return arm_group, dp_group, mesh_group
 
 
 def all_gather_arms(local: torch.Tensor, plan: MeshPlan, group) -> torch.Tensor:
@@ -131,43 +145,99 @@ def allreduce_mean(tensors: Sequence[torch.Tensor], group, world: int, async_op:
     return works
 
 
-class ShardedTrainer:
-    """One training step on a (arm x dp) mesh.  Each rank constructs it after init_dist_env()."""
+def slice_arm_state(sd: Dict[str, torch.Tensor], a0: int, a1: int) -> Dict[str, torch.Tensor]:
+    """Entries of a full reference-layout state dict (``fc1.{a}.weight`` ...) for arms [a0, a1), renumbered from 0."""
+    out = {}
+    for k, v in sd.items():
+        name, a, rest = k.split(".", 2)
+        a = int(a)
+        if a0 <= a < a1:
+            out[f"{name}.{a - a0}.{rest}"] = v
+    return out
 
-    def __init__(self, model_kwargs: dict, lr: float = 1e-3, mode: str = "auto", temp: float = 1.0,
+
+def merge_arm_states(parts, plan: MeshPlan, n_layers: int = 14):
+    """Inverse of the arm sharding for checkpoints.  ``parts[r] = (model_state_dict, optimizer_state)`` of arm rank r
+    (keys / indices local to that rank) -> reference-layout dicts of the whole model: model keys ``name.{a}.rest`` in
+    the reference's key order, optimizer state indexed in ``model.parameters()`` order (layer-major, arm-minor)."""
+    per = plan.n_arm // plan.arm_ranks
+    full = {}
+    for r, (sd_r, _) in enumerate(parts):
+        a0 = plan.arm_ranges[r][0]
+        for k, v in sd_r.items():
+            name, a, rest = k.split(".", 2)
+            full[(name, int(a) + a0, rest)] = v
+    layout = {}                                     # module name -> its per-arm entries, both in the reference's order
+    for k in parts[0][0].keys():
+        name, _, rest = k.split(".", 2)
+        rests = layout.setdefault(name, [])
+        if rest not in rests:
+            rests.append(rest)
+    ordered = {f"{name}.{a}.{rest}": full[(name, a, rest)]
+               for name, rests in layout.items() for a in range(plan.n_arm) for rest in rests}
+    state = {}
+    for li in range(n_layers):
+        for a in range(plan.n_arm):
+            r, la = a // per, a % per
+            for wb in range(2):
+                src = parts[r][1].get((li * per + la) * 2 + wb)
+                if src is not None:
+                    state[(li * plan.n_arm + a) * 2 + wb] = src
+    return ordered, state
+
+
+class ShardedTrainer:
+    """One training step on a (arm x dp) mesh.  Each rank constructs it after init_dist_env().
+
+    ``model_kwargs``: constructor arguments of the FULL model (all arms), built under ``torch.manual_seed(seed)`` so
+    that arm a has the same initial weights on every rank (and the same as the single-GPU model); or ``model``: an
+    existing full model whose state is taken over.  ``ranks``: global ranks forming the mesh (default: the whole
+    world); ranks outside it get ``self.active == False`` and must not call ``step``.
+    """
+
+    def __init__(self, model_kwargs: Optional[dict] = None, lr: float = 1e-3, mode: str = "auto", temp: float = 1.0,
                  seed: int = 546, rank: Optional[int] = None, world_size: Optional[int] = None,
-                 overlap: Optional[bool] = None):
+                 overlap: Optional[bool] = None, model=None, ranks: Optional[Sequence[int]] = None,
+                 use_cuda_graph: bool = True):
         from .nn_model import mixVAE_model
         from .optim import FusedAdam
         self.rank = dist.get_rank() if rank is None else rank
-        self.world = dist.get_world_size() if world_size is None else world_size
+        self.ranks = list(range(dist.get_world_size() if world_size is None else world_size)) if ranks is None else list(ranks)
+        self.world = len(self.ranks)
+        self.active = self.rank in self.ranks
+        if model is not None:
+            model_kwargs = model.ctor_kwargs()
         n_arm = model_kwargs["n_arm"]
         self.plan = plan_mesh(self.world, n_arm, mode)
-        self.arm_group, self.dp_group = make_groups(self.plan, self.rank)
-        a0, a1 = self.plan.local_arms(self.rank)
+        self.arm_group, self.dp_group, self.mesh_group = make_groups(self.plan, self.rank, self.ranks)
+        self.temp = temp
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+        self._graph_misses = 0
+        if not self.active:
+            self.model = self.optimizer = None
+            return
+        self.mesh_rank = self.ranks.index(self.rank)
+        a0, a1 = self.plan.local_arms(self.mesh_rank)
         dev = torch.device("cuda", torch.cuda.current_device())
-        # construct every arm with the shared seed so that arm a has the same initial weights on
-        # every rank (and the same as the single-GPU model), then keep only the local arms
-        torch.manual_seed(seed)
-        full = mixVAE_model(**dict(model_kwargs, device="cpu"))
-        kw = dict(model_kwargs, n_arm=a1 - a0, device=dev)
-        local = mixVAE_model(**kw)
-        sd = full.state_dict()
-        lsd = {}
-        for k, v in sd.items():
-            name, a, rest = k.split(".", 2)
-            a = int(a)
-            if a0 <= a < a1:
-                lsd[f"{name}.{a - a0}.{rest}"] = v
-        local.load_state_dict(lsd)
-        local.n_arm_total = n_arm
-        local.arm_offset = a0
+        if model is not None:
+            sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        else:
+            torch.manual_seed(seed)
+            sd = mixVAE_model(**dict(model_kwargs, device="cpu")).state_dict()
+        local = mixVAE_model(**dict(model_kwargs, n_arm=a1 - a0, device=dev))
+        local.load_state_dict(slice_arm_state(sd, a0, a1))
         self.model = local.to(dev)
         self.model.n_arm_total = n_arm
         self.model.arm_offset = a0
         self.model.materialize_recon = False
+        # noise: arms are told apart by their global index inside the generators; data-parallel replicas by a seed salt,
+        # and torch's own device generator (keep_s masks) is re-seeded per rank after the shared-seed weight init
+        _, dp_coord = self.plan.coords(self.mesh_rank)
+        self.dp_coord = dp_coord
+        self.model.seed_salt = (dp_coord * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        torch.cuda.manual_seed(seed + 7919 * (self.rank + 1))
         self.optimizer = FusedAdam(self.model.parameters(), lr=lr, model=self.model)
-        self.temp = temp
         self.comm_stream = torch.cuda.Stream(dev)
         self.off_fc11 = int(self.model._layout.offset[26])
         self.device = dev
@@ -178,19 +248,17 @@ class ShardedTrainer:
         grad_bytes = self.model.flat_grads().numel() * 4
         self.overlap = (grad_bytes > 32 * 2 ** 20) if overlap is None else bool(overlap)
 
-    def step(self, x_local: torch.Tensor, noise=None) -> torch.Tensor:
-        """x_local: this dp-replica's cells [B_local, D] (identical on the ranks of one arm group).
-        Returns the loss vector of the local replica (global over arms)."""
+    # ------------------------------------------------------------------------------------------
+    def _step_eager(self, x_local: torch.Tensor, noise=None) -> torch.Tensor:
         m, plan = self.model, self.plan
         if plan.world_size == 1:
             return m.fused_train_step(x_local.expand(m.n_arm, -1, -1), self.temp, self.optimizer, noise=noise)
-        m.train()
         xs = x_local.expand(m.n_arm, -1, -1)
         x_recs, _, _, _, cs, _, c_smps, s_means, s_logvars, _ = m(xs, self.temp, 0.0, noise=noise)
         ot = m.last_outputs()
         qc_all = all_gather_arms(ot["qc"], plan, self.arm_group)
         cs_all = all_gather_arms(ot["c_smp"], plan, self.arm_group)
-        ls = m.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0, qc_all=qc_all, c_smp_all=cs_all)
+        m.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0, qc_all=qc_all, c_smp_all=cs_all)
         cur = torch.cuda.current_stream(self.device)
         if plan.dp_ranks > 1 and self.overlap:
             late, early = grad_buckets(m.flat_grads(), self.off_fc11)
@@ -207,3 +275,69 @@ class ShardedTrainer:
                 allreduce_mean([m.flat_grads()], self.dp_group, plan.dp_ranks)
         self.optimizer.step()
         return fixup_loss_vector(m._ctx.loss_vec, plan, self.arm_group, float(m.beta))
+
+    def step(self, x_local: torch.Tensor, noise=None) -> torch.Tensor:
+        """x_local: this dp-replica's cells [B_local, D] (identical on the ranks of one arm group).
+        Returns the loss vector of the local replica (global over arms)."""
+        if not self.active:
+            raise RuntimeError("this rank is not part of the mesh")
+        m = self.model
+        m.train()
+        graphable = (self.use_cuda_graph and noise is None and m.s_drop == 0.0 and x_local.is_cuda
+                     and x_local.dtype == torch.float32 and x_local.stride(-1) == 1 and self._graph_misses < 32)
+        if not graphable:
+            return self._step_eager(x_local, noise)
+        from .nn_model import StepGraph
+        key = (x_local.data_ptr(), tuple(x_local.shape), x_local.stride(0), float(self.optimizer.param_groups[0]["lr"]))
+        g = self._graphs.get(key)
+        if g is None:
+            if not self._graphs and self._graph_misses == 0:
+                self._graph_misses += 1          # very first step: eager (lazy allocations, communicator warm-up)
+                return self._step_eager(x_local, noise)
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graph_misses += 1
+            torch.cuda.synchronize(self.device)
+            g = StepGraph(m, self.optimizer, lambda: self._step_eager(x_local, None))
+            self._graphs[key] = g
+        else:
+            self._graph_misses = 1
+        return g.replay()
+
+    # ------------------------------------------------------------------------------------------
+    def eval_batch(self, x_local: torch.Tensor):
+        """Eval-mode forward + loss of one batch (cpl_mixvae.py:563-775 on a mesh): returns (loss vector over all arms,
+        int32 labels [A_total, B] of every arm), both on the device."""
+        m, plan = self.model, self.plan
+        m.eval()
+        with torch.no_grad():
+            xs = [x_local for _ in range(m.n_arm)]
+            x_recs, _, _, _, cs, _, c_smps, s_means, s_logvars, _ = m(x=xs, temp=self.temp, prior_c=0.0, eval=True)
+            ot = m.last_outputs()
+            qc_all = all_gather_arms(ot["qc"], plan, self.arm_group)
+            cs_all = all_gather_arms(ot["c_smp"], plan, self.arm_group)
+            m.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0, qc_all=qc_all, c_smp_all=cs_all)
+            lv = fixup_loss_vector(m._ctx.loss_vec, plan, self.arm_group, float(m.beta))
+            labels = m.argmax_labels(qc_all)
+        return lv, labels
+
+    def all_labels(self, q_local: torch.Tensor) -> torch.Tensor:
+        """argmax labels of every arm of the model for the cells of this replica: int32 [A_total, B]."""
+        return self.model.argmax_labels(all_gather_arms(q_local, self.plan, self.arm_group))
+
+    def full_state_dicts(self):
+        """Reference-layout model and optimizer state dicts of the WHOLE model (cpl_mixvae.py:782-788), gathered over
+        the arm axis; every rank of the mesh must call this, every rank gets the result.  dp replicas hold identical
+        parameters (averaged gradients, same Adam); BN running buffers are the local replica's, as they would be under
+        the reference's FSDP wrap."""
+        m, plan = self.model, self.plan
+        msd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        osd = self.optimizer.state_dict()
+        if plan.arm_ranks == 1:
+            return msd, osd
+        mine = (msd, {i: {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in s.items()} for i, s in osd["state"].items()})
+        parts = [None] * plan.arm_ranks
+        dist.all_gather_object(parts, mine, group=self.arm_group)
+        ordered, state = merge_arm_states(parts, plan)
+        groups = [dict(g, params=list(range(28 * plan.n_arm))) for g in osd["param_groups"]]
+        return ordered, {"state": state, "param_groups": groups}

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MVAE_ABI_VERSION 1
+#define MVAE_ABI_VERSION 2
 #define MVAE_N_PARAM_TENSORS 28 /* 14 Linear layers x {weight, bias} per arm */
 #define MVAE_MAX_ARMS 16
 
@@ -75,9 +75,11 @@ typedef struct mvae_state {
   float* work;          /* [work_floats]     activations + partials                  */
 } mvae_state;
 
-/* Per-step inputs.  Null noise pointers are only legal in eval mode (U, keep_*) — the Python
- * mirror draws U and E with torch's device RNG; keep_x==NULL in training selects the in-kernel
- * counter-based dropout generator seeded by (seed, step). */
+/* Per-step inputs.  The reference draws its noise with torch's RNG inside forward (nn_model.py:264 dropout, :440 Gumbel
+ * uniforms, :427 state noise) and has no injection hook; here every noise tensor may be injected (parity tests) or left
+ * NULL, in which case it is drawn in-kernel by a counter-based generator keyed on (seed, step, global arm index, stream):
+ * arms sharded over ranks (arm_offset > 0) draw the streams of their global index, and a step counter that lives on the
+ * device (counters) lets a captured CUDA graph draw fresh noise on every replay. */
 typedef struct mvae_inputs {
   const float* x;          /* [A or 1][B][D]                                                  */
   int64_t x_arm_stride;    /* floats between arms' inputs; 0 = all arms share x (x.expand)     */
@@ -87,8 +89,13 @@ typedef struct mvae_inputs {
                            /* NULL: drawn in-kernel, counter-based on (seed, step, arm, cell, k) */
   const uint8_t* keep_x;   /* [A][B][D] input-dropout keep mask or NULL                        */
   const uint8_t* keep_s;   /* [A][B][S] state-dropout keep mask or NULL (s_drop == 0)          */
-  uint64_t seed;           /* in-kernel dropout generator                                      */
-  uint64_t step;
+  const uint8_t* cat_mask; /* [C] 1 = category kept, or NULL: forward(mask=...) of the pruning path (nn_model.py:332-335):
+                              q = softmax(c_prob[:, kept] / tau) on the kept categories, exactly 0 elsewhere */
+  uint64_t seed;           /* in-kernel generators                                             */
+  uint64_t step;           /* step index of this forward (ignored when counters != NULL)       */
+  uint64_t* counters;      /* NULL, or device {forward counter, Adam step counter}: mvae_forward increments
+                              counters[0] and uses the new value as `step`; mvae_train_step also increments
+                              counters[1] and uses it as Adam's step (CUDA-graph replay)        */
   int32_t training;        /* 1: batch-stat BN, dropout, Gumbel; 0: mixVAE_model.forward(eval=True) on .eval() */
 } mvae_inputs;
 
@@ -138,11 +145,11 @@ int mvae_backward(const mvae_dims* dims, const mvae_hparams* hp, const mvae_stat
                   void* stream);
 
 /* torch.optim.Adam.step (cpl_mixvae.py:463, defaults of :274) over a flat buffer.
- * step_count: device pointer to the fp32 step counter (incremented by the kernel of block 0) or
- * NULL, in which case `step` (1-based, already incremented) is used. */
+ * step: 1-based index of this update (already incremented).  step_counter: NULL, or a device counter that is
+ * incremented on the stream and then used instead of `step` (CUDA-graph replay). */
 int mvae_adam(float* params, const float* grads, float* m, float* v, int64_t n, float lr,
               float beta1, float beta2, float eps, float weight_decay, int32_t adamw,
-              int64_t step, void* stream);
+              int64_t step, uint64_t* step_counter, void* stream);
 
 /* zero_grad + forward + loss + backward + Adam in one call (cpl_mixvae.py:434-463). */
 int mvae_train_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state* st,
@@ -163,6 +170,14 @@ int mvae_confmat(const int32_t* labels, int64_t n_cells, int32_t n_arm, int32_t 
  * the fc1 forward and fc1 weight-gradient kernels regenerate it on the fly instead of reading it. */
 int mvae_dropout_mask(const mvae_dims* dims, const mvae_hparams* hp, const mvae_inputs* in,
                       uint8_t* keep_out, void* stream);
+
+/* The host->device hand-over of a batch (`x = x.to(rank)`, cpl_mixvae.py:416) for a row-packed host batch: expression
+ * matrices are sparse (Smart-seq ~35 % non-zeros, 10x ~8 %), so the host keeps a batch as a bitmap (bit j of word w of a
+ * row = gene 32 w + j is non-zero; ceil(n_cols / 32) uint32 words per row), the non-zero fp32 values in row-major order and
+ * row_ptr[rows + 1] (int64 offsets into values).  This expands the three device arrays into the dense [rows][n_cols] fp32
+ * matrix, bit-exactly (zeros come back as +0.0f). */
+int mvae_unpack_rows(const uint32_t* bitmap, const float* values, const int64_t* row_ptr, int64_t rows, int32_t n_cols,
+                     float* out, int64_t out_row_stride, void* stream);
 
 /* Number of kernels launched by the library in this process (for bench.py's gpu_launches). */
 int64_t mvae_launch_count(void);

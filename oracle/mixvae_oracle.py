@@ -174,10 +174,11 @@ def _dropout(x, keep, p):
 
 
 def forward(sd: Dict[str, torch.Tensor], xs: Sequence[torch.Tensor], noise: Dict[str, torch.Tensor],
-            hp: HP, train: bool = True, new_buffers: Optional[dict] = None) -> Dict[str, List[torch.Tensor]]:
+            hp: HP, train: bool = True, new_buffers: Optional[dict] = None, mask=None) -> Dict[str, List[torch.Tensor]]:
     """mixVAE_model.forward (nn_model.py:297-368).  ``train=False`` is the reference's
     ``eval=True`` on a module in ``.eval()`` mode: running-stat BN, no dropout, no Gumbel noise,
-    straight-through one-hot sample; the state noise E is still applied (nn_model.py:351)."""
+    straight-through one-hot sample; the state noise E is still applied (nn_model.py:351).
+    ``mask`` (indices of kept categories): the pruning path of nn_model.py:332-335."""
     out = {k: [] for k in ("x_rec", "x_low", "qc", "s_smp", "c_smp", "s_mean", "s_logvar", "c_prob",
                            "h_dec")}
     eps = hp.eps
@@ -191,7 +192,11 @@ def forward(sd: Dict[str, torch.Tensor], xs: Sequence[torch.Tensor], noise: Dict
             h = _bn(F.relu(F.linear(h, W(f"fc{i}"), b(f"fc{i}"))), sd, f"batch_l{i}.{a}", hp, train, new_buffers)
         x_low = h
         c_prob = F.softmax(F.linear(x_low, W("fcc"), b("fcc")), dim=-1)          # :269
-        qc = F.softmax(c_prob / hp.tau, dim=-1)                                  # :337
+        if mask is not None:                                                     # :332-335
+            idx = torch.as_tensor(mask, dtype=torch.long)
+            qc = torch.zeros_like(c_prob).index_copy(1, idx, F.softmax(c_prob[:, idx] / hp.tau, dim=-1))
+        else:
+            qc = F.softmax(c_prob / hp.tau, dim=-1)                              # :337
         if train:
             U = noise["U"][a].to(dt)
             g = -torch.log(-torch.log(U + eps) + eps)                            # :440-441
@@ -281,7 +286,7 @@ class TrainState:
 
 
 def train_step(st: TrainState, xs: Sequence[torch.Tensor], noise: Dict[str, torch.Tensor],
-               return_grads: bool = False) -> Dict[str, object]:
+               return_grads: bool = False, mask=None) -> Dict[str, object]:
     """One optimiser step in the reference's order (cpl_mixvae.py:434-463)."""
     hp = st.hp
     names = param_names(hp)
@@ -291,7 +296,7 @@ def train_step(st: TrainState, xs: Sequence[torch.Tensor], noise: Dict[str, torc
         leaves[n] = st.sd[n].detach().clone().requires_grad_(True)
         sd[n] = leaves[n]
     new_buffers: dict = {}
-    fw = forward(sd, xs, noise, hp, train=True, new_buffers=new_buffers)
+    fw = forward(sd, xs, noise, hp, train=True, new_buffers=new_buffers, mask=mask)
     ls = loss(fw, xs, hp)
     grads = torch.autograd.grad(ls["total"], [leaves[n] for n in names])
     st.step += 1

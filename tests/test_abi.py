@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(lib_mod.EXPORTS) == declared
-    assert lib.mvae_abi_version() == 1
+    assert lib.mvae_abi_version() == 2
 
 
 def test_layout_matches_reference_parameter_count():

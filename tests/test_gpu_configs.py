@@ -1,0 +1,443 @@
+"""Parity of the CUDA path on the shapes and placements BASELINE.json names beyond config 2 (needs a B200, ``-m gpu``):
+
+* A=3 / A=5 at B=5000 and config 5's batch (B=16384) — the shapes whose encoder chain does not fit one co-resident
+  wave of 80-cell tiles (gene dimension reduced to keep the fp64 oracle fast; the narrow path does not depend on D);
+* the arm shard (``n_arm_total > n_arm``, ``arm_offset > 0``): mvae_loss with gathered posteriors, coupling gradients of
+  the local arm, noise streams keyed by the GLOBAL arm index;
+* teacher-forced multi-step training in the default precision: per-step losses and Adam moments;
+* eval-mode forward in the default precision; the category-mask path; a checkpoint written by the reference trainer
+  evaluated through ``eval_model``; the row-packed host batch; the captured CUDA graph of the step.
+"""
+import ctypes as C
+import dataclasses
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mixvae_oracle as O
+from golden_cases import GOLDEN, SEED, case_inputs, sample_idx
+from gpu_utils import (build_model, cuda_grads, load_oracle_state, loss_vector, oracle_step, rel_l2, shard_model,
+                       to_dev_noise)
+from test_gpu_parity import ENC, FLOORS, K, _fwd_loss_bwd
+
+pytestmark = pytest.mark.gpu
+
+
+def _synth(hp, B, density=0.35, seed=546):
+    gen = torch.Generator().manual_seed(seed)
+    x = O.synth_x(B, hp.input_dim, gen, density)
+    return x, O.synth_noise(hp, B, gen)
+
+
+def _check_step0(hp, x, noise, precision, amp=1.0, genc_floor=None, mask=None):
+    sd0 = O.init_state_dict(hp, 546)
+    _, o32 = oracle_step(hp, sd0, x, noise, torch.float32)
+    _, o64 = oracle_step(hp, sd0, x, noise, torch.float64)
+    fl = {k: v * amp for k, v in FLOORS[precision].items()}
+    if genc_floor:
+        fl["genc"] = max(fl["genc"], genc_floor)
+    model = build_model(hp, precision)
+    out, ls = _fwd_loss_bwd(model, x.cuda(), to_dev_noise(noise), hp.temp)
+    x_recs, _, _, x_lows, cs, s_smps, c_smps, s_means, s_logvars, c_probs = out
+    torch.cuda.synchronize()
+    flips = int((torch.stack(cs).argmax(-1).cpu() != torch.stack(o32["fw"]["qc"]).argmax(-1)).sum())
+    assert flips == 0, flips                                              # bit-exact assignments
+    flips = int((torch.stack(c_smps).argmax(-1).cpu() != torch.stack(o32["fw"]["c_smp"]).argmax(-1)).sum())
+    assert flips == 0, flips
+    got = {"qc": cs, "c_smp": c_smps, "s_mean": s_means, "s_logvar": s_logvars, "x_low": x_lows, "c_prob": c_probs,
+           "x_rec": x_recs}
+    for key, lst in got.items():
+        c = torch.stack(lst).cpu().numpy()
+        r64, r32 = torch.stack(o64["fw"][key]).numpy(), torch.stack(o32["fw"][key]).numpy()
+        tol = max(K * rel_l2(r32, r64), fl["xrec" if key == "x_rec" else "fwd"])
+        assert rel_l2(c, r64) <= tol, (key, rel_l2(c, r64), tol)
+    lv = np.array([ls[0].item(), ls[2].item(), ls[3].item(), ls[4].item(), ls[5].item()])
+    l64, l32 = loss_vector(o64["loss"]), loss_vector(o32["loss"])
+    for i, nm in enumerate(("total", "joint", "ent", "dist", "l2")):
+        tol = max(K * abs(l32[i] / l64[i] - 1), fl["loss"])
+        assert abs(lv[i] / l64[i] - 1) <= tol, (nm, lv[i], l64[i], tol)
+    for a in range(hp.n_arm):
+        for nm, got_v in (("rec", ls[1][a].item()), ("kl", ls[6][a].item()), ("ll", ls[8][a].item())):
+            want, w32 = float(o64["loss"][nm][a]), float(o32["loss"][nm][a])
+            assert abs(got_v / want - 1) <= max(K * abs(w32 / want - 1), fl["loss"], 1e-5), (nm, a, got_v, want)
+    grads = cuda_grads(model)
+    for n in O.param_names(hp):
+        r64, r32 = o64["grads"][n].numpy(), o32["grads"][n].numpy()
+        floor = fl["genc"] if n.split(".")[0] in ENC else fl["gdec"]
+        e = rel_l2(grads[n], r64)
+        assert e <= max(K * rel_l2(r32, r64), floor), (precision, n, e, rel_l2(r32, r64))
+    return model, o64
+
+
+# (A, B): BASELINE configs 3 and 4 in data-parallel placement and config 5's batch; D reduced (the gene kernels are
+# covered at full D by test_full_size_cfg2_properties / test_ragged_shapes_match_oracle)
+@pytest.mark.parametrize("A,B", [(3, 5000), (5, 5000), (2, 16384)], ids=["a3_b5000", "a5_b5000", "a2_b16384"])
+@pytest.mark.parametrize("precision", ["tf32x3_fc1", "fp32_simt"])
+def test_baseline_shapes_beyond_one_wave(A, B, precision):
+    if precision == "fp32_simt" and A == 5:
+        pytest.skip("covered by a3 (same kernels)")
+    hp = O.HP(input_dim=520, n_categories=100, state_dim=2, n_arm=A, x_drop=0.5, s_drop=0.0)
+    x, noise = _synth(hp, B)
+    _check_step0(hp, x, noise, precision)
+
+
+@pytest.mark.parametrize("case", ["a3_hard", "a3_wide"])
+@pytest.mark.parametrize("precision", ["fp32_simt", "tf32x3_fc1"])
+def test_arm_shard_equals_unsharded_model(case, precision):
+    """One arm per 'rank' on ONE GPU: the shard (n_arm=1, n_arm_total=3, arm_offset=a) fed the other arms' posteriors
+    must produce arm a's gradients and loss entries of the unsharded model — which is pinned to the oracle."""
+    if case == "a3_hard":
+        hp, x, noises, _, _ = case_inputs("a3_hard")
+        noise = noises[0]
+        amp, genc = 50.0, None
+    else:
+        hp = O.HP(input_dim=520, n_categories=100, state_dim=2, n_arm=3, x_drop=0.5, s_drop=0.0)
+        x, noise = _synth(hp, 1200)
+        amp, genc = 1.0, None
+    amp = amp if precision != "fp32_simt" else 1.0
+    full, o64 = _check_step0(hp, x, noise, precision, amp=amp, genc_floor=genc)
+    sd0 = O.init_state_dict(hp, 546)
+    xc = x.cuda()
+    # (rerun the full model: _check_step0 consumed its outputs)
+    out, ls = _fwd_loss_bwd(full, xc, to_dev_noise(noise), hp.temp)
+    qc_all, cs_all = torch.stack(out[4]).clone(), torch.stack(out[6]).clone()
+    full_grads = cuda_grads(full)
+    full_lv = full._ctx.loss_vec.clone()
+    At = hp.n_arm
+    tol = 2e-5 if precision == "fp32_simt" else 2e-3
+    for a in range(At):
+        m = shard_model(hp, sd0, a, a + 1, precision)
+        m.train()
+        nz = {k: v[a:a + 1] for k, v in to_dev_noise(noise).items()}
+        xs = xc.expand(1, -1, -1)
+        o = m(xs, hp.temp, 0.0, noise=nz)
+        # the shard's own forward equals arm a of the full model
+        assert rel_l2(o[4][0].cpu().numpy(), qc_all[a].cpu().numpy()) < 1e-4
+        assert torch.equal(o[4][0].argmax(-1), qc_all[a].argmax(-1))
+        with pytest.raises(RuntimeError):
+            m.loss(o[0], [], [], xs, o[7], o[8], o[4], o[6], 0.0)             # sharded arms need the gathered tensors
+        l = m.loss(o[0], [], [], xs, o[7], o[8], o[4], o[6], 0.0, qc_all=qc_all, c_smp_all=cs_all)
+        l[0].backward()
+        lv = m._ctx.loss_vec
+        torch.cuda.synchronize()
+        # pair terms are global; per-arm entries only for the local arm
+        np.testing.assert_allclose(lv[1:5].cpu().numpy(), full_lv[1:5].cpu().numpy(), rtol=1e-5)
+        for blk in range(3):
+            i = 5 + blk * At + a
+            assert abs(lv[i].item() / full_lv[i].item() - 1) < 1e-5, (blk, a)
+        g = cuda_grads(m)
+        for n, v in g.items():
+            name, _, rest = n.split(".", 2)
+            ref = full_grads[f"{name}.{a}.{rest}"]
+            assert rel_l2(v, ref) <= tol, (a, n, rel_l2(v, ref))
+            r64 = o64["grads"][f"{name}.{a}.{rest}"].numpy()
+            floor = (FLOORS[precision]["genc"] if name in ENC else FLOORS[precision]["gdec"]) * amp
+            assert rel_l2(v, r64) <= max(10 * floor, 1e-3 if case == "a3_hard" else 0), (a, n, rel_l2(v, r64))
+
+
+def test_noise_streams_follow_the_global_arm_index():
+    """In-kernel dropout / Gumbel / state noise are keyed on (seed, step, GLOBAL arm): a shard with arm_offset=1 draws
+    what arm 1 of the unsharded model draws, arms differ from each other, steps differ, replicas with another seed salt
+    differ (identical masks on every rank of an arm-sharded mesh)."""
+    from mmidas_b200 import _lib
+    hp = O.HP(input_dim=520, n_categories=100, state_dim=2, n_arm=2, x_drop=0.5, s_drop=0.0)
+    B = 256
+    x, _ = _synth(hp, B)
+    xc = x.cuda()
+    sd0 = O.init_state_dict(hp, 546)
+
+    def mask_of(model):
+        ctx = model._ctx
+        keep = torch.empty(model.n_arm, B, hp.input_dim, dtype=torch.uint8, device="cuda")
+        _lib.check(_lib.load().mvae_dropout_mask(C.byref(ctx.dims), C.byref(ctx.hp), C.byref(ctx.inputs), keep.data_ptr(), None),
+                   "mvae_dropout_mask")
+        torch.cuda.synchronize()
+        return keep
+
+    torch.manual_seed(99)
+    full = build_model(hp, "tf32x3_fc1")
+    full.train()
+    of = full(xc.expand(2, -1, -1), hp.temp, 0.0)
+    kf = mask_of(full)
+    assert not torch.equal(kf[0], kf[1])
+    # correlation between the arms' masks and between consecutive steps ~ 0
+    a, b = kf[0].float().flatten() - 0.5, kf[1].float().flatten() - 0.5
+    assert abs(float((a * b).mean()) / 0.25) < 0.01
+    shards = []
+    for off in (0, 1):
+        m = shard_model(hp, sd0, off, off + 1, "tf32x3_fc1")
+        m.train()
+        o = m(xc.expand(1, -1, -1), hp.temp, 0.0)
+        k = mask_of(m)
+        assert torch.equal(k[0], kf[off]), off                              # same mask as global arm `off`
+        # Gumbel sample and state sample: same draws as the unsharded arm (fc1 summation order may differ by an ulp)
+        assert rel_l2(o[6][0].cpu().numpy(), of[6][off].cpu().numpy()) < 1e-3, off
+        assert rel_l2(o[5][0].cpu().numpy(), of[5][off].cpu().numpy()) < 1e-3, off
+        shards.append(o)
+    assert rel_l2(shards[1][5][0].cpu().numpy(), of[5][0].cpu().numpy()) > 0.1   # ... and NOT arm 0's
+    # next step: new masks; another replica (seed salt): new masks
+    full(xc.expand(2, -1, -1), hp.temp, 0.0)
+    k2 = mask_of(full)
+    c = k2[0].float().flatten() - 0.5
+    assert abs(float((a * c).mean()) / 0.25) < 0.01
+    rep = build_model(hp, "tf32x3_fc1")
+    rep.seed_salt = 0x9E3779B97F4A7C15
+    rep.train()
+    rep(xc.expand(2, -1, -1), hp.temp, 0.0)
+    k3 = mask_of(rep)
+    d = k3[0].float().flatten() - 0.5
+    assert abs(float((a * d).mean()) / 0.25) < 0.01 and abs(float(k3.float().mean()) - 0.5) < 0.01
+
+
+@pytest.mark.parametrize("name,precision", [("mid", "tf32x3_fc1"), ("mid", "fp32_simt"), ("cfg1", "tf32x3_fc1")])
+def test_teacher_forced_multi_step(name, precision):
+    """N steps, each from the ORACLE's state (parameters, BN buffers, Adam moments): per-step loss and the Adam moments
+    after the step are functions of one gradient evaluation and do not suffer the sign flips that make free-running
+    parameter comparisons vacuous."""
+    from mmidas_b200 import FusedAdam
+    if name == "cfg1":
+        hp = O.HP(input_dim=5032, n_categories=92, state_dim=2, n_arm=2, x_drop=0.5, s_drop=0.0)
+        gen = torch.Generator().manual_seed(SEED)
+        x = O.synth_x(1000, hp.input_dim, gen, 0.35)
+        noises = [O.synth_noise(hp, 1000, gen) for _ in range(3)]
+        amp = 1.0
+    else:
+        hp, x, noises, _, _ = case_inputs(name)
+        gen = torch.Generator().manual_seed(SEED + 7)
+        noises = list(noises) + [O.synth_noise(hp, x.shape[0], gen) for _ in range(2)]
+        amp = 20.0 if precision != "fp32_simt" else 1.0
+    fl = {k: v * amp for k, v in FLOORS[precision].items()}
+    model = build_model(hp, precision)
+    opt = FusedAdam(model.parameters(), lr=hp.lr, model=model)
+    st = O.TrainState(hp, O.init_state_dict(hp, 546))
+    xc = x.cuda()
+    names = O.param_names(hp)
+    for step, noise in enumerate(noises):
+        load_oracle_state(model, opt, st)
+        ref = O.train_step(st, [x] * hp.n_arm, noise, return_grads=True)
+        opt.zero_grad()
+        _, ls = _fwd_loss_bwd(model, xc, to_dev_noise(noise), hp.temp)
+        opt.step()
+        torch.cuda.synchronize()
+        assert abs(ls[0].item() / float(ref["loss"]["total"]) - 1) <= max(10 * fl["loss"], 1e-4), (step, ls[0].item())
+        assert opt.step_count == st.step
+        osd = opt.state_dict()["state"]
+        for i, n in enumerate(names):
+            tol = 10 * (fl["genc"] if n.split(".")[0] in ENC else fl["gdec"])
+            em = rel_l2(osd[i]["exp_avg"].cpu().numpy(), st.m[n].numpy())
+            ev = rel_l2(osd[i]["exp_avg_sq"].cpu().numpy(), st.v[n].numpy())
+            assert em <= tol and ev <= 2 * tol, (step, n, em, ev, tol)
+        sd = model.state_dict()
+        for k, v in st.sd.items():
+            if "running" in k:
+                np.testing.assert_allclose(sd[k].cpu().numpy(), v.numpy(), rtol=1e-4, atol=1e-6, err_msg=k)
+            elif v.is_floating_point():
+                d = np.abs(sd[k].cpu().numpy().astype(np.float64) - v.numpy())
+                assert d.max() <= 2 * hp.lr + 1e-6, (k, d.max())              # one Adam step from the same state
+
+
+@pytest.mark.parametrize("name", ["tiny", "a3_hard", "mid"])
+def test_eval_forward_default_precision(name):
+    """eval=True forward through the kernels the trainer's eval passes use (default precision, running-stat BN)."""
+    hp, x, noises, eval_noise, _ = case_inputs(name)
+    st = O.TrainState(hp, O.init_state_dict(hp, 546))
+    for noise in noises:
+        O.train_step(st, [x] * hp.n_arm, noise)
+    model = build_model(hp, "tf32x3_fc1")
+    model.load_state_dict(st.sd)
+    model.eval()
+    with torch.no_grad():
+        xs = [x.cuda()] * hp.n_arm
+        out = model(x=xs, temp=hp.temp, prior_c=0.0, eval=True, noise=to_dev_noise(eval_noise))
+        x_recs, _, _, x_lows, cs, s_smps, c_smps, s_means, s_logvars, c_probs = out
+        ls = model.loss(x_recs, [], [], xs, s_means, s_logvars, cs, c_smps, 0.0)
+    fw = O.forward(O.cast_state_dict(st.sd, torch.float64), [x.double()] * hp.n_arm, eval_noise, hp, train=False)
+    fw32 = O.forward(st.sd, [x] * hp.n_arm, eval_noise, hp, train=False)
+    lo = O.loss(fw, [x.double()] * hp.n_arm, hp)
+    np.testing.assert_array_equal(torch.stack(cs).argmax(-1).cpu().numpy(), torch.stack(fw32["qc"]).argmax(-1).numpy())
+    np.testing.assert_array_equal(torch.stack(c_smps).argmax(-1).cpu().numpy(), torch.stack(fw32["c_smp"]).argmax(-1).numpy())
+    for key, lst, floor in (("qc", cs, 2e-3), ("s_mean", s_means, 2e-3), ("s_logvar", s_logvars, 2e-3), ("x_low", x_lows, 2e-3),
+                            ("x_rec", x_recs, 5e-3)):
+        r64, r32 = torch.stack(fw[key]).numpy(), torch.stack(fw32[key]).numpy()
+        e = rel_l2(torch.stack(lst).cpu().numpy(), r64)
+        assert e <= max(K * rel_l2(r32, r64), floor), (key, e)
+    got = np.array([ls[0].item(), ls[2].item(), ls[3].item(), ls[4].item(), ls[5].item()])
+    np.testing.assert_allclose(got, loss_vector(lo), rtol=5e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "tf32x3_fc1"])
+def test_masked_forward_matches_reference(precision):
+    """forward(mask=...) (nn_model.py:332-335) in training and eval mode against the reference's own outputs."""
+    g = np.load(os.path.join(GOLDEN, "mask.npz"))
+    hp = O.HP(input_dim=64, n_categories=12, state_dim=2, n_arm=2, x_drop=0.5, s_drop=0.0)
+    gen = torch.Generator().manual_seed(SEED)
+    x = O.synth_x(48, hp.input_dim, gen, 0.35)
+    n_train, n_eval = O.synth_noise(hp, 48, gen), O.synth_noise(hp, 48, gen)
+    mask = g["mask"]
+    dropped = np.setdiff1d(np.arange(hp.n_categories), mask)
+    model = build_model(hp, precision)
+    model.train()
+    xs = x.cuda().expand(hp.n_arm, -1, -1)
+    out = model(xs, hp.temp, 0.0, mask=mask, noise=to_dev_noise(n_train))
+    ls = model.loss(out[0], [], [], xs, out[7], out[8], out[4], out[6], 0.0)
+    ls[0].backward()
+    torch.cuda.synchronize()
+    q = torch.stack(out[4]).cpu().numpy()
+    assert (q[..., dropped] == 0).all()
+    amp = 1.0 if precision == "fp32_simt" else 50.0
+    np.testing.assert_array_equal(q.argmax(-1), g["train_qc"].argmax(-1))
+    assert rel_l2(q, g["train_qc"]) < 1e-3 * amp
+    assert rel_l2(torch.stack(out[0]).cpu().numpy(), g["train_x_rec"]) < 1e-4 * amp
+    lv = np.array([ls[0].item(), ls[2].item(), ls[3].item(), ls[4].item(), ls[5].item()])
+    np.testing.assert_allclose(lv, g["train_losses"], rtol=2e-4 * amp)
+    grads = cuda_grads(model)
+    names = [str(n) for n in g["param_names"]]
+    gn = np.array([np.linalg.norm(grads[n].astype(np.float64)) for n in names])
+    np.testing.assert_allclose(gn, g["train_grad_norm"], rtol=2e-3 * amp)
+    # eval mode with the mask (the call eval_model makes), BN running statistics after that one training forward
+    model.eval()
+    with torch.no_grad():
+        xl = [x.cuda()] * hp.n_arm
+        out = model(x=xl, temp=hp.temp, prior_c=0.0, eval=True, mask=mask, noise=to_dev_noise(n_eval))
+        ls = model.loss(out[0], [], [], xl, out[7], out[8], out[4], out[6], 0.0)
+    q = torch.stack(out[4]).cpu().numpy()
+    assert (q[..., dropped] == 0).all()
+    np.testing.assert_array_equal(torch.stack(out[6]).cpu().numpy(), g["eval_c_smp"])       # one-hot samples: exact
+    assert rel_l2(q, g["eval_qc"]) < 1e-3 * amp
+    assert rel_l2(torch.stack(out[7]).cpu().numpy(), g["eval_s_mean"]) < 1e-4 * amp
+    lv = np.array([ls[0].item(), ls[2].item(), ls[3].item(), ls[4].item(), ls[5].item()])
+    np.testing.assert_allclose(lv, g["eval_losses"], rtol=2e-4 * amp)
+
+
+def test_reference_checkpoint_through_eval_model(tmp_path):
+    """A checkpoint written by the reference's cpl_mixVAE.train loads through init_model(trained_model=...) and
+    eval_model returns the reference's dictionary (keys, shapes, 1-based labels, values)."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from mmidas_b200.cpl_mixvae import cpl_mixVAE
+    g = np.load(os.path.join(GOLDEN, "ref_ckpt_eval.npz"))
+    gen = torch.Generator().manual_seed(SEED + 1)
+    xall = O.synth_x(192 + 48, 64, gen, 0.35)
+    x, idx = xall[192:], torch.arange(192, 240, dtype=torch.float32)
+    t = cpl_mixVAE(saving_folder=str(tmp_path), aug_file="", device="cuda")
+    t.precision = "fp32_simt"
+    t.init_model(n_categories=7, state_dim=2, input_dim=64, fc_dim=32, lowD_dim=6, x_drop=0.5, s_drop=0.0, n_arm=2,
+                 trained_model=os.path.join(GOLDEN, "ref_ckpt.pth"))
+    assert t.init is False and t.optimizer.step_count == 6           # 2 epochs x 3 batches in the reference run
+    ck = torch.load(os.path.join(GOLDEN, "ref_ckpt.pth"), map_location="cpu")
+    for k, v in t.model.state_dict().items():
+        assert torch.equal(v.cpu(), ck["model_state_dict"][k]), k
+    osd = t.optimizer.state_dict()
+    for i, s in ck["optimizer_state_dict"]["state"].items():
+        assert torch.equal(osd["state"][i]["exp_avg"].cpu(), s["exp_avg"]), i
+    dl = DataLoader(TensorDataset(x, idx), batch_size=16)
+    E = torch.from_numpy(g["E"]).cuda()
+    res = t.eval_model(dl, noise={"E": E})
+    want_keys = {"state_mu", "state_var", "state_cat", "prob_cat", "total_loss_rec", "total_likelihood", "total_dist_z",
+                 "total_dist_qz", "mean_test_rec", "predicted_label", "data_indx", "z_prob", "z_sample", "x_low", "recon_c",
+                 "prune_indx", "cnss"}
+    assert want_keys <= set(res)
+    for k in want_keys:
+        assert np.asarray(res[k]).shape == g[k].shape, (k, np.asarray(res[k]).shape, g[k].shape)
+    np.testing.assert_array_equal(res["predicted_label"], g["predicted_label"])
+    np.testing.assert_array_equal(res["state_cat"], g["state_cat"])
+    np.testing.assert_array_equal(res["data_indx"], g["data_indx"])
+    np.testing.assert_array_equal(res["z_sample"], g["z_sample"])
+    np.testing.assert_array_equal(res["prune_indx"], g["prune_indx"])
+    for k, tol in (("z_prob", 1e-4), ("state_mu", 1e-4), ("state_var", 1e-4), ("x_low", 1e-4), ("recon_c", 1e-4),
+                   ("prob_cat", 1e-4)):
+        assert rel_l2(res[k], g[k]) < tol, (k, rel_l2(res[k], g[k]))
+    for k in ("total_loss_rec", "total_likelihood", "total_dist_z", "total_dist_qz", "cnss"):
+        np.testing.assert_allclose(res[k], g[k], rtol=1e-4, err_msg=k)
+    # save_file / load_file (cpl_mixvae.py:1621-1650)
+    t.save_file(str(tmp_path / "summary"), z_prob=res["z_prob"], cnss=res["cnss"])
+    back = t.load_file(str(tmp_path / "summary"))
+    assert set(back) == {"z_prob", "cnss"} and np.array_equal(back["z_prob"], res["z_prob"])
+
+
+def test_packed_host_batch_unpacks_bit_exactly():
+    from mmidas_b200.cpl_mixvae import HostBatchFeeder
+    from mmidas_b200.dataloader import PackedBatch
+    gen = torch.Generator().manual_seed(3)
+    for B, D, dens in ((5, 31, 0.5), (64, 64, 0.0), (333, 1348, 0.35), (700, 5032, 0.08), (17, 1030, 1.0)):
+        x = O.synth_x(B, D, gen, dens) if dens < 1.0 else torch.rand(B, D, generator=gen) + 0.5
+        p = PackedBatch(x)
+        assert p.nbytes <= 4 * B * D * dens * 1.3 + 8 * (B + 1) + 4 * B * ((D + 31) // 32) + 64
+        out = p.unpack("cuda")
+        torch.cuda.synchronize()
+        assert torch.equal(out.cpu(), x), (B, D, dens)
+    # through the feeder: packed and dense items give the same device batches, ring buffers repeat
+    xs = [O.synth_x(128, 520, gen, 0.35) for _ in range(5)]
+    ptrs = set()
+    for (xd, _), x in zip(HostBatchFeeder([PackedBatch(x) for x in xs], "cuda"), xs):
+        torch.cuda.synchronize()
+        assert torch.equal(xd.cpu(), x)
+        ptrs.add(xd.data_ptr())
+    assert len(ptrs) == 2
+    for (xd, item), x in zip(HostBatchFeeder([(x, torch.arange(128.)) for x in xs], "cuda"), xs):
+        torch.cuda.synchronize()
+        assert torch.equal(xd.cpu(), x) and item[1].shape == (128,)
+
+
+def test_cuda_graph_replay_equals_eager_steps():
+    """mvae_train_step captured in a CUDA graph (static input buffer, step counters on the device) and replayed: same
+    parameters, moments, BN buffers and losses as the same steps launched eagerly — the in-kernel noise of step i is a
+    function of (seed, i), read from the device counter under replay."""
+    from mmidas_b200 import FusedAdam
+    from mmidas_b200.nn_model import StepGraph
+    hp = O.HP(input_dim=520, n_categories=100, state_dim=2, n_arm=2, x_drop=0.5, s_drop=0.0)
+    B, steps = 600, 4
+    gen = torch.Generator().manual_seed(546)
+    xb = [O.synth_x(B, hp.input_dim, gen).cuda() for _ in range(steps)]
+    res = []
+    for graphed in (False, True, True):
+        torch.manual_seed(1234)
+        model = build_model(hp, "tf32x3_fc1")
+        opt = FusedAdam(model.parameters(), lr=hp.lr, model=model)
+        model.train()
+        buf = torch.empty(B, hp.input_dim, device="cuda")
+        losses = []
+        buf.copy_(xb[0])
+        losses.append(model.fused_train_step(buf.expand(2, -1, -1), hp.temp, opt)[0].item())     # step 1 eager (warm-up)
+        g = StepGraph(model, opt, lambda: model.fused_train_step(buf.expand(2, -1, -1), hp.temp, opt)) if graphed else None
+        for i in range(1, steps):
+            buf.copy_(xb[i])
+            lv = g.replay() if graphed else model.fused_train_step(buf.expand(2, -1, -1), hp.temp, opt)
+            losses.append(lv[0].item())
+        torch.cuda.synchronize()
+        assert opt.step_count == steps and model._step_counter == steps
+        m, v = opt.flat_state()
+        res.append((losses, model.flat_parameters().clone(), m.clone(), v.clone(), model._flat_bn.clone(), model._flat_nbt.clone(),
+                    model.last_outputs()["qc"].clone()))
+    for other in res[1:]:
+        np.testing.assert_allclose(other[0], res[0][0], rtol=1e-6)
+        assert torch.equal(other[5], res[0][5])
+        for i in (1, 2, 3, 4, 6):
+            d = (other[i] - res[0][i]).abs()
+            # fp64 atomics order the batch statistics differently from launch to launch: equal up to that
+            assert float((d > 1e-6 * (1 + res[0][i].abs())).float().mean()) < 1e-3, (i, float(d.max()))
+    assert torch.equal(res[1][1], res[2][1]) or float((res[1][1] - res[2][1]).abs().max()) <= 2 * hp.lr
+
+
+def test_trainer_uses_graphs_and_matches_eager_trainer():
+    """cpl_mixVAE.train_batch replays graphs once a batch buffer repeats; results match the eager trainer."""
+    from mmidas_b200.cpl_mixvae import HostBatchFeeder, cpl_mixVAE
+    gen = torch.Generator().manual_seed(5)
+    host = [O.synth_x(256, 520, gen) for _ in range(3)]
+    outs = []
+    for use_graph in (False, True):
+        torch.manual_seed(546)
+        t = cpl_mixVAE(saving_folder="", aug_file="", device="cuda", save_flag=False)
+        t.use_cuda_graph = use_graph
+        t.init_model(n_categories=20, state_dim=2, input_dim=520, x_drop=0.5, s_drop=0.0, n_arm=2)
+        t.model.train()
+        tot = []
+        for x, _ in HostBatchFeeder((host[i % 3] for i in range(9)), "cuda"):
+            tot.append(t.train_batch(x)[0].item())
+        outs.append((tot, t.model.flat_parameters().clone(), len(t._graphs), t.optimizer.step_count))
+    assert outs[0][2] == 0 and outs[1][2] == 2          # two ring buffers -> two graphs
+    assert outs[0][3] == outs[1][3] == 9
+    np.testing.assert_allclose(outs[1][0], outs[0][0], rtol=1e-5)
+    d = (outs[0][1] - outs[1][1]).abs()
+    assert float((d > 1e-6).float().mean()) < 1e-2 and float(d.max()) <= 2e-3 * 9

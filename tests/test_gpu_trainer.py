@@ -66,8 +66,10 @@ def test_train_loop_checkpoints_and_resume(tmp_path):
     assert t2.init is False and t2.optimizer.step_count == 6
     for (k, a), (_, b) in zip(t.model.state_dict().items(), t2.model.state_dict().items()):
         assert torch.equal(a.cpu(), b.cpu()), k
-    res = t2.eval_model(test)
-    assert res["qc"].shape == (2, 64, 9) and res["labels"].shape == (2, 64) and np.isfinite(res["total_loss"])
+    res = t2.eval_model(test)        # the reference's dictionary (cpl_mixvae.py:1590-1619)
+    assert res["z_prob"].shape == (2, 64, 9) and res["predicted_label"].shape == (2, 64) and np.isfinite(res["total_loss"])
+    assert res["predicted_label"].min() >= 1 and res["predicted_label"].max() <= 9 and res["recon_c"].shape == (2, 64, 128)
+    assert np.array_equal(res["data_indx"], np.arange(320, 384)) and 0.0 <= res["cnss"] <= 1.0
 
 
 def test_caller_replaced_optimizer_still_trains():
@@ -90,9 +92,38 @@ def test_caller_replaced_optimizer_still_trains():
 
 
 def test_sharded_trainer_single_process_matches_fused_step():
-    from mmidas_b200 import FusedAdam
-    from mmidas_b200.parallel import plan_mesh
-    assert plan_mesh(1, 2).arm_ranks == 1
+    """ShardedTrainer on a one-rank world is the fused step (eager and graph-replayed): same losses and parameters as
+    cpl_mixVAE.train_batch from the same seed."""
+    import torch.distributed as dist
+    from mmidas_b200 import _dist_utils as D
+    from mmidas_b200.cpl_mixvae import cpl_mixVAE
+    from mmidas_b200.parallel import ShardedTrainer
+    kw = dict(input_dim=128, fc_dim=100, n_categories=9, state_dim=2, lowD_dim=10, x_drop=0.5, s_drop=0.0, n_arm=2, lam=1,
+              lam_pc=1, tau=0.005, beta=1.0, hard=False, variational=True, device="cuda", eps=1e-8, momentum=0.01,
+              ref_prior=False, loss_mode="MSE")
+    gen = torch.Generator().manual_seed(1)
+    xs = [O.synth_x(128, 128, gen).cuda() for _ in range(2)]
+    D.init_dist_env(0, 1, "127.0.0.1", str(D.find_port("127.0.0.1")), backend="nccl")
+    try:
+        torch.manual_seed(546)
+        st = ShardedTrainer(kw, lr=1e-3, mode="auto", seed=546)
+        assert st.plan.arm_ranks == 1 and st.plan.dp_ranks == 1 and st.active
+        torch.manual_seed(546)                      # noise seed of the steps (the constructor re-seeded the device generator)
+        got = [st.step(xs[i % 2])[0].item() for i in range(6)]
+        assert len(st._graphs) == 2                 # two input buffers -> two captured graphs
+        p_sharded = st.model.flat_parameters().clone()
+    finally:
+        D.destroy_dist_env()
+    torch.manual_seed(546)
+    t = cpl_mixVAE(saving_folder="", aug_file="", device="cuda", save_flag=False)
+    t.use_cuda_graph = False
+    t.init_model(n_categories=9, state_dim=2, input_dim=128, x_drop=0.5, s_drop=0.0, n_arm=2)
+    t.model.train()
+    torch.manual_seed(546)
+    want = [t.train_batch(xs[i % 2])[0].item() for i in range(6)]
+    np.testing.assert_allclose(got, want, rtol=1e-5)
+    d = (p_sharded - t.model.flat_parameters()).abs()
+    assert float((d > 1e-6).float().mean()) < 1e-2
 
 
 def test_training_step_on_augmented_input_matches_oracle(tmp_path):

@@ -77,7 +77,8 @@ def _worker(rank, world, port, mode, out):
         noise = O.synth_noise(hp, B, gen)
         sd = O.init_state_dict(hp, 546)
         plan = plan_mesh(world, hp.n_arm, mode)
-        arm_group, dp_group = make_groups(plan, rank)
+        arm_group, dp_group, mesh_group = make_groups(plan, rank)
+        assert mesh_group is not None
         if mode == "arm":
             # each rank owns one arm; q(c|x) and the samples are all-gathered, the coupling terms are
             # evaluated on the full set, rec/KL only for the local arm, then fixed up.
@@ -152,3 +153,70 @@ def test_dist_utils_surface():
         assert callable(getattr(D, name))                      # mmidas/_dist_utils.py:12,20,54,58,62
     port = D.find_port("127.0.0.1")
     assert 1024 < port < 65536
+
+
+def test_arm_shard_state_round_trip():
+    """slice_arm_state / merge_arm_states: a full reference-layout checkpoint cut into arm shards and merged back is the
+    same checkpoint (model keys in the reference's order, optimizer state in model.parameters() order)."""
+    from mmidas_b200 import FusedAdam, mixVAE_model
+    from mmidas_b200.parallel import merge_arm_states, plan_mesh, slice_arm_state
+    kw = dict(input_dim=64, fc_dim=32, n_categories=12, state_dim=2, lowD_dim=6, x_drop=0.5, s_drop=0.0, lam=1, lam_pc=1,
+              tau=0.005, beta=1.0, hard=False, variational=True, device="cpu", eps=1e-8, momentum=0.01, ref_prior=False,
+              loss_mode="MSE")
+    torch.manual_seed(546)
+    full = mixVAE_model(n_arm=4, **kw)
+    assert full.ctor_kwargs()["n_arm"] == 4 and full.ctor_kwargs()["fc_dim"] == 32
+    opt = FusedAdam(full.parameters(), model=full)
+    m, v = opt.flat_state()
+    m.copy_(torch.randn_like(m)); v.copy_(torch.rand_like(v)); opt.step_count = 3
+    sd, osd = full.state_dict(), opt.state_dict()
+    plan = plan_mesh(2, 4, "arm")
+    parts = []
+    for r in range(2):
+        a0, a1 = plan.arm_ranges[r]
+        local = mixVAE_model(n_arm=a1 - a0, **kw)
+        local.load_state_dict(slice_arm_state(sd, a0, a1))
+        lopt = FusedAdam(local.parameters(), model=local)
+        # the shard's optimizer state = the full state's entries of its arms, renumbered (layer-major, local-arm-minor)
+        lstate = {}
+        for li in range(14):
+            for la in range(a1 - a0):
+                for wb in range(2):
+                    lstate[(li * (a1 - a0) + la) * 2 + wb] = osd["state"][(li * 4 + a0 + la) * 2 + wb]
+        lopt.load_state_dict({"state": lstate, "param_groups": lopt.state_dict()["param_groups"]})
+        parts.append((local.state_dict(), lopt.state_dict()["state"]))
+    msd, state = merge_arm_states(parts, plan)
+    assert list(msd.keys()) == list(sd.keys())
+    for k in sd:
+        assert torch.equal(msd[k], sd[k]), k
+    assert set(state) == set(osd["state"])
+    for i in osd["state"]:
+        assert torch.equal(state[i]["exp_avg"], osd["state"][i]["exp_avg"]), i
+        assert torch.equal(state[i]["exp_avg_sq"], osd["state"][i]["exp_avg_sq"]), i
+
+
+def _subset_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    from mmidas_b200 import _dist_utils as D
+    from mmidas_b200.parallel import make_groups, plan_mesh
+    D.init_dist_env(rank, world, "127.0.0.1", str(port), backend="gloo")
+    try:
+        plan = plan_mesh(2, 2, "arm")                      # a 2-rank mesh on ranks [2, 0] of a 3-rank world
+        arm_g, dp_g, mesh_g = make_groups(plan, rank, ranks=[2, 0])
+        if rank in (0, 2):
+            t = torch.tensor([float(rank)])
+            dist.all_reduce(t, group=arm_g)
+            out[rank] = (float(t), mesh_g is not None, dp_g is None)
+        else:
+            out[rank] = (None, mesh_g is not None, dp_g is None)
+    finally:
+        D.destroy_dist_env()
+
+
+def test_mesh_on_a_subset_of_ranks():
+    """BASELINE config 3 runs A=3 on 3 of the 4 GPUs gpurun hands out: groups must form on a subset of the world."""
+    world = 3
+    out = mp.Manager().dict()
+    mp.spawn(_subset_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0] == (2.0, True, True) and out[2] == (2.0, True, True) and out[1] == (None, False, True)
