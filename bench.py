@@ -2,15 +2,24 @@
 """bench.py — train cells/sec of the coupled mixture-VAE (cpl-mixVAE / MMIDAS) training step.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU
+    python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference on the host CPU cores
 
 One "step" = zero_grad + forward + loss + backward + Adam over one batch of synthetic cells
 (mmidas/cpl_mixvae.py:434-463).  Workload at N=1: BASELINE.json configs[1] (A=2 arms, B=5000 cells,
 D=5032 genes, C=100 categories, S=2).  N>1: weak scaling, every GPU a data-parallel replica with
 its own 5000 cells and an NCCL gradient all-reduce (the reference has no runnable multi-GPU path).
 
-Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM; `e2e`: the trainer's public
-per-batch call with pinned HOST batches, H2D copy and loss read-back inside the timed region.
+Prints ONE JSON line (rank 0).
+  value        device step rate, inputs resident in HBM (4 rotating batches > L2), the step replayed from a CUDA graph
+  e2e          the trainer's public per-batch call fed from pinned HOST batches: H2D copy of every step's batch and the
+               loss read-back inside the timed region; the host batch is row-packed (bitmap + non-zero values, bit-exact)
+               and expanded on the device.  e2e.dense: the same with dense fp32 host batches; e2e.resident: the
+               device-resident loader (ResidentLoader, 8 bytes per cell over PCIe).
+  roofline     dominant kernel group against the measured HBM bandwidth + the step against both bounds (HBM bytes,
+               TF32 tensor FLOPs against a cuBLAS TF32 GEMM timed here)
+  cpu_baseline the unmodified reference (baseline/_ref) on the host cores, bounded sample
+  reference_gpu  the unmodified reference classes (eager fp32, TF32 off, torch.optim.Adam) on the same B200
+  extra        N=4: BASELINE configs[2] (A=3, one arm per GPU on 3 of the 4 ranks); N=8: configs[3] (A=5 on 8 GPUs)
 """
 import argparse
 import json
@@ -36,7 +45,8 @@ WORKLOADS = {
                  desc="cpl_mixvae A=2, 30000 genes x batch 16384 (BASELINE configs[4], 10x-shaped)"),
     "cfg1": dict(A=2, B=1000, D=5032, C=92, S=2, density=0.35,
                  desc="cpl_mixvae A=2, 5032 genes x batch 1000, 92 categories (BASELINE configs[0])"),
-    "a5": dict(A=5, B=5000, D=5032, C=100, S=2, density=0.35, desc="cpl_mixvae A=5, 5032 genes x batch 5000"),
+    "a3": dict(A=3, B=5000, D=5032, C=100, S=2, density=0.35, desc="cpl_mixvae A=3, 5032 genes x batch 5000 (BASELINE configs[2])"),
+    "a5": dict(A=5, B=5000, D=5032, C=100, S=2, density=0.35, desc="cpl_mixvae A=5, 5032 genes x batch 5000 (BASELINE configs[3])"),
 }
 N_ROTATING_BATCHES = 4
 
@@ -45,9 +55,18 @@ def p_arm(D, H, L, C, S):
     return 2 * D * H + 6 * H * H + 2 * H * L + L * C + 2 * (L + C) * S + (C + S) * L + D + 8 * H + 2 * L + C + 2 * S
 
 
-def algorithmic_bytes(w):
+def algorithmic_bytes(w, A=None):
     """A * (16*B*D + 28*P_arm) — four fp32 passes over the gene matrix per arm + Adam."""
-    return w["A"] * (16 * w["B"] * w["D"] + 28 * p_arm(w["D"], 100, 10, w["C"], w["S"]))
+    A = w["A"] if A is None else A
+    return A * (16 * w["B"] * w["D"] + 28 * p_arm(w["D"], 100, 10, w["C"], w["S"]))
+
+
+def tensor_flops(w, precision):
+    """TF32 tensor-core FLOPs the gene kernels ISSUE per step: fc1 forward (x3 when error-compensated), fc11 row pass
+    (x_hat + d h10), fc11 gene pass (x_hat recomputed + dW11), fc1 weight gradient; each 2*B*D*H per arm."""
+    f1 = 3 if precision in ("tf32x3_fc1", "tf32x3") else 1
+    rest = 3 if precision == "tf32x3" else 1
+    return (f1 + 5 * rest) * 2.0 * w["B"] * w["D"] * 100 * w["A"]
 
 
 def synth_x_device(B, D, density, gen, device):
@@ -64,6 +83,29 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measure_tf32_peak(dev):
+    """One cuBLAS TF32 GEMM (8192^3), best of 10: the tensor-pipe denominator MEASURED_PEAKS.json lacks."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(2):
+            a @ b
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best / 1e3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 class ClockSampler:
@@ -120,63 +162,166 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the reference algorithm (oracle port) on the host cores
+# The reference itself (baseline/_ref, installed by baseline/install_ref.py) and its oracle port
 # -------------------------------------------------------------------------------------------------
-def cpu_reference(w, steps, warmup, max_seconds=25.0, device="cpu"):
-    """Times oracle.train_step (the CPU restatement of mmidas/nn_model.py + Adam, pinned to the
-    reference by tests/test_oracle_golden.py) on a bounded sample: same shapes, full batch.
-    device="cuda" (--ref-device cuda, informational only) runs the same eager torch ops on the GPU:
-    the stock-PyTorch path the reference would take there, including its loss.item() sync per step."""
+def load_reference_model():
+    """mixVAE_model of the UNMODIFIED reference, or None when baseline/_ref did not travel."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref, "mmidas", "nn_model.py")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        from mmidas.nn_model import mixVAE_model as RefModel   # mmidas/__init__.py is empty: needs torch + numpy only
+        return RefModel
+    except Exception:
+        return None
+
+
+def reference_step_loop(RefModel, w, device, steps, warmup, readbacks=True, max_seconds=60.0, allow_tf32=False):
+    """The reference's own step, unmodified classes and stock code path (cpl_mixvae.py:434-477): zero_grad,
+    mixVAE_model.forward (its own RNG: dropout, Gumbel, state noise), .loss, backward, torch.optim.Adam.step, then the
+    per-step read-backs of :469 and :476.  Returns (seconds per step, steps timed)."""
+    A, B, D, C, S = w["A"], w["B"], w["D"], w["C"], w["S"]
+    torch.manual_seed(546)
+    torch.backends.cuda.matmul.allow_tf32 = allow_tf32
+    torch.backends.cudnn.allow_tf32 = allow_tf32
+    model = RefModel(input_dim=D, fc_dim=100, n_categories=C, state_dim=S, lowD_dim=10, x_drop=0.5, s_drop=0.0, n_arm=A,
+                     lam=1, lam_pc=1, tau=0.005, beta=1.0, hard=False, variational=True, device=device, eps=1e-8,
+                     momentum=0.01, ref_prior=False, loss_mode="MSE").to(device)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     from oracle import mixvae_oracle as O
+    gen = torch.Generator().manual_seed(546)
+    batches = [O.synth_x(B, D, gen, w["density"]).to(device) for _ in range(2)]
+    model.train()
+    on_gpu = str(device) != "cpu"
+
+    def one(i):
+        x = batches[i % 2]
+        xs = x.expand(A, -1, -1)
+        opt.zero_grad()
+        x_recs, _, _, _, cs, _, c_smps, s_means, s_logvars, _ = model(xs, 1.0, 0.0)
+        _loss, _loss_rec, _loss_joint, _c_ent, _c_dist, _c_l2, _, _, _ = model.loss(x_recs, [], [], xs, s_means, s_logvars, cs,
+                                                                                     c_smps, 0.0)
+        _loss.backward()
+        opt.step()
+        if readbacks:
+            _loss.item()
+            for a in range(A):
+                cs[a].cpu().detach().numpy()
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(warmup):
+            one(i)
+        if on_gpu:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        done = 0
+        for i in range(steps):
+            one(i)
+            done += 1
+            if time.perf_counter() - t0 > max_seconds:
+                break
+        if on_gpu:
+            torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return dt / done, done
+
+
+def cpu_reference(w, steps, warmup, max_seconds=25.0):
+    """The reference's CPU path on all host cores, on a bounded sample of the workload (full batches, `steps` steps or
+    `max_seconds`): the unmodified reference when baseline/_ref is present (kind "reference"), else its oracle port."""
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
+    RefModel = load_reference_model()
+    if RefModel is not None:
+        sps, done = reference_step_loop(RefModel, w, "cpu", steps, warmup, readbacks=True, max_seconds=max_seconds)
+        return {"value": w["B"] / sps, "unit": "cells/s", "cores": cores, "kind": "reference",
+                "sample": f"{done} full steps of the same workload (B={w['B']}, D={w['D']}, A={w['A']}) through the unmodified "
+                          f"mmidas.nn_model.mixVAE_model + torch.optim.Adam incl. its RNG and per-step read-backs, fp32, torch "
+                          f"{torch.__version__} CPU, {sps * 1e3:.1f} ms/step"}, sps
+    from oracle import mixvae_oracle as O
     hp = O.HP(input_dim=w["D"], n_categories=w["C"], state_dim=w["S"], n_arm=w["A"], x_drop=0.5, s_drop=0.0)
     gen = torch.Generator().manual_seed(546)
-    x = O.synth_x(w["B"], w["D"], gen, w["density"]).to(device)
-    st = O.TrainState(hp, {k: v.to(device) for k, v in O.init_state_dict(hp, 546).items()})
+    x = O.synth_x(w["B"], w["D"], gen, w["density"])
+    st = O.TrainState(hp, O.init_state_dict(hp, 546))
     xs = [x] * hp.n_arm
-    noise = {k: (v.to(device) if torch.is_tensor(v) else [t.to(device) for t in v])
-             for k, v in O.synth_noise(hp, w["B"], gen).items()}
-    on_gpu = device != "cpu"
+    noise = O.synth_noise(hp, w["B"], gen)
     for _ in range(max(1, warmup)):
         O.train_step(st, xs, noise)
-    if on_gpu:
-        torch.cuda.synchronize()
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
-        out = O.train_step(st, xs, noise)
-        if on_gpu:
-            float(out["loss"]["total"].item())           # cpl_mixvae.py:469
+        O.train_step(st, xs, noise)
         done += 1
         if time.perf_counter() - t0 > max_seconds:
             break
-    if on_gpu:
-        torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    where = f"torch {torch.__version__} eager on {torch.cuda.get_device_name(0)}" if on_gpu else f"torch {torch.__version__} CPU"
     return {"value": w["B"] * done / dt, "unit": "cells/s", "cores": cores, "kind": "port",
-            "sample": f"{done} full steps of the same workload (B={w['B']}, D={w['D']}, A={w['A']}), fp32, "
-                      f"{where}, {dt / done * 1e3:.1f} ms/step"}, dt / done
+            "sample": f"{done} full steps of the same workload (B={w['B']}, D={w['D']}, A={w['A']}) through the oracle port "
+                      f"(baseline/_ref absent), noise precomputed, fp32, torch {torch.__version__} CPU, {dt / done * 1e3:.1f} ms/step"}, dt / done
 
 
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(args.steps, 20)
-    cb, ms = cpu_reference(w, steps, min(args.warmup, 2), max_seconds=60.0, device=args.ref_device)
+    cb, sps = cpu_reference(w, args.steps, args.warmup, max_seconds=150.0)
     line = {"impl": "reference", "metric": "train cells/sec", "value": cb["value"], "unit": "cells/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": ms * 1e3,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "note": "reference algorithm (oracle port of mmidas/nn_model.py + "
-                       "torch Adam) on the host CPU cores; the reference has no runnable multi-GPU path"},
+            "config": {"workload": w["desc"]},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "cells/s", "h2d_bytes_per_step": 0,
                                         "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+def reference_gpu(w, dev):
+    """The north star's denominator: the unmodified reference classes on this B200 (eager, fp32, TF32 off as on the
+    reference's single-GPU path — allow_tf32 is only set under ws > 1, mmidas/_dist_utils.py:30-40)."""
+    RefModel = load_reference_model()
+    if RefModel is None:
+        return {"unavailable": "baseline/_ref is absent (run baseline/install_ref.py in the build container)"}
+    out = {}
+    for key, rb, tf in (("with_readbacks", True, False), ("without_readbacks", False, False), ("tf32_allowed", True, True)):
+        sps, done = reference_step_loop(RefModel, w, dev, 10, 3, readbacks=rb, max_seconds=30.0, allow_tf32=tf)
+        out[key] = {"cells_per_s": w["B"] / sps, "ms_per_step": sps * 1e3, "steps": done}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out["note"] = ("unmodified mmidas.nn_model.mixVAE_model + torch.optim.Adam (foreach) from baseline/_ref, eager, RNG included, "
+                   "x resident on the device; with_readbacks = cpl_mixvae.py:469 (_loss.item()) and :476 (to_np(cs[a])) every step")
+    return out
+
+
 # -------------------------------------------------------------------------------------------------
+def time_steps(step_fn, batches, steps, warmup, dev, group=None):
+    """W untimed + K timed steps on the device (CUDA events on the launching stream), barrier + synchronize on both
+    sides, MAX over the ranks of `group`.  Returns (ms total, last loss vector)."""
+    import torch.distributed as dist
+
+    def sync():
+        if group is not None:
+            dist.barrier(group=group)
+        torch.cuda.synchronize()
+    lv = None
+    for i in range(warmup):
+        lv = step_fn(batches[i % len(batches)])
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for i in range(steps):
+        lv = step_fn(batches[i % len(batches)])
+    e1.record()
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if group is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item()), lv
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -186,23 +331,25 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--precision", default="tf32x3_fc1", choices=["tf32x3_fc1", "tf32x3", "tf32", "fp32_simt"])
     ap.add_argument("--mesh", default="dp", choices=["dp", "arm", "auto"])
-    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
-                    help="--impl reference only: cpu (the contract) or cuda (informational: eager torch on the GPU)")
     ap.add_argument("--augment", default="off", choices=["off", "tf32x3", "tf32"],
                     help="single GPU only: run the VAE-GAN augmenter forward (SURVEY f1, production default "
                          "--augmentation True) in front of every step, random-init weights; adds an `augmenter` object")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA-graph replay)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w)
         return
+    args.warmup = max(args.warmup, 5)          # >= 3 by contract; 5 so that every rotating batch has its graph before t0
 
     import torch.distributed as dist
     from mmidas_b200 import FusedAdam, _lib, mixVAE_model
     from mmidas_b200.cpl_mixvae import HostBatchFeeder, cpl_mixVAE
+    from mmidas_b200.dataloader import PackedBatch, ResidentLoader
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -215,15 +362,18 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     A, B, D, C, S = w["A"], w["B"], w["D"], w["C"], w["S"]
-    model_kwargs = dict(input_dim=D, fc_dim=100, n_categories=C, state_dim=S, lowD_dim=10, x_drop=0.5, s_drop=0.0,
-                        n_arm=A, lam=1, lam_pc=1, tau=0.005, beta=1.0, hard=False, variational=True, device=dev,
-                        eps=1e-8, momentum=0.01, ref_prior=False, loss_mode="MSE", precision=args.precision)
+
+    def kwargs_for(n_arm):
+        return dict(input_dim=D, fc_dim=100, n_categories=C, state_dim=S, lowD_dim=10, x_drop=0.5, s_drop=0.0,
+                    n_arm=n_arm, lam=1, lam_pc=1, tau=0.005, beta=1.0, hard=False, variational=True, device=dev,
+                    eps=1e-8, momentum=0.01, ref_prior=False, loss_mode="MSE", precision=args.precision)
     gen = torch.Generator(device=dev).manual_seed(546 + rank)
     batches = [synth_x_device(B, D, w["density"], gen, dev) for _ in range(N_ROTATING_BATCHES)]
 
     if world == 1:
         trainer = cpl_mixVAE(saving_folder="", aug_file="", device=dev, save_flag=False)
         trainer.precision = args.precision
+        trainer.use_cuda_graph = not args.no_graph
         torch.manual_seed(546)
         trainer.init_model(n_categories=C, state_dim=S, input_dim=D, x_drop=0.5, s_drop=0.0, n_arm=A)
         trainer.model.train()
@@ -241,7 +391,7 @@ def main():
             trainer.netA = netA.to(dev).eval()
     else:
         from mmidas_b200.parallel import ShardedTrainer
-        st = ShardedTrainer(model_kwargs, lr=1e-3, mode=args.mesh)
+        st = ShardedTrainer(kwargs_for(A), lr=1e-3, mode=args.mesh, use_cuda_graph=not args.no_graph)
         step_fn = st.step
         parallelism = f"mesh arm{st.plan.arm_ranks} x dp{st.plan.dp_ranks}, NCCL"
         dp_ranks = st.plan.dp_ranks          # ranks of one arm group see the SAME cells: count them once
@@ -249,50 +399,48 @@ def main():
             # every rank of an arm group must be fed the same batch
             gen = torch.Generator(device=dev).manual_seed(546 + rank // st.plan.arm_ranks)
             batches = [synth_x_device(B, D, w["density"], gen, dev) for _ in range(N_ROTATING_BATCHES)]
-
-    def sync():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    grp = dist.group.WORLD if world > 1 else None
 
     # ---- device-resident throughput --------------------------------------------------------------
-    for i in range(args.warmup):
-        lv = step_fn(batches[i % N_ROTATING_BATCHES])
-    sync()
     sampler = ClockSampler(local_rank)
+    for i in range(args.warmup):               # (also captures the graphs: outside the sampled / timed region)
+        step_fn(batches[i % N_ROTATING_BATCHES])
+    torch.cuda.synchronize()
     if rank == 0:
         sampler.start()
     n0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync()
-    e0.record()
-    for i in range(args.steps):
-        lv = step_fn(batches[i % N_ROTATING_BATCHES])
-    e1.record()
-    sync()
-    ms = e0.elapsed_time(e1)
+    ms, lv = time_steps(step_fn, batches, args.steps, 0, dev, grp)
     launches = _lib.launch_count() - n0
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     last_loss = float(lv[0].item())
     if not (last_loss == last_loss) or abs(last_loss) == float("inf"):
         raise SystemExit(f"non-finite loss {last_loss}")
     ms_per_step = ms / args.steps
     value = dp_ranks * B * args.steps / (ms / 1e3)
 
-    # ---- per-kernel-group device time (CUDA events inside the library, on the launching stream) --
+    # ---- per-kernel-group device time (CUDA events inside the library, on the launching stream; eager launches) --
     roofline = None
-    groups = None
     if rank == 0:
         peak, peak_src = measured_peak()
+    if world == 1:
+        trainer.use_cuda_graph = False
+        eager_fn = trainer.train_batch
+    else:
+        st.use_cuda_graph = False
+        eager_fn = st.step
+    for i in range(2):
+        eager_fn(batches[i % N_ROTATING_BATCHES])
+    torch.cuda.synchronize()
     _lib.timing_enable(True)
     for i in range(args.steps):
-        step_fn(batches[i % N_ROTATING_BATCHES])
+        eager_fn(batches[i % N_ROTATING_BATCHES])
     torch.cuda.synchronize()
     tim = _lib.timing_read()
     _lib.timing_enable(False)
+    ms_eager, _ = time_steps(eager_fn, batches, args.steps, 1, dev, grp)
+    if world == 1:
+        trainer.use_cuda_graph = not args.no_graph
+    else:
+        st.use_cuda_graph = not args.no_graph
     if rank == 0:
         groups = {g: {"ms_per_step": v[0] / args.steps, "spans": v[1]} for g, v in tim.items() if v[1]}
         gbytes = {"fc1_fwd": A * 4 * B * D, "fc11_loss_grad": A * 8 * B * D, "fc1_wgrad": A * 4 * B * D,
@@ -306,13 +454,23 @@ def main():
             except Exception:
                 traffic = None
         ach = gbytes[dom] / (groups[dom]["ms_per_step"] / 1e3) / 1e9
+        tf32_peak = measure_tf32_peak(dev)
+        tflops = tensor_flops(w, args.precision)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": gbytes[dom],
                     "step": {"algorithmic_bytes": algorithmic_bytes(w),
                              "achieved": algorithmic_bytes(w) / (ms_per_step / 1e3) / 1e9,
-                             "frac": algorithmic_bytes(w) / (ms_per_step / 1e3) / 1e9 / peak},
-                    "groups_ms_per_step": {g: round(v["ms_per_step"], 4) for g, v in groups.items()}}
+                             "frac": algorithmic_bytes(w) / (ms_per_step / 1e3) / 1e9 / peak,
+                             "hbm_floor_ms": algorithmic_bytes(w) / (peak * 1e9) * 1e3},
+                    "tensor": {"issued_tf32_flops_per_step": tflops, "achieved_tflops": tflops / (ms_per_step / 1e3) / 1e12,
+                               "peak_tflops": tf32_peak, "peak_source": "cuBLAS TF32 GEMM 8192^3 timed in this run (best of 10)",
+                               "frac": tflops / (ms_per_step / 1e3) / 1e12 / tf32_peak,
+                               "tensor_floor_ms": tflops / (tf32_peak * 1e12) * 1e3,
+                               "note": "gene GEMMs incl. the x_hat recompute of the fc11 gene pass and the 3 products of "
+                                       "error-compensated fc1; the step is bound by max(HBM floor, tensor floor)"},
+                    "groups_ms_per_step": {g: round(v["ms_per_step"], 4) for g, v in groups.items()},
+                    "ms_per_step_eager_launches": ms_eager / args.steps}
 
     # ---- the augmenter forward alone (when enabled): device time and achieved tensor throughput ----
     aug = None
@@ -334,71 +492,136 @@ def main():
         a1.record()
         torch.cuda.synchronize()
         ams = a0.elapsed_time(a1) / args.steps
-        aug_cpu = None
-        if not args.no_cpu_baseline:
-            # the reference's own path for this row on the host cores: the oracle restatement of Augmenter_smartseq.forward
-            # (eval mode, pinned to the reference class by tests/test_augmenter_oracle.py) on a bounded sample of the cells
-            from oracle import augmenter_oracle as AO
-            cores = len(os.sched_getaffinity(0))
-            torch.set_num_threads(cores)
-            Bs = min(B, 500)
-            sd_cpu = {k: v.detach().cpu() for k, v in netA.state_dict().items()}
-            xc = batches[0][:Bs].cpu().expand(A, -1, -1)
-            zc, ec = torch.randn(A, Bs, nz), torch.randn(A, Bs, nl)
-            with torch.no_grad():
-                AO.forward(sd_cpu, xc, zc, ec, 0.1)
-                t0 = time.perf_counter()
-                reps = 0
-                while reps < 5 and time.perf_counter() - t0 < 15.0:
-                    AO.forward(sd_cpu, xc, zc, ec, 0.1)
-                    reps += 1
-            dtc = (time.perf_counter() - t0) / reps
-            aug_cpu = {"value": Bs / dtc, "unit": "cells/s", "cores": cores, "kind": "port",
-                       "sample": f"{reps} forwards of {Bs} cells x {A} arms (fp32 torch CPU, {dtc * 1e3:.0f} ms each; the reference "
-                                 "evaluates fc1..fc4 per arm)"}
         aug = {"ms_per_step": ams, "precision": args.augment, "gflop_per_step": flops / 1e9, "cells_per_s": B / (ams / 1e3),
-               "cpu_baseline": aug_cpu,
                "achieved_tflops": flops / (ams / 1e3) / 1e12, "launches_per_step": (_lib.launch_count() - l0) / args.steps,
                "note": "Augmenter_smartseq eval forward (udagan.py:285-329), x.expand over arms: fc1..fc4 evaluated once per cell; "
                        "3xTF32 issues 3 MMAs per product (achieved_tflops counts the fp32-equivalent product once)"}
 
-    # ---- end to end: pinned host batches -> H2D -> step -> loss read-back -------------------------
+    # ---- end to end: pinned host batches -> H2D -> step -> loss read-back, n copies for n steps ------
     e2e = None
     if not args.no_e2e:
-        host = [b.cpu().pin_memory() for b in batches]
+        host_dense = [b.cpu().pin_memory() for b in batches]
+        host_packed = [PackedBatch(b.cpu()) for b in batches]
         n_e2e = args.steps
 
-        def host_iter():
-            for i in range(args.warmup + n_e2e):
-                yield host[i % N_ROTATING_BATCHES]
-        feeder = HostBatchFeeder(host_iter(), dev)
-        it = iter(feeder)
-        for _ in range(args.warmup):
-            xd, _ = next(it)
-            float(step_fn(xd)[0].item())
-        sync()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            xd, _ = next(it)
-            lv = step_fn(xd)
-            float(lv[0].item())                     # D2H of the step's loss, every step
-        sync()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": dp_ranks * B * n_e2e / dt, "unit": "cells/s", "h2d_bytes_per_step": B * D * 4,
-               "d2h_bytes_per_step": 4, "ms_per_step": dt / n_e2e * 1e3,
-               "h2d_gbs_per_gpu": B * D * 4 / (dt / n_e2e) / 1e9,   # ~56 GB/s = the PCIe ceiling: e2e is copy-bound
-               "api": "cpl_mixVAE.train_batch via HostBatchFeeder (pinned host batch -> side-stream H2D -> fused step -> loss.item())"}
+        def e2e_run(host, label):
+            def it(n):
+                for i in range(n):
+                    yield host[i % N_ROTATING_BATCHES]
+            # every step's loss is read back on the host: an async 4-byte copy into pinned memory + an event per step, waited
+            # for after the NEXT step has been enqueued, so the device never idles on the host's read
+            pin = torch.zeros(2, 1).pin_memory()
+            evs = [torch.cuda.Event(), torch.cuda.Event()]
+            seen = []
 
-    # the sampler ran from before the timed region through the per-group and end-to-end passes (the same steps, same load):
-    # a 20 ms timed region alone would see a single 200 ms sample
+            def run(n):
+                feeder = HostBatchFeeder(it(n), dev)                    # (timed call: the first copy starts inside the region)
+                k = 0
+                for xd, _ in feeder:
+                    lv = step_fn(xd)
+                    pin[k & 1].copy_(lv[0:1], non_blocking=True)        # D2H of the step's loss, every step
+                    evs[k & 1].record()
+                    if k > 0:
+                        evs[(k - 1) & 1].synchronize()
+                        seen.append(float(pin[(k - 1) & 1]))
+                    k += 1
+                evs[(k - 1) & 1].synchronize()
+                seen.append(float(pin[(k - 1) & 1]))
+                return feeder
+            run(args.warmup)                                            # warm-up: ring buffers, graphs for their pointers
+            if grp is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            seen.clear()
+            t0 = time.perf_counter()
+            feeder = run(n_e2e)
+            torch.cuda.synchronize()
+            if grp is not None:
+                dist.barrier()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            assert feeder.batches_copied == n_e2e and len(seen) == n_e2e and all(v == v for v in seen)
+            bps = feeder.h2d_bytes / n_e2e
+            return {"value": dp_ranks * B * n_e2e / dt, "unit": "cells/s", "h2d_bytes_per_step": int(bps), "d2h_bytes_per_step": 4,
+                    "ms_per_step": dt / n_e2e * 1e3, "h2d_gbs_per_gpu": bps / (dt / n_e2e) / 1e9, "host_batch": label}
+        e2e = e2e_run(host_packed, "row-packed (bitmap + non-zero fp32 values + row offsets, pinned), expanded bit-exactly on the "
+                                   "device by mvae_unpack_rows on the copy stream")
+        e2e["api"] = ("cpl_mixVAE.train_batch / ShardedTrainer.step fed by HostBatchFeeder (pinned host batch -> side-stream H2D -> "
+                      "graph-replayed fused step -> loss read back every step through pinned memory, one step behind the launches); "
+                      "n copies timed for n steps")
+        e2e["dense"] = e2e_run(host_dense, "dense fp32 [B, D], pinned")
+        if world == 1:
+            # the device-resident loader: the data set lives in HBM, only shuffled indices cross PCIe
+            n_cells = 4 * B
+            xs_all = torch.cat(batches[:4]).cpu()
+            loader = ResidentLoader(xs_all, torch.arange(n_cells, dtype=torch.float32), batch_size=B, device=dev, reuse_buffers=True)
+            for x, _ in loader:
+                float(step_fn(x)[0].item())
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            done = 0
+            while done < n_e2e:
+                for x, _ in loader:
+                    float(step_fn(x)[0].item())
+                    done += 1
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            e2e["resident"] = {"value": B * done / dt, "unit": "cells/s", "ms_per_step": dt / done * 1e3,
+                               "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4,
+                               "api": "ResidentLoader (DataLoader permutation stream, data set resident in HBM) -> train_batch -> loss.item()"}
+        del host_dense, host_packed
+
+    # ---- BASELINE configs[2] / configs[3] on the meshes the north star names ---------------------
+    extra = None
+    if world in (4, 8) and not args.no_extra and args.workload == "cfg2":
+        from mmidas_b200.parallel import ShardedTrainer
+        extra = {}
+        name, An, mode, ranks = ("cfg3", 3, "arm", [0, 1, 2]) if world == 4 else ("cfg4", 5, "dp", list(range(8)))
+        wx = WORKLOADS["a3" if An == 3 else "a5"]
+        stx = ShardedTrainer(kwargs_for(An), lr=1e-3, mode=mode, ranks=ranks, use_cuda_graph=not args.no_graph)
+        res = None
+        if stx.active:
+            rep = stx.dp_coord
+            g2 = torch.Generator(device=dev).manual_seed(900 + rep)
+            xb = [synth_x_device(B, D, w["density"], g2, dev) for _ in range(N_ROTATING_BATCHES)]
+            msx, lvx = time_steps(stx.step, xb, args.steps, args.warmup, dev, stx.mesh_group)
+            # the same per-GPU work without any collective: the local arms alone on this GPU
+            torch.manual_seed(546)
+            a_loc = stx.model.n_arm
+            solo = None
+            if a_loc >= 2:
+                m1 = mixVAE_model(**kwargs_for(a_loc)).to(dev)
+                o1 = FusedAdam(m1.parameters(), lr=1e-3, model=m1)
+                m1.train()
+                ms1, _ = time_steps(lambda x: m1.fused_train_step(x.expand(a_loc, -1, -1), 1.0, o1), xb, args.steps, args.warmup, dev,
+                                    stx.mesh_group)
+                solo = ms1 / args.steps
+                del m1, o1
+            per_gpu_bytes = algorithmic_bytes(wx, A=a_loc)
+            res = {"workload": wx["desc"], "mesh": f"arm{stx.plan.arm_ranks} x dp{stx.plan.dp_ranks} on ranks {ranks}",
+                   "ms_per_step": msx / args.steps, "cells_per_s": stx.plan.dp_ranks * B * args.steps / (msx / 1e3),
+                   "step_roofline_frac": per_gpu_bytes / (msx / args.steps / 1e3) / 1e9 / measured_peak()[0],
+                   "ms_per_step_local_arms_no_collective": solo,
+                   "collective_exposed_ms": (msx / args.steps - solo) if solo is not None else None,
+                   "collectives": ("all-gather of q(c|x) and the samples over the arm axis (2 x 2 MB per arm), all-reduce of 3A "
+                                   "loss scalars" if mode == "arm" else f"all-reduce (AVG) of the {An}-arm flat gradient buffer "
+                                   f"({An * 4.31:.1f} MB) over 8 ranks"),
+                   "last_total_loss": float(lvx[0].item())}
+        del stx
+        if rank == 0:
+            extra[name] = res
+
     clocks = sampler.stop() if rank == 0 else None
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base, _ = cpu_reference(w, 20, 2)
+    ref_gpu = None
+    if rank == 0 and world == 1:
+        if not args.no_reference_gpu:
+            ref_gpu = reference_gpu(w, dev)
+        if not args.no_cpu_baseline:
+            cpu_base, _ = cpu_reference(w, 20, 2)
 
     if rank == 0:
         line = {"metric": "train cells/sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
@@ -410,15 +633,18 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": w["desc"], "cells_per_step_per_gpu": B, "parallelism": parallelism,
                            "precision": args.precision, "dropout": "x_drop=0.5 in-kernel counter-based generator",
+                           "launch": "eager" if args.no_graph else "one CUDA-graph replay per step (graphs captured during warm-up)",
                            "l2": f"inputs rotate over {N_ROTATING_BATCHES} distinct batches "
                                  f"({N_ROTATING_BATCHES * B * D * 4 / 1e6:.0f} MB > 126 MB L2)",
                            "last_total_loss": last_loss,
                            **({"augmenter": f"Augmenter_smartseq forward ({args.augment}) in front of every step"} if aug else {})},
                 **({"augmenter": aug} if aug else {}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu_base}
+                "cpu_baseline": cpu_base, "reference_gpu": ref_gpu, **({"extra": extra} if extra else {})}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

@@ -79,16 +79,6 @@ static BnOff bn_off(const Plan& p) {
     if (_rc) return _rc; \
   } while (0)
 
-// MVAE_LEGACY_FC1=1 keeps the round-1 split-K SS kernels for fc1 (A/B comparisons)
-static bool legacy_fc1() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MVAE_LEGACY_FC1");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
 static bool use_tc(const Plan& p, const mvae_hparams& hp) {
   return hp.precision != 3 && gemm_tc_supported(p.B, p.D, p.H);
 }
@@ -117,11 +107,9 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   Fc1EpiArgs epi;
   memset(&epi, 0, sizeof(epi));
   timing_begin(TG_FC1_FWD, s);
-  const bool ts_path = use_tc(p, hp) && !legacy_fc1();
+  const bool ts_path = use_tc(p, hp);
   if (ts_path) {
     RC(ts_fc1_forward(p.d, hp, st, in, drop, w, work + w.a[0], acc_fwd + acc_bn(0, A, 0), s));
-  } else if (use_tc(p, hp)) {
-    RC(tc_fc1_forward(p.d, hp, st, in, drop, w, s, &epi));
   } else {
     GemmArgs g;
     memset(&g, 0, sizeof(g));
@@ -141,7 +129,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
 
   // ---- fc2..fc5 with the BatchNorm of the previous layer folded into the load (:265-268)
   int chain_rc = 1;
-  if (training && hp.precision != 3 && !legacy_fc1()) {
+  if (training && hp.precision != 3) {
     float* aout[4] = {work + w.a[1], work + w.a[2], work + w.a[3], work + w.a[4]};
     chain_rc = launch_enc_chain_fwd(st.params, p.L.arm_stride, p.L.offset, A, B, H, Ld, work + w.a[0], aout, acc_fwd, bn_mean,
                                     bn_rstd, hp.eps, s);
@@ -212,8 +200,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
 
   // ---- optional materialised reconstruction x_rec = relu(fc11(h10)) (:287)
   if (out.x_rec && use_tc(p, hp) && hp.precision != 1) {
-    if (legacy_gene_kernels()) RC(tc_fc11_rows(p.d, st, in, w, 0.f, 0, nullptr, out.x_rec, nullptr, s));
-    else RC(ts_fc11_rows(p.d, st, in, w, 0.f, 0, out.x_rec, nullptr, s));
+    RC(ts_fc11_rows(p.d, st, in, w, 0.f, 0, out.x_rec, nullptr, s));
   } else if (out.x_rec) {
     GemmArgs g;
     memset(&g, 0, sizeof(g));
@@ -254,7 +241,7 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
   memset(&c, 0, sizeof(c));
   c.A = A; c.At = At; c.arm_off = p.d.arm_offset; c.B = B; c.C = C;
   c.qc_all = qc_all; c.csmp_all = csmp_all; c.acc = acc_loss;
-  c.rsum = work + w.rsum; c.wcat = work + w.wcat; c.eps = hp.eps; c.lam = hp.lam;
+  c.gdiff = work + w.rsum; c.wcat = work + w.wcat; c.eps = hp.eps; c.lam = hp.lam;
   RC(launch_qstats(c, s));
   RC(launch_coupling_rows(c, s));
   timing_end(TG_COUPLING, s);
@@ -359,7 +346,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   h.x_low = out.x_low; h.c_prob = out.c_prob; h.qc = out.qc; h.c_smp = out.c_smp;
   h.s_mean = out.s_mean; h.s_logvar = out.s_logvar; h.s_smp = out.s_smp;
   h.ysoft = work + w.ysoft; h.svar = work + w.svar; h.yy = work + w.yy; h.zc = work + w.zc; h.d6 = work + w.d[0];
-  h.g_d6 = g_cur; h.rsum = work + w.rsum; h.colc = work + w.colc;
+  h.g_d6 = g_cur; h.gdiff = work + w.rsum; h.colc = work + w.colc;
   const float scale = (float)(At - 1 > 1 ? At - 1 : 1);
   h.kl_coef = scale * hp.beta / (float)B;
   h.ent_coef = (float)(At - 1) / (float)B;
@@ -372,7 +359,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   // ---- encoder fc5..fc2, then the BatchNorm+ReLU backward of layer 1
   g_cur = work + w.g_xlow;
   int bchain_rc = 1;
-  if (hp.precision != 3 && !legacy_fc1()) {
+  if (hp.precision != 3) {
     const float* act[5] = {work + w.a[0], work + w.a[1], work + w.a[2], work + w.a[3], work + w.a[4]};
     float* dl[5] = {work + w.delta_enc[0], work + w.delta_enc[1], work + w.delta_enc[2], work + w.delta_enc[3],
                     work + w.delta_enc[4]};
@@ -433,7 +420,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   // ---- d fc1.weight = delta1^T * dropout(x)
   DropSpec drop = make_drop(p, hp, st, in);
   timing_begin(TG_FC1_WGRAD, s);
-  if (tc && hp.precision != 1 && !legacy_fc1()) {
+  if (tc && hp.precision != 1) {
     RC(ts_fc1_wgrad(p.d, st, in, drop, w, s));
   } else if (tc) {
     RC(tc_fc1_wgrad(p.d, hp, st, in, drop, w, s));
@@ -550,7 +537,7 @@ int mvae_confmat(const int32_t* labels, int64_t n_cells, int32_t n_arm, int32_t 
 
 int mvae_unpack_rows(const uint32_t* bitmap, const float* values, const int64_t* row_ptr, int64_t rows, int32_t n_cols,
                      float* out, int64_t out_row_stride, void* stream) {
-  MVAE_CHECK_ARG(bitmap && values && row_ptr && out, "null argument");
+  MVAE_CHECK_ARG(bitmap && row_ptr && out, "null argument");     // values may be null when the batch has no non-zero
   MVAE_CHECK_ARG(rows >= 0 && n_cols >= 1 && out_row_stride >= n_cols, "bad shape");
   RC(check_device());
   return launch_unpack_rows(bitmap, values, row_ptr, rows, n_cols, out, out_row_stride, (cudaStream_t)stream);

@@ -88,7 +88,7 @@ struct Work {
   int64_t delta1_t;    // [A][Hpad128][Bpad]  delta1 transposed (tensor-core fc1 dW operand)
   int64_t d10_t;       // [A][Hpad128][Bpad]  h10 transposed     (tensor-core fc11 dW operand)
   int64_t w11_t;       // [A][Hpad128][Dpad]  fc11.weight transposed (tensor-core d h10 operand)
-  int64_t rsum;        // [B][C]  sum over ALL arms of r = log(q+eps)*w
+  int64_t rsum;        // [A][B][C]  Gd_a = sum over all arms b of (r_a - r_b), r = log(q+eps)*w
   int64_t colc;        // [A][4][128]  per category: w, cvar, mean, T   (coupling-gradient constants)
   int64_t wcat;        // [At][128]    w of every arm of the model
   int64_t fc1_part;    // [splitk][A][B][Hpad] split-K partials of fc1 (tensor-core path)

@@ -880,16 +880,6 @@ int tc_narrow_wgrad(WgArgs& a, const int* idx, int n, int split3, cudaStream_t s
   return 0;
 }
 
-static bool legacy_fc11() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MVAE_LEGACY_FC11");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-bool legacy_gene_kernels() { return legacy_fc11(); }
-
 bool gemm_tc_supported(int B, int D, int H) {
   // TMA needs 16-byte aligned row pitches: D % 4 == 0 (x, W1 rows) and H % 4 == 0 (h10, W11, delta1 rows)
   return D % 4 == 0 && H % 4 == 0 && H <= 128 && get_encode() != nullptr;
@@ -898,26 +888,6 @@ bool gemm_tc_supported(int B, int D, int H) {
 int tc_part_floats(int A, int Bpad, int Dpad) {
   int64_t a = (int64_t)4 * A * Bpad * 128, b = (int64_t)2 * A * Dpad * 128;
   return (int)(a > b ? a : b);
-}
-
-int tc_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
-                   const DropSpec& drop, const Work& w, cudaStream_t s, Fc1EpiArgs* epi) {
-  mvae_layout L;
-  compute_layout(d, &L);
-  const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
-  const int BN = round16(H);
-  Operand x{in.x, in.x_row_stride, in.x_arm_stride, false};
-  Operand W1{st.params + L.offset[FC1_W], D, L.arm_stride, false};
-  int flags = (hp.precision == 2) ? 0 : (F_SPLIT_A | F_SPLIT_B);
-  if (drop.mode) flags |= F_DROP_A;
-  const int mt = (B + BM - 1) / BM;
-  const int nsplit = choose_split(mt * A, (D + BK - 1) / BK, w.fc1_splitk);
-  float* part = st.work + w.fc1_part;
-  const int64_t batch_stride = (int64_t)w.Bpad * 128, split_stride = (int64_t)A * batch_stride;
-  int rc = run_tc_gemm(x, W1, B, H, D, BN, A, nsplit, flags, drop, part, 128, batch_stride, split_stride, s);
-  if (rc) return rc;
-  epi->part = part; epi->split_stride = split_stride; epi->arm_stride = batch_stride; epi->ld = 128; epi->nsplit = nsplit;
-  return 0;
 }
 
 // every gene GEMM as 3xTF32 (precision == 1): separate GEMMs around a materialised x_hat / dY
@@ -986,14 +956,9 @@ int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_sta
   memset(&nodrop, 0, sizeof(nodrop));
   if (hp.precision == 1) return tc_fc11_loss_grad_unfused(d, hp, st, in, w, gscale, want_grad, s);
   // fused passes: row owner (x_hat, loss sums, d h10), then gene owner (d fc11.weight, d fc11.bias)
-  if (!legacy_fc11()) {
-    int rc = ts_fc11_rows(d, st, in, w, gscale, want_grad, nullptr, acc_loss, s);
-    if (rc || !want_grad) return rc;
-    return ts_fc11_genes(d, st, in, w, gscale, s);
-  }
-  int rc = tc_fc11_rows(d, st, in, w, gscale, want_grad, nullptr, nullptr, acc_loss, s);
+  int rc = ts_fc11_rows(d, st, in, w, gscale, want_grad, nullptr, acc_loss, s);
   if (rc || !want_grad) return rc;
-  return tc_fc11_genes(d, st, in, w, gscale, s);
+  return ts_fc11_genes(d, st, in, w, gscale, s);
 }
 
 int tc_fc1_wgrad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
@@ -1083,24 +1048,10 @@ int launch_fma_rows(const float* a, int64_t lda, const float* b, int64_t ldb, co
   MVAE_LAUNCH_CHECK();
   return 0;
 }
-static bool legacy_linear() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MVAE_LEGACY_LINEAR"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
 // y[rows][n_out] (pitch y_pitch) = act((x[rows][k] . w[n_out][k]^T) * scale + shift)
 int tc_linear_act(const float* x, int64_t x_pitch, const float* w, int64_t w_pitch, float* y, int64_t y_pitch, int64_t rows,
                   int n_out, int k, const float* scale, const float* shift, int act, int split3, cudaStream_t s) {
   int BN = n_out >= 128 ? 128 : round16(n_out);
-  if (legacy_linear()) {          // one tile per CTA (tc_gemm_kernel with the fused epilogue), kept for A/B comparisons
-    Operand a{x, x_pitch, 0, false};
-    Operand b{w, w_pitch, 0, false};
-    DropSpec nodrop;
-    memset(&nodrop, 0, sizeof(nodrop));
-    return run_tc_gemm(a, b, (int)rows, n_out, k, BN, 1, 1, split3 ? (F_SPLIT_A | F_SPLIT_B) : 0, nodrop, y, y_pitch, 0, 0, s, scale,
-                       shift, act);
-  }
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, x, k, rows, x_pitch, 1, 0, BM, false);
   if (rc) return rc;
@@ -1108,19 +1059,15 @@ int tc_linear_act(const float* x, int64_t x_pitch, const float* w, int64_t w_pit
   if (rc) return rc;
   // single-pass TF32 is bound by L2 -> shared-memory operand traffic: 256-column tiles move 24 KB instead of 32 KB per
   // 128 x 128 x 32 block of products (3xTF32 is MMA-issue-bound and its four tiles per stage leave no room for them)
-  static int wide_ok = -1;
-  if (wide_ok < 0) { const char* e = getenv("MVAE_LINEAR_BN256"); wide_ok = (e && e[0] == '0') ? 0 : 1; }
-  if (!split3 && wide_ok && n_out >= 384 && k >= 768) BN = 256;   // short-K layers are epilogue-bound: more, smaller tiles win there
+  if (!split3 && n_out >= 384 && k >= 768) BN = 256;   // short-K layers are epilogue-bound: more, smaller tiles win there
   LinArgs a;
   memset(&a, 0, sizeof(a));
   a.M = (int)rows; a.N = n_out; a.K = k; a.BN = BN;
-  static int ts_ok = -1;
-  if (ts_ok < 0) { const char* e = getenv("MVAE_LINEAR_TS"); ts_ok = (e && e[0] == '0') ? 0 : 1; }
-  a.split3 = split3 ? (ts_ok ? 2 : 1) : 0;      // 2: 3xTF32 with the activation halves in tensor memory (TS-form MMAs)
-  a.stages = split3 ? (ts_ok ? 4 : 3) : (BN > 128 ? 4 : 6);
+  a.split3 = split3 ? 2 : 0;                    // 2: 3xTF32 with the activation halves in tensor memory (TS-form MMAs)
+  a.stages = split3 ? 4 : (BN > 128 ? 4 : 6);
   a.tiles_m = (int)((rows + BM - 1) / BM); a.tiles_n = (n_out + BN - 1) / BN;
   a.C = y; a.ldc = y_pitch; a.scale = scale; a.shift = shift; a.act = act;
-  const size_t smem = (size_t)a.stages * (split3 ? (ts_ok ? 3 : 4) : (BN > 128 ? 3 : 2)) * TILE_BYTES + (3 * a.stages + 6) * 8 + 1024;
+  const size_t smem = (size_t)a.stages * (split3 ? 3 : (BN > 128 ? 3 : 2)) * TILE_BYTES + (3 * a.stages + 6) * 8 + 1024;
   static bool attr = false;
   if (!attr) {
     MVAE_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

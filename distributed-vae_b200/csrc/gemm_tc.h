@@ -9,20 +9,9 @@ namespace mvae {
 // true when the tensor-core kernels can run this shape (TMA needs 16-byte aligned row pitches)
 bool gemm_tc_supported(int B, int D, int H);
 
-// fc1 partial products into work.fc1_part; fills the split-K description of `epi`.
-int tc_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
-                   const DropSpec& drop, const Work& w, cudaStream_t s, Fc1EpiArgs* epi);
-
 // fc11 GEMM fused with the reconstruction loss and (want_grad) d fc11.weight / d fc11.bias / d h10.
 int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
                       const Work& w, float gscale, int want_grad, cudaStream_t s);
-
-// fc11_fused.cu: x_hat / reconstruction loss / dY / d h10 in one pass over x (dY_out, x_rec optional)
-int tc_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale,
-                 int want_grad, float* dY_out, float* x_rec, double* recon_acc, cudaStream_t s);
-
-int tc_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale,
-                  cudaStream_t s);
 
 // d fc1.weight = delta1^T * dropout(x)
 int tc_fc1_wgrad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
@@ -51,6 +40,5 @@ int launch_fma_rows(const float* a, int64_t lda, const float* b, int64_t ldb, co
                     int64_t rows, int n, float a_scale, cudaStream_t s);
 int tc_linear_act(const float* x, int64_t x_pitch, const float* w, int64_t w_pitch, float* y, int64_t y_pitch, int64_t rows,
                   int n_out, int k, const float* scale, const float* shift, int act, int split3, cudaStream_t s);
-bool legacy_gene_kernels();   // MVAE_LEGACY_FC1=1 / MVAE_LEGACY_FC11=1: round-1 first-generation kernels (A/B comparisons)
 
 }  // namespace mvae

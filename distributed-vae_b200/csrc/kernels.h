@@ -67,7 +67,7 @@ struct HeadArgs {
   float* bn_running; int64_t bn_stride; BnOff bn_off; int64_t* nbt; const double* bn_sums_all; float momentum;
   // backward-only
   const float* g_d6;          // [A][B][L]
-  const float* rsum;          // [B][C]
+  const float* gdiff;         // [A][B][C]  sum_b (r_a - r_b) of the local arms
   const float* colc;          // [A][4][128]  w, cvar, mean, T
   float kl_coef, ent_coef, g_coef;   // max(At-1,1)*beta/B, (At-1)/B, 2*lam/B
   float *delta6, *delta_mu, *delta_sig, *delta_z, *g_xlow;
@@ -82,7 +82,7 @@ struct CouplingArgs {
   const float* qc_all;    // [At][B][C]
   const float* csmp_all;  // [At][B][C]
   double* acc;            // acc_loss block
-  float* rsum;            // [B][C]
+  float* gdiff;           // [A][B][C]  sum_b (r_a - r_b) of the local arms, r = log(q+eps)*w
   float* wcat;            // [At][128]
   float eps, lam;
 };

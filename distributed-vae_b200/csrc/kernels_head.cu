@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_bwd_kernel(const HeadA
         const float qe = q[k] + p.eps;
         const float lq = logf(qe);
         const float rr = lq * cw[kk];
-        const float G = p.g_coef * (At * rr - p.rsum[(int64_t)row * C + kk]);
+        const float G = p.g_coef * p.gdiff[r * C + kk];             // sum_b (r_a - r_b), coupling_rows_kernel
         float g = dl / (p.temp * qe);
         g += G * cw[kk] / qe - cT[kk] * ccv[kk] * (q[k] - cmean[kk]);
         g += p.ent_coef * (lq + q[k] / qe);

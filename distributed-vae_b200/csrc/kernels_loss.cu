@@ -58,8 +58,11 @@ int launch_qstats(const CouplingArgs& a, cudaStream_t s) {
 
 // ---------------------------------------------------------------------------------------------
 // per cell: r_a = log(q_a+eps)*w_a, pairwise ||r_a-r_b||^2 and ||c_a-c_b||^2, per-arm entropy,
-// R = sum_a r_a, and for the local arms T_a[k] = sum_b G_a[b,k]*log(q_a[b,k]+eps),
-// G_a = (2 lam / B) (A r_a - R)   (gradient of the distance through inv_var)
+// and for the local arms Gd_a = sum_b (r_a - r_b) and T_a[k] = sum_cells G_a[cell,k]*log(q_a[cell,k]+eps),
+// G_a = (2 lam / B) Gd_a   (gradient of the distance through inv_var).
+// Gd_a is formed from differences against arm 0 (d_b = r_b - r_0, S = sum_b d_b, Gd_a = A d_a - S): categories that no
+// arm uses have r = log(eps) / sqrt(eps) ~ -1.8e5 in EVERY arm, and A r_a - sum_b r_b in fp32 would round at that
+// magnitude while the true difference is tiny (it showed up as 3e-4 relative error in the encoder gradients at A = 3).
 // ---------------------------------------------------------------------------------------------
 // ATC: compile-time number of arms (0: run-time); C96: n_categories > 96 (only the last category slot of a lane is guarded)
 template <int ATC, bool C96>
@@ -94,8 +97,8 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
 
   const float gcoef = 2.f * p.lam / (float)B;
   for (int row = blockIdx.x * kRowWarps + warp; row < B; row += gridDim.x * kRowWarps) {
-    float rs[KC] = {0.f, 0.f, 0.f, 0.f};
-    // pass 1: R = sum_a r_a ; entropy per arm
+    float r0[KC] = {0.f, 0.f, 0.f, 0.f}, rs[KC] = {0.f, 0.f, 0.f, 0.f};
+    // pass 1: r_0 and S = sum_b (r_b - r_0) ; entropy per arm
     for (int a = 0; a < At; ++a) {
       const float* q = p.qc_all + ((int64_t)a * B + row) * C;
       float ent = 0.f;
@@ -105,17 +108,14 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
         if (kk < C) {
           const float qv = q[kk];
           const float lq = logf(qv + p.eps);
-          rs[k] += lq * w[a][kk];
+          const float rv = lq * w[a][kk];
+          if (a == 0) r0[k] = rv;
+          else rs[k] += rv - r0[k];
           ent = fmaf(qv, lq, ent);
         }
       }
       ent = warp_sum(ent);
       if (lane == 0) atomicAdd(&sEnt[a], (double)ent);
-    }
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-      const int kk = lane + 32 * k;
-      if (kk < C) p.rsum[(int64_t)row * C + kk] = rs[k];
     }
     // pass 2: pairs and T (q rows are L1/L2 resident)
     int pair = 0;
@@ -133,8 +133,9 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
           ya[k] = ca[kk];
           const int la = a - p.arm_off;
           if (la >= 0 && la < p.A) {
-            const float G = gcoef * ((float)At * ra[k] - rs[k]);
-            sTw[(warp * p.A + la) * 128 + kk] += G * lq;   // a handful of rows per warp: fp32 here, fp64 across warps
+            const float Gd = (float)At * (ra[k] - r0[k]) - rs[k];
+            p.gdiff[((int64_t)la * B + row) * C + kk] = Gd;
+            sTw[(warp * p.A + la) * 128 + kk] += gcoef * Gd * lq;   // a handful of rows per warp: fp32 here, fp64 across warps
           }
         }
       }

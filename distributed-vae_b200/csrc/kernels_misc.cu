@@ -229,13 +229,16 @@ __global__ void __launch_bounds__(256) unpack_rows_kernel(const uint32_t* __rest
       const int excl = base + incl - cnt;
       base += __shfl_sync(0xffffffffu, incl, 31);
       const int nw = W - w0 < 32 ? W - w0 : 32;
-      for (int j = 0; j < nw; ++j) {
-        const uint32_t wj = __shfl_sync(0xffffffffu, word, j);
-        const int oj = __shfl_sync(0xffffffffu, excl, j);
-        const int col = (w0 + j) * 32 + lane;
-        float val = 0.f;
-        if ((wj >> lane) & 1u) val = v[oj + __popc(wj & below)];
-        if (col < D) o[col] = val;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        if (j < nw) {                 // (warp-uniform)
+          const uint32_t wj = __shfl_sync(0xffffffffu, word, j);
+          const int oj = __shfl_sync(0xffffffffu, excl, j);
+          const int col = (w0 + j) * 32 + lane;
+          float val = 0.f;
+          if ((wj >> lane) & 1u) val = __ldg(v + oj + __popc(wj & below));
+          if (col < D) o[col] = val;
+        }
       }
     }
   }

@@ -841,21 +841,9 @@ int launch_dense_bwd_mma(const DenseBwdArgs& a, int A, int split3, cudaStream_t 
   return 0;
 }
 
-static bool legacy_wgrad() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MVAE_LEGACY_WGRAD"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
-static bool no_tc_wgrad() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MVAE_NO_TC_WGRAD"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
 int launch_wgrad_mma(const WgArgs& a0, int split3, cudaStream_t s) {
   WgArgs a = a0;
-  bool fits = !legacy_wgrad();
+  bool fits = true;
   for (int i = 0; i < a.nprob; ++i) fits = fits && a.prob[i].nout <= 128 && a.prob[i].nin <= 127;
   if (fits) {
     // the wide problems (many MMA tiles per chunk of cells) run on tcgen05 when TMA can read their operands
@@ -863,7 +851,7 @@ int launch_wgrad_mma(const WgArgs& a0, int split3, cudaStream_t s) {
     bool on_tc[13];
     for (int i = 0; i < a.nprob; ++i) {
       const int tiles = ((a.prob[i].nout + 15) / 16) * ((a.prob[i].nin + 1 + 7) / 8);
-      on_tc[i] = !no_tc_wgrad() && tiles > 40 && ntc < 8 && tc_narrow_wgrad_ok(a, a.prob[i]);
+      on_tc[i] = tiles > 40 && ntc < 8 && tc_narrow_wgrad_ok(a, a.prob[i]);
       if (on_tc[i]) tc_idx[ntc++] = i;
     }
     if (ntc > 0) {

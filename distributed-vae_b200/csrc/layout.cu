@@ -122,7 +122,7 @@ Work make_work(const mvae_dims& d) {
   w.delta1_t = take(A * (int64_t)w.Hpad * w.Bpad);
   w.d10_t = take(A * (int64_t)w.Hpad * w.Bpad);
   w.w11_t = take(A * (int64_t)w.Hpad * w.Dpad);
-  w.rsum = take(B * C);
+  w.rsum = take(A * B * C);
   w.colc = take(A * 4 * 128);
   w.wcat = take(At * 128);
   w.fc1_splitk = 8;

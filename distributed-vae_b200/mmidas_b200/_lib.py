@@ -145,5 +145,20 @@ def timing_read():
     return {g: (float(ms[i]), int(cnt[i])) for i, g in enumerate(TIMING_GROUPS)}
 
 
+_replayed_launches = 0     # kernels run by CUDA-graph replays (the library's counter only sees launch CALLS)
+_captured_launches = 0     # launch calls that were recorded into a graph instead of running
+
+
+def note_capture(n: int):
+    global _captured_launches
+    _captured_launches += n
+
+
+def note_replay(n: int):
+    global _replayed_launches
+    _replayed_launches += n
+
+
 def launch_count() -> int:
-    return int(load().mvae_launch_count())
+    """Kernels of this library that ran on the device in this process: direct launches + graph replays."""
+    return int(load().mvae_launch_count()) - _captured_launches + _replayed_launches

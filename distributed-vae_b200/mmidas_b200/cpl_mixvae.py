@@ -38,15 +38,20 @@ class HostBatchFeeder:
     """Iterates over host batches and yields device tensors, copying batch i+1 on a side stream while batch i is being
     consumed (the reference does a blocking ``x.to(rank)`` at :416).
 
-    Batches land in a small ring of device staging buffers per batch shape, so consecutive steps see the same few
-    device pointers (what lets the trainer replay a captured CUDA graph).  Items may be dense CPU tensors (pinned on the
-    fly when they are not), tuples ``(x, idx)`` as a DataLoader yields, device tensors (passed through) or
-    ``PackedBatch`` objects, which cross PCIe in row-packed form and are expanded into the staging buffer on the copy
-    stream (bit-exact).  A buffer is refilled only after the work that read it was enqueued two ``next()`` calls ago
-    has finished (event edge to the copy stream).
+    Items may be dense CPU tensors (pinned on the fly when they are not), tuples ``(x, idx)`` as a DataLoader yields,
+    device tensors (passed through) or ``PackedBatch`` objects.  Dense batches land in a small ring of device buffers
+    per batch shape.  Packed batches cross PCIe in row-packed form into a ring of staging buffers and are expanded
+    (bit-exactly) on the COMPUTE stream right before they are handed out, into one dense buffer per shape: the copy
+    stream then carries nothing but the copy, which is what bounds an end-to-end step.  Either way consecutive steps
+    see the same few device pointers — what lets the trainer replay a captured CUDA graph.  A ring slot is refilled
+    only after the work that read it has finished (event edge to the copy stream).  Rings are pooled per
+    (device, shape) and handed from an exhausted feeder to the next one, so the pointers — and the graphs captured for
+    them — survive across epochs.
     """
 
-    def __init__(self, batches: Iterable, device, pin: bool = True, depth: int = 2):
+    _ring_pool = {}       # (device, kind, shape, depth) -> [ring, ...] not in use by a live feeder
+
+    def __init__(self, batches: Iterable, device, pin: bool = True, depth: int = 3):
         self.it = iter(batches)
         self.device = torch.device(device)
         self.pin = pin
@@ -54,19 +59,40 @@ class HostBatchFeeder:
         self.stream = torch.cuda.Stream(self.device)
         self.h2d_bytes = 0
         self.batches_copied = 0
-        self._rings = {}          # shape -> [buffers], next slot
-        self._packed_staging = {}
+        self._rings = {}          # (kind, shape) -> [[buffers], next slot]
+        self._events = []         # event k: everything enqueued on the compute stream before the k-th hand-over
         self._next = None
+        self._mark()
         self._preload()
 
-    def _slot(self, shape):
-        ring = self._rings.get(shape)
+    def _release(self):
+        for key, ring in self._rings.items():
+            HostBatchFeeder._ring_pool.setdefault((self.device, self.depth) + key, []).append(ring)
+        self._rings = {}
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _slot(self, kind, shape, make, n=None):
+        key = (kind, shape)
+        ring = self._rings.get(key)
         if ring is None:
-            ring = [[torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(self.depth)], 0]
-            self._rings[shape] = ring
+            free = HostBatchFeeder._ring_pool.get((self.device, self.depth) + key)
+            ring = free.pop() if free else [[make() for _ in range(n or self.depth)], 0]
+            self._rings[key] = ring
         buf = ring[0][ring[1]]
-        ring[1] = (ring[1] + 1) % self.depth
+        ring[1] = (ring[1] + 1) % len(ring[0])
         return buf
+
+    def _mark(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._events.append(ev)
+        if len(self._events) > self.depth:
+            self._events.pop(0)
 
     def _preload(self):
         try:
@@ -75,19 +101,20 @@ class HostBatchFeeder:
             self._next = None
             return
         x = item[0] if isinstance(item, (tuple, list)) else item
-        # everything enqueued on the compute stream so far (the steps that read the ring) must finish before a refill
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        # the slot about to be refilled held the batch handed out `depth` calls ago; whatever read it was enqueued before
+        # the call after that one, i.e. before event[-(depth - 1)]
+        ev = self._events[-(self.depth - 1)] if len(self._events) >= self.depth - 1 else None
+        if ev is not None:
+            self.stream.wait_event(ev)
+        packed = None
         with torch.cuda.stream(self.stream):
             if isinstance(x, PackedBatch):
-                buf = self._slot(tuple(x.shape))
-                st = self._packed_staging.get(x.shape)
-                need = (x.bitmap.numel(), x.values.numel(), x.row_ptr.numel())
-                if st is None or st[1].numel() < need[1]:
-                    st = (torch.empty(need[0], dtype=torch.int32, device=self.device),
-                          torch.empty(int(need[1] * 1.25) + 1024, dtype=torch.float32, device=self.device),
-                          torch.empty(need[2], dtype=torch.int64, device=self.device))
-                    self._packed_staging[x.shape] = st
-                xd = x.unpack(self.device, out=buf, staging=st)
+                cap = (x.nbytes * 5 // 4 + 4095) // 4096 * 4096
+                st = self._slot("packed", tuple(x.shape), lambda: torch.empty(cap, dtype=torch.uint8, device=self.device))
+                if st.numel() < x.nbytes:          # a denser batch than the ring was sized for: one-off buffer
+                    st = torch.empty(x.nbytes, dtype=torch.uint8, device=self.device)
+                st[:x.nbytes].copy_(x.buffer, non_blocking=True)
+                packed, xd = (x, st), None
                 self.h2d_bytes += x.nbytes
                 self.batches_copied += 1
             elif x.device.type == "cpu":
@@ -95,22 +122,32 @@ class HostBatchFeeder:
                     x = x.float()
                 if self.pin and not x.is_pinned():
                     x = x.pin_memory()
-                xd = self._slot(tuple(x.shape))
+                shape = tuple(x.shape)
+                xd = self._slot("dense", shape, lambda: torch.empty(shape, dtype=torch.float32, device=self.device))
                 xd.copy_(x, non_blocking=True)
                 self.h2d_bytes += x.numel() * x.element_size()
                 self.batches_copied += 1
             else:
                 xd = x
-        self._next = (xd, item)
+        self._next = (xd, item, packed)
 
     def __iter__(self):
         return self
 
     def __next__(self):
         if self._next is None:
+            self._release()
             raise StopIteration
-        torch.cuda.current_stream(self.device).wait_stream(self.stream)
-        xd, item = self._next
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.stream)
+        xd, item, packed = self._next
+        if packed is not None:       # expand on the compute stream: ordered before the step that reads it, after the last one
+            pb, st = packed
+            shape = tuple(pb.shape)
+            out = self._slot("unpacked", shape, lambda: torch.empty(shape, dtype=torch.float32, device=self.device), n=1)
+            xd = pb.expand_from(st, out)
+            st.record_stream(cur)
+        self._mark()
         self._preload()
         return xd, item
 

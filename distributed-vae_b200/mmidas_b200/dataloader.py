@@ -31,7 +31,7 @@ class _Tensors:
 
 
 class ResidentLoader:
-    def __init__(self, *tensors, batch_size, device, shuffle=True, drop_last=True, generator=None):
+    def __init__(self, *tensors, batch_size, device, shuffle=True, drop_last=True, generator=None, reuse_buffers=False):
         if not tensors or any(t.shape[0] != tensors[0].shape[0] for t in tensors):
             raise ValueError("tensors must share their first dimension")
         self.device = torch.device(device)
@@ -40,7 +40,10 @@ class ResidentLoader:
         self.dataset = _Tensors(t.to(self.device) for t in tensors)       # the one H2D copy of the data set
         self.batch_size, self.shuffle, self.drop_last, self.generator = int(batch_size), shuffle, drop_last, generator
         self.h2d_bytes_per_epoch = 0
-        self._ring = None      # two sets of batch buffers: batches alternate between the same device pointers (graph replay)
+        # reuse_buffers: full batches are gathered into two alternating sets of buffers, so the step sees the same device
+        # pointers again and again (CUDA-graph replay); a batch is then only valid until the one after next is drawn
+        self.reuse_buffers = bool(reuse_buffers)
+        self._ring = None
 
     def __len__(self):
         n = len(self.dataset)
@@ -66,12 +69,12 @@ class ResidentLoader:
         perm = self.epoch_permutation(n, self.shuffle, self.generator)
         idx = perm.to(self.device, non_blocking=True)                      # 8 bytes per cell per epoch
         self.h2d_bytes_per_epoch = idx.numel() * idx.element_size()
-        if self._ring is None:
+        if self.reuse_buffers and self._ring is None:
             self._ring = [[torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
                            for t in self.dataset.tensors] for _ in range(2)]
         for b in range(len(self)):
             sel = idx[b * B:(b + 1) * B]
-            if sel.numel() == B:      # full batches gather into the ring (producer and consumer share one stream)
+            if self.reuse_buffers and sel.numel() == B:      # (producer and consumer share one stream)
                 bufs = self._ring[b & 1]
                 yield tuple(torch.index_select(t, 0, sel, out=o) for t, o in zip(self.dataset.tensors, bufs))
             else:
@@ -97,42 +100,63 @@ class PackedBatch:
         pad = W * 32 - D
         bits = torch.nn.functional.pad(nz, (0, pad)).view(B, W, 32).to(torch.int64)
         words = (bits << torch.arange(32, dtype=torch.int64)).sum(-1)               # bit j of word w = gene 32 w + j
-        self.bitmap = words.to(torch.uint32).view(torch.int32).contiguous()
-        self.values = x[nz].contiguous()                                            # row-major order of the non-zeros
+        bitmap = words.to(torch.uint32).view(torch.int32).contiguous()
+        values = x[nz].contiguous()                                                 # row-major order of the non-zeros
         rp = torch.zeros(B + 1, dtype=torch.int64)
         rp[1:] = nz.sum(1).cumsum(0)
-        self.row_ptr = rp
-        self.shape = (B, D)
+        # ONE contiguous (pinned) buffer [row_ptr | bitmap | values] -> one host->device copy per batch
+        n_rp, n_bm, n_va = rp.numel() * 8, bitmap.numel() * 4, values.numel() * 4
+        self._off = (0, n_rp, n_rp + n_bm, n_rp + n_bm + n_va)
+        buf = torch.empty(self._off[3], dtype=torch.uint8)
         if pin and torch.cuda.is_available():
-            self.bitmap, self.values, self.row_ptr = self.bitmap.pin_memory(), self.values.pin_memory(), self.row_ptr.pin_memory()
+            buf = buf.pin_memory()
+        buf[:n_rp].view(torch.int64).copy_(rp)
+        buf[n_rp:n_rp + n_bm].view(torch.int32).copy_(bitmap.reshape(-1))
+        buf[n_rp + n_bm:].view(torch.float32).copy_(values)
+        self.buffer = buf
+        self.shape = (B, D)
+        self.words = W
+
+    def views(self, buf):
+        """(bitmap [B, W] int32, values [nnz] fp32, row_ptr [B + 1] int64) as views of a byte buffer laid out like ours."""
+        o = self._off
+        B = self.shape[0]
+        return (buf[o[1]:o[2]].view(torch.int32).view(B, self.words), buf[o[2]:o[3]].view(torch.float32),
+                buf[o[0]:o[1]].view(torch.int64))
+
+    bitmap = property(lambda self: self.views(self.buffer)[0])
+    values = property(lambda self: self.views(self.buffer)[1])
+    row_ptr = property(lambda self: self.views(self.buffer)[2])
 
     @property
     def nbytes(self) -> int:
         """Bytes that cross PCIe for this batch."""
-        return sum(t.numel() * t.element_size() for t in (self.bitmap, self.values, self.row_ptr))
+        return self.buffer.numel()
 
-    def unpack(self, device, out: torch.Tensor = None, staging=None) -> torch.Tensor:
-        """Copy the packed arrays to ``device`` (async on the current stream) and expand them into ``out`` [B, D]
-        (allocated when None).  ``staging``: optional (bitmap, values, row_ptr) device buffers to reuse."""
+    def expand_from(self, dbuf: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """Expand a device copy ``dbuf`` of ``self.buffer`` into the dense matrix ``out`` [B, D] on the current stream."""
         import ctypes as C
         from . import _lib
         B, D = self.shape
+        bm, va, rp = self.views(dbuf)
+        stream = torch.cuda.current_stream(out.device).cuda_stream
+        _lib.check(_lib.load().mvae_unpack_rows(bm.data_ptr(), va.data_ptr() if va.numel() else None, rp.data_ptr(), B, D,
+                                                out.data_ptr(), out.stride(0), C.c_void_p(stream)), "mvae_unpack_rows")
+        return out
+
+    def unpack(self, device, out: torch.Tensor = None, staging: torch.Tensor = None) -> torch.Tensor:
+        """Copy the packed buffer to ``device`` (one async copy on the current stream) and expand it into ``out`` [B, D]
+        (allocated when None).  ``staging``: optional device byte buffer (>= nbytes, 16-byte aligned) to reuse."""
+        B, D = self.shape
         device = torch.device(device)
         if staging is None:
-            bm = self.bitmap.to(device, non_blocking=True)
-            va = self.values.to(device, non_blocking=True)
-            rp = self.row_ptr.to(device, non_blocking=True)
+            dbuf = self.buffer.to(device, non_blocking=True)
         else:
-            bm, va, rp = staging[0][:self.bitmap.numel()].view(self.bitmap.shape), staging[1][:self.values.numel()], staging[2][:B + 1]
-            bm.copy_(self.bitmap, non_blocking=True)
-            va.copy_(self.values, non_blocking=True)
-            rp.copy_(self.row_ptr, non_blocking=True)
+            dbuf = staging[:self.nbytes]
+            dbuf.copy_(self.buffer, non_blocking=True)
         if out is None:
             out = torch.empty(B, D, dtype=torch.float32, device=device)
-        stream = torch.cuda.current_stream(device).cuda_stream
-        _lib.check(_lib.load().mvae_unpack_rows(bm.data_ptr(), va.data_ptr(), rp.data_ptr(), B, D, out.data_ptr(), out.stride(0),
-                                                C.c_void_p(stream)), "mvae_unpack_rows")
+        self.expand_from(dbuf, out)
         if staging is None:
-            for t in (bm, va, rp):
-                t.record_stream(torch.cuda.current_stream(device))
+            dbuf.record_stream(torch.cuda.current_stream(device))
         return out

@@ -553,6 +553,7 @@ class StepGraph:
         self.counters = torch.zeros(2, dtype=torch.int64, device=dev)
         self._sync_counters()
         self.graph = torch.cuda.CUDAGraph()
+        n0 = int(_lib.load().mvae_launch_count())
         model._graph_counters = self.counters
         optimizer._graph_counters = self.counters
         try:
@@ -564,6 +565,8 @@ class StepGraph:
         # capture enqueues nothing: the host mirrors were advanced by step_fn's bookkeeping, undo that
         model._step_counter = self._held[0]
         optimizer.step_count = self._held[1]
+        self.n_launches = int(_lib.load().mvae_launch_count()) - n0      # kernels of the library per replay
+        _lib.note_capture(self.n_launches)
         self.ctx = model._ctx               # its output tensors live in the graph's pool: rewritten by every replay
 
     def _sync_counters(self):
@@ -577,6 +580,7 @@ class StepGraph:
         """Run the captured step; returns the (static) device loss vector of this replay."""
         self._sync_counters()          # eager steps / eval forwards in between moved the host-side counters
         self.graph.replay()
+        _lib.note_replay(self.n_launches)
         self.model._step_counter += 1
         self.optimizer.step_count += 1
         self._held = (self.model._step_counter, self.optimizer.step_count)

@@ -303,8 +303,8 @@ def test_rejects_bad_usage():
     out2 = model(xs, 1.0, 0.0, noise=to_dev_noise(noises[0]))
     with pytest.raises(RuntimeError):
         model.loss(out[0], [], [], xs, out[7], out[8], out[4], out[6], 0.0)   # stale forward outputs
-    with pytest.raises(NotImplementedError):
-        model(xs, 1.0, 0.0, mask=torch.arange(3))
+    with pytest.raises(ValueError):
+        model(xs, 1.0, 0.0, mask=torch.arange(3) + hp.n_categories)          # category indices out of range
     with pytest.raises(ValueError):
         model([xs[0]], 1.0, 0.0)
 
