@@ -643,8 +643,10 @@ def main():
                 "cpu_baseline": cpu_base, "reference_gpu": ref_gpu, **({"extra": extra} if extra else {})}
         print(json.dumps(line), flush=True)
     if world > 1:
+        from mmidas_b200.nn_model import release_all_graphs
         dist.barrier()
         torch.cuda.synchronize()
+        release_all_graphs()           # captured NCCL collectives pin their communicator: destroy would block on them
         dist.destroy_process_group()
 
 

@@ -49,6 +49,8 @@ def set_print(rank) -> None:
 
 def _teardown(*_signal_args) -> None:
     if dist.is_available() and dist.is_initialized():
+        from .nn_model import release_all_graphs
+        release_all_graphs()          # graphs that captured NCCL collectives pin the communicator: destroy would block
         dist.destroy_process_group()
 
 

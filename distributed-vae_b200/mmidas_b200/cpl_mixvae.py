@@ -259,7 +259,7 @@ class cpl_mixVAE:
             key = (x.data_ptr(), tuple(x.shape), x.stride(0), float(self.temp), float(g0["lr"]), tuple(g0["betas"]), float(g0["eps"]),
                    id(model), id(opt))
             g = self._graphs.get(key)
-            if g is not None:
+            if g is not None and g.graph is not None:
                 self._graph_misses = 1
                 return g.replay()
             if self._graph_misses > 0 or self._graphs:        # (the very first step runs eagerly: lazy allocations)

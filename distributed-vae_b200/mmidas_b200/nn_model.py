@@ -14,6 +14,7 @@ There is no CPU path: a model can be constructed and (de)serialised on the CPU (
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -536,6 +537,17 @@ class mixVAE_model(nn.Module):
         return out
 
 
+_LIVE_GRAPHS = weakref.WeakSet()
+
+
+def release_all_graphs():
+    """Reset every captured step graph of this process.  A graph that captured NCCL collectives pins their communicator:
+    ``destroy_process_group`` blocks until such graphs are gone (measured: the teardown of a 2-rank run hung for good), so
+    ``_dist_utils.destroy_dist_env`` calls this first."""
+    for g in list(_LIVE_GRAPHS):
+        g.release()
+
+
 class StepGraph:
     """One training step captured in a CUDA graph and replayed with ONE launch.
 
@@ -568,6 +580,13 @@ class StepGraph:
         self.n_launches = int(_lib.load().mvae_launch_count()) - n0      # kernels of the library per replay
         _lib.note_capture(self.n_launches)
         self.ctx = model._ctx               # its output tensors live in the graph's pool: rewritten by every replay
+        _LIVE_GRAPHS.add(self)
+
+    def release(self):
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
 
     def _sync_counters(self):
         want = (self.model._step_counter, self.optimizer.step_count)
@@ -578,6 +597,8 @@ class StepGraph:
 
     def replay(self) -> torch.Tensor:
         """Run the captured step; returns the (static) device loss vector of this replay."""
+        if self.graph is None:
+            raise RuntimeError("this step graph was released (process group torn down)")
         self._sync_counters()          # eager steps / eval forwards in between moved the host-side counters
         self.graph.replay()
         _lib.note_replay(self.n_launches)

@@ -290,6 +290,8 @@ class ShardedTrainer:
         from .nn_model import StepGraph
         key = (x_local.data_ptr(), tuple(x_local.shape), x_local.stride(0), float(self.optimizer.param_groups[0]["lr"]))
         g = self._graphs.get(key)
+        if g is not None and g.graph is None:        # released (process group torn down and re-created)
+            g = None
         if g is None:
             if not self._graphs and self._graph_misses == 0:
                 self._graph_misses += 1          # very first step: eager (lazy allocations, communicator warm-up)
