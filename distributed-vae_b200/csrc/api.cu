@@ -484,6 +484,16 @@ int mvae_adam(float* params, const float* grads, float* m, float* v, int64_t n, 
                      (cudaStream_t)stream);
 }
 
+int mvae_adam_peer(float* const* peer_params, const float* const* peer_grads, float* m, float* v, int64_t n, int32_t rank,
+                   int32_t world, float lr, float beta1, float beta2, float eps, int64_t step, uint64_t* step_counter,
+                   void* stream) {
+  MVAE_CHECK_ARG(peer_params && peer_grads && m && v, "null argument");
+  RC(check_device());
+  if (step_counter) RC(launch_counter_inc(step_counter, (cudaStream_t)stream));
+  return launch_adam_peer(peer_params, peer_grads, m, v, n, rank, world, lr, beta1, beta2, eps, step, step_counter,
+                          (cudaStream_t)stream);
+}
+
 int mvae_train_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state* st, const mvae_inputs* in,
                     const mvae_outputs* out, float* loss_out, float lr, float beta1, float beta2, float adam_eps,
                     int64_t step, void* stream) {

@@ -150,6 +150,9 @@ int launch_enc_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
 // ---- optimiser / misc ------------------------------------------------------------------------
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                 float wd, int adamw, int64_t step, const uint64_t* step_dev, cudaStream_t s);
+int launch_adam_peer(float* const* peer_params, const float* const* peer_grads, float* m, float* v, int64_t n, int rank,
+                     int world, float lr, float b1, float b2, float eps, int64_t step, const uint64_t* step_dev,
+                     cudaStream_t s);
 int launch_scale(float* p, int64_t n, const float* scale_dev, cudaStream_t s);
 int launch_counter_inc(uint64_t* counter, cudaStream_t s);
 int launch_unpack_rows(const uint32_t* bitmap, const float* values, const int64_t* row_ptr, int64_t rows, int D, float* out,

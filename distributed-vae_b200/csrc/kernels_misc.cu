@@ -177,6 +177,89 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float l
   return 0;
 }
 
+// =============================================================================================
+// Gradient all-reduce fused with Adam over peer memory (data-parallel replicas on NVLink / NVSwitch).
+// Rank r owns the float4 range [i0, i1) of the flat buffer: it sums that range of EVERY replica's gradient buffer (peer
+// loads, fixed rank order -> every replica ends up with bit-identical parameters), averages, applies Adam with its
+// slice of the moments, and stores the new parameters into every replica's parameter buffer (peer stores).  Two-shot
+// traffic: (W-1)/W of the buffer in and out per GPU instead of a separate all-reduce pass + a local Adam pass.
+// The caller brackets the launch with cross-rank barriers on the stream (gradients final before, parameters final after).
+// =============================================================================================
+constexpr int kMaxPeers = 16;
+struct PeerPtrs { float* p[kMaxPeers]; const float* g[kMaxPeers]; };
+__global__ void __launch_bounds__(256) adam_peer_kernel(const PeerPtrs peers, float* __restrict__ m, float* __restrict__ v,
+                                                        int64_t i0, int64_t i1, int rank, int world, float inv_world, float lr,
+                                                        float b1, float b2, float eps, float step_size, float inv_sqrt_bc2,
+                                                        const uint64_t* step_dev) {
+  if (step_dev) {
+    __shared__ float sh[2];
+    if (threadIdx.x == 0) {
+      const double st = (double)*step_dev;
+      const double bc1 = 1.0 - pow((double)b1, st), bc2 = 1.0 - pow((double)b2, st);
+      sh[0] = (float)((double)lr / bc1);
+      sh[1] = (float)(1.0 / sqrt(bc2));
+    }
+    __syncthreads();
+    step_size = sh[0];
+    inv_sqrt_bc2 = sh[1];
+  }
+  float4* pl = reinterpret_cast<float4*>(peers.p[rank]);
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < world; ++q) {
+      const float4 t = __ldcv(reinterpret_cast<const float4*>(peers.g[q]) + i);   // peer memory: never from a stale cache line
+      gv.x += t.x; gv.y += t.y; gv.z += t.z; gv.w += t.w;
+    }
+    float4 pv = pl[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gg = gp[k] * inv_world;
+      mp[k] = fmaf(1.f - b1, gg - mp[k], mp[k]);
+      vp[k] = fmaf(vp[k], b2, (1.f - b2) * gg * gg);
+      const float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;
+      pp[k] = pp[k] - step_size * (mp[k] / denom);
+    }
+    for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(peers.p[q])[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  __threadfence_system();
+}
+
+int launch_adam_peer(float* const* peer_params, const float* const* peer_grads, float* m, float* v, int64_t n, int rank,
+                     int world, float lr, float b1, float b2, float eps, int64_t step, const uint64_t* step_dev,
+                     cudaStream_t s) {
+  MVAE_CHECK_ARG(n % 4 == 0, "adam_peer: n=%lld must be a multiple of 4", (long long)n);
+  MVAE_CHECK_ARG(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "adam_peer: rank %d of %d", rank, world);
+  MVAE_CHECK_ARG(step_dev != nullptr || step >= 1, "adam_peer: step must be >= 1");
+  PeerPtrs peers;
+  memset(&peers, 0, sizeof(peers));
+  for (int q = 0; q < world; ++q) {
+    MVAE_CHECK_ARG(peer_params[q] && peer_grads[q], "adam_peer: null peer buffer %d", q);
+    peers.p[q] = peer_params[q];
+    peers.g[q] = peer_grads[q];
+  }
+  float step_size = 0.f, inv_sqrt_bc2 = 0.f;
+  if (!step_dev) {
+    const double bc1 = 1.0 - pow((double)b1, (double)step);
+    const double bc2 = 1.0 - pow((double)b2, (double)step);
+    step_size = (float)((double)lr / bc1);
+    inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  }
+  const int64_t n4 = n / 4;
+  const int64_t i0 = n4 * rank / world, i1 = n4 * (rank + 1) / world;
+  int gx = (int)((i1 - i0 + 255) / 256);
+  if (gx > 148 * 4) gx = 148 * 4;
+  if (gx < 1) gx = 1;
+  adam_peer_kernel<<<gx, 256, 0, s>>>(peers, m, v, i0, i1, rank, world, 1.0f / (float)world, lr, b1, b2, eps, step_size,
+                                      inv_sqrt_bc2, step_dev);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
 // Generator keys of one step (common.cuh: stream_key) + the step counters, written to Work::keys.  With device counters
 // the kernel increments them first: every launch of a replayed graph then draws fresh noise / uses the next Adam step
 // although its arguments never change.

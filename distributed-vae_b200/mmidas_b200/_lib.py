@@ -59,7 +59,7 @@ PRECISIONS = {"tf32x3_fc1": 0, "tf32x3": 1, "tf32": 2, "fp32_simt": 3}
 EXPORTS = ("mvae_last_error", "mvae_abi_version", "mvae_compute_layout", "mvae_forward", "mvae_loss",
            "mvae_backward", "mvae_adam", "mvae_train_step", "mvae_argmax", "mvae_dropout_mask", "mvae_launch_count",
            "mvae_timing_enable", "mvae_timing_read", "mvae_debug_tc_gemm", "mvae_confmat", "mvae_fold_affine",
-           "mvae_linear_act", "mvae_fma_rows", "mvae_unpack_rows")
+           "mvae_linear_act", "mvae_fma_rows", "mvae_unpack_rows", "mvae_adam_peer")
 
 _lib = None
 
@@ -99,6 +99,9 @@ def load():
     lib.mvae_fma_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_int64, C.c_int32, C.c_float, C.c_void_p]
     lib.mvae_fma_rows.restype = C.c_int
+    lib.mvae_adam_peer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float,
+                                   C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.mvae_adam_peer.restype = C.c_int
     lib.mvae_unpack_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
     lib.mvae_unpack_rows.restype = C.c_int
     lib.mvae_debug_tc_gemm.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int,

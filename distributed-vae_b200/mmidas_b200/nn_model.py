@@ -155,6 +155,7 @@ class mixVAE_model(nn.Module):
         self._gen = 0
         self._step_counter = 0
         self._grad_anchor = None
+        self._flat_alloc = None
         self._graph_counters = None
         self._flatten()
 
@@ -175,8 +176,10 @@ class mixVAE_model(nn.Module):
         lay = self._layout
         p0 = self.fc1[0].weight
         dev, A = p0.device, self.n_arm
-        flat = torch.zeros(A, lay.arm_stride, dtype=torch.float32, device=dev)
-        grads = torch.zeros(A, lay.arm_stride, dtype=torch.float32, device=dev)
+        # (mmidas_b200.parallel swaps in a peer-accessible allocator for the two buffers replicas exchange)
+        alloc = self._flat_alloc or (lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev))
+        flat = alloc(A, lay.arm_stride)
+        grads = alloc(A, lay.arm_stride)
         with torch.no_grad():
             for t, a, p in self._named_slots():
                 off, n = lay.offset[t], lay.numel[t]

@@ -17,6 +17,7 @@ libmixvae_b200.so.  The helpers take plain tensors so that the host logic is tes
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -198,7 +199,7 @@ class ShardedTrainer:
     def __init__(self, model_kwargs: Optional[dict] = None, lr: float = 1e-3, mode: str = "auto", temp: float = 1.0,
                  seed: int = 546, rank: Optional[int] = None, world_size: Optional[int] = None,
                  overlap: Optional[bool] = None, model=None, ranks: Optional[Sequence[int]] = None,
-                 use_cuda_graph: bool = True):
+                 use_cuda_graph: bool = True, peer_adam: Optional[bool] = None):
         from .nn_model import mixVAE_model
         from .optim import FusedAdam
         self.rank = dist.get_rank() if rank is None else rank
@@ -247,6 +248,84 @@ class ShardedTrainer:
         # latency-bound: below ~32 MB of gradients one call beats 2*A overlapped ones (measured at N=2: 0.99 -> 0.8x ms).
         grad_bytes = self.model.flat_grads().numel() * 4
         self.overlap = (grad_bytes > 32 * 2 ** 20) if overlap is None else bool(overlap)
+        # peer_adam: the gradient exchange fused with Adam over NVLink peer memory (mvae_adam_peer) instead of an NCCL
+        # all-reduce followed by a local Adam; falls back to NCCL when symmetric memory cannot be set up
+        self.peer = None
+        want_peer = (self.plan.dp_ranks > 1) if peer_adam is None else (bool(peer_adam) and self.plan.dp_ranks > 1)
+        if want_peer and dist.get_backend(self.dp_group) == "nccl":
+            self._setup_peer_adam()
+
+    # ------------------------------------------------------------------------------------------
+    def _setup_peer_adam(self):
+        """Move the flat parameter / gradient buffers into symmetric memory shared by the dp replicas (every rank of the dp
+        group calls this; the ranks agree on success through an all-reduce, so either all use the fused kernel or none)."""
+        ok, err, hp, hg = 1, None, None, None
+        m = self.model
+        try:
+            import torch.distributed._symmetric_memory as symm
+            gname = self.dp_group.group_name
+            if hasattr(symm, "enable_symm_mem_for_group"):
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    symm.enable_symm_mem_for_group(gname)
+            dev = self.device
+            m._flat_alloc = lambda *shape: symm.empty(*shape, dtype=torch.float32, device=dev).zero_()
+            m._flatten()
+            torch.cuda.synchronize(dev)
+        except Exception as e:          # allocation refused on this rank
+            ok, err = 0, e
+        flag = torch.tensor([float(ok)], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.dp_group)
+        if flag.item() > 0:
+            try:
+                hp = symm.rendezvous(m.flat_parameters(), self.dp_group)
+                hg = symm.rendezvous(m.flat_grads(), self.dp_group)
+            except Exception as e:
+                ok, err = 0, e
+            flag = torch.tensor([float(ok)], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.dp_group)
+        if flag.item() <= 0:
+            if err is not None and self.rank == self.ranks[0]:
+                print(f"ShardedTrainer: peer-memory Adam unavailable ({err}); using the NCCL all-reduce")
+            if m._flat_alloc is not None:
+                m._flat_alloc = None
+                m._flatten()
+            self._reset_optimizer()
+            return
+        W = hp.world_size
+        self.peer = {"hp": hp, "hg": hg, "rank": hp.rank, "world": W,
+                     "pp": (C.c_void_p * W)(*[int(x) for x in hp.buffer_ptrs]),
+                     "pg": (C.c_void_p * W)(*[int(x) for x in hg.buffer_ptrs])}
+        self._reset_optimizer()
+
+    def _reset_optimizer(self):
+        from .optim import FusedAdam
+        lr = self.optimizer.param_groups[0]["lr"]
+        self.optimizer = FusedAdam(self.model.parameters(), lr=lr, model=self.model)
+
+    def _owned_range(self):
+        """[start, end) in floats of the flat buffer whose Adam moments live on this rank (peer_adam), else everything."""
+        n = self.model.flat_parameters().numel()
+        if self.peer is None:
+            return 0, n
+        n4, r, W = n // 4, self.peer["rank"], self.peer["world"]
+        return 4 * (n4 * r // W), 4 * (n4 * (r + 1) // W)
+
+    def _peer_adam_step(self):
+        from . import _lib
+        m, opt, pr = self.model, self.optimizer, self.peer
+        mm, vv = opt.flat_state()
+        g = opt.param_groups[0]
+        opt.step_count += 1
+        ctr = opt._graph_counters[1:].data_ptr() if opt._graph_counters is not None else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        pr["hg"].barrier(channel=0)            # every replica's gradients are final
+        _lib.check(_lib.load().mvae_adam_peer(pr["pp"], pr["pg"], mm.data_ptr(), vv.data_ptr(), m.flat_parameters().numel(),
+                                              pr["rank"], pr["world"], float(g["lr"]), float(g["betas"][0]),
+                                              float(g["betas"][1]), float(g["eps"]), opt.step_count, ctr,
+                                              C.c_void_p(stream)), "mvae_adam_peer")
+        pr["hp"].barrier(channel=1)            # every replica's parameters are final
 
     # ------------------------------------------------------------------------------------------
     def _step_eager(self, x_local: torch.Tensor, noise=None) -> torch.Tensor:
@@ -269,6 +348,10 @@ class ShardedTrainer:
             m._run_backward(m._ctx.gen, None)
             allreduce_mean(early, self.dp_group, plan.dp_ranks)
             cur.wait_stream(self.comm_stream)
+        elif self.peer is not None:
+            m._run_backward(m._ctx.gen, None)
+            self._peer_adam_step()
+            return fixup_loss_vector(m._ctx.loss_vec, plan, self.arm_group, float(m.beta))
         else:
             m._run_backward(m._ctx.gen, None)
             if plan.dp_ranks > 1:
@@ -334,7 +417,21 @@ class ShardedTrainer:
         the reference's FSDP wrap."""
         m, plan = self.model, self.plan
         msd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
-        osd = self.optimizer.state_dict()
+        if self.peer is not None:
+            # the Adam moments are sharded over the dp replicas (each owns the range it updates): sum the owned ranges
+            mm, vv = self.optimizer.flat_state()
+            a, b = self._owned_range()
+            keep = (mm.clone(), vv.clone())
+            for t in (mm, vv):
+                flat = t.view(-1)
+                flat[:a] = 0
+                flat[b:] = 0
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.dp_group)
+            osd = self.optimizer.state_dict()
+            mm.copy_(keep[0])
+            vv.copy_(keep[1])
+        else:
+            osd = self.optimizer.state_dict()
         if plan.arm_ranks == 1:
             return msd, osd
         mine = (msd, {i: {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in s.items()} for i, s in osd["state"].items()})

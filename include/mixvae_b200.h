@@ -151,6 +151,18 @@ int mvae_adam(float* params, const float* grads, float* m, float* v, int64_t n, 
               float beta1, float beta2, float eps, float weight_decay, int32_t adamw,
               int64_t step, uint64_t* step_counter, void* stream);
 
+/* Data-parallel replicas (the reference's FSDP wrap, train.py:140-143, would reduce-scatter the gradients and all-gather
+ * the parameters around torch.optim.Adam.step, cpl_mixvae.py:463): gradient averaging fused with Adam over peer memory.
+ * peer_params / peer_grads: HOST arrays of `world` device pointers, entry q = the flat parameter / gradient buffer of
+ * replica q (peer-accessible: CUDA IPC / symmetric memory; entry `rank` is this replica's own).  Rank `rank` sums its
+ * 1/world share of all replicas' gradients in rank order, divides by `world`, applies Adam with its share of m / v and
+ * stores the new parameters into every replica's buffer.  The caller orders the call between two cross-replica barriers
+ * on `stream`: every replica's gradients final before, every replica's parameters final after.  step / step_counter
+ * as for mvae_adam. */
+int mvae_adam_peer(float* const* peer_params, const float* const* peer_grads, float* m, float* v, int64_t n, int32_t rank,
+                   int32_t world, float lr, float beta1, float beta2, float eps, int64_t step, uint64_t* step_counter,
+                   void* stream);
+
 /* zero_grad + forward + loss + backward + Adam in one call (cpl_mixvae.py:434-463). */
 int mvae_train_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state* st,
                     const mvae_inputs* in, const mvae_outputs* out, float* loss_out, float lr,
