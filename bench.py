@@ -393,7 +393,9 @@ def main():
         from mmidas_b200.parallel import ShardedTrainer
         st = ShardedTrainer(kwargs_for(A), lr=1e-3, mode=args.mesh, use_cuda_graph=not args.no_graph)
         step_fn = st.step
-        parallelism = f"mesh arm{st.plan.arm_ranks} x dp{st.plan.dp_ranks}, NCCL"
+        parallelism = (f"mesh arm{st.plan.arm_ranks} x dp{st.plan.dp_ranks}; gradient exchange: " +
+                       ("fused with Adam over NVLink peer memory (mvae_adam_peer)" if st.peer is not None
+                        else "NCCL all-reduce" if st.plan.dp_ranks > 1 else "none"))
         dp_ranks = st.plan.dp_ranks          # ranks of one arm group see the SAME cells: count them once
         if st.plan.arm_ranks > 1:
             # every rank of an arm group must be fed the same batch
@@ -607,8 +609,9 @@ def main():
                    "ms_per_step_local_arms_no_collective": solo,
                    "collective_exposed_ms": (msx / args.steps - solo) if solo is not None else None,
                    "collectives": ("all-gather of q(c|x) and the samples over the arm axis (2 x 2 MB per arm), all-reduce of 3A "
-                                   "loss scalars" if mode == "arm" else f"all-reduce (AVG) of the {An}-arm flat gradient buffer "
-                                   f"({An * 4.31:.1f} MB) over 8 ranks"),
+                                   "loss scalars" if mode == "arm" else f"gradient averaging of the {An}-arm flat buffer "
+                                   f"({An * 4.31:.1f} MB) over 8 replicas, " + ("fused with Adam over NVLink peer memory"
+                                                                             if stx.peer is not None else "NCCL all-reduce")),
                    "last_total_loss": float(lvx[0].item())}
         del stx
         if rank == 0:
