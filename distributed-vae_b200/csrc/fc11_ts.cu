@@ -1,21 +1,25 @@
-// fc11_ts.cu — the last decoder layer fused with the reconstruction loss and its own backward, second generation.
+// fc11_ts.cu — the last decoder layer fused with the reconstruction loss and its own backward, third generation.
 //
 // Reference ops (mmidas/nn_model.py): x_hat = relu(fc11(h10)) :287; 0.5*mse_sum/B + 0.5*BCE(bin(x_hat), bin(x))
 // :542-546; autograd of both (dY = max(A-1,1)/B * (x_hat - x) * [x_hat > 0]; the BCE half acts on constants).
 // Two passes over x, nothing [B,D]-sized is ever written:
 //
-//   ROW  pass (thread = cell):  X[128 cells x 32 genes] = h10 . W11^T ; loss sums ; dY ; d h10 += dY . W11
-//   GENE pass (thread = gene):  X^T[128 genes x 32 cells] = W11 . h10^T ; dY^T ; d fc11.weight += dY^T . h10 ; d fc11.bias
+//   ROW  pass (thread = cell):  X[128 cells x 64 genes] = h10 . W11^T ; loss sums ; dY ; d h10 += dY . W11
+//   GENE pass (thread = gene):  X^T[128 genes x 64 cells] = W11 . h10^T ; dY^T ; d fc11.weight += dY^T . h10 ; d fc11.bias
 //
 // Same skeleton for both (roles of h10 and W11 swapped through the tensor maps):
 //   * the resident operand R (128 rows x H: h10 block / W11 block) lives in TENSOR MEMORY and feeds MMA1 in the TS form;
-//   * streamed per unit (32 columns): the raw x tile (own deep ring: it comes from HBM) and the small operand tile in
-//     two images (K-major for MMA1, MN-major for MMA2; separate rings, L2-resident);
-//   * MMA1 -> acc1[g] (TMEM) -> 4 epilogue groups (unit i belongs to group i % 4; lane = row of R) compute x_hat, the
-//     loss terms and dY in registers and store dY as the A operand of MMA2 straight into TMEM (tcgen05.st);
-//   * MMA2 (TS form) accumulates into acc2 (TMEM) over the whole segment;
+//   * a unit is a PAIR of 32-column halves.  Streamed per unit: two raw x tiles (16 KB each, own deep ring: they come
+//     from HBM) and ONE image of the small operand tile T (64 rows x H, L2-resident) that serves both MMAs: the
+//     SWIZZLE_128B_BASE32B layout is the only one MN-major TF32 operands may use, and the tensor core reads it K-major
+//     as well when the descriptor's stride between row groups is that of its 4-row atoms (512 B) -- measured, the
+//     second-generation kernel pulled every T tile from L2 twice, once per swizzle;
+//   * MMA1 (N = 64: 51 cycles of issue per K = 8 step instead of 2 x 47 at N = 32) -> acc1[pair] (TMEM) -> 4 epilogue
+//     groups (half-unit j belongs to group j % 4; lane = row of R) compute x_hat, the loss terms and dY in registers and
+//     store dY as the A operand of MMA2 straight into TMEM (tcgen05.st);
+//   * MMA2 (TS form, per half) accumulates into acc2 (TMEM) over the whole segment;
 //   * stream-K over (tile, unit): one CTA per SM, one wave; partial tiles are summed in a fixed order by a fix-up kernel.
-// TMEM columns: acc2 [0,128) | acc1 4 x 32 [128,256) | dY stages 4 x 32 [256,384) | R [384,512).
+// TMEM columns: acc2 [0,128) | acc1 2 x 64 [128,256) | dY stages 4 x 32 [256,384) | R [384,512).
 #include "gemm_tc.h"
 #include "tc_common.cuh"
 
@@ -24,20 +28,25 @@ namespace mvae {
 namespace {
 using namespace tc;
 
-constexpr int UN = 32;                     // columns per unit (genes for ROW, cells for GENE)
-constexpr int NG = 4;                      // epilogue groups (4 warps each)
+constexpr int UN = 32;                     // columns per half-unit (genes for ROW, cells for GENE)
+constexpr int NG = 4;                      // epilogue groups (4 warps each); group g owns the half-units j = g (mod 4)
 constexpr int CTRL_WARPS = 4;              // x TMA, small-operand TMA, MMA1 issue, MMA2 issue
 constexpr int THREADS = 32 * (CTRL_WARPS + 4 * NG);
 constexpr int X_BYTES = 16384;
-constexpr int IMG_BYTES = 16384;           // one image of the small operand tile: 4 slabs of [32 rows x 128 B]
+constexpr int SLAB_BYTES = 8192;           // [64 rows x 128 B] of T: 32 columns of H
+constexpr int IMG_BYTES = 4 * SLAB_BYTES;  // the T tile of a unit: 64 rows x 128 columns of H (SWIZZLE_128B_BASE32B)
+constexpr uint32_t LT_BASE32B = 1;         // descriptor layout type
+#ifndef F11_NW
+#define F11_NW 4                           // T-tile ring depth (measured: 4 stages + 4 x slots beat 3 + 8)
+#endif
 constexpr int TILE_FLOATS = 128 * 128;
 constexpr uint32_t COL_ACC2 = 0, COL_ACC1 = 128, COL_A2 = 256, COL_R = 384;
 
 struct F11Args {
   int B, D, H, HN;
-  int batch, rtiles, ktiles;        // arms, 128-row blocks of R per arm, units per tile
+  int batch, rtiles, ktiles;        // arms, 128-row blocks of R per arm, units (pairs of 32-column halves) per tile
   int x_batched;
-  int nx, nk, nm;                   // ring depths: x, K-image, MN-image
+  int nx, nw;                       // ring depths: x tiles, T tiles
   int want_grad;
   float gscale;
   const float* R; int64_t r_arm_stride; int r_rows;     // resident operand: [arm][r_rows][H]
@@ -50,46 +59,80 @@ struct F11Args {
 
 __host__ __device__ inline int64_t cta_of_unit(int64_t u, int64_t U, int64_t G) { return ((u + 1) * G - 1) / U; }
 
+__device__ __forceinline__ uint64_t make_desc_lt(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+#ifdef F11_DEBUG
+__device__ int g_f11_dead = 0;
+__device__ __forceinline__ void dbg_wait(uint64_t* bar, uint32_t parity, int tag, int idx, int gene) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*(volatile int*)&g_f11_dead) return;
+    if (clock64() - t0 > 400000000LL) {
+      if ((threadIdx.x & 31) == 0)
+        printf("F11 timeout gene %d blk %d warp %d tag %d idx %d parity %u\n", gene, blockIdx.x, threadIdx.x >> 5, tag, idx, parity);
+      *(volatile int*)&g_f11_dead = 1;
+      return;
+    }
+  }
+}
+#define WAIT(bar, par, tag, idx) dbg_wait(bar, par, tag, idx, (int)GENE)
+#else
+#define WAIT(bar, par, tag, idx) mbar_wait(bar, par)
+#endif
+__device__ __forceinline__ void mbar_wait3(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb, uint64_t* c, uint32_t pc) {
+  const bool ra = mbar_try_wait(a, pa), rb = mbar_try_wait(b, pb), rc = mbar_try_wait(c, pc);
+  if (!ra) mbar_wait(a, pa);
+  if (!rb) mbar_wait(b, pb);
+  if (!rc) mbar_wait(c, pc);
+}
+
 // TRAIN = true: the training-step instance (gradients wanted, no materialised reconstruction): the flags are compile-time
 // so the epilogue carries no per-element branches for them.
+// Index conventions: a CTA owns the units [u0, u1) of the (tile, unit) sequence; inside the CTA, unit i consists of the
+// half-units j = 2 i and 2 i + 1; KT = 2 * ktiles is the number of half-units per tile (the last one may lie entirely
+// beyond the matrix: TMA fills zeros, the epilogue guards its stores).
 template <bool GENE, bool TRAIN>
 __global__ void __launch_bounds__(THREADS, 1)
-fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmTk,
-               const __grid_constant__ CUtensorMap tmTm, const F11Args a) {
+fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmT, const F11Args a) {
   const bool want_grad = TRAIN || a.want_grad;
   float* const x_rec = TRAIN ? nullptr : a.x_rec;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto xs = [&](int s) { return smem + (size_t)s * X_BYTES; };
-  auto tk = [&](int s) { return smem + (size_t)a.nx * X_BYTES + (size_t)s * IMG_BYTES; };
-  auto tm = [&](int s) { return smem + (size_t)a.nx * X_BYTES + (size_t)(a.nk + s) * IMG_BYTES; };
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.nx * X_BYTES + (size_t)(a.nk + a.nm) * IMG_BYTES);
+  auto ts = [&](int s) { return smem + (size_t)a.nx * X_BYTES + (size_t)s * IMG_BYTES; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.nx * X_BYTES + (size_t)a.nw * IMG_BYTES);
   uint64_t* x_full = bars;                 uint64_t* x_empty = x_full + a.nx;
-  uint64_t* k_full = x_empty + a.nx;       uint64_t* k_empty = k_full + a.nk;
-  uint64_t* m_full = k_empty + a.nk;       uint64_t* m_empty = m_full + a.nm;
-  uint64_t* acc1_full = m_empty + a.nm;    uint64_t* acc1_empty = acc1_full + NG;
+  uint64_t* w_full = x_empty + a.nx;       uint64_t* w_empty = w_full + a.nw;
+  uint64_t* acc1_full = w_empty + a.nw;    uint64_t* acc1_empty = acc1_full + NG;
   uint64_t* a2_full = acc1_empty + NG;     uint64_t* a2_empty = a2_full + NG;
   uint64_t* r_full = a2_empty + NG;        // R of the current segment is in TMEM (and acc2 of the previous one drained)
-  // segment s complete: barrier s % NG.  An epilogue group can be up to NG units -- hence NG segments when a CTA's share
-  // of a tile is a single unit -- ahead of the tensor pipe; one parity bit cannot tell those apart, NG barriers can.
+  // segment s complete: barrier s % NG.  An epilogue group can be up to NG half-units -- hence several segments when a
+  // CTA's share of a tile is a single unit -- ahead of the tensor pipe; one parity bit cannot tell those apart.
   uint64_t* acc2_full = r_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + NG);
 
-  const int KT = a.ktiles;
-  const int64_t U = (int64_t)a.batch * a.rtiles * KT, G = gridDim.x;
+  const int KP = a.ktiles, KT = 2 * KP;
+  const int64_t U = (int64_t)a.batch * a.rtiles * KP, G = gridDim.x;
   const int64_t u0 = (int64_t)blockIdx.x * U / G, u1 = ((int64_t)blockIdx.x + 1) * U / G;
-  const int nu = (int)(u1 - u0);
+  const int np = (int)(u1 - u0), nu = 2 * np;          // units and half-units of this CTA
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.nx; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 4); }
-    for (int s = 0; s < a.nk; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
-    for (int s = 0; s < a.nm; ++s) { mbar_init(m_full + s, 1); mbar_init(m_empty + s, 1); }
+    for (int s = 0; s < a.nw; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, want_grad ? 2 : 1); }
     for (int s = 0; s < NG; ++s) {
       mbar_init(acc1_full + s, 1); mbar_init(acc1_empty + s, 4);
       mbar_init(a2_full + s, 4);   mbar_init(a2_empty + s, 1);
     }
-    mbar_init(r_full, 4);
+    mbar_init(r_full, 8);
     for (int s = 0; s < NG; ++s) mbar_init(acc2_full + s, 1);
     fence_barrier_init();
   }
@@ -99,16 +142,17 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int t_first = (int)(u0 / KT), kt_first = (int)(u0 - (int64_t)t_first * KT);
+  const int t_first = (int)(u0 / KP), kp_first = (int)(u0 - (int64_t)t_first * KP);
+  const int kt_first = 2 * kp_first;
   const int rb_first = t_first / a.batch, arm_first = t_first - rb_first * a.batch;
 
   if (warp == 0) {
-    // ===== TMA producer: raw x tiles =====
+    // ===== TMA producer: raw x tiles, one per half-unit =====
     int kt = kt_first, rb = rb_first, arm = arm_first, sx = 0;
     uint32_t phx = 1;
-    for (int i = 0; i < nu; ++i) {
+    for (int j = 0; j < nu; ++j) {
       const int xb = a.x_batched ? arm : 0;
-      mbar_wait(x_empty + sx, phx);
+      WAIT(x_empty + sx, phx, 1, j);
       if (elect_one()) {
         mbar_expect_tx(x_full + sx, X_BYTES);
         if (!GENE) tma_load_3d(&tmX, x_full + sx, xs(sx), kt * UN, rb * 128, xb);    // [128 cells][32 genes], SW128
@@ -119,120 +163,131 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (++kt == KT) { kt = 0; if (++arm == a.batch) { arm = 0; ++rb; } }
     }
   } else if (warp == 1) {
-    // ===== TMA producer: the small operand tile (32 rows x H) in its two images =====
-    int kt = kt_first, arm = arm_first, sk = 0, sm = 0;
-    uint32_t phk = 1, phm = 1;
-    for (int i = 0; i < nu; ++i) {
-      mbar_wait(k_empty + sk, phk);
+    // ===== TMA producer: the T tile of a unit (64 rows x H), four slabs of 32 columns =====
+    int kp = kp_first, arm = arm_first, sw = 0;
+    uint32_t phw = 1;
+    for (int i = 0; i < np; ++i) {
+      WAIT(w_empty + sw, phw, 2, i);
       if (elect_one()) {
-        mbar_expect_tx(k_full + sk, IMG_BYTES);
+        mbar_expect_tx(w_full + sw, IMG_BYTES);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_3d(&tmTk, k_full + sk, tk(sk) + j * 4096, 32 * j, kt * UN, arm);
+        for (int q = 0; q < 4; ++q) tma_load_3d(&tmT, w_full + sw, ts(sw) + q * SLAB_BYTES, 32 * q, kp * 2 * UN, arm);
       }
       __syncwarp();
-      if (want_grad) {
-        mbar_wait(m_empty + sm, phm);
-        if (elect_one()) {
-          mbar_expect_tx(m_full + sm, IMG_BYTES);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_3d(&tmTm, m_full + sm, tm(sm) + j * 4096, 32 * j, kt * UN, arm);
-        }
-        __syncwarp();
-        if (++sm == a.nm) { sm = 0; phm ^= 1; }
-      }
-      if (++sk == a.nk) { sk = 0; phk ^= 1; }
-      if (++kt == KT) { kt = 0; if (++arm == a.batch) arm = 0; }
+      if (++sw == a.nw) { sw = 0; phw ^= 1; }
+      if (++kp == KP) { kp = 0; if (++arm == a.batch) arm = 0; }
     }
   } else if (warp == 2) {
-    // ===== MMA1 issuer: acc1[g] = R . T_K^T (uniform loop, one elected lane issues).  MMA1 and MMA2 are issued by two
-    // warps: one warp doing both spent ~1900 cycles per unit in its own serial latencies (four satisfied mbarrier
-    // waits at ~170 cycles each, commits, fences) and was the bottleneck of the kernel, not the tensor pipe.
-    const uint32_t idesc1 = make_idesc(128, UN, false, false);
+    // ===== MMA1 issuer: acc1[unit] = R . T^T, N = 64 (uniform loop, one elected lane issues).  MMA1 and MMA2 are issued
+    // by two warps: one warp doing both spent ~1900 cycles per 32 columns in its own serial latencies (four satisfied
+    // mbarrier waits at ~170 cycles each, commits, fences) and was the bottleneck of the kernel, not the tensor pipe.
+    const uint32_t idesc1 = make_idesc(128, 2 * UN, false, false);
     const int ksteps1 = (a.H + 7) / 8;
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    int kt = kt_first, sk = 0, seg = 0;
-    uint32_t phk = 0;
-    for (int i = 0; i < nu; ++i) {
-      const int g = i & (NG - 1);
-      if ((i == 0) || (kt == 0)) {                 // new segment: R (and the drained acc2) must be in place
-        mbar_wait(r_full, seg & 1);
+    int kp = kp_first, sw = 0, seg = 0;
+    uint32_t phw = 0;
+    for (int i = 0; i < np; ++i) {
+      const int g0 = 2 * (i & 1);                  // the two epilogue groups of this unit: g0, g0 + 1
+      if ((i == 0) || (kp == 0)) {                 // new segment: R (and the drained acc2) must be in place
+        WAIT(r_full, seg & 1, 3, i);
         ++seg;
       }
-      mbar_wait2(k_full + sk, phk, acc1_empty + g, ((i / NG) & 1) ^ 1);
+      const uint32_t pe = (uint32_t)(((i >> 1) & 1) ^ 1);
+#ifdef F11_DEBUG
+      WAIT(w_full + sw, phw, 4, i); WAIT(acc1_empty + g0, pe, 5, i); WAIT(acc1_empty + g0 + 1, pe, 6, i);
+#else
+      mbar_wait3(w_full + sw, phw, acc1_empty + g0, pe, acc1_empty + g0 + 1, pe);
+#endif
       tc_fence_after();
-      const uint32_t tka = smem_u32(tk(sk));
+      const uint32_t ta = smem_u32(ts(sw));
       if (elect_one()) {
-        // fully unrolled with one descriptor per unit: the k-step offsets are immediates
-        const uint64_t kd0 = make_smem_desc(tka, 0, 1024, false);
-        const uint32_t dacc = tb + COL_ACC1 + (uint32_t)g * 32u, aR = tb + COL_R;
+        // K-major read of the BASE32B image: row groups are its 4-row atoms (SBO = 512); k-step ks = 32 bytes inside
+        // slab ks / 4.  Fully unrolled with one descriptor per unit: the k-step offsets are immediates.
+        const uint64_t kd0 = make_desc_lt(ta, 0, 512, LT_BASE32B);
+        const uint32_t dacc = tb + COL_ACC1 + (uint32_t)g0 * 32u, aR = tb + COL_R;
 #pragma unroll
         for (int ks = 0; ks < 16; ++ks)
           if (ks < ksteps1)
-            umma_tf32_ts(dacc, aR + ks * 8, kd0 + (uint64_t)(((ks >> 2) * 4096 + (ks & 3) * 32) >> 4), idesc1, ks > 0 ? 1u : 0u);
-        umma_commit(acc1_full + g);
-        umma_commit(k_empty + sk);
-        if (!want_grad && ((kt + 1 == KT) || (i == nu - 1))) umma_commit(acc2_full + ((seg - 1) & (NG - 1)));   // loss-only: segment end marker
+            umma_tf32_ts(dacc, aR + ks * 8, kd0 + (uint64_t)(((ks >> 2) * SLAB_BYTES + (ks & 3) * 32) >> 4), idesc1, ks > 0 ? 1u : 0u);
+        umma_commit(acc1_full + g0);
+        umma_commit(acc1_full + g0 + 1);
+        umma_commit(w_empty + sw);
+        if (!want_grad && ((kp + 1 == KP) || (i == np - 1))) umma_commit(acc2_full + ((seg - 1) & (NG - 1)));   // loss-only: segment end marker
       }
       __syncwarp();
-      if (++sk == a.nk) { sk = 0; phk ^= 1; }
-      if (++kt == KT) kt = 0;
+      if (++sw == a.nw) { sw = 0; phw ^= 1; }
+      if (++kp == KP) kp = 0;
     }
   } else if (warp == 3) {
-    // ===== MMA2 issuer: acc2 += dY[g] . T_MN (dY was written to TMEM by epilogue group g) =====
+    // ===== MMA2 issuer: acc2 += dY[g] . T (rows 32 s .. 32 s + 31 of the unit's tile, MN-major; dY was written to TMEM
+    // by epilogue group g) =====
     if (want_grad) {
       const uint32_t idesc2 = make_idesc(128, a.HN, false, true);
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-      int kt = kt_first, sm = 0, seg = 0;
-      uint32_t phm = 0, acc2 = 0;
+      int kt = kt_first, sw = 0, seg = 0;
+      uint32_t phw = 0, acc2 = 0;
       for (int j = 0; j < nu; ++j) {
-        const int g = j & (NG - 1);
-        const bool last = (kt + 1 == KT) || (j == nu - 1);       // the segment ends with this unit
-        mbar_wait2(m_full + sm, phm, a2_full + g, (j / NG) & 1);
+        const int g = j & (NG - 1), half = j & 1;
+        const bool last = (kt + 1 == KT) || (j == nu - 1);       // the segment ends with this half-unit
+#ifdef F11_DEBUG
+        WAIT(w_full + sw, phw, 7, j); WAIT(a2_full + g, (j / NG) & 1, 8, j);
+#else
+        mbar_wait2(w_full + sw, phw, a2_full + g, (j / NG) & 1);
+#endif
         tc_fence_after();
-        const uint32_t tma = smem_u32(tm(sm));
+        const uint32_t ta = smem_u32(ts(sw)) + (uint32_t)half * 4096u;
         if (elect_one()) {
-          const uint64_t md0 = make_smem_desc(tma, 4096, 512, true);
+          const uint64_t md0 = make_desc_lt(ta, SLAB_BYTES, 512, LT_BASE32B);
           const uint32_t a2 = tb + COL_A2 + (uint32_t)g * 32u;
 #pragma unroll
           for (int ks = 0; ks < UN / 8; ++ks)
             umma_tf32_ts(tb + COL_ACC2, a2 + ks * 8, md0 + (uint64_t)((ks * 1024) >> 4), idesc2, (acc2 | (uint32_t)ks) ? 1u : 0u);
           umma_commit(a2_empty + g);
-          umma_commit(m_empty + sm);
+          if (half) umma_commit(w_empty + sw);
           if (last) umma_commit(acc2_full + (seg & (NG - 1)));
         }
         __syncwarp();
         acc2 = last ? 0u : 1u;
         if (last) ++seg;
-        if (++sm == a.nm) { sm = 0; phm ^= 1; }
+        if (half && ++sw == a.nw) { sw = 0; phw ^= 1; }
         if (++kt == KT) kt = 0;
       }
     }
   } else {
     // ===== epilogue groups =====
     const int quad = warp & 3, grp = (warp - CTRL_WARPS) >> 2;
+    const int hs = grp & 1;                                // which half of its units this group owns
     const int r = quad * 32 + lane;                        // TMEM lane = row of R within the block
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
     const uint32_t tacc1 = tmem_base + lane_bits + COL_ACC1 + (uint32_t)grp * 32u;
     const uint32_t ta2 = tmem_base + lane_bits + COL_A2 + (uint32_t)grp * 32u;
     const uint32_t tR = tmem_base + lane_bits + COL_R;
-    const int ksteps1 = (a.H + 7) / 8;
+    // the two groups of a segment's last unit share the segment change: k-steps of R and 16-column chunks of acc2
 
-    // R block of tile (rb, arm) -> TMEM (rows beyond r_rows and columns beyond H are zero)
-    auto load_R = [&](int rb, int arm) {
+    // this group's k-steps of the R block of tile (rb, arm): global -> registers (all loads in flight together) ...
+    auto fetch_R = [&](uint32_t (&rv)[8][8], int rb, int arm) {
+      const int ksteps1 = (a.H + 7) / 8, kc0 = hs ? (ksteps1 + 1) / 2 : 0, kc1 = hs ? ksteps1 : (ksteps1 + 1) / 2;
       const int row = rb * 128 + r;
       const float* src = a.R + (int64_t)arm * a.r_arm_stride + (int64_t)row * a.H;
       const bool ok = row < a.r_rows;
-      for (int c = 0; c < ksteps1; ++c) {
-        uint32_t v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int kc = kc0 + c;
         float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
-        if (ok) {
-          f0 = __ldg(reinterpret_cast<const float4*>(src + 8 * c));
-          if (8 * c + 4 < a.H) f1 = __ldg(reinterpret_cast<const float4*>(src + 8 * c + 4));
+        if (ok && kc < kc1) {
+          f0 = __ldg(reinterpret_cast<const float4*>(src + 8 * kc));
+          if (8 * kc + 4 < a.H) f1 = __ldg(reinterpret_cast<const float4*>(src + 8 * kc + 4));
         }
-        v[0] = __float_as_uint(f0.x); v[1] = __float_as_uint(f0.y); v[2] = __float_as_uint(f0.z); v[3] = __float_as_uint(f0.w);
-        v[4] = __float_as_uint(f1.x); v[5] = __float_as_uint(f1.y); v[6] = __float_as_uint(f1.z); v[7] = __float_as_uint(f1.w);
-        tmem_st8(tR + 8 * c, v);
+        rv[c][0] = __float_as_uint(f0.x); rv[c][1] = __float_as_uint(f0.y); rv[c][2] = __float_as_uint(f0.z); rv[c][3] = __float_as_uint(f0.w);
+        rv[c][4] = __float_as_uint(f1.x); rv[c][5] = __float_as_uint(f1.y); rv[c][6] = __float_as_uint(f1.z); rv[c][7] = __float_as_uint(f1.w);
       }
+    };
+    // ... -> TMEM (rows beyond r_rows and columns beyond H are zero)
+    auto store_R = [&](const uint32_t (&rv)[8][8]) {
+      const int ksteps1 = (a.H + 7) / 8, kc0 = hs ? (ksteps1 + 1) / 2 : 0, kc1 = hs ? ksteps1 : (ksteps1 + 1) / 2;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (kc0 + c < kc1) tmem_st8(tR + 8 * (kc0 + c), rv[c]);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -243,7 +298,11 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     while (kt >= KT) { kt -= KT; ++t; if (++arm == a.batch) { arm = 0; ++rb; } }
     int sx = grp % a.nx;
     uint32_t phx = (uint32_t)((grp / a.nx) & 1), ph1 = 0, pha = 1;
-    if (grp == 0 && nu > 0) load_R(rb_first, arm_first);
+    if (grp < 2) {
+      uint32_t rv[8][8];
+      fetch_R(rv, rb_first, arm_first);
+      store_R(rv);
+    }      // (np >= 1: the grid never exceeds the unit count)
     double sse = 0.0, mism = 0.0;      // ROW: loss partial sums of the current tile
     float dbsum = 0.f;                 // GENE: d fc11.bias partial of the current tile
     float bj = 0.f;                    // GENE: bias of this thread's gene
@@ -251,14 +310,14 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const float* __restrict__ bias_arm = a.bias;
     bool row_ok = false;
     for (int i = grp; i < nu; i += NG) {
-      if (t != t_cur) {                 // this group's first unit of a tile
+      if (t != t_cur) {                 // this group's first half-unit of a tile
         t_cur = t;
         bias_arm = a.bias + (int64_t)arm * a.bias_arm_stride;
         row_ok = rb * 128 + r < a.r_rows;
         if (GENE) bj = row_ok ? __ldg(bias_arm + rb * 128 + r) : 0.f;
       }
-      const int c0 = kt * UN;           // first gene (ROW) / cell (GENE) of the unit
-      mbar_wait(x_full + sx, phx);
+      const int c0 = kt * UN;           // first gene (ROW) / cell (GENE) of the half-unit
+      WAIT(x_full + sx, phx, 9, i);
       const uint8_t* tile = xs(sx);
       // the x tile does not depend on MMA1: read it while the accumulator is still being produced
       float xv[32];
@@ -272,7 +331,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) xv[j] = *reinterpret_cast<const float*>(tile + j * 512 + r * 4);
       }
-      mbar_wait(acc1_full + grp, ph1);
+      WAIT(acc1_full + grp, ph1, 10, i);
       tc_fence_after();
       uint32_t acc[32];
       tmem_ld16(tacc1, acc);
@@ -330,7 +389,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         if (want_grad) {
           if (!a2_waited) {
-            mbar_wait(a2_empty + grp, pha);
+            WAIT(a2_empty + grp, pha, 11, i);
             tc_fence_after();
             a2_waited = true;
           }
@@ -349,8 +408,9 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       ph1 ^= 1;
       pha ^= 1;
-      const bool seg_end = (kt == KT - 1) || (i == nu - 1);
-      // position of this group's next unit
+      // this half-unit belongs to the last unit of the CTA's share of tile t (both of that unit's groups see it)
+      const bool seg_end = (kt >= KT - 2) || (i >= nu - 2);
+      // position of this group's next half-unit
       int kt_n = kt + NG, t_n = t, rb_n = rb, arm_n = arm;
       while (kt_n >= KT) { kt_n -= KT; ++t_n; if (++arm_n == a.batch) { arm_n = 0; ++rb_n; } }
       const bool leaving = (t_n != t) || (i + NG >= nu);
@@ -369,12 +429,15 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
       }
       if (seg_end) {
-        // ---- drain acc2 (this CTA's share of tile t), then bring in R of the next tile
-        mbar_wait(acc2_full + ((t - t_first) & (NG - 1)), ((t - t_first) / NG) & 1);
+        // ---- the R block of the next tile is fetched while the tensor pipe finishes the segment; then this group's
+        // share of acc2 (the CTA's partial of tile t) is drained and its share of R stored
+        const bool more = i < nu - 2;
+        WAIT(acc2_full + ((t - t_first) & (NG - 1)), ((t - t_first) / NG) & 1, 12, i);
         tc_fence_after();
         if (want_grad) {
           float* prt = a.part + ((int64_t)blockIdx.x + t) * TILE_FLOATS + r * 128;
-          for (int j = 0; j < a.HN / 16; ++j) {
+          const int nch = a.HN / 16, ch0 = hs ? (nch + 1) / 2 : 0, ch1 = hs ? nch : (nch + 1) / 2;
+          for (int j = ch0; j < ch1; ++j) {
             uint32_t rr[16];
             tmem_ld16(tmem_base + lane_bits + COL_ACC2 + (uint32_t)(j * 16), rr);
             tmem_ld_wait();
@@ -385,13 +448,14 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
           tc_fence_before();
         }
-        if (i != nu - 1) {
+        if (more) {
+          uint32_t rv[8][8];
           int arm2 = arm + 1, rb2 = rb;
           if (arm2 == a.batch) { arm2 = 0; ++rb2; }
-          load_R(rb2, arm2);
+          fetch_R(rv, rb2, arm2);
+          store_R(rv);
         }
       }
-      // GENE: groups that did not see the tile at all must still define their db partial (zero) -- handled by the fix-up
       sx += NG;
       if (sx >= a.nx) { sx -= a.nx; phx ^= 1; }
       kt = kt_n; t = t_n; rb = rb_n; arm = arm_n;
@@ -432,8 +496,9 @@ __global__ void __launch_bounds__(256) f11_fixup_kernel(const float* part, int b
   }
 }
 
-// d fc11.bias[arm][gene] = sum over CTAs and epilogue groups of the partials; a (CTA, group) pair that processed no unit
-// of the tile wrote nothing: its units are i = g (mod NG) counted from the CTA's first unit.
+// d fc11.bias[arm][gene] = sum over CTAs and epilogue groups of the partials; a (CTA, group) pair that processed no
+// half-unit of the tile wrote nothing: group g owns the half-units j = g (mod NG) counted from the CTA's first one.
+// (ktiles, U: units = pairs of half-units, as in the main kernel)
 __global__ void __launch_bounds__(128) f11_db_fixup_kernel(const float* db_part, int batch, int ktiles, int64_t U, int64_t G,
                                                            float* out, int64_t out_arm_stride, int D) {
   const int arm = blockIdx.y;
@@ -445,10 +510,10 @@ __global__ void __launch_bounds__(128) f11_db_fixup_kernel(const float* db_part,
   float v = 0.f;
   for (int64_t c = c0; c <= c1; ++c) {
     const int64_t s0 = c * U / G, s1 = (c + 1) * U / G;       // units of CTA c
-    const int64_t lo = ua > s0 ? ua : s0, hi = ub < s1 ? ub : s1;
+    const int64_t lo = 2 * (ua > s0 ? ua : s0), hi = 2 * (ub < s1 ? ub : s1);   // half-units of the tile in CTA c
     for (int g = 0; g < NG; ++g) {
-      // first unit >= lo with (u - s0) % NG == g
-      int64_t first = lo + ((g - (lo - s0)) % NG + NG) % NG;
+      // first half-unit >= lo with (j - 2 s0) % NG == g
+      const int64_t first = lo + ((g - (lo - 2 * s0)) % NG + NG) % NG;
       if (first < hi) v += db_part[((c + t) * NG + g) * 128 + threadIdx.x];
     }
   }
@@ -467,22 +532,35 @@ int sm_count2() {
 }
 
 template <bool GENE, bool TRAIN>
-int launch_f11(const CUtensorMap& tmX, const CUtensorMap& tmTk, const CUtensorMap& tmTm, F11Args& a, int64_t* U_out,
-               int64_t* G_out, cudaStream_t s) {
+int launch_f11(const CUtensorMap& tmX, const CUtensorMap& tmT, F11Args& a, int64_t* U_out, int64_t* G_out, cudaStream_t s) {
   const int64_t U = (int64_t)a.batch * a.rtiles * a.ktiles;
   int64_t G = sm_count2();
   if (G > U) G = U;
-  a.nk = 4; a.nm = 4;
-  a.nx = (227 * 1024 - 2048 - (a.nk + a.nm) * IMG_BYTES) / X_BYTES;
-  if (a.nx > 8) a.nx = 8;
-  const size_t smem = (size_t)a.nx * X_BYTES + (size_t)(a.nk + a.nm) * IMG_BYTES + (2 * a.nx + 2 * a.nk + 2 * a.nm + 5 * NG + 4) * 8 + 1024;
-  static bool attr = false;
-  if (!attr) {
+  // a T tile lives from its load until MMA2 of its second half: one being loaded, MMA1 up to two units ahead of the
+  // epilogue, MMA2 behind it -> 4 stages.  The x ring depth must be a multiple of NG, so that a slot is always refilled
+  // for the group that emptied it: with any other depth a slot alternates between two groups, and a group can reach
+  // "its" fill k while fill k - 1 (the other group's; TMA completions are not ordered) is still in flight -- the parity
+  // wait for fill k then succeeds on the completed fill k - 2 (stale tile, early release, two fills pending on one
+  // barrier: intermittent launch failures when x rows are not 128-byte aligned, D = 5032 with 6 slots).
+  a.nw = F11_NW;
+  a.nx = (227 * 1024 - 2048 - a.nw * IMG_BYTES) / X_BYTES >= 2 * NG ? 2 * NG : NG;
+  const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * IMG_BYTES + (2 * a.nx + 2 * a.nw + 5 * NG + 4) * 8 + 1024;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr[64] = {};
+  if (dev >= 0 && dev < 64 && !attr[dev]) {
     MVAE_CUDA(cudaFuncSetAttribute(fc11_ts_kernel<GENE, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+    attr[dev] = true;
   }
-  fc11_ts_kernel<GENE, TRAIN><<<dim3((unsigned)G), THREADS, smem, s>>>(tmX, tmTk, tmTm, a);
-  MVAE_LAUNCH_CHECK();
+  fc11_ts_kernel<GENE, TRAIN><<<dim3((unsigned)G), THREADS, smem, s>>>(tmX, tmT, a);
+  {
+    ::mvae::g_launches++;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      ::mvae::set_error("fc11 %s pass: kernel launch failed: %s (%s:%d)", GENE ? "gene" : "row", cudaGetErrorString(e), __FILE__, __LINE__);
+      return (int)e;
+    }
+  }
   *U_out = U; *G_out = G;
   return 0;
 }
@@ -499,7 +577,7 @@ int ts_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
   F11Args a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.D = D; a.H = H; a.HN = (H + 15) / 16 * 16;
-  a.batch = A; a.rtiles = (B + 127) / 128; a.ktiles = (D + UN - 1) / UN;
+  a.batch = A; a.rtiles = (B + 127) / 128; a.ktiles = (D + 2 * UN - 1) / (2 * UN);
   a.x_batched = in.x_arm_stride > 0;
   a.want_grad = want_grad; a.gscale = gscale;
   a.R = work + w.d[4]; a.r_arm_stride = (int64_t)B * H; a.r_rows = B;
@@ -507,16 +585,14 @@ int ts_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
   a.x_rec = x_rec; a.xrec_arm_stride = (int64_t)B * D;
   a.recon_acc = recon_acc;
   a.part = work + w.fc1_part;
-  CUtensorMap tmX, tmTk, tmTm;
+  CUtensorMap tmX, tmT;
   int rc = make_map_ex(&tmX, in.x, D, B, in.x_row_stride, A, in.x_arm_stride, 32, 128, 1);
   if (rc) return rc;
-  rc = make_map_ex(&tmTk, st.params + L.offset[FC11_W], H, D, H, A, L.arm_stride, 32, UN, 1);
-  if (rc) return rc;
-  rc = make_map_ex(&tmTm, st.params + L.offset[FC11_W], H, D, H, A, L.arm_stride, 32, UN, 2);
+  rc = make_map_ex(&tmT, st.params + L.offset[FC11_W], H, D, H, A, L.arm_stride, 32, 2 * UN, 2);
   if (rc) return rc;
   int64_t U, G;
-  rc = (want_grad && !x_rec) ? launch_f11<false, true>(tmX, tmTk, tmTm, a, &U, &G, s)
-                             : launch_f11<false, false>(tmX, tmTk, tmTm, a, &U, &G, s);
+  rc = (want_grad && !x_rec) ? launch_f11<false, true>(tmX, tmT, a, &U, &G, s)
+                             : launch_f11<false, false>(tmX, tmT, a, &U, &G, s);
   if (rc || !want_grad) return rc;
   f11_fixup_kernel<<<dim3((B + 127) / 128 * 8, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, work + w.g_d10, (int64_t)B * H, H, B, H);
   MVAE_LAUNCH_CHECK();
@@ -532,22 +608,20 @@ int ts_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& i
   F11Args a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.D = D; a.H = H; a.HN = (H + 15) / 16 * 16;
-  a.batch = A; a.rtiles = (D + 127) / 128; a.ktiles = (B + UN - 1) / UN;
+  a.batch = A; a.rtiles = (D + 127) / 128; a.ktiles = (B + 2 * UN - 1) / (2 * UN);
   a.x_batched = in.x_arm_stride > 0;
   a.want_grad = 1; a.gscale = gscale;
   a.R = st.params + L.offset[FC11_W]; a.r_arm_stride = L.arm_stride; a.r_rows = D;
   a.bias = st.params + L.offset[FC11_B]; a.bias_arm_stride = L.arm_stride;
   a.part = work + w.fc1_part;
   a.db_part = work + w.db_part;
-  CUtensorMap tmX, tmTk, tmTm;
+  CUtensorMap tmX, tmT;
   int rc = make_map_ex(&tmX, in.x, D, B, in.x_row_stride, A, in.x_arm_stride, 128, 32, 0);
   if (rc) return rc;
-  rc = make_map_ex(&tmTk, work + w.d[4], H, B, H, A, (int64_t)B * H, 32, UN, 1);
-  if (rc) return rc;
-  rc = make_map_ex(&tmTm, work + w.d[4], H, B, H, A, (int64_t)B * H, 32, UN, 2);
+  rc = make_map_ex(&tmT, work + w.d[4], H, B, H, A, (int64_t)B * H, 32, 2 * UN, 2);
   if (rc) return rc;
   int64_t U, G;
-  rc = launch_f11<true, true>(tmX, tmTk, tmTm, a, &U, &G, s);
+  rc = launch_f11<true, true>(tmX, tmT, a, &U, &G, s);
   if (rc) return rc;
   f11_fixup_kernel<<<dim3((D + 127) / 128 * 8, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, st.grads + L.offset[FC11_W], L.arm_stride,
                                                            H, D, H);

@@ -476,10 +476,15 @@ int launch_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap&
   if (G > U) G = U;
   const int w_stage = a.w_tile_bytes * (a.split3 ? 2 : 1);
   // rings: the small operand gets 4-5 stages, the raw x ring the rest of the 227 KB
+  // The x ring depth must be a multiple of NG: then a slot is always refilled for the group that emptied it.  With any
+  // other depth a slot alternates between two groups, and a group can reach "its" fill k while fill k - 1 -- the other
+  // group's, TMA completions are not ordered -- is still in flight: the parity wait for fill k then succeeds on the
+  // completed fill k - 2 and the protocol falls apart (stale tile, early release, two fills pending on one barrier:
+  // seen as intermittent launch failures when x rows are not 128-byte aligned).
   a.nw = a.split3 ? 4 : 5;
-  const int budget = 227 * 1024 - 1024 - 512 - a.nw * w_stage;
-  a.nx = budget / X_BYTES;
-  if (a.nx > 8) a.nx = 8;
+  auto nx_for = [&](int nw) { return (227 * 1024 - 1024 - 512 - nw * w_stage) / X_BYTES; };
+  if (nx_for(a.nw) < 2 * NG && nx_for(a.nw - 1) >= 2 * NG) --a.nw;
+  a.nx = nx_for(a.nw) >= 2 * NG ? 2 * NG : NG;
   const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * w_stage + (2 * a.nx + 2 * a.nw + 3 * NA + 6) * 8 + 1024;
   static bool attr = false;
   if (!attr) {

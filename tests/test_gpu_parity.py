@@ -294,6 +294,36 @@ def test_full_size_cfg2_properties():
             assert e <= max(K * floor32, floor), (precision, n, e, floor32)
 
 
+@pytest.mark.parametrize("B,D", [(15000, 5032), (12000, 1000)], ids=["b15000_d5032", "b12000_d1000"])
+def test_large_batch_unaligned_rows_run_to_run_identical(B, D):
+    """Ring-protocol stress of the gene kernels: many units per CTA, x rows that are not 128-byte aligned (TMA tiles
+    complete out of order), several stream-K segments per CTA.  A slot-protocol slip showed up here as an intermittent
+    launch failure (x ring depth not a multiple of the group count).  Property checked: 30 fused steps run twice from
+    the same seed agree to rounding (the tile reductions are ordered; only the fp64 atomics of the batch statistics are
+    not, and they vanish in the cast to fp32) -- a stale or torn tile would show up at the percent level."""
+    from mmidas_b200 import FusedAdam
+    hp = O.HP(input_dim=D, n_categories=100, state_dim=2, n_arm=2, x_drop=0.5, s_drop=0.0)
+    gen = torch.Generator().manual_seed(7)
+    x = O.synth_x(B, D, gen).cuda()
+    runs = []
+    for rep in range(2):
+        model = build_model(hp, "tf32x3_fc1")
+        opt = FusedAdam(model.parameters(), lr=hp.lr, model=model)
+        model.train()
+        torch.manual_seed(11)
+        losses = []
+        for step in range(30):
+            lv = model.fused_train_step(x.expand(hp.n_arm, -1, -1), hp.temp, opt)
+            losses.append(lv[0:1].clone())
+        torch.cuda.synchronize()
+        losses = torch.cat(losses)
+        assert torch.isfinite(losses).all()
+        runs.append((losses, model.flat_parameters().clone()))
+    torch.testing.assert_close(runs[0][0], runs[1][0], rtol=1e-5, atol=0.0)
+    torch.testing.assert_close(runs[0][1], runs[1][1], rtol=1e-5, atol=1e-7)
+    assert runs[0][0][-1] < runs[0][0][0]          # and it trains
+
+
 def test_rejects_bad_usage():
     hp, x, noises, _, _ = case_inputs("tiny")
     model = build_model(hp, "fp32_simt")
