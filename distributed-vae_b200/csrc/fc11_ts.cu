@@ -543,7 +543,11 @@ int launch_f11(const CUtensorMap& tmX, const CUtensorMap& tmT, F11Args& a, int64
   // wait for fill k then succeeds on the completed fill k - 2 (stale tile, early release, two fills pending on one
   // barrier: intermittent launch failures when x rows are not 128-byte aligned, D = 5032 with 6 slots).
   a.nw = F11_NW;
+#ifdef F11_NX
+  a.nx = F11_NX;
+#else
   a.nx = (227 * 1024 - 2048 - a.nw * IMG_BYTES) / X_BYTES >= 2 * NG ? 2 * NG : NG;
+#endif
   const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * IMG_BYTES + (2 * a.nx + 2 * a.nw + 5 * NG + 4) * 8 + 1024;
   int dev = 0;
   cudaGetDevice(&dev);

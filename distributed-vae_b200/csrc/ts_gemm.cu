@@ -483,8 +483,12 @@ int launch_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap&
   // seen as intermittent launch failures when x rows are not 128-byte aligned).
   a.nw = a.split3 ? 4 : 5;
   auto nx_for = [&](int nw) { return (227 * 1024 - 1024 - 512 - nw * w_stage) / X_BYTES; };
+#ifdef TS_NX
+  a.nx = TS_NX;
+#else
   if (nx_for(a.nw) < 2 * NG && nx_for(a.nw - 1) >= 2 * NG) --a.nw;
   a.nx = nx_for(a.nw) >= 2 * NG ? 2 * NG : NG;
+#endif
   const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * w_stage + (2 * a.nx + 2 * a.nw + 3 * NA + 6) * 8 + 1024;
   static bool attr = false;
   if (!attr) {
