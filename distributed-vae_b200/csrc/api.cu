@@ -364,7 +364,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
     float* dl[5] = {work + w.delta_enc[0], work + w.delta_enc[1], work + w.delta_enc[2], work + w.delta_enc[3],
                     work + w.delta_enc[4]};
     bchain_rc = launch_enc_chain_bwd(st.params, p.L.arm_stride, p.L.offset, A, B, H, Ld, work + w.g_xlow, act, dl, acc_bwd,
-                                     bn_mean, bn_rstd, hp.precision == 1, s);
+                                     bn_mean, bn_rstd, work + w.gtmp[0], hp.precision == 1, s);
     if (bchain_rc < 0 || bchain_rc > 1) return bchain_rc;
   }
   for (int l = 4; l >= 0 && bchain_rc == 1; --l) {

@@ -145,7 +145,7 @@ int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_
 // encoder middle backward (batch_l5 .. batch_l1 and fc5 .. fc2): deltas of layers 5..1, one cooperative kernel
 int launch_enc_chain_bwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
                          const float* g_xlow, const float* const act[5], float* const delta[5], double* acc_bwd,
-                         const float* bn_mean, const float* bn_rstd, int split3, cudaStream_t s);
+                         const float* bn_mean, const float* bn_rstd, float* g_scratch, int split3, cudaStream_t s);
 
 // ---- optimiser / misc ------------------------------------------------------------------------
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,

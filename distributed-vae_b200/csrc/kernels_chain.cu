@@ -480,6 +480,145 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same chain for batches that need more row tiles than there are SMs (A * ceil(B / 80) > #SM: three or more arms at
+// B = 5000, B = 16384): the grid is still one co-resident wave, and a CTA walks over SEVERAL row tiles of its arm inside
+// every layer (tile j of CTA x: row block x + j * gridDim.x).  Its tiles cannot all stay in shared memory, so the layer's
+// input tile comes back from global memory (it was written there for the backward pass anyway, by this same CTA) into a
+// two-deep ring -- tile j + 1 is in flight while tile j is multiplied -- and the column sums of all its tiles are added
+// up in shared memory before the one round of atomics per layer.
+// ---------------------------------------------------------------------------------------------
+template <int MT, int NWC, int HC, int LC>
+__global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_multi_kernel(const EncChainArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int CR = 16 * MT, CT = 32 * MT * NWC, NTW = 16 / NWC;
+  constexpr bool FAST = HC > 0;
+  const int XP = FAST ? (((HC + 7) & ~7) + 4) : p.XP, Hp = FAST ? ((HC + 7) & ~7) : p.Hp;
+  float* Ws0 = smem;                       // [Hp][XP]  W natural [out][in]
+  float* Ws1 = Ws0 + Hp * XP;
+  float* Xs0 = Ws1 + Hp * XP;              // [CR][XP]
+  float* Xs1 = Xs0 + CR * XP;
+  float* bias = Xs1 + CR * XP;             // [4][128]
+  float* mean = bias + 4 * 128;            // [128]
+  float* rstd = mean + 128;                // [128]
+  double* red = reinterpret_cast<double*>(rstd + 128);   // [MT][2][128]
+  double* tot = red + MT * 2 * 128;                      // [2][128] sums over this CTA's tiles of the layer
+  const int arm = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int warp = tid >> 5, wr = warp % MT, wc = warp / MT;
+  const int g = lane >> 2, tig = lane & 3;
+  const int H = FAST ? HC : p.H, L = FAST ? LC : p.L, B = p.B;
+  const float* par = p.params + (int64_t)arm * p.p_arm_stride;
+  const unsigned int nctas = gridDim.x * gridDim.y;
+  const int ntiles = (B + CR - 1) / CR;
+  const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  for (int idx = tid; idx < 2 * Hp * XP + 2 * CR * XP; idx += CT) smem[idx] = 0.f;
+  for (int idx = tid; idx < 4 * 128; idx += CT) {
+    const int l = idx >> 7, j = idx & 127;
+    const int nout = l < 3 ? H : L;
+    bias[idx] = j < nout ? par[p.offB[l] + j] : 0.f;
+  }
+  __syncthreads();
+  float* Ws[2] = {Ws0, Ws1};
+  float* Xs[2] = {Xs0, Xs1};
+  auto load_tile = [&](int l, int j, float* dst) {      // input tile j of layer l (a1 / a2 / a3 / a4), valid rows only
+    const int row0 = ((int)blockIdx.x + j * (int)gridDim.x) * CR;
+    const float* src = (l == 0 ? p.a1 : p.aout[l - 1]) + ((int64_t)arm * B + row0) * H;
+    async_tile(dst, XP, src, H, min(CR, B - row0), H, tid, CT);
+  };
+  async_tile(Ws0, XP, par + p.offW[0], H, H, H, tid, CT);
+  if (mine > 0) load_tile(0, 0, Xs0);
+  cp_async_commit();
+  async_tile(Ws1, XP, par + p.offW[1], H, H, H, tid, CT);
+  cp_async_commit();
+
+  for (int l = 0; l < 4; ++l) {
+    const int nout = l < 3 ? H : L;
+    if (tid < H) {
+      const double* sums = p.sums + (int64_t)(l * p.A + arm) * 256;
+      const double s1 = __ldcg(sums + tid), s2 = __ldcg(sums + 128 + tid);
+      const double m = s1 / (double)B;
+      double var = s2 / (double)B - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mf = (float)m, rf = (float)(1.0 / sqrt(var + (double)p.eps));
+      mean[tid] = mf;
+      rstd[tid] = rf;
+      if (blockIdx.x == 0) {
+        p.bn_mean[(l * p.A + arm) * 128 + tid] = mf;
+        p.bn_rstd[(l * p.A + arm) * 128 + tid] = rf;
+      }
+    }
+    for (int j = tid; j < 256; j += CT) tot[j] = 0.0;
+    const int nt_used = max(0, min(NTW, (nout + 7) / 8 - wc * NTW));
+    for (int j = 0; j < mine; ++j) {
+      const int row0 = ((int)blockIdx.x + j * (int)gridDim.x) * CR;
+      const int rows_valid = min(CR, B - row0);
+      cp_async_wait<0>();                  // tile j and the weights of this layer have landed
+      __syncthreads();                     // ... for everyone; the other tile buffer is free (tile j - 1 is finished)
+      if (j + 1 < mine) {
+        load_tile(l, j + 1, Xs[(j + 1) & 1]);
+        cp_async_commit();
+      }
+      float* Xc = Xs[j & 1];
+      for (int idx = tid; idx < rows_valid * H; idx += CT) {
+        const int r = idx / H, c = idx - r * H;
+        Xc[r * XP + c] = (Xc[r * XP + c] - mean[c]) * rstd[c];
+      }
+      __syncthreads();
+      float acc[NTW][4];
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+      if (nt_used == NTW)                  // (a literal count folds the per-tile guards of the MMA loop away)
+        warp_gemm2<NTW, true, true>(Xc + wr * 16 * XP, XP, Ws[l & 1] + wc * NTW * 8 * XP, XP, (H + 7) / 8, NTW, acc, lane);
+      else if (nt_used > 0)
+        warp_gemm2<NTW, true, true>(Xc + wr * 16 * XP, XP, Ws[l & 1] + wc * NTW * 8 * XP, XP, (H + 7) / 8, nt_used, acc, lane);
+      float* out = p.aout[l] + ((int64_t)arm * B + row0) * nout;
+      const int ra = wr * 16 + g, rb = ra + 8;
+      const bool va = ra < rows_valid, vb = rb < rows_valid;
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        if (nt < nt_used) {
+          const int c = (wc * NTW + nt) * 8 + 2 * tig;
+          const float b0 = bias[l * 128 + c], b1 = bias[l * 128 + c + 1];
+          const float v00 = fmaxf(acc[nt][0] + b0, 0.f), v01 = fmaxf(acc[nt][1] + b1, 0.f);
+          const float v10 = fmaxf(acc[nt][2] + b0, 0.f), v11 = fmaxf(acc[nt][3] + b1, 0.f);
+          if (va) { if (c < nout) out[(int64_t)ra * nout + c] = v00; if (c + 1 < nout) out[(int64_t)ra * nout + c + 1] = v01; }
+          if (vb) { if (c < nout) out[(int64_t)rb * nout + c] = v10; if (c + 1 < nout) out[(int64_t)rb * nout + c + 1] = v11; }
+          const double a0 = va ? (double)v00 : 0.0, a1 = va ? (double)v01 : 0.0;
+          const double c0 = vb ? (double)v10 : 0.0, c1 = vb ? (double)v11 : 0.0;
+          const double s0 = group_sum_d(a0 + c0), s1 = group_sum_d(a1 + c1);
+          const double q0 = group_sum_d(a0 * a0 + c0 * c0), q1 = group_sum_d(a1 * a1 + c1 * c1);
+          if (g == 0) {
+            red[(wr * 2 + 0) * 128 + c] = s0; red[(wr * 2 + 0) * 128 + c + 1] = s1;
+            red[(wr * 2 + 1) * 128 + c] = q0; red[(wr * 2 + 1) * 128 + c + 1] = q1;
+          }
+        }
+      }
+      __syncthreads();                     // red complete; everyone is done with this tile
+      for (int jj = tid; jj < 256; jj += CT) {
+        if ((jj & 127) < nout) {
+          double sacc = 0.0;
+          for (int w = 0; w < MT; ++w) sacc += red[(w * 2 + (jj >> 7)) * 128 + (jj & 127)];
+          tot[jj] += sacc;                 // (thread jj owns tot[jj])
+        }
+      }
+    }
+    __syncthreads();                       // every warp has finished the layer: its weight buffer is free
+    for (int jj = tid; jj < 256; jj += CT)
+      if ((jj & 127) < nout && mine > 0)
+        atomicAdd(p.sums + (int64_t)((l + 1) * p.A + arm) * 256 + jj, tot[jj]);
+    if (l + 2 < 4) {
+      if (l + 2 == 3) async_tile(Ws[l & 1], XP, par + p.offW[3], H, L, H, tid, CT);      // fc5 is [L][H]; stale rows are never stored
+      else async_tile(Ws[l & 1], XP, par + p.offW[l + 2], H, H, H, tid, CT);
+    }
+    if (l < 3 && mine > 0) load_tile(l + 1, 0, Xs0);   // this CTA's own rows of the layer it has just written
+    cp_async_commit();
+    if (l < 3) grid_barrier(p.bar + l, nctas);
+  }
+}
+
 // =============================================================================================
 // encoder middle, backward: for l = 5..1 (array index 4..0)
 //   g_l (gradient wrt the BatchNorm output of layer l) -> BatchNorm backward (needs the batch means of g and g*n:
@@ -642,6 +781,148 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncB
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward chain over several row tiles per CTA (see enc_chain_fwd_multi_kernel).  The gradient tile cannot stay in shared
+// memory between layers here: g_{l-1} goes to a global scratch buffer [A][B][H] and comes back at the next layer (always
+// this CTA's own rows).  Per tile: (g_l, a_l) and a_{l-1} arrive in two cp.async groups, so that the BatchNorm/ReLU
+// backward of the tile runs while the second group is still in flight.
+// ---------------------------------------------------------------------------------------------
+template <int MT, int NWC, bool SPLIT, int HC, int LC>
+__global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_multi_kernel(const EncBwdArgs p, float* __restrict__ gscr) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int CR = 16 * MT, CT = 32 * MT * NWC, NTW = 16 / NWC;
+  constexpr bool FAST = HC > 0;
+  constexpr int HPC = (HC + 7) & ~7;
+  const int XP = FAST ? HPC + 4 : p.XP, Hp = FAST ? HPC : p.Hp;
+  const int WPB = FAST ? (((HPC & 31) == 8 || (HPC & 31) == 24) ? HPC : p.WPB) : p.WPB;
+  float* Ws0 = smem;                       // [Hp][WPB]  W_l natural: row j (out), col i (in)
+  float* Ws1 = Ws0 + Hp * WPB;
+  float* Gs = Ws1 + Hp * WPB;              // [CR][XP]   g_l, then delta_l in place
+  float* Ac = Gs + CR * XP;                // [CR][XP]   a_l tile
+  float* An = Ac + CR * XP;                // [CR][XP]   a_{l-1} tile
+  float* c1 = An + CR * XP;                // [128] each: mean_b(g), mean_b(g*n), mean/rstd of layer l and of layer l-1
+  float* c2 = c1 + 128;
+  float* mo = c2 + 128;
+  float* ro = mo + 128;
+  float* mi = ro + 128;
+  float* ri = mi + 128;
+  double* red = reinterpret_cast<double*>(ri + 128);     // [MT][2][128]
+  double* tot = red + MT * 2 * 128;                      // [2][128]
+  const int arm = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int warp = tid >> 5, wr = warp % MT, wc = warp / MT;
+  const int g = lane >> 2, tig = lane & 3;
+  const int H = FAST ? HC : p.H, L = FAST ? LC : p.L, B = p.B;
+  const float* par = p.params + (int64_t)arm * p.p_arm_stride;
+  const unsigned int nctas = gridDim.x * gridDim.y;
+  const int ntiles = (B + CR - 1) / CR;
+  const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  for (int idx = tid; idx < 2 * Hp * WPB + 3 * CR * XP; idx += CT) smem[idx] = 0.f;
+  __syncthreads();
+  async_tile(Ws0, WPB, par + p.offW[4], H, L, H, tid, CT);       // fc5: [L][H]
+  cp_async_commit();
+  async_tile(Ws1, WPB, par + p.offW[3], H, H, H, tid, CT);
+  cp_async_commit();
+  float* Ws[2] = {Ws0, Ws1};
+
+  for (int it = 0; it < 5; ++it) {
+    const int l = 4 - it;
+    const int nout = l == 4 ? L : H;
+    if (tid < nout) {
+      const double* sums = p.sums + (int64_t)(l * p.A + arm) * 256;
+      c1[tid] = (float)(__ldcg(sums + tid) / (double)B);
+      c2[tid] = (float)(__ldcg(sums + 128 + tid) / (double)B);
+      mo[tid] = p.bn_mean[(l * p.A + arm) * 128 + tid];
+      ro[tid] = p.bn_rstd[(l * p.A + arm) * 128 + tid];
+    }
+    if (l > 0 && tid < H) {
+      mi[tid] = p.bn_mean[((l - 1) * p.A + arm) * 128 + tid];
+      ri[tid] = p.bn_rstd[((l - 1) * p.A + arm) * 128 + tid];
+    }
+    for (int j = tid; j < 256; j += CT) tot[j] = 0.0;
+    const int nt_used = max(0, min(NTW, (H + 7) / 8 - wc * NTW));
+    for (int j = 0; j < mine; ++j) {
+      const int row0 = ((int)blockIdx.x + j * (int)gridDim.x) * CR;
+      const int rows_valid = min(CR, B - row0);
+      const int64_t rbase = (int64_t)arm * B + row0;
+      // (the previous tile's epilogue ended with a __syncthreads: the three tile buffers are free)
+      async_tile(Gs, XP, (l == 4 ? p.g_xlow : gscr) + rbase * nout, nout, rows_valid, nout, tid, CT);
+      async_tile(Ac, XP, p.act[l] + rbase * nout, nout, rows_valid, nout, tid, CT);
+      cp_async_commit();
+      if (l > 0) async_tile(An, XP, p.act[l - 1] + rbase * H, H, rows_valid, H, tid, CT);
+      cp_async_commit();
+      cp_async_wait<1>();                  // g_l, a_l (and this layer's weights, issued a whole layer ago)
+      __syncthreads();
+      float* dout = p.delta[l] + rbase * nout;
+      for (int idx = tid; idx < rows_valid * nout; idx += CT) {
+        const int r = idx / nout, jj = idx - r * nout;
+        const float a = Ac[r * XP + jj];
+        const float n = (a - mo[jj]) * ro[jj];
+        const float gg = ro[jj] * (Gs[r * XP + jj] - c1[jj] - n * c2[jj]);
+        const float d = a > 0.f ? gg : 0.f;
+        Gs[r * XP + jj] = d;
+        dout[(int64_t)r * nout + jj] = d;
+      }
+      if (l == 0) { __syncthreads(); continue; }
+      // rows beyond the batch of a partial tile must not carry another tile's values into the product's valid rows:
+      // they do not (rows are independent), and their results are neither stored nor summed
+      cp_async_wait<0>();
+      __syncthreads();
+      float acc[NTW][4];
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+      {
+        const float* Aw = Gs + wr * 16 * XP;
+        const float* Bw = Ws[it & 1] + wc * NTW * 8;
+        if (nt_used == NTW) warp_gemm2<NTW, false, SPLIT>(Aw, XP, Bw, WPB, (nout + 7) / 8, NTW, acc, lane);
+        else if (nt_used > 0) warp_gemm2<NTW, false, SPLIT>(Aw, XP, Bw, WPB, (nout + 7) / 8, nt_used, acc, lane);
+      }
+      float* gout = gscr + rbase * H;
+      const int ra = wr * 16 + g, rb = ra + 8;
+      const bool va = ra < rows_valid, vb = rb < rows_valid;
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        if (nt < nt_used) {
+          const int c = (wc * NTW + nt) * 8 + 2 * tig;
+          const bool c0ok = c < H, c1ok = c + 1 < H;
+          double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
+          if (c0ok) {
+            if (va) { gout[(int64_t)ra * H + c] = acc[nt][0]; const double n = (double)((An[ra * XP + c] - mi[c]) * ri[c]); s0 += (double)acc[nt][0]; q0 += (double)acc[nt][0] * n; }
+            if (vb) { gout[(int64_t)rb * H + c] = acc[nt][2]; const double n = (double)((An[rb * XP + c] - mi[c]) * ri[c]); s0 += (double)acc[nt][2]; q0 += (double)acc[nt][2] * n; }
+          }
+          if (c1ok) {
+            if (va) { gout[(int64_t)ra * H + c + 1] = acc[nt][1]; const double n = (double)((An[ra * XP + c + 1] - mi[c + 1]) * ri[c + 1]); s1 += (double)acc[nt][1]; q1 += (double)acc[nt][1] * n; }
+            if (vb) { gout[(int64_t)rb * H + c + 1] = acc[nt][3]; const double n = (double)((An[rb * XP + c + 1] - mi[c + 1]) * ri[c + 1]); s1 += (double)acc[nt][3]; q1 += (double)acc[nt][3] * n; }
+          }
+          s0 = group_sum_d(s0); s1 = group_sum_d(s1); q0 = group_sum_d(q0); q1 = group_sum_d(q1);
+          if (g == 0) {
+            red[(wr * 2 + 0) * 128 + c] = s0; red[(wr * 2 + 0) * 128 + c + 1] = s1;
+            red[(wr * 2 + 1) * 128 + c] = q0; red[(wr * 2 + 1) * 128 + c + 1] = q1;
+          }
+        }
+      }
+      __syncthreads();                     // red complete, Gs / Ac / An free
+      for (int jj = tid; jj < 256; jj += CT) {
+        if ((jj & 127) < H) {
+          double sacc = 0.0;
+          for (int w = 0; w < MT; ++w) sacc += red[(w * 2 + (jj >> 7)) * 128 + (jj & 127)];
+          tot[jj] += sacc;
+        }
+      }
+      __syncthreads();                     // red is rewritten by the next tile
+    }
+    if (l == 0) break;
+    for (int jj = tid; jj < 256; jj += CT)
+      if ((jj & 127) < H && mine > 0) atomicAdd(p.sums + (int64_t)((l - 1) * p.A + arm) * 256 + jj, tot[jj]);
+    // W_{l-2} into the weight buffer of this iteration (layer 0 has no data gradient: no weights)
+    if (l - 2 >= 1) async_tile(Ws[it & 1], WPB, par + p.offW[l - 2], H, H, H, tid, CT);
+    cp_async_commit();
+    grid_barrier(p.bar + it, nctas);
+  }
+}
+
 }  // namespace
 
 static int b_pitch2(int n) {
@@ -726,17 +1007,26 @@ int launch_dec_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
 
 namespace mvae {
 
+// cooperative-launch capability and SM count of the current device (a process may drive several)
+static int coop_sms() {
+  static int cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 0;
+  if (!cache[dev]) {
+    int coop = 0, nsm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = coop ? nsm : -1;
+  }
+  return cache[dev] > 0 ? cache[dev] : 0;
+}
+
 int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
                          const float* a1, float* const aout[4], double* acc_fwd, float* bn_mean, float* bn_rstd, float eps,
                          cudaStream_t s) {
-  static int coop = -1, nsm = 0;
-  if (coop < 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  }
-  if (!coop || H > 128 || L > 64 || H % 4 != 0) return 1;
+  const int nsm = coop_sms();
+  if (!nsm || H > 128 || L > 64 || H % 4 != 0 || A > nsm) return 1;
   EncChainArgs c;
   memset(&c, 0, sizeof(c));
   c.Hp = (H + 7) & ~7;
@@ -755,34 +1045,25 @@ int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_
   c.eps = eps;
   constexpr int MT = 5, NWC = 4, CR = 16 * MT;
   const int tiles = (B + CR - 1) / CR;
-  if ((int64_t)tiles * A > nsm) return 1;             // must be one co-resident wave (grid barrier)
-  const size_t smem = (size_t)(2 * c.Hp * c.XP + 2 * CR * c.XP + 4 * 128 + 256) * 4 + (size_t)MT * 2 * 128 * 8;
-  static bool attr = false;
-  if (!attr) {
-    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_fwd_kernel<MT, NWC, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_fwd_kernel<MT, NWC, 100, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  // one co-resident wave (grid barrier): one row tile per CTA while that fits, else several tiles per CTA
+  const bool multi = (int64_t)tiles * A > nsm;
+  const int gx = multi ? nsm / A : tiles;
+  const size_t smem = (size_t)(2 * c.Hp * c.XP + 2 * CR * c.XP + 4 * 128 + 256) * 4 + (size_t)MT * 2 * 128 * 8 + (multi ? 2 * 128 * 8 : 0);
+  const bool fast = (H == 100 && L == 10);
   void* args[] = {(void*)&c};
-  if (H == 100 && L == 10)
-    MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_fwd_kernel<MT, NWC, 100, 10>, dim3(tiles, A), dim3(32 * MT * NWC), args, smem, s));
-  else
-    MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_fwd_kernel<MT, NWC, 0, 0>, dim3(tiles, A), dim3(32 * MT * NWC), args, smem, s));
+  const void* fn = multi ? (fast ? (const void*)enc_chain_fwd_multi_kernel<MT, NWC, 100, 10> : (const void*)enc_chain_fwd_multi_kernel<MT, NWC, 0, 0>)
+                         : (fast ? (const void*)enc_chain_fwd_kernel<MT, NWC, 100, 10> : (const void*)enc_chain_fwd_kernel<MT, NWC, 0, 0>);
+  MVAE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MVAE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(gx, A), dim3(32 * MT * NWC), args, smem, s));
   MVAE_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_enc_chain_bwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
                          const float* g_xlow, const float* const act[5], float* const delta[5], double* acc_bwd,
-                         const float* bn_mean, const float* bn_rstd, int split3, cudaStream_t s) {
-  static int coop = -1, nsm = 0;
-  if (coop < 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  }
-  if (!coop || H > 128 || L > 64 || H % 4 != 0) return 1;
+                         const float* bn_mean, const float* bn_rstd, float* g_scratch, int split3, cudaStream_t s) {
+  const int nsm = coop_sms();
+  if (!nsm || H > 128 || L > 64 || H % 4 != 0 || A > nsm) return 1;
   EncBwdArgs c;
   memset(&c, 0, sizeof(c));
   c.Hp = (H + 7) & ~7;
@@ -801,22 +1082,23 @@ int launch_enc_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
   c.bar = reinterpret_cast<unsigned int*>(acc_bwd + accb_sync(A));
   constexpr int MT = 5, NWC = 4, CR = 16 * MT;
   const int tiles = (B + CR - 1) / CR;
-  if ((int64_t)tiles * A > nsm) return 1;             // must be one co-resident wave (grid barrier)
-  const size_t smem = (size_t)(2 * c.Hp * c.WPB + 3 * CR * c.XP + 6 * 128) * 4 + (size_t)MT * 2 * 128 * 8;
-  void* args[] = {(void*)&c};
-#define ENC_BWD(SP, HCV, LCV)                                                                                              \
-  do {                                                                                                                     \
-    MVAE_CUDA(cudaFuncSetAttribute(enc_chain_bwd_kernel<MT, NWC, SP, HCV, LCV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                   (int)smem));                                                                           \
-    MVAE_CUDA(cudaLaunchCooperativeKernel((void*)enc_chain_bwd_kernel<MT, NWC, SP, HCV, LCV>, dim3(tiles, A),               \
-                                          dim3(32 * MT * NWC), args, smem, s));                                           \
-  } while (0)
+  const bool multi = (int64_t)tiles * A > nsm;
+  if (multi && !g_scratch) return 1;
+  const int gx = multi ? nsm / A : tiles;
+  const size_t smem = (size_t)(2 * c.Hp * c.WPB + 3 * CR * c.XP + 6 * 128) * 4 + (size_t)MT * 2 * 128 * 8 + (multi ? 2 * 128 * 8 : 0);
   const bool fast = (H == 100 && L == 10);
-  if (split3 && fast) ENC_BWD(true, 100, 10);
-  else if (split3) ENC_BWD(true, 0, 0);
-  else if (fast) ENC_BWD(false, 100, 10);
-  else ENC_BWD(false, 0, 0);
-#undef ENC_BWD
+  const void* fn;
+  if (multi) {
+    fn = split3 ? (fast ? (const void*)enc_chain_bwd_multi_kernel<MT, NWC, true, 100, 10> : (const void*)enc_chain_bwd_multi_kernel<MT, NWC, true, 0, 0>)
+                : (fast ? (const void*)enc_chain_bwd_multi_kernel<MT, NWC, false, 100, 10> : (const void*)enc_chain_bwd_multi_kernel<MT, NWC, false, 0, 0>);
+  } else {
+    fn = split3 ? (fast ? (const void*)enc_chain_bwd_kernel<MT, NWC, true, 100, 10> : (const void*)enc_chain_bwd_kernel<MT, NWC, true, 0, 0>)
+                : (fast ? (const void*)enc_chain_bwd_kernel<MT, NWC, false, 100, 10> : (const void*)enc_chain_bwd_kernel<MT, NWC, false, 0, 0>);
+  }
+  void* args1[] = {(void*)&c};
+  void* args2[] = {(void*)&c, (void*)&g_scratch};
+  MVAE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MVAE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(gx, A), dim3(32 * MT * NWC), multi ? args2 : args1, smem, s));
   MVAE_LAUNCH_CHECK();
   return 0;
 }
