@@ -42,6 +42,34 @@ static int check_device() {
   return ok == 1 ? 0 : -2;
 }
 
+// Side branch of the fused step (mvae_train_step): the coupling kernels run beside the decoder chain and the first fc11
+// pass, the loss finalisation beside the decoder's backward chain -- small latency-bound kernels that need no SM the main
+// branch can use at those points.  Fork and join are event edges, so the step still captures into one CUDA graph.
+// One set of resources per host thread and device, created outside any stream capture (every entry point passes through
+// check_device first; a step captured before the resources exist simply runs unforked).
+struct SideBranch {
+  cudaStream_t side = nullptr;
+  cudaEvent_t head_done = nullptr, fc11_done = nullptr, final_done = nullptr;
+};
+static SideBranch* side_branch(cudaStream_t s) {
+  static thread_local SideBranch sb[64];
+  static thread_local int state[64];      // 0: not tried, 1: ready, -1: unavailable
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (state[dev] == 0) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
+    SideBranch& b = sb[dev];
+    const bool ok = cudaStreamCreateWithFlags(&b.side, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&b.head_done, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&b.fc11_done, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&b.final_done, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    state[dev] = ok ? 1 : -1;
+  }
+  return state[dev] == 1 ? &sb[dev] : nullptr;
+}
+
 static uint64_t* step_keys(const Plan& p, const mvae_state& st) { return reinterpret_cast<uint64_t*>(st.work + p.w.keys); }
 
 static DropSpec make_drop(const Plan& p, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in) {
@@ -84,6 +112,16 @@ static bool use_tc(const Plan& p, const mvae_hparams& hp) {
 }
 
 // ---------------------------------------------------------------------------------------------
+static CouplingArgs coupling_args(const Plan& p, const mvae_hparams& hp, const mvae_state& st, const float* qc_all,
+                                  const float* csmp_all) {
+  CouplingArgs c;
+  memset(&c, 0, sizeof(c));
+  c.A = p.A; c.At = p.At; c.arm_off = p.d.arm_offset; c.B = p.B; c.C = p.C;
+  c.qc_all = qc_all; c.csmp_all = csmp_all; c.acc = reinterpret_cast<double*>(st.work + p.w.acc_loss);
+  c.gdiff = st.work + p.w.rsum; c.wcat = st.work + p.w.wcat; c.eps = hp.eps; c.lam = hp.lam;
+  return c;
+}
+
 static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
                         const mvae_outputs& out, int bump_adam, cudaStream_t s) {
   const int A = p.A, B = p.B, D = p.D, H = p.H, Ld = p.Ld, C = p.C, S = p.S;
@@ -222,7 +260,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
 // ---------------------------------------------------------------------------------------------
 static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
                      const mvae_outputs& out, const float* qc_all, const float* csmp_all, float* loss_out,
-                     int want_grad, cudaStream_t s) {
+                     int want_grad, cudaStream_t s, SideBranch* fork = nullptr) {
   const int A = p.A, At = p.At, B = p.B, D = p.D, H = p.H, C = p.C, S = p.S;
   const Work& w = p.w;
   float* work = st.work;
@@ -231,20 +269,18 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
   MVAE_CHECK_ARG(qc_all && csmp_all && loss_out, "null argument");
   double* acc_loss = reinterpret_cast<double*>(work + w.acc_loss);
   double* acc_fwd = reinterpret_cast<double*>(work + w.acc_fwd);
-  MVAE_CUDA(cudaMemsetAsync(acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
   const float gscale = (float)(At - 1 > 1 ? At - 1 : 1) / (float)B;
 
-  timing_begin(TG_COUPLING, s);
-  // ---- coupling terms over every arm of the model (:558-569): first, while q / c_smp (just written by the head kernel or
-  // gathered) are in L2 -- the fc11 passes below stream the gene matrix through it
-  CouplingArgs c;
-  memset(&c, 0, sizeof(c));
-  c.A = A; c.At = At; c.arm_off = p.d.arm_offset; c.B = B; c.C = C;
-  c.qc_all = qc_all; c.csmp_all = csmp_all; c.acc = acc_loss;
-  c.gdiff = work + w.rsum; c.wcat = work + w.wcat; c.eps = hp.eps; c.lam = hp.lam;
-  RC(launch_qstats(c, s));
-  RC(launch_coupling_rows(c, s));
-  timing_end(TG_COUPLING, s);
+  {
+    MVAE_CUDA(cudaMemsetAsync(acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
+    timing_begin(TG_COUPLING, s);
+    // ---- coupling terms over every arm of the model (:558-569): first, while q / c_smp (just written by the head kernel
+    // or gathered) are in L2 -- the fc11 passes below stream the gene matrix through it
+    const CouplingArgs c = coupling_args(p, hp, st, qc_all, csmp_all);
+    RC(launch_qstats(c, s));
+    RC(launch_coupling_rows(c, s));
+    timing_end(TG_COUPLING, s);
+  }
 
   // ---- reconstruction term: fc11 GEMM fused with loss (+ its own backward)
   timing_begin(TG_FC11, s);
@@ -290,14 +326,23 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
   f.A = A; f.At = At; f.arm_off = p.d.arm_offset; f.B = B; f.D = D; f.C = C; f.S = S;
   f.acc_loss = acc_loss; f.kl_sums = acc_fwd + acc_kl(A, 0);
   f.colc = work + w.colc; f.loss_out = loss_out; f.eps = hp.eps; f.lam = hp.lam; f.beta = hp.beta;
-  RC(launch_loss_finalize(f, s));
+  if (fork) {
+    // the side branch turns the sums into the loss vector and the coupling constants while the main branch goes on with
+    // the decoder's backward chain; join before the head kernel, which needs the constants
+    MVAE_CUDA(cudaEventRecord(fork->fc11_done, s));
+    MVAE_CUDA(cudaStreamWaitEvent(fork->side, fork->fc11_done, 0));
+    RC(launch_loss_finalize(f, fork->side));
+    MVAE_CUDA(cudaEventRecord(fork->final_done, fork->side));
+  } else {
+    RC(launch_loss_finalize(f, s));
+  }
   timing_end(TG_COUPLING, s);
   return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
-                         const mvae_outputs& out, const float* grad_scale, cudaStream_t s) {
+                         const mvae_outputs& out, const float* grad_scale, cudaStream_t s, SideBranch* fork = nullptr) {
   const int A = p.A, At = p.At, B = p.B, D = p.D, H = p.H, Ld = p.Ld, C = p.C, S = p.S;
   const Work& w = p.w;
   float* work = st.work;
@@ -354,6 +399,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   h.delta6 = work + w.delta_dec[0]; h.delta_mu = work + w.delta_mu; h.delta_sig = work + w.delta_sig;
   h.delta_z = work + w.delta_z; h.g_xlow = work + w.g_xlow;
   h.bnb_sums5 = acc_bwd + accb_bn(4, A, 0);
+  if (fork) MVAE_CUDA(cudaStreamWaitEvent(s, fork->final_done, 0));      // join: coupling constants and the loss vector
   RC(launch_head_bwd(h, s));
 
   // ---- encoder fc5..fc2, then the BatchNorm+ReLU backward of layer 1
@@ -505,9 +551,10 @@ int mvae_train_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_st
   cudaStream_t s = (cudaStream_t)stream;
   mvae_outputs o = *out;
   o.x_rec = nullptr;
+  SideBranch* fork = timing_enabled() ? nullptr : side_branch(s);     // (per-group timing measures the serial order)
   RC(forward_impl(p, *hp, *st, *in, o, 1, s));
-  RC(loss_impl(p, *hp, *st, *in, o, o.qc, o.c_smp, loss_out, 1, s));
-  RC(backward_impl(p, *hp, *st, *in, o, nullptr, s));
+  RC(loss_impl(p, *hp, *st, *in, o, o.qc, o.c_smp, loss_out, 1, s, fork));
+  RC(backward_impl(p, *hp, *st, *in, o, nullptr, s, fork));
   TimedScope ts(TG_ADAM, s);
   return launch_adam(st->params, st->grads, st->adam_m, st->adam_v, (int64_t)p.A * p.L.arm_stride, lr, beta1, beta2,
                      adam_eps, 0.f, 0, step, in->counters ? in->counters + 1 : nullptr, s);

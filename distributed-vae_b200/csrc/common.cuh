@@ -124,6 +124,7 @@ __host__ __device__ inline int64_t acc_bwd_doubles(int A) { return (int64_t)5 * 
 
 // optional per-group device timing (CUDA events on the launching stream), for bench.py's roofline
 enum TimedGroup { TG_FC1_FWD = 0, TG_FC11, TG_FC1_WGRAD, TG_NARROW_FWD, TG_NARROW_BWD, TG_COUPLING, TG_WGRAD, TG_ADAM, TG_COUNT };
+bool timing_enabled();
 void timing_begin(int group, cudaStream_t s);
 void timing_end(int group, cudaStream_t s);
 struct TimedScope {

@@ -23,6 +23,7 @@ static bool g_timing_on = false;
 static std::vector<TimedSpan> g_spans;
 static cudaEvent_t g_open[TG_COUNT];
 
+bool timing_enabled() { return g_timing_on; }
 void timing_begin(int group, cudaStream_t s) {
   if (!g_timing_on) return;
   cudaEvent_t e;
