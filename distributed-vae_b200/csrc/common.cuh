@@ -122,6 +122,9 @@ __host__ __device__ inline int64_t accb_bn(int layer, int A, int a) { return ((i
 __host__ __device__ inline int64_t accb_sync(int A) { return (int64_t)5 * A * 256; }   // grid-barrier counters (8 doubles)
 __host__ __device__ inline int64_t acc_bwd_doubles(int A) { return (int64_t)5 * A * 256 + 8; }
 
+// first partial-tile slot of the fc11 gene pass: behind the row pass's slots (CTA + tile < A * ceil(B / 128) + #SM)
+inline int64_t f11_gene_slot0(int A, int B) { return (int64_t)A * ((B + 127) / 128) + 160; }
+
 // optional per-group device timing (CUDA events on the launching stream), for bench.py's roofline
 enum TimedGroup { TG_FC1_FWD = 0, TG_FC11, TG_FC1_WGRAD, TG_NARROW_FWD, TG_NARROW_BWD, TG_COUPLING, TG_WGRAD, TG_ADAM, TG_COUNT };
 bool timing_enabled();

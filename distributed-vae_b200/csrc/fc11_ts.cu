@@ -466,58 +466,87 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == CTRL_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
-// out[arm][row][col] = sum over the CTAs that touched tile (row / 128, arm) of their partial, in CTA order
-__global__ void __launch_bounds__(256) f11_fixup_kernel(const float* part, int batch, int ktiles, int64_t U, int64_t G, float* out,
-                                                        int64_t out_arm_stride, int ld, int rows, int cols) {
-  // block = one 128-row tile; thread = (row mod 8, float4 column): 16 rows each (cols % 4 == 0 on this path)
-  __shared__ int cc[2];
-  const int arm = blockIdx.y;
+// Fix-up of the stream-K partials.  One launch after the gene pass serves both passes (the row pass keeps its partial
+// tiles in a region of their own until then; nothing between the two passes needs d h10):
+//   rows:  d h10[arm][cell][h]      = sum over the CTAs that touched tile (cell / 128, arm) of their partial, in CTA order
+//   genes: d fc11.weight[arm][gene][h] likewise;  d fc11.bias[arm][gene] = sum over CTAs and epilogue groups
+struct F11FixOne {               // one stream-K pass
+  const float* part; int batch, ktiles; int64_t U, G;
+  float* out; int64_t out_arm_stride; int ld, rows, cols;
+  int nblk;                      // blocks of this part: ceil(rows / 128) * 8 * batch
+};
+struct F11FixArgs {
+  F11FixOne row, gene;
+  const float* db_part; float* db_out; int64_t db_arm_stride; int D;
+  int nblk_db;                   // ceil(D / 256) * batch blocks (256 genes each)
+};
+
+// block = 16 rows of one 128-row tile; thread = (row mod 8, float4 column): 2 rows each (cols % 4 == 0 on this path)
+__device__ __forceinline__ void f11_fix_tile(const F11FixOne& p, int bx, int arm, int* cc) {
   const int tid = threadIdx.x, r8 = tid >> 5, c4 = tid & 31;
-  const int row0 = (blockIdx.x >> 3) * 128, sub0 = (blockIdx.x & 7) * 16;
-  const int64_t t = (int64_t)(blockIdx.x >> 3) * batch + arm;
+  const int row0 = (bx >> 3) * 128, sub0 = (bx & 7) * 16;
+  const int64_t t = (int64_t)(bx >> 3) * p.batch + arm;
   if (tid == 0) {
-    cc[0] = (int)cta_of_unit(t * ktiles, U, G);
-    cc[1] = (int)cta_of_unit(t * ktiles + ktiles - 1, U, G);
+    cc[0] = (int)cta_of_unit(t * p.ktiles, p.U, p.G);
+    cc[1] = (int)cta_of_unit(t * p.ktiles + p.ktiles - 1, p.U, p.G);
   }
   __syncthreads();
-  if (4 * c4 >= cols) return;
+  if (4 * c4 >= p.cols) return;
   const int c0 = cc[0], c1 = cc[1];
-  const float* base = part + (int64_t)(c0 + t) * TILE_FLOATS + 4 * c4;
-  float* o = out + (int64_t)arm * out_arm_stride + 4 * c4;
+  const float* base = p.part + (int64_t)(c0 + t) * TILE_FLOATS + 4 * c4;
+  float* o = p.out + (int64_t)arm * p.out_arm_stride + 4 * c4;
   for (int k = 0; k < 2; ++k) {
     const int rl = sub0 + r8 + 8 * k, row = row0 + rl;
-    if (row >= rows) break;
+    if (row >= p.rows) break;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = c0; c <= c1; ++c) {
       const float4 q = *reinterpret_cast<const float4*>(base + (int64_t)(c - c0) * TILE_FLOATS + rl * 128);
       v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
     }
-    *reinterpret_cast<float4*>(o + (int64_t)row * ld) = v;
+    *reinterpret_cast<float4*>(o + (int64_t)row * p.ld) = v;
   }
 }
 
-// d fc11.bias[arm][gene] = sum over CTAs and epilogue groups of the partials; a (CTA, group) pair that processed no
-// half-unit of the tile wrote nothing: group g owns the half-units j = g (mod NG) counted from the CTA's first one.
-// (ktiles, U: units = pairs of half-units, as in the main kernel)
-__global__ void __launch_bounds__(128) f11_db_fixup_kernel(const float* db_part, int batch, int ktiles, int64_t U, int64_t G,
-                                                           float* out, int64_t out_arm_stride, int D) {
-  const int arm = blockIdx.y;
-  const int gene = blockIdx.x * 128 + threadIdx.x;
-  if (gene >= D) return;
-  const int64_t t = (int64_t)blockIdx.x * batch + arm;
-  const int64_t ua = t * ktiles, ub = ua + ktiles;            // units of the tile
-  const int64_t c0 = cta_of_unit(ua, U, G), c1 = cta_of_unit(ub - 1, U, G);
+// a (CTA, group) pair that processed no half-unit of the tile wrote nothing: group g owns the half-units j = g (mod NG)
+// counted from the CTA's first one.  (ktiles, U: units = pairs of half-units, as in the main kernel)
+__device__ __forceinline__ void f11_fix_bias(const F11FixArgs& p, int gene, int arm) {
+  if (gene >= p.D) return;
+  const F11FixOne& q = p.gene;
+  const int64_t t = (int64_t)(gene >> 7) * q.batch + arm;
+  const int64_t ua = t * q.ktiles, ub = ua + q.ktiles;        // units of the tile
+  const int64_t c0 = cta_of_unit(ua, q.U, q.G), c1 = cta_of_unit(ub - 1, q.U, q.G);
   float v = 0.f;
   for (int64_t c = c0; c <= c1; ++c) {
-    const int64_t s0 = c * U / G, s1 = (c + 1) * U / G;       // units of CTA c
+    const int64_t s0 = c * q.U / q.G, s1 = (c + 1) * q.U / q.G;     // units of CTA c
     const int64_t lo = 2 * (ua > s0 ? ua : s0), hi = 2 * (ub < s1 ? ub : s1);   // half-units of the tile in CTA c
     for (int g = 0; g < NG; ++g) {
-      // first half-unit >= lo with (j - 2 s0) % NG == g
-      const int64_t first = lo + ((g - (lo - 2 * s0)) % NG + NG) % NG;
-      if (first < hi) v += db_part[((c + t) * NG + g) * 128 + threadIdx.x];
+      const int64_t first = lo + ((g - (lo - 2 * s0)) % NG + NG) % NG;           // first half-unit >= lo of group g
+      if (first < hi) v += p.db_part[((c + t) * NG + g) * 128 + (gene & 127)];
     }
   }
-  out[(int64_t)arm * out_arm_stride + gene] = v;
+  p.db_out[(int64_t)arm * p.db_arm_stride + gene] = v;
+}
+
+__global__ void __launch_bounds__(256) f11_fixup_kernel(const F11FixArgs p) {
+  __shared__ int cc[2];
+  int b = blockIdx.x;
+  if (b < p.row.nblk) {
+    f11_fix_tile(p.row, b / p.row.batch, b % p.row.batch, cc);
+  } else if ((b -= p.row.nblk) < p.gene.nblk) {
+    f11_fix_tile(p.gene, b / p.gene.batch, b % p.gene.batch, cc);
+  } else {
+    b -= p.gene.nblk;
+    f11_fix_bias(p, (b / p.gene.batch) * 256 + threadIdx.x, b % p.gene.batch);
+  }
+}
+
+static F11FixOne fix_one(const float* part, int batch, int ktiles, int64_t U, int64_t G, float* out, int64_t out_arm_stride, int ld,
+                         int rows, int cols) {
+  F11FixOne f;
+  f.part = part; f.batch = batch; f.ktiles = ktiles; f.U = U; f.G = G;
+  f.out = out; f.out_arm_stride = out_arm_stride; f.ld = ld; f.rows = rows; f.cols = cols;
+  f.nblk = (rows + 127) / 128 * 8 * batch;
+  return f;
 }
 
 int sm_count2() {
@@ -572,8 +601,8 @@ int launch_f11(const CUtensorMap& tmX, const CUtensorMap& tmT, F11Args& a, int64
 }  // namespace
 
 // x_hat / loss sums / d h10 in one pass over x (x_rec optional: materialised reconstruction)
-int ts_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale, int want_grad,
-                 float* x_rec, double* recon_acc, cudaStream_t s) {
+static int fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale, int want_grad,
+                     float* x_rec, double* recon_acc, F11FixOne* fix, cudaStream_t s) {
   mvae_layout L;
   compute_layout(d, &L);
   const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
@@ -598,13 +627,21 @@ int ts_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
   rc = (want_grad && !x_rec) ? launch_f11<false, true>(tmX, tmT, a, &U, &G, s)
                              : launch_f11<false, false>(tmX, tmT, a, &U, &G, s);
   if (rc || !want_grad) return rc;
-  f11_fixup_kernel<<<dim3((B + 127) / 128 * 8, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, work + w.g_d10, (int64_t)B * H, H, B, H);
+  if (fix) {           // the gene pass that follows sums these partials in its own fix-up launch
+    *fix = fix_one(a.part, A, a.ktiles, U, G, work + w.g_d10, (int64_t)B * H, H, B, H);
+    return 0;
+  }
+  F11FixArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.row = fix_one(a.part, A, a.ktiles, U, G, work + w.g_d10, (int64_t)B * H, H, B, H);
+  f11_fixup_kernel<<<fa.row.nblk, 256, 0, s>>>(fa);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
 
 // d fc11.weight and d fc11.bias by the gene pass (x_hat recomputed)
-int ts_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale, cudaStream_t s) {
+static int fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale,
+                      const F11FixOne* row_fix, cudaStream_t s) {
   mvae_layout L;
   compute_layout(d, &L);
   const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
@@ -617,7 +654,8 @@ int ts_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& i
   a.want_grad = 1; a.gscale = gscale;
   a.R = st.params + L.offset[FC11_W]; a.r_arm_stride = L.arm_stride; a.r_rows = D;
   a.bias = st.params + L.offset[FC11_B]; a.bias_arm_stride = L.arm_stride;
-  a.part = work + w.fc1_part;
+  // partial tiles behind those of the row pass (slot = CTA + tile < tiles + #SM): layout.cu sizes the region for both
+  a.part = work + w.fc1_part + (int64_t)f11_gene_slot0(A, B) * TILE_FLOATS;
   a.db_part = work + w.db_part;
   CUtensorMap tmX, tmT;
   int rc = make_map_ex(&tmX, in.x, D, B, in.x_row_stride, A, in.x_arm_stride, 128, 32, 0);
@@ -627,13 +665,30 @@ int ts_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& i
   int64_t U, G;
   rc = launch_f11<true, true>(tmX, tmT, a, &U, &G, s);
   if (rc) return rc;
-  f11_fixup_kernel<<<dim3((D + 127) / 128 * 8, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, st.grads + L.offset[FC11_W], L.arm_stride,
-                                                           H, D, H);
-  MVAE_LAUNCH_CHECK();
-  f11_db_fixup_kernel<<<dim3((D + 127) / 128, A), 128, 0, s>>>(a.db_part, A, a.ktiles, U, G, st.grads + L.offset[FC11_B],
-                                                             L.arm_stride, D);
+  F11FixArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  if (row_fix) fa.row = *row_fix;
+  fa.gene = fix_one(a.part, A, a.ktiles, U, G, st.grads + L.offset[FC11_W], L.arm_stride, H, D, H);
+  fa.db_part = a.db_part; fa.db_out = st.grads + L.offset[FC11_B]; fa.db_arm_stride = L.arm_stride; fa.D = D;
+  fa.nblk_db = (D + 255) / 256 * A;
+  f11_fixup_kernel<<<fa.row.nblk + fa.gene.nblk + fa.nblk_db, 256, 0, s>>>(fa);
   MVAE_LAUNCH_CHECK();
   return 0;
+}
+
+// x_hat / loss sums (/ d h10) alone: the evaluation paths and mvae_forward's materialised reconstruction
+int ts_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale, int want_grad,
+                 float* x_rec, double* recon_acc, cudaStream_t s) {
+  return fc11_rows(d, st, in, w, gscale, want_grad, x_rec, recon_acc, nullptr, s);
+}
+
+// both passes of the training step: row owner (loss sums, d h10), gene owner (d fc11.weight, d fc11.bias), one fix-up
+int ts_fc11_loss_grad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale,
+                      double* recon_acc, cudaStream_t s) {
+  F11FixOne row_fix;
+  int rc = fc11_rows(d, st, in, w, gscale, 1, nullptr, recon_acc, &row_fix, s);
+  if (rc) return rc;
+  return fc11_genes(d, st, in, w, gscale, &row_fix, s);
 }
 
 }  // namespace mvae

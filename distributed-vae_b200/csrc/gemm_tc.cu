@@ -956,9 +956,8 @@ int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_sta
   memset(&nodrop, 0, sizeof(nodrop));
   if (hp.precision == 1) return tc_fc11_loss_grad_unfused(d, hp, st, in, w, gscale, want_grad, s);
   // fused passes: row owner (x_hat, loss sums, d h10), then gene owner (d fc11.weight, d fc11.bias)
-  int rc = ts_fc11_rows(d, st, in, w, gscale, want_grad, nullptr, acc_loss, s);
-  if (rc || !want_grad) return rc;
-  return ts_fc11_genes(d, st, in, w, gscale, s);
+  if (!want_grad) return ts_fc11_rows(d, st, in, w, gscale, 0, nullptr, acc_loss, s);
+  return ts_fc11_loss_grad(d, st, in, w, gscale, acc_loss, s);
 }
 
 int tc_fc1_wgrad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,

@@ -27,7 +27,8 @@ int ts_fc1_wgrad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
 // fc11_ts.cu: second-generation fused fc11 passes (resident operand and dY in tensor memory, stream-K)
 int ts_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale, int want_grad,
                  float* x_rec, double* recon_acc, cudaStream_t s);
-int ts_fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale, cudaStream_t s);
+int ts_fc11_loss_grad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale,
+                      double* recon_acc, cudaStream_t s);
 // gemm_tc.cu: grouped tcgen05 weight-gradient GEMM of the wide narrow-layer problems (delta^T . bn(input), bias gradient
 // through a column of ones); partials in the layout of wgrad_reduce2_kernel
 bool tc_narrow_wgrad_ok(const WgArgs& a, const WgProblem& q);

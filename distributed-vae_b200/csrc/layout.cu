@@ -135,6 +135,9 @@ Work make_work(const mvae_dims& d) {
     const int64_t p3 = ((t1 > t2 ? t1 : t2) + 2 * A + 320) * 128 * 128;
     int64_t pm = p1 > p2 ? p1 : p2;
     if (p3 > pm) pm = p3;
+    // fc11_ts.cu keeps the row pass's partial tiles until the gene pass's fix-up: two regions
+    const int64_t p4 = (f11_gene_slot0((int)A, (int)B) + t2 + 160) * 128 * 128;
+    if (p4 > pm) pm = p4;
     w.fc1_part = take(pm);
   }
   w.db_part = take((int64_t)8 * A * w.Dpad + 160 * 512);   // also [slot][4 groups][128] of fc11_ts.cu
