@@ -49,7 +49,7 @@ static int check_device() {
 // check_device first; a step captured before the resources exist simply runs unforked).
 struct SideBranch {
   cudaStream_t side = nullptr;
-  cudaEvent_t head_done = nullptr, fc11_done = nullptr, final_done = nullptr;
+  cudaEvent_t head_done = nullptr, qstats_done = nullptr, fc11_done = nullptr, final_done = nullptr;
 };
 static SideBranch* side_branch(cudaStream_t s) {
   static thread_local SideBranch sb[64];
@@ -62,6 +62,7 @@ static SideBranch* side_branch(cudaStream_t s) {
     SideBranch& b = sb[dev];
     const bool ok = cudaStreamCreateWithFlags(&b.side, cudaStreamNonBlocking) == cudaSuccess &&
                     cudaEventCreateWithFlags(&b.head_done, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&b.qstats_done, cudaEventDisableTiming) == cudaSuccess &&
                     cudaEventCreateWithFlags(&b.fc11_done, cudaEventDisableTiming) == cudaSuccess &&
                     cudaEventCreateWithFlags(&b.final_done, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) cudaGetLastError();
@@ -123,7 +124,7 @@ static CouplingArgs coupling_args(const Plan& p, const mvae_hparams& hp, const m
 }
 
 static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
-                        const mvae_outputs& out, int bump_adam, cudaStream_t s) {
+                        const mvae_outputs& out, int bump_adam, cudaStream_t s, SideBranch* fork = nullptr) {
   const int A = p.A, B = p.B, D = p.D, H = p.H, Ld = p.Ld, C = p.C, S = p.S;
   const Work& w = p.w;
   float* work = st.work;
@@ -216,6 +217,15 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
     h.bn_sums_all = acc_fwd; h.momentum = hp.momentum;
   }
   RC(launch_head_fwd(h, s));
+  if (fork) {
+    // q is final: its column statistics (inv_var of the coupling term) start now, beside the decoder chain; the loss
+    // accumulators they add to are cleared first
+    MVAE_CUDA(cudaMemsetAsync(work + w.acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
+    MVAE_CUDA(cudaEventRecord(fork->head_done, s));
+    MVAE_CUDA(cudaStreamWaitEvent(fork->side, fork->head_done, 0));
+    RC(launch_qstats(coupling_args(p, hp, st, out.qc, out.c_smp), fork->side));
+    MVAE_CUDA(cudaEventRecord(fork->qstats_done, fork->side));
+  }
 
   // ---- fc7..fc10 (:281-284)
   if (hp.precision != 3) {
@@ -272,12 +282,16 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
   const float gscale = (float)(At - 1 > 1 ? At - 1 : 1) / (float)B;
 
   {
-    MVAE_CUDA(cudaMemsetAsync(acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
     timing_begin(TG_COUPLING, s);
     // ---- coupling terms over every arm of the model (:558-569): first, while q / c_smp (just written by the head kernel
     // or gathered) are in L2 -- the fc11 passes below stream the gene matrix through it
     const CouplingArgs c = coupling_args(p, hp, st, qc_all, csmp_all);
-    RC(launch_qstats(c, s));
+    if (fork) {          // cleared and summed on the side branch since the head kernel (forward_impl)
+      MVAE_CUDA(cudaStreamWaitEvent(s, fork->qstats_done, 0));
+    } else {
+      MVAE_CUDA(cudaMemsetAsync(acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
+      RC(launch_qstats(c, s));
+    }
     RC(launch_coupling_rows(c, s));
     timing_end(TG_COUPLING, s);
   }
@@ -552,7 +566,7 @@ int mvae_train_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_st
   mvae_outputs o = *out;
   o.x_rec = nullptr;
   SideBranch* fork = timing_enabled() ? nullptr : side_branch(s);     // (per-group timing measures the serial order)
-  RC(forward_impl(p, *hp, *st, *in, o, 1, s));
+  RC(forward_impl(p, *hp, *st, *in, o, 1, s, fork));
   RC(loss_impl(p, *hp, *st, *in, o, o.qc, o.c_smp, loss_out, 1, s, fork));
   RC(backward_impl(p, *hp, *st, *in, o, nullptr, s, fork));
   TimedScope ts(TG_ADAM, s);

@@ -65,10 +65,13 @@ int launch_qstats(const CouplingArgs& a, cudaStream_t s) {
 // magnitude while the true difference is tiny (it showed up as 3e-4 relative error in the encoder gradients at A = 3).
 // ---------------------------------------------------------------------------------------------
 // ATC: compile-time number of arms (0: run-time); C96: n_categories > 96 (only the last category slot of a lane is guarded)
+// One CTA of kCoupWarps warps per SM: every CTA ends with ~200 fp64 atomics on the same 200 addresses, whose cost grows
+// with the number of CTAs (444 CTAs of 8 warps spent a third of the kernel there).
+constexpr int kCoupWarps = 24;
 template <int ATC, bool C96>
-__global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const CouplingArgs p) {
+__global__ void __launch_bounds__(kCoupWarps * 32) coupling_rows_kernel(const CouplingArgs p) {
   __shared__ float w[MVAE_MAX_ARMS][128];
-  extern __shared__ float sTw[];            // [kRowWarps][A local arms][128]: every lane owns its categories of its warp's slice
+  extern __shared__ float sTw[];            // [kCoupWarps][A local arms][128]: every lane owns its categories of its warp's slice
   __shared__ double sPair[kMaxPairs][2];
   __shared__ double sEnt[MVAE_MAX_ARMS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -90,14 +93,15 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
     }
     w[a][k] = wv;
   }
-  for (int idx = tid; idx < kRowWarps * p.A * 128; idx += blockDim.x) sTw[idx] = 0.f;
+  for (int idx = tid; idx < kCoupWarps * p.A * 128; idx += blockDim.x) sTw[idx] = 0.f;
   for (int idx = tid; idx < kMaxPairs * 2; idx += blockDim.x) (&sPair[0][0])[idx] = 0.0;
   if (tid < MVAE_MAX_ARMS) sEnt[tid] = 0.0;
   __syncthreads();
 
   const float gcoef = 2.f * p.lam / (float)B;
-  for (int row = blockIdx.x * kRowWarps + warp; row < B; row += gridDim.x * kRowWarps) {
+  for (int row = blockIdx.x * kCoupWarps + warp; row < B; row += gridDim.x * kCoupWarps) {
     float r0[KC] = {0.f, 0.f, 0.f, 0.f}, rs[KC] = {0.f, 0.f, 0.f, 0.f};
+    float lqc[ATC ? ATC : 1][KC];      // compile-time arm count: log(q + eps) of pass 1 kept for pass 2 (same values)
     // pass 1: r_0 and S = sum_b (r_b - r_0) ; entropy per arm
     for (int a = 0; a < At; ++a) {
       const float* q = p.qc_all + ((int64_t)a * B + row) * C;
@@ -108,6 +112,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
         if (kk < C) {
           const float qv = q[kk];
           const float lq = logf(qv + p.eps);
+          if (ATC) lqc[ATC ? a : 0][k] = lq;
           const float rv = lq * w[a][kk];
           if (a == 0) r0[k] = rv;
           else rs[k] += rv - r0[k];
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
         const int kk = lane + 32 * k;
         ra[k] = 0.f; ya[k] = 0.f;
         if (kk < C) {
-          const float lq = logf(qa[kk] + p.eps);
+          const float lq = ATC ? lqc[ATC ? a : 0][k] : logf(qa[kk] + p.eps);
           ra[k] = lq * w[a][kk];
           ya[k] = ca[kk];
           const int la = a - p.arm_off;
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
         for (int k = 0; k < KC; ++k) {
           const int kk = lane + 32 * k;
           if (kk < C) {
-            const float rb = logf(qb[kk] + p.eps) * w[b][kk];
+            const float rb = (ATC ? lqc[ATC ? b : 0][k] : logf(qb[kk] + p.eps)) * w[b][kk];
             const float d = ra[k] - rb;
             dist = fmaf(d, d, dist);
             const float e = ya[k] - cb[kk];
@@ -172,33 +177,23 @@ __global__ void __launch_bounds__(kRowWarps * 32) coupling_rows_kernel(const Cou
     if (k < C) {
       double t = 0.0;
 #pragma unroll
-      for (int wp = 0; wp < kRowWarps; ++wp) t += (double)sTw[(wp * p.A + a) * 128 + k];
+      for (int wp = 0; wp < kCoupWarps; ++wp) t += (double)sTw[(wp * p.A + a) * 128 + k];
       atomicAdd(p.acc + accl_T(a) + k, t);
     }
   }
 }
 
 int launch_coupling_rows(const CouplingArgs& a, cudaStream_t s) {
-  int gx = (a.B + kRowWarps - 1) / kRowWarps;
-  static bool attr = false;
-  const int max_dyn = kRowWarps * MVAE_MAX_ARMS * 128 * (int)sizeof(float);
-  if (!attr) {
-    MVAE_CUDA(cudaFuncSetAttribute(coupling_rows_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-    MVAE_CUDA(cudaFuncSetAttribute(coupling_rows_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-    MVAE_CUDA(cudaFuncSetAttribute(coupling_rows_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-    MVAE_CUDA(cudaFuncSetAttribute(coupling_rows_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-    attr = true;
-  }
-  if (gx > 444) gx = 444;              // 3 CTAs per SM: a few rows per warp, 3x fewer global fp64 atomics than one row per warp
-  const size_t dyn = (size_t)kRowWarps * a.A * 128 * sizeof(float);
+  int gx = (a.B + kCoupWarps - 1) / kCoupWarps;
+  if (gx > 148) gx = 148;              // one CTA per SM, a couple of rows per warp
+  const size_t dyn = (size_t)kCoupWarps * a.A * 128 * sizeof(float);
   const bool c96 = a.C > 96;
-  if (a.At == 2) {                     // the reference default n_arm = 2 gets compile-time arm loops
-    if (c96) coupling_rows_kernel<2, true><<<gx, kRowWarps * 32, dyn, s>>>(a);
-    else coupling_rows_kernel<2, false><<<gx, kRowWarps * 32, dyn, s>>>(a);
-  } else {
-    if (c96) coupling_rows_kernel<0, true><<<gx, kRowWarps * 32, dyn, s>>>(a);
-    else coupling_rows_kernel<0, false><<<gx, kRowWarps * 32, dyn, s>>>(a);
-  }
+  const void* fn = a.At == 2 ? (c96 ? (const void*)coupling_rows_kernel<2, true> : (const void*)coupling_rows_kernel<2, false>)
+                             : (c96 ? (const void*)coupling_rows_kernel<0, true> : (const void*)coupling_rows_kernel<0, false>);
+  MVAE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  CouplingArgs arg = a;
+  void* args[] = {(void*)&arg};
+  MVAE_CUDA(cudaLaunchKernel(fn, dim3(gx), dim3(kCoupWarps * 32), args, dyn, s));   // (At == 2: compile-time arm loops)
   MVAE_LAUNCH_CHECK();
   return 0;
 }
