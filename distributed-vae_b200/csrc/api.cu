@@ -124,7 +124,8 @@ static CouplingArgs coupling_args(const Plan& p, const mvae_hparams& hp, const m
 }
 
 static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
-                        const mvae_outputs& out, int bump_adam, cudaStream_t s, SideBranch* fork = nullptr) {
+                        const mvae_outputs& out, int bump_adam, cudaStream_t s, SideBranch* fork = nullptr,
+                        bool clear_all = false) {
   const int A = p.A, B = p.B, D = p.D, H = p.H, Ld = p.Ld, C = p.C, S = p.S;
   const Work& w = p.w;
   float* work = st.work;
@@ -134,7 +135,9 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   MVAE_CHECK_ARG(!training || B >= 2, "training needs at least 2 cells (batch statistics)");
   MVAE_CHECK_ARG(!(training && hp.s_drop > 0.f) || in.keep_s != nullptr, "keep_s is required when s_drop > 0");
   MVAE_CHECK_ARG(in.x_row_stride >= D, "x_row_stride < D");
-  MVAE_CUDA(cudaMemsetAsync(acc_fwd, 0, (size_t)w.acc_fwd_floats * 4, s));
+  // the accumulator blocks of the forward, the loss and the backward are adjacent in the work buffer: the fused step
+  // clears all three with one node
+  MVAE_CUDA(cudaMemsetAsync(acc_fwd, 0, (size_t)(clear_all ? w.acc_bwd + w.acc_bwd_floats - w.acc_fwd : w.acc_fwd_floats) * 4, s));
   RC(launch_step_prep(in.seed, in.step, in.counters, bump_adam, p.d.arm_offset, step_keys(p, st), s));
   float* bn_mean = work + w.bn_mean;
   float* bn_rstd = work + w.bn_rstd;
@@ -147,8 +150,16 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   memset(&epi, 0, sizeof(epi));
   timing_begin(TG_FC1_FWD, s);
   const bool ts_path = use_tc(p, hp);
+  // the single-tile encoder chain takes fc1's partial tiles and forms a1 itself (no separate fix-up launch)
+  Fc1Deferred fc1d;
+  memset(&fc1d, 0, sizeof(fc1d));
+#ifdef MVAE_NO_FC1_FUSE      // (compile-time switch for A/B measurements)
+  const bool defer_fix = false;
+#else
+  const bool defer_fix = ts_path && training && enc_chain_fwd_is_single(A, B, H, Ld);
+#endif
   if (ts_path) {
-    RC(ts_fc1_forward(p.d, hp, st, in, drop, w, work + w.a[0], acc_fwd + acc_bn(0, A, 0), s));
+    RC(ts_fc1_forward(p.d, hp, st, in, drop, w, work + w.a[0], acc_fwd + acc_bn(0, A, 0), defer_fix ? &fc1d : nullptr, s));
   } else {
     GemmArgs g;
     memset(&g, 0, sizeof(g));
@@ -171,7 +182,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   if (training && hp.precision != 3) {
     float* aout[4] = {work + w.a[1], work + w.a[2], work + w.a[3], work + w.a[4]};
     chain_rc = launch_enc_chain_fwd(st.params, p.L.arm_stride, p.L.offset, A, B, H, Ld, work + w.a[0], aout, acc_fwd, bn_mean,
-                                    bn_rstd, hp.eps, s);
+                                    bn_rstd, hp.eps, &fc1d, s);
     if (chain_rc < 0 || chain_rc > 1) return chain_rc;
   }
   for (int l = 1; l <= 4 && chain_rc == 1; ++l) {
@@ -220,7 +231,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   if (fork) {
     // q is final: its column statistics (inv_var of the coupling term) start now, beside the decoder chain; the loss
     // accumulators they add to are cleared first
-    MVAE_CUDA(cudaMemsetAsync(work + w.acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
+    if (!clear_all) MVAE_CUDA(cudaMemsetAsync(work + w.acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
     MVAE_CUDA(cudaEventRecord(fork->head_done, s));
     MVAE_CUDA(cudaStreamWaitEvent(fork->side, fork->head_done, 0));
     RC(launch_qstats(coupling_args(p, hp, st, out.qc, out.c_smp), fork->side));
@@ -270,7 +281,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
 // ---------------------------------------------------------------------------------------------
 static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
                      const mvae_outputs& out, const float* qc_all, const float* csmp_all, float* loss_out,
-                     int want_grad, cudaStream_t s, SideBranch* fork = nullptr) {
+                     int want_grad, cudaStream_t s, SideBranch* fork = nullptr, bool cleared = false) {
   const int A = p.A, At = p.At, B = p.B, D = p.D, H = p.H, C = p.C, S = p.S;
   const Work& w = p.w;
   float* work = st.work;
@@ -289,7 +300,7 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
     if (fork) {          // cleared and summed on the side branch since the head kernel (forward_impl)
       MVAE_CUDA(cudaStreamWaitEvent(s, fork->qstats_done, 0));
     } else {
-      MVAE_CUDA(cudaMemsetAsync(acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
+      if (!cleared) MVAE_CUDA(cudaMemsetAsync(acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
       RC(launch_qstats(c, s));
     }
     RC(launch_coupling_rows(c, s));
@@ -356,13 +367,14 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
 
 // ---------------------------------------------------------------------------------------------
 static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
-                         const mvae_outputs& out, const float* grad_scale, cudaStream_t s, SideBranch* fork = nullptr) {
+                         const mvae_outputs& out, const float* grad_scale, cudaStream_t s, SideBranch* fork = nullptr,
+                         bool cleared = false) {
   const int A = p.A, At = p.At, B = p.B, D = p.D, H = p.H, Ld = p.Ld, C = p.C, S = p.S;
   const Work& w = p.w;
   float* work = st.work;
   MVAE_CHECK_ARG(in.training, "backward needs a training-mode forward");
   double* acc_bwd = reinterpret_cast<double*>(work + w.acc_bwd);
-  MVAE_CUDA(cudaMemsetAsync(acc_bwd, 0, (size_t)w.acc_bwd_floats * 4, s));
+  if (!cleared) MVAE_CUDA(cudaMemsetAsync(acc_bwd, 0, (size_t)w.acc_bwd_floats * 4, s));
   float* bn_mean = work + w.bn_mean;
   float* bn_rstd = work + w.bn_rstd;
   const bool tc = use_tc(p, hp);
@@ -566,12 +578,28 @@ int mvae_train_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_st
   mvae_outputs o = *out;
   o.x_rec = nullptr;
   SideBranch* fork = timing_enabled() ? nullptr : side_branch(s);     // (per-group timing measures the serial order)
-  RC(forward_impl(p, *hp, *st, *in, o, 1, s, fork));
-  RC(loss_impl(p, *hp, *st, *in, o, o.qc, o.c_smp, loss_out, 1, s, fork));
-  RC(backward_impl(p, *hp, *st, *in, o, nullptr, s, fork));
+  RC(forward_impl(p, *hp, *st, *in, o, 1, s, fork, true));
+  RC(loss_impl(p, *hp, *st, *in, o, o.qc, o.c_smp, loss_out, 1, s, fork, true));
+  RC(backward_impl(p, *hp, *st, *in, o, nullptr, s, fork, true));
   TimedScope ts(TG_ADAM, s);
   return launch_adam(st->params, st->grads, st->adam_m, st->adam_v, (int64_t)p.A * p.L.arm_stride, lr, beta1, beta2,
                      adam_eps, 0.f, 0, step, in->counters ? in->counters + 1 : nullptr, s);
+}
+
+int mvae_grad_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state* st, const mvae_inputs* in,
+                   const mvae_outputs* out, float* loss_out, void* stream) {
+  Plan p;
+  RC(make_plan(dims, &p));
+  MVAE_CHECK_ARG(hp && st && in && out && loss_out, "null argument");
+  MVAE_CHECK_ARG(dims->n_arm == dims->n_arm_total, "mvae_grad_step needs every arm local; with sharded arms call forward/loss/backward around the all-gather");
+  RC(check_device());
+  cudaStream_t s = (cudaStream_t)stream;
+  mvae_outputs o = *out;
+  o.x_rec = nullptr;
+  SideBranch* fork = timing_enabled() ? nullptr : side_branch(s);
+  RC(forward_impl(p, *hp, *st, *in, o, 0, s, fork, true));
+  RC(loss_impl(p, *hp, *st, *in, o, o.qc, o.c_smp, loss_out, 1, s, fork, true));
+  return backward_impl(p, *hp, *st, *in, o, nullptr, s, fork, true);
 }
 
 int mvae_dropout_mask(const mvae_dims* dims, const mvae_hparams* hp, const mvae_inputs* in, uint8_t* keep_out,

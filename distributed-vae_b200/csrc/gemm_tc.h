@@ -20,7 +20,7 @@ int tc_fc1_wgrad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& s
 // ts_gemm.cu: stream-K kernels with the x operand transformed in registers and fed to the MMA from tensor memory
 int64_t ts_part_floats(int A, int Bpad, int Dpad);
 int ts_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
-                   const DropSpec& drop, const Work& w, float* a1_out, double* stats_out, cudaStream_t s);
+                   const DropSpec& drop, const Work& w, float* a1_out, double* stats_out, Fc1Deferred* defer, cudaStream_t s);
 int ts_fc1_wgrad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const DropSpec& drop, const Work& w,
                  cudaStream_t s);
 

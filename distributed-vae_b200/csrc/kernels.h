@@ -138,8 +138,15 @@ int launch_dec_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
 
 // encoder middle fc2..fc5 (+ batch_l1..l4 folded in, column sums for batch_l2..l5) as ONE cooperative kernel; returns 1 when
 // the shape does not fit a single co-resident wave (the caller then runs the per-layer kernels)
+// fc1's stream-K partial tiles handed to the encoder chain, which then forms a1 = relu(scale * sum + b1) itself (first phase of
+// the single-tile chain kernel) instead of a separate fix-up launch: ts_gemm.cu fills it, kernels_chain.cu consumes it
+struct Fc1Deferred {
+  const float* part; int batch, ktiles; int64_t U, G; float scale; int64_t offB; int valid;
+};
+// 1: launch_enc_chain_fwd will run the one-tile-per-CTA cooperative kernel for this shape (and can take an Fc1Deferred)
+int enc_chain_fwd_is_single(int A, int B, int H, int L);
 int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
-                         const float* a1, float* const aout[4], double* acc_fwd, float* bn_mean, float* bn_rstd, float eps,
+                         const float* a1, float* const aout[4], double* acc_fwd, float* bn_mean, float* bn_rstd, float eps, const Fc1Deferred* fc1,
                          cudaStream_t s);
 
 // encoder middle backward (batch_l5 .. batch_l1 and fc5 .. fc2): deltas of layers 5..1, one cooperative kernel

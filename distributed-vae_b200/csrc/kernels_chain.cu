@@ -316,6 +316,8 @@ struct EncChainArgs {
   int64_t offW[4], offB[4];      // fc2..fc5
   int A, B, H, L;
   const float* a1;               // [A][B][H] relu(fc1), before batch_l1
+  float* a1_out;                 // same buffer, written by the kernel when fx.valid (fc1 fix-up fused in)
+  Fc1Deferred fx;                // fc1's stream-K partial tiles (ts_gemm.cu), or valid == 0
   float* aout[4];                // a2..a4 [A][B][H], a5 [A][B][L]
   double* sums;                  // acc_fwd: column sums / sums of squares, layer l at (l * A + arm) * 256
   float* bn_mean; float* bn_rstd;   // [5][A][128]
@@ -377,10 +379,83 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
   }
   __syncthreads();
   async_tile(Ws0, XP, par + p.offW[0], H, H, H, tid, CT);
-  async_tile(Xs0, XP, p.a1 + ((int64_t)arm * B + row0) * H, H, rows_valid, H, tid, CT);
+  if (!p.fx.valid) async_tile(Xs0, XP, p.a1 + ((int64_t)arm * B + row0) * H, H, rows_valid, H, tid, CT);
   cp_async_commit();
   async_tile(Ws1, XP, par + p.offW[1], H, H, H, tid, CT);
   cp_async_commit();
+
+  if (p.fx.valid) {
+    // ---- fc1 fix-up fused in (instead of a separate launch): a1 = relu(scale * (sum of the stream-K partials of fc1, in
+    // CTA order) + b1) for this CTA's rows -> global (backward, weight gradients) and the layer-0 operand tile; fp64 column
+    // sums for batch_l1 -> one more grid barrier.  Warp w owns rows w, w + nwarps, ...; lane = float4 column.  (H % 4 == 0.)
+    constexpr int NWARP = MT * NWC;
+    double* red0 = reinterpret_cast<double*>(Xs1);        // [NWARP][2][Hp] scratch: Xs1 is rewritten by layer 0's epilogue
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    const bool col_ok = 4 * lane < H;
+    float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col_ok) bj = *reinterpret_cast<const float4*>(par + p.fx.offB + 4 * lane);
+    // (rows in groups of 4 with up to 4 partials each issued together: the loop is bound by L2 latency, not by bytes)
+    for (int rr0 = warp; rr0 < rows_valid; rr0 += 4 * NWARP) {
+      const float* base[4];
+      int np_[4];
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rr = rr0 + k * NWARP, r = row0 + rr;
+        const int64_t t = (int64_t)(r >> 8) * p.fx.batch + arm;          // 256-row stream-K tile of fc1 (two 128-row blocks)
+        const int c0 = (int)(((t * p.fx.ktiles + 1) * p.fx.G - 1) / p.fx.U);
+        const int c1 = (int)(((t * p.fx.ktiles + p.fx.ktiles) * p.fx.G - 1) / p.fx.U);
+        np_[k] = (rr < rows_valid && col_ok) ? c1 - c0 + 1 : 0;
+        base[k] = p.fx.part + ((int64_t)(c0 + t) * 2 + ((r >> 7) & 1)) * (128 * 128) + (r & 127) * 128 + 4 * lane;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float4 q[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          q[k][j] = j < np_[k] ? __ldcg(reinterpret_cast<const float4*>(base[k] + (int64_t)j * 2 * (128 * 128))) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {           // CTA order: j = 0 first (adding the zeros of absent partials changes nothing)
+          v[k].x += q[k][j].x; v[k].y += q[k][j].y; v[k].z += q[k][j].z; v[k].w += q[k][j].w;
+        }
+        for (int j = 4; j < np_[k]; ++j) {      // a tile cut into more than 4 CTA shares (tiny grids)
+          const float4 qq = __ldcg(reinterpret_cast<const float4*>(base[k] + (int64_t)j * 2 * (128 * 128)));
+          v[k].x += qq.x; v[k].y += qq.y; v[k].z += qq.z; v[k].w += qq.w;
+        }
+        if (np_[k] > 0) {
+          const int rr = rr0 + k * NWARP, r = row0 + rr;
+          float4 o;
+          o.x = fmaxf(fmaf(v[k].x, p.fx.scale, bj.x), 0.f); o.y = fmaxf(fmaf(v[k].y, p.fx.scale, bj.y), 0.f);
+          o.z = fmaxf(fmaf(v[k].z, p.fx.scale, bj.z), 0.f); o.w = fmaxf(fmaf(v[k].w, p.fx.scale, bj.w), 0.f);
+          *reinterpret_cast<float4*>(p.a1_out + ((int64_t)arm * B + r) * H + 4 * lane) = o;
+          *reinterpret_cast<float4*>(Xs0 + rr * XP + 4 * lane) = o;
+          s1[0] += (double)o.x; s1[1] += (double)o.y; s1[2] += (double)o.z; s1[3] += (double)o.w;
+          s2[0] += (double)o.x * (double)o.x; s2[1] += (double)o.y * (double)o.y;
+          s2[2] += (double)o.z * (double)o.z; s2[3] += (double)o.w * (double)o.w;
+        }
+      }
+    }
+    if (col_ok) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        red0[(warp * 2 + 0) * Hp + 4 * lane + e] = s1[e];
+        red0[(warp * 2 + 1) * Hp + 4 * lane + e] = s2[e];
+      }
+    }
+    __syncthreads();
+    for (int j = tid; j < 256; j += CT) {
+      const int which = j >> 7, cc = j & 127;
+      if (cc < H) {
+        double sacc = 0.0;
+        for (int w = 0; w < NWARP; ++w) sacc += red0[(w * 2 + which) * Hp + cc];
+        atomicAdd(p.sums + (int64_t)arm * 256 + which * 128 + cc, sacc);
+      }
+    }
+    grid_barrier(p.bar + 3, nctas);
+  }
 
   float* Ws[2] = {Ws0, Ws1};
   float* Xs[2] = {Xs0, Xs1};
@@ -1022,9 +1097,15 @@ static int coop_sms() {
   return cache[dev] > 0 ? cache[dev] : 0;
 }
 
+int enc_chain_fwd_is_single(int A, int B, int H, int L) {
+  const int nsm = coop_sms();
+  if (!nsm || H > 128 || L > 64 || H % 4 != 0 || A > nsm) return 0;
+  return (int64_t)((B + 79) / 80) * A <= nsm ? 1 : 0;
+}
+
 int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
                          const float* a1, float* const aout[4], double* acc_fwd, float* bn_mean, float* bn_rstd, float eps,
-                         cudaStream_t s) {
+                         const Fc1Deferred* fc1, cudaStream_t s) {
   const int nsm = coop_sms();
   if (!nsm || H > 128 || L > 64 || H % 4 != 0 || A > nsm) return 1;
   EncChainArgs c;
@@ -1038,7 +1119,8 @@ int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_
     c.aout[l] = aout[l];
   }
   c.A = A; c.B = B; c.H = H; c.L = L;
-  c.a1 = a1;
+  c.a1 = a1; c.a1_out = const_cast<float*>(a1);
+  if (fc1 && fc1->valid) c.fx = *fc1;
   c.sums = acc_fwd;
   c.bn_mean = bn_mean; c.bn_rstd = bn_rstd;
   c.bar = reinterpret_cast<unsigned int*>(acc_fwd + acc_sync(A));
@@ -1047,6 +1129,7 @@ int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_
   const int tiles = (B + CR - 1) / CR;
   // one co-resident wave (grid barrier): one row tile per CTA while that fits, else several tiles per CTA
   const bool multi = (int64_t)tiles * A > nsm;
+  MVAE_CHECK_ARG(!(multi && c.fx.valid), "internal: the multi-tile encoder chain takes no deferred fc1 fix-up");
   const int gx = multi ? nsm / A : tiles;
   const size_t smem = (size_t)(2 * c.Hp * c.XP + 2 * CR * c.XP + 4 * 128 + 256) * 4 + (size_t)MT * 2 * 128 * 8 + (multi ? 2 * 128 * 8 : 0);
   const bool fast = (H == 100 && L == 10);

@@ -510,7 +510,7 @@ int64_t ts_part_floats(int A, int Bpad, int Dpad) {
 
 // fc1 forward: a1 = relu(dropout(x) . W1^T + b1) and the batch_l1 column sums (replaces GEMM + epilogue kernel)
 int ts_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
-                   const DropSpec& drop, const Work& w, float* a1_out, double* stats_out, cudaStream_t s) {
+                   const DropSpec& drop, const Work& w, float* a1_out, double* stats_out, Fc1Deferred* defer, cudaStream_t s) {
   mvae_layout L;
   compute_layout(d, &L);
   const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
@@ -542,6 +542,11 @@ int ts_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state&
   int64_t U, G;
   rc = launch_ts<false>(tmX, tmW, tmWlo, a, &U, &G, s);
   if (rc) return rc;
+  if (defer) {          // the encoder chain sums the partials itself (kernels_chain.cu)
+    defer->part = a.part; defer->batch = A; defer->ktiles = a.ktiles; defer->U = U; defer->G = G;
+    defer->scale = drop.mode ? drop.scale : 1.f; defer->offB = L.offset[FC1_B]; defer->valid = 1;
+    return 0;
+  }
   Fc1FixArgs f;
   memset(&f, 0, sizeof(f));
   f.part = a.part; f.batch = A; f.ktiles = a.ktiles; f.U = U; f.G = G;

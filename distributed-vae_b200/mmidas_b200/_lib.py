@@ -57,7 +57,7 @@ PRECISIONS = {"tf32x3_fc1": 0, "tf32x3": 1, "tf32": 2, "fp32_simt": 3}
 
 # every symbol include/mixvae_b200.h declares
 EXPORTS = ("mvae_last_error", "mvae_abi_version", "mvae_compute_layout", "mvae_forward", "mvae_loss",
-           "mvae_backward", "mvae_adam", "mvae_train_step", "mvae_argmax", "mvae_dropout_mask", "mvae_launch_count",
+           "mvae_backward", "mvae_adam", "mvae_train_step", "mvae_grad_step", "mvae_argmax", "mvae_dropout_mask", "mvae_launch_count",
            "mvae_timing_enable", "mvae_timing_read", "mvae_debug_tc_gemm", "mvae_confmat", "mvae_fold_affine",
            "mvae_linear_act", "mvae_fma_rows", "mvae_unpack_rows", "mvae_adam_peer")
 
@@ -87,6 +87,7 @@ def load():
                               C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
     lib.mvae_train_step.argtypes = [P(Dims), P(HParams), P(State), P(Inputs), P(Outputs), C.c_void_p, C.c_float,
                                     C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]
+    lib.mvae_grad_step.argtypes = [P(Dims), P(HParams), P(State), P(Inputs), P(Outputs), C.c_void_p, C.c_void_p]
     lib.mvae_argmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     lib.mvae_dropout_mask.argtypes = [P(Dims), P(HParams), P(Inputs), C.c_void_p, C.c_void_p]
     lib.mvae_confmat.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
@@ -112,7 +113,7 @@ def load():
     lib.mvae_timing_read.argtypes = [P(C.c_float), P(C.c_int32), C.c_int32]
     lib.mvae_timing_read.restype = C.c_int
     for name in ("mvae_compute_layout", "mvae_forward", "mvae_loss", "mvae_backward", "mvae_adam",
-                 "mvae_train_step", "mvae_argmax", "mvae_dropout_mask"):
+                 "mvae_train_step", "mvae_grad_step", "mvae_argmax", "mvae_dropout_mask"):
         getattr(lib, name).restype = C.c_int
     if lib.mvae_abi_version() != 2:
         raise RuntimeError("libmixvae_b200.so ABI version mismatch")

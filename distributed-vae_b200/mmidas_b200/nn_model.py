@@ -512,6 +512,39 @@ class mixVAE_model(nn.Module):
         self._ctx = ctx
         return loss_vec
 
+    def fused_grad_step(self, x, temp, noise=None):
+        """zero_grad + forward + loss + backward in one C call (``mvae_grad_step``), no optimiser step: what a data-parallel
+        replica runs before its gradients are averaged.  Returns the device loss vector; gradients are in ``flat_grads()``."""
+        if not self.training:
+            raise RuntimeError("fused_grad_step needs model.train()")
+        if self.n_arm != self.n_arm_total:
+            raise RuntimeError("sharded arms run forward / loss / backward around the all-gather")
+        dev = self._require_cuda()
+        lib = _lib.load()
+        xt, x_arm_stride, x_row_stride, B = self._prep_x(x)
+        U, E, keep_x, keep_s = self._prep_noise(noise, B, True)
+        dims = self._dims(B)
+        hp = self._hparams(temp)
+        st = self._state(dims)
+        self._step_counter += 1
+        inp = self._inputs(xt, x_arm_stride, x_row_stride, U, E, keep_x, keep_s, True)
+        ot = self._static_outputs(B)
+        out = _lib.Outputs(*[ot[k].data_ptr() for k in ("x_low", "c_prob", "qc", "c_smp", "s_mean", "s_logvar", "s_smp")],
+                           None)
+        loss_vec = torch.empty(5 + 3 * self.n_arm, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.mvae_grad_step(C.byref(dims), C.byref(hp), C.byref(st), C.byref(inp), C.byref(out),
+                                      loss_vec.data_ptr(), C.c_void_p(stream)), "mvae_grad_step")
+        self._gen += 1
+        ctx = _StepContext()
+        ctx.gen = self._gen
+        ctx.keep = [xt, U, E, keep_x, keep_s]
+        ctx.out_tensors = ot
+        ctx.loss_vec = loss_vec
+        self._ctx = ctx
+        self.bind_grads()
+        return loss_vec
+
     def _static_outputs(self, B):
         key = ("static", B)
         cache = getattr(self, "_static_out", None)

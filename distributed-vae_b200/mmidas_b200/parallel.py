@@ -333,6 +333,15 @@ class ShardedTrainer:
         if plan.world_size == 1:
             return m.fused_train_step(x_local.expand(m.n_arm, -1, -1), self.temp, self.optimizer, noise=noise)
         xs = x_local.expand(m.n_arm, -1, -1)
+        if plan.arm_ranks == 1 and not self.overlap:
+            # pure data parallel: the replica's forward + loss + backward is one C call (mvae_grad_step), then the exchange
+            lv = m.fused_grad_step(xs, self.temp, noise=noise)
+            if self.peer is not None:
+                self._peer_adam_step()
+            else:
+                allreduce_mean([m.flat_grads()], self.dp_group, plan.dp_ranks)
+                self.optimizer.step()
+            return lv
         x_recs, _, _, _, cs, _, c_smps, s_means, s_logvars, _ = m(xs, self.temp, 0.0, noise=noise)
         ot = m.last_outputs()
         qc_all = all_gather_arms(ot["qc"], plan, self.arm_group)

@@ -168,6 +168,12 @@ int mvae_train_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_st
                     const mvae_inputs* in, const mvae_outputs* out, float* loss_out, float lr,
                     float beta1, float beta2, float adam_eps, int64_t step, void* stream);
 
+/* zero_grad + forward + loss + backward in one call, WITHOUT the optimiser step: the step of a data-parallel replica
+ * (all arms local), whose gradients are then averaged and applied by mvae_adam_peer (or an all-reduce + mvae_adam).
+ * Same kernels and side branches as mvae_train_step; in->counters[0] is advanced as by mvae_forward. */
+int mvae_grad_step(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state* st,
+                   const mvae_inputs* in, const mvae_outputs* out, float* loss_out, void* stream);
+
 /* Device-side argmax of q(c|x) -> int32 labels [A][B] (replaces the per-step D2H of
  * cpl_mixvae.py:476 + mmidas/_utils.py:78 classify). */
 int mvae_argmax(const float* q, int32_t* labels, int64_t rows, int32_t cols, void* stream);

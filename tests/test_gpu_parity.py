@@ -237,6 +237,25 @@ def test_fused_step_equals_api_step():
     assert torch.equal(res[0][3], res[1][3])
 
 
+def test_fused_grad_step_equals_api_gradients():
+    """mvae_grad_step (the data-parallel replica's step without the optimiser; side branches, one accumulator clear) gives
+    the loss vector and gradients of forward / loss / backward through the reference-shaped API, bit for bit."""
+    hp, x, noises, _, _ = case_inputs("mid")
+    xc = x.cuda()
+    nz = to_dev_noise(noises[0])
+    m1 = build_model(hp, "tf32x3_fc1")
+    _, ls = _fwd_loss_bwd(m1, xc, nz, hp.temp)
+    lv1 = m1._ctx.loss_vec.clone()
+    g1 = m1.flat_grads().clone()
+    m2 = build_model(hp, "tf32x3_fc1")
+    m2.train()
+    lv2 = m2.fused_grad_step(xc.expand(hp.n_arm, -1, -1), hp.temp, noise=nz)
+    torch.cuda.synchronize()
+    assert torch.equal(lv1, lv2)
+    assert torch.equal(g1, m2.flat_grads())
+    assert m2.fc1[0].weight.grad is not None          # p.grad views are bound as after backward()
+
+
 def test_in_kernel_dropout_equals_injected_mask():
     """The counter-based generator used by the fc1 forward and fc1 weight-gradient kernels: same mask
     in both (checked by injecting the materialised mask), keep rate ~ 1-p."""
