@@ -122,6 +122,15 @@ __host__ __device__ inline int64_t accb_bn(int layer, int A, int a) { return ((i
 __host__ __device__ inline int64_t accb_sync(int A) { return (int64_t)5 * A * 256; }   // grid-barrier counters (8 doubles)
 __host__ __device__ inline int64_t acc_bwd_doubles(int A) { return (int64_t)5 * A * 256 + 8; }
 
+// cudaFuncSetAttribute is per device: "set it once" guards are per device too (one process may drive several GPUs)
+inline bool first_on_device(bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 // first partial-tile slot of the fc11 gene pass: behind the row pass's slots (CTA + tile < A * ceil(B / 128) + #SM)
 inline int64_t f11_gene_slot0(int A, int B) { return (int64_t)A * ((B + 127) / 128) + 160; }
 

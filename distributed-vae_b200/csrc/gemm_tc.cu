@@ -774,10 +774,9 @@ int run_tc_gemm(const Operand& A, const Operand& B, int M, int N, int K, int BN,
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch * nsplit);
 #define TC_LAUNCH(AM, BMJ)                                                                                         \
   do {                                                                                                             \
-    static bool attr = false;                                                                                      \
-    if (!attr) {                                                                                                   \
+    static bool attr[64] = {};                                                                                      \
+    if (first_on_device(attr)) {                                                                                                   \
       MVAE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr = true;                                                                                                 \
     }                                                                                                              \
     tc_gemm_kernel<AM, BMJ><<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, a);                                          \
   } while (0)
@@ -870,10 +869,9 @@ int tc_narrow_wgrad(WgArgs& a, const int* idx, int n, int split3, cudaStream_t s
   P.bn_mean = a.bn_mean; P.bn_rstd = a.bn_rstd;
   for (int t = 0; t < n; ++t) a.prob[idx[t]].nsplit = nsplit;
   const size_t smem = (size_t)P.stages * (split3 ? 4 : 2) * TILE_BYTES + (3 * P.stages + 2) * 8 + 16 + 256 * 4 + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (first_on_device(attr)) {
     MVAE_CUDA(cudaFuncSetAttribute(wg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
   }
   wg_tc_kernel<<<dim3(nsplit, n, a.A), NUM_THREADS, smem, s>>>(P);
   MVAE_LAUNCH_CHECK();
@@ -1067,10 +1065,9 @@ int tc_linear_act(const float* x, int64_t x_pitch, const float* w, int64_t w_pit
   a.tiles_m = (int)((rows + BM - 1) / BM); a.tiles_n = (n_out + BN - 1) / BN;
   a.C = y; a.ldc = y_pitch; a.scale = scale; a.shift = shift; a.act = act;
   const size_t smem = (size_t)a.stages * (split3 ? 3 : (BN > 128 ? 3 : 2)) * TILE_BYTES + (3 * a.stages + 6) * 8 + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (first_on_device(attr)) {
     MVAE_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
   }
   const int ntiles = a.tiles_m * a.tiles_n;
   const int grid = ntiles < mma_sm_count_tc() ? ntiles : mma_sm_count_tc();

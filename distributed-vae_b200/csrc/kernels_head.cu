@@ -511,15 +511,14 @@ static int head_set_attr(F* f) {
   return 0;
 }
 static int head_attrs() {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  if (first_on_device(attr_done)) {
 #define HEAD_ATTR(...)                                                     \
   if (int rc = head_set_attr(head_fwd_kernel<__VA_ARGS__>)) return rc;     \
   if (int rc = head_set_attr(head_bwd_kernel<__VA_ARGS__>)) return rc;
     HEAD_ATTR(16, false, 0, 0) HEAD_ATTR(16, true, 0, 0) HEAD_ATTR(32, false, 0, 0) HEAD_ATTR(32, true, 0, 0)
     HEAD_ATTR(16, false, 10, 2) HEAD_ATTR(16, true, 10, 2)
 #undef HEAD_ATTR
-    attr_done = true;
   }
   return 0;
 }

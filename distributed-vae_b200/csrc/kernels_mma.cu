@@ -796,10 +796,9 @@ int launch_dense_fwd_mma(const DenseFwdArgs& a, int A, cudaStream_t s) {
   dim3 grid(ntiles > per_arm ? per_arm : ntiles, A);
 #define LAUNCH(NT)                                                                                                 \
   do {                                                                                                             \
-    static bool attr = false;                                                                                      \
-    if (!attr) {                                                                                                   \
+    static bool attr[64] = {};                                                                                      \
+    if (first_on_device(attr)) {                                                                                                   \
       MVAE_CUDA(cudaFuncSetAttribute(dense_fwd_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
-      attr = true;                                                                                                 \
     }                                                                                                              \
     dense_fwd_mma_kernel<NT><<<grid, MMA_THREADS, fwd_smem<NT>(a.nin), s>>>(a);                                    \
   } while (0)
@@ -879,11 +878,10 @@ int launch_wgrad_mma(const WgArgs& a0, int split3, cudaStream_t s) {
       ctas += n;
     }
     if (ctas > 0) {
-      static bool attr = false;
-      if (!attr) {
+      static bool attr[64] = {};
+      if (first_on_device(attr)) {
         MVAE_CUDA(cudaFuncSetAttribute(wgrad2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_FLOATS * 4));
         MVAE_CUDA(cudaFuncSetAttribute(wgrad2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_FLOATS * 4));
-        attr = true;
       }
       if (split3) wgrad2_kernel<true><<<dim3(ctas, a.A), 512, WG2_SMEM_FLOATS * 4, s>>>(a);
       else wgrad2_kernel<false><<<dim3(ctas, a.A), 512, WG2_SMEM_FLOATS * 4, s>>>(a);

@@ -150,10 +150,9 @@ int launch_dense_fwd(const DenseFwdArgs& a, int A, cudaStream_t s) {
   dim3 grid(gx, A);
 #define LAUNCH_DF(K)                                                                                   \
   case K: {                                                                                            \
-    static bool attr_done = false;                                                                     \
-    if (!attr_done) {                                                                                  \
+    static bool attr_done[64] = {};                                                                     \
+    if (first_on_device(attr_done)) {                                                                                  \
       MVAE_CUDA(cudaFuncSetAttribute(dense_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
-      attr_done = true;                                                                                \
     }                                                                                                  \
     dense_fwd_kernel<K><<<grid, kRowWarps * 32, smem, s>>>(a);                                         \
   } break;
@@ -322,10 +321,9 @@ int launch_dense_bwd(const DenseBwdArgs& a, int A, cudaStream_t s) {
   dim3 grid(gx, A);
 #define LAUNCH_DB(K)                                                                                   \
   case K: {                                                                                            \
-    static bool attr_done = false;                                                                     \
-    if (!attr_done) {                                                                                  \
+    static bool attr_done[64] = {};                                                                     \
+    if (first_on_device(attr_done)) {                                                                                  \
       MVAE_CUDA(cudaFuncSetAttribute(dense_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
-      attr_done = true;                                                                                \
     }                                                                                                  \
     dense_bwd_kernel<K><<<grid, kRowWarps * 32, smem, s>>>(a);                                         \
   } break;

@@ -490,10 +490,9 @@ int launch_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap&
   a.nx = nx_for(a.nw) >= 2 * NG ? 2 * NG : NG;
 #endif
   const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * w_stage + (2 * a.nx + 2 * a.nw + 3 * NA + 6) * 8 + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (first_on_device(attr)) {
     MVAE_CUDA(cudaFuncSetAttribute(ts_gemm_kernel<WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
   }
   ts_gemm_kernel<WGRAD><<<dim3((unsigned)G), THREADS, smem, s>>>(tmX, tmW, tmWlo, a);
   MVAE_LAUNCH_CHECK();
