@@ -30,6 +30,7 @@ static int make_plan(const mvae_dims* dims, Plan* p) {
 }
 
 static int check_device() {
+  tl_pdl = 0;            // every entry point passes through here: its first launch is an ordinary one
   static int ok = -1;
   if (ok < 0) {
     int dev = 0;
@@ -40,6 +41,18 @@ static int check_device() {
     if (!ok) set_error("libmixvae_b200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
   }
   return ok == 1 ? 0 : -2;
+}
+
+// Programmatic dependent launch (see common.cuh).  MVAE_PDL=0 turns it off, =2 also lets the cooperative chain kernels be
+// primaries; per-group timing (events between the launches) measures the serial order and runs without it.
+thread_local int tl_pdl = 0;
+int pdl_level() {
+  static int level = -1;
+  if (level < 0) {
+    const char* e = getenv("MVAE_PDL");
+    level = e ? atoi(e) : 1;
+  }
+  return timing_enabled() ? 0 : level;
 }
 
 // Side branch of the fused step (mvae_train_step): the coupling kernels run beside the decoder chain and the first fc11
@@ -138,6 +151,7 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   // the accumulator blocks of the forward, the loss and the backward are adjacent in the work buffer: the fused step
   // clears all three with one node
   MVAE_CUDA(cudaMemsetAsync(acc_fwd, 0, (size_t)(clear_all ? w.acc_bwd + w.acc_bwd_floats - w.acc_fwd : w.acc_fwd_floats) * 4, s));
+  tl_pdl = 0;            // (a memset node: the step's first kernel is fully ordered behind everything before it)
   RC(launch_step_prep(in.seed, in.step, in.counters, bump_adam, p.d.arm_offset, step_keys(p, st), s));
   float* bn_mean = work + w.bn_mean;
   float* bn_rstd = work + w.bn_rstd;
@@ -231,11 +245,17 @@ static int forward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state&
   if (fork) {
     // q is final: its column statistics (inv_var of the coupling term) start now, beside the decoder chain; the loss
     // accumulators they add to are cleared first
-    if (!clear_all) MVAE_CUDA(cudaMemsetAsync(work + w.acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
+    if (!clear_all) {
+      MVAE_CUDA(cudaMemsetAsync(work + w.acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
+      tl_pdl = 0;
+    }
     MVAE_CUDA(cudaEventRecord(fork->head_done, s));
     MVAE_CUDA(cudaStreamWaitEvent(fork->side, fork->head_done, 0));
+    const int main_pdl = tl_pdl;       // the side branch's launch is an ordinary one; the main branch goes on behind head_fwd
+    tl_pdl = 0;
     RC(launch_qstats(coupling_args(p, hp, st, out.qc, out.c_smp), fork->side));
     MVAE_CUDA(cudaEventRecord(fork->qstats_done, fork->side));
+    tl_pdl = main_pdl;
   }
 
   // ---- fc7..fc10 (:281-284)
@@ -303,6 +323,7 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
       if (!cleared) MVAE_CUDA(cudaMemsetAsync(acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
       RC(launch_qstats(c, s));
     }
+    tl_pdl = 0;          // (join / memset / ordinary launches in front)
     RC(launch_coupling_rows(c, s));
     timing_end(TG_COUPLING, s);
   }
@@ -356,10 +377,11 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
     // the decoder's backward chain; join before the head kernel, which needs the constants
     MVAE_CUDA(cudaEventRecord(fork->fc11_done, s));
     MVAE_CUDA(cudaStreamWaitEvent(fork->side, fork->fc11_done, 0));
-    RC(launch_loss_finalize(f, fork->side));
+    RC(launch_loss_finalize(f, fork->side));        // (an ordinary launch; tl_pdl still describes the main branch)
     MVAE_CUDA(cudaEventRecord(fork->final_done, fork->side));
   } else {
     RC(launch_loss_finalize(f, s));
+    tl_pdl = 0;
   }
   timing_end(TG_COUPLING, s);
   return 0;
@@ -374,7 +396,10 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   float* work = st.work;
   MVAE_CHECK_ARG(in.training, "backward needs a training-mode forward");
   double* acc_bwd = reinterpret_cast<double*>(work + w.acc_bwd);
-  if (!cleared) MVAE_CUDA(cudaMemsetAsync(acc_bwd, 0, (size_t)w.acc_bwd_floats * 4, s));
+  if (!cleared) {
+    MVAE_CUDA(cudaMemsetAsync(acc_bwd, 0, (size_t)w.acc_bwd_floats * 4, s));
+    tl_pdl = 0;
+  }
   float* bn_mean = work + w.bn_mean;
   float* bn_rstd = work + w.bn_rstd;
   const bool tc = use_tc(p, hp);
@@ -425,7 +450,10 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   h.delta6 = work + w.delta_dec[0]; h.delta_mu = work + w.delta_mu; h.delta_sig = work + w.delta_sig;
   h.delta_z = work + w.delta_z; h.g_xlow = work + w.g_xlow;
   h.bnb_sums5 = acc_bwd + accb_bn(4, A, 0);
-  if (fork) MVAE_CUDA(cudaStreamWaitEvent(s, fork->final_done, 0));      // join: coupling constants and the loss vector
+  if (fork) {
+    MVAE_CUDA(cudaStreamWaitEvent(s, fork->final_done, 0));      // join: coupling constants and the loss vector
+    tl_pdl = 0;
+  }
   RC(launch_head_bwd(h, s));
 
   // ---- encoder fc5..fc2, then the BatchNorm+ReLU backward of layer 1

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <utility>
+
 #include "../../include/mixvae_b200.h"
 
 namespace mvae {
@@ -122,6 +124,33 @@ __host__ __device__ inline int64_t accb_bn(int layer, int A, int a) { return ((i
 __host__ __device__ inline int64_t accb_sync(int A) { return (int64_t)5 * A * 256; }   // grid-barrier counters (8 doubles)
 __host__ __device__ inline int64_t acc_bwd_doubles(int A) { return (int64_t)5 * A * 256 + 8; }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Inside one API call the library's kernels follow each other on one stream; a
+// kernel launched through launch_pdl() right after another kernel of the library carries the programmatic-stream-
+// serialization attribute (captured as a programmatic edge in a CUDA graph): its CTAs may become resident -- and run
+// the part of the kernel in front of pdl_wait() -- while the kernels before it are still running.  Rules:
+//   * every kernel launched through launch_pdl() executes pdl_wait() before it reads anything an earlier kernel of
+//     the step wrote and before it writes global memory at all; in front of it only step constants (parameters, x)
+//     may be read -- the kernels of a PDL chain cascade, so "earlier" is not just the direct predecessor;
+//   * tl_pdl says "the previous operation enqueued by this thread for this step was a kernel of the library on the same
+//     stream"; api.cu clears it at every entry point and around memsets, event edges and cooperative launches.
+// ---------------------------------------------------------------------------------------------
+extern thread_local int tl_pdl;
+int pdl_level();     // 0: off, 1: between ordinary launches, 2: cooperative kernels may be primaries too
+inline bool pdl_enabled() { return pdl_level() >= 1; }
+template <typename... KP, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (tl_pdl && pdl_enabled()) ? 1 : 0;
+  tl_pdl = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // cudaFuncSetAttribute is per device: "set it once" guards are per device too (one process may drive several GPUs)
 inline bool first_on_device(bool (&done)[64]) {
   int dev = 0;
@@ -173,6 +202,10 @@ MVAE_HD inline uint64_t stream_key(uint64_t seed, uint64_t step, uint32_t arm_gl
 // device helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+// PDL: wait until every kernel this one depends on has completed and its writes are visible / let the dependent kernel's
+// CTAs become resident (they block in their own pdl_wait until this grid has completed)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -141,6 +141,10 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the set-up above and the first ring fills of the step's constants -- x, and for the row pass the fc11.weight
+  // tiles -- overlap the tail of the previous kernel; h10 (R of the row pass, T of the gene pass) and every store wait
+  pdl_trigger();
+  if (!(warp == 0 || (!GENE && warp == 1))) pdl_wait();
 
   const int t_first = (int)(u0 / KP), kp_first = (int)(u0 - (int64_t)t_first * KP);
   const int kt_first = 2 * kp_first;
@@ -530,6 +534,8 @@ __device__ __forceinline__ void f11_fix_bias(const F11FixArgs& p, int gene, int 
 __global__ void __launch_bounds__(256) f11_fixup_kernel(const F11FixArgs p) {
   __shared__ int cc[2];
   int b = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (b < p.row.nblk) {
     f11_fix_tile(p.row, b / p.row.batch, b % p.row.batch, cc);
   } else if ((b -= p.row.nblk) < p.gene.nblk) {
@@ -585,7 +591,7 @@ int launch_f11(const CUtensorMap& tmX, const CUtensorMap& tmT, F11Args& a, int64
     MVAE_CUDA(cudaFuncSetAttribute(fc11_ts_kernel<GENE, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr[dev] = true;
   }
-  fc11_ts_kernel<GENE, TRAIN><<<dim3((unsigned)G), THREADS, smem, s>>>(tmX, tmT, a);
+  launch_pdl(fc11_ts_kernel<GENE, TRAIN>, dim3((unsigned)G), dim3(THREADS), smem, s, tmX, tmT, a);
   {
     ::mvae::g_launches++;
     const cudaError_t e = cudaGetLastError();
@@ -634,7 +640,7 @@ static int fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs
   F11FixArgs fa;
   memset(&fa, 0, sizeof(fa));
   fa.row = fix_one(a.part, A, a.ktiles, U, G, work + w.g_d10, (int64_t)B * H, H, B, H);
-  f11_fixup_kernel<<<fa.row.nblk, 256, 0, s>>>(fa);
+  launch_pdl(f11_fixup_kernel, dim3(fa.row.nblk), dim3(256), 0, s, fa);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -671,7 +677,7 @@ static int fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_input
   fa.gene = fix_one(a.part, A, a.ktiles, U, G, st.grads + L.offset[FC11_W], L.arm_stride, H, D, H);
   fa.db_part = a.db_part; fa.db_out = st.grads + L.offset[FC11_B]; fa.db_arm_stride = L.arm_stride; fa.D = D;
   fa.nblk_db = (D + 255) / 256 * A;
-  f11_fixup_kernel<<<fa.row.nblk + fa.gene.nblk + fa.nblk_db, 256, 0, s>>>(fa);
+  launch_pdl(f11_fixup_kernel, dim3(fa.row.nblk + fa.gene.nblk + fa.nblk_db), dim3(256), 0, s, fa);
   MVAE_LAUNCH_CHECK();
   return 0;
 }

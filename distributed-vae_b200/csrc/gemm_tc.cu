@@ -382,13 +382,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wg_tc_kernel(const __grid_cons
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
+  if (warp == 2) tmem_alloc(tmem_slot, 128);
+  pdl_trigger();
+  pdl_wait();          // PDL: barriers and tensor memory are set up while the backward chain drains
   if (threadIdx.x >= 64 && threadIdx.x < 192) {
     const int i = threadIdx.x - 64;
     const bool have = do_norm && i < pr.N;
     bm[i] = have ? P.bn_mean[(pr.bn_layer * P.A + arm) * 128 + i] : 0.f;
     br[i] = have ? P.bn_rstd[(pr.bn_layer * P.A + arm) * 128 + i] : 1.f;
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -873,7 +875,7 @@ int tc_narrow_wgrad(WgArgs& a, const int* idx, int n, int split3, cudaStream_t s
   if (first_on_device(attr)) {
     MVAE_CUDA(cudaFuncSetAttribute(wg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
-  wg_tc_kernel<<<dim3(nsplit, n, a.A), NUM_THREADS, smem, s>>>(P);
+  launch_pdl(wg_tc_kernel, dim3(nsplit, n, a.A), dim3(NUM_THREADS), smem, s, P);
   MVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(128 * MT) dec_chain_fwd_kernel(const ChainArgs
   const int rows_valid = min(CR, B - row0);
   const float* par = p.params + (int64_t)arm * p.p_arm_stride;
 
+  pdl_trigger();
   for (int idx = tid; idx < 2 * Hp * WPF + 2 * CR * XP; idx += CT) smem[idx] = 0.f;
   for (int idx = tid; idx < 4 * 128; idx += CT) {
     const int l = idx >> 7, j = idx & 127;
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(128 * MT) dec_chain_fwd_kernel(const ChainArgs
   __syncthreads();
   // layer 0 operands (fc7: [H][L], rows of L floats: scalar path) + prefetch of fc8
   async_tile(Ws0, WPF, par + p.offW[0], L, H, L, tid, CT);
+  pdl_wait();          // PDL: everything above touches parameters only and overlaps the tail of the head kernel
   async_tile(Xs0, XP, p.h6 + ((int64_t)arm * B + row0) * L, L, rows_valid, L, tid, CT);
   cp_async_commit();
   async_tile(Ws1, WPF, par + p.offW[1], H, H, H, tid, CT);
@@ -216,12 +218,14 @@ __global__ void __launch_bounds__(128 * MT) dec_chain_bwd_kernel(const ChainArgs
   const float* par = p.params + (int64_t)arm * p.p_arm_stride;
   const int64_t rbase = (int64_t)arm * B + row0;
 
+  pdl_trigger();
   for (int idx = tid; idx < 2 * Hp * WPB + 3 * CR * XP; idx += CT) smem[idx] = 0.f;
   __syncthreads();
   // group 0: g10, h10, W10 ; group 1: h9, W9
+  async_tile(Ws0, WPB, par + p.offW[3], H, H, H, tid, CT);
+  pdl_wait();          // PDL: the set-up and the first weight tile overlap the tail of the fc11 fix-up
   async_tile(Gs, XP, p.g10 + rbase * H, H, rows_valid, H, tid, CT);
   async_tile(Ms0, XP, p.act[3] + rbase * H, H, rows_valid, H, tid, CT);
-  async_tile(Ws0, WPB, par + p.offW[3], H, H, H, tid, CT);
   cp_async_commit();
   async_tile(Ms1, XP, p.act[2] + rbase * H, H, rows_valid, H, tid, CT);
   async_tile(Ws1, WPB, par + p.offW[2], H, H, H, tid, CT);
@@ -351,6 +355,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int n) 
 template <int MT, int NWC, int HC, int LC>
 __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncChainArgs p) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   constexpr int CR = 16 * MT, CT = 32 * MT * NWC, NTW = 16 / NWC;   // MT row groups x NWC column groups of warps
   constexpr bool FAST = HC > 0;
   const int XP = FAST ? (((HC + 7) & ~7) + 4) : p.XP, Hp = FAST ? ((HC + 7) & ~7) : p.Hp;
@@ -566,6 +571,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
 template <int MT, int NWC, int HC, int LC>
 __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_multi_kernel(const EncChainArgs p) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   constexpr int CR = 16 * MT, CT = 32 * MT * NWC, NTW = 16 / NWC;
   constexpr bool FAST = HC > 0;
   const int XP = FAST ? (((HC + 7) & ~7) + 4) : p.XP, Hp = FAST ? ((HC + 7) & ~7) : p.Hp;
@@ -716,6 +722,7 @@ struct EncBwdArgs {
 template <int MT, int NWC, bool SPLIT, int HC, int LC>
 __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncBwdArgs p) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   constexpr int CR = 16 * MT, CT = 32 * MT * NWC, NTW = 16 / NWC;
   constexpr bool FAST = HC > 0;
   constexpr int HPC = (HC + 7) & ~7;
@@ -865,6 +872,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncB
 template <int MT, int NWC, bool SPLIT, int HC, int LC>
 __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_multi_kernel(const EncBwdArgs p, float* __restrict__ gscr) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   constexpr int CR = 16 * MT, CT = 32 * MT * NWC, NTW = 16 / NWC;
   constexpr bool FAST = HC > 0;
   constexpr int HPC = (HC + 7) & ~7;
@@ -1035,10 +1043,10 @@ int launch_dec_chain_fwd(const float* params, int64_t p_arm_stride, const int64_
   do {                                                                                                              \
     if (H == 100 && L == 10) {                                                                                      \
       MVAE_CUDA(cudaFuncSetAttribute(dec_chain_fwd_kernel<MTV, SP, 100, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      dec_chain_fwd_kernel<MTV, SP, 100, 10><<<dim3((B + cr - 1) / cr, A), 128 * MTV, smem, s>>>(c);                  \
+      launch_pdl(dec_chain_fwd_kernel<MTV, SP, 100, 10>, dim3((B + cr - 1) / cr, A), dim3(128 * MTV), smem, s, c);                  \
     } else {                                                                                                        \
       MVAE_CUDA(cudaFuncSetAttribute(dec_chain_fwd_kernel<MTV, SP, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      dec_chain_fwd_kernel<MTV, SP, 0, 0><<<dim3((B + cr - 1) / cr, A), 128 * MTV, smem, s>>>(c);                     \
+      launch_pdl(dec_chain_fwd_kernel<MTV, SP, 0, 0>, dim3((B + cr - 1) / cr, A), dim3(128 * MTV), smem, s, c);                     \
     }                                                                                                               \
   } while (0)
   if (mt == 5 && split3) CHAIN_LAUNCH(5, true);
@@ -1063,10 +1071,10 @@ int launch_dec_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
   do {                                                                                                              \
     if (H == 100 && L == 10) {                                                                                      \
       MVAE_CUDA(cudaFuncSetAttribute(dec_chain_bwd_kernel<MTV, SP, 100, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      dec_chain_bwd_kernel<MTV, SP, 100, 10><<<dim3((B + cr - 1) / cr, A), 128 * MTV, smem, s>>>(c);                  \
+      launch_pdl(dec_chain_bwd_kernel<MTV, SP, 100, 10>, dim3((B + cr - 1) / cr, A), dim3(128 * MTV), smem, s, c);                  \
     } else {                                                                                                        \
       MVAE_CUDA(cudaFuncSetAttribute(dec_chain_bwd_kernel<MTV, SP, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      dec_chain_bwd_kernel<MTV, SP, 0, 0><<<dim3((B + cr - 1) / cr, A), 128 * MTV, smem, s>>>(c);                     \
+      launch_pdl(dec_chain_bwd_kernel<MTV, SP, 0, 0>, dim3((B + cr - 1) / cr, A), dim3(128 * MTV), smem, s, c);                     \
     }                                                                                                               \
   } while (0)
   if (mt == 5 && split3) CHAIN_LAUNCH(5, true);
@@ -1138,6 +1146,7 @@ int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_
                          : (fast ? (const void*)enc_chain_fwd_kernel<MT, NWC, 100, 10> : (const void*)enc_chain_fwd_kernel<MT, NWC, 0, 0>);
   MVAE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MVAE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(gx, A), dim3(32 * MT * NWC), args, smem, s));
+  tl_pdl = pdl_level() >= 2 ? 1 : 0;      // a cooperative launch is never a PDL secondary; it may be a primary
   MVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -1182,6 +1191,7 @@ int launch_enc_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
   void* args2[] = {(void*)&c, (void*)&g_scratch};
   MVAE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MVAE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(gx, A), dim3(32 * MT * NWC), multi ? args2 : args1, smem, s));
+  tl_pdl = pdl_level() >= 2 ? 1 : 0;
   MVAE_LAUNCH_CHECK();
   return 0;
 }

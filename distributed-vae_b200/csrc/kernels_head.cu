@@ -68,8 +68,10 @@ __device__ __forceinline__ void head_load_weights(const HeadArgs& p, const HeadS
     h.bsig[s] = base[p.oBsig + s];
   }
   for (int i = tid; i < L; i += nt) h.b6[i] = base[p.oB6 + i];
-  if (with_colc)
+  if (with_colc) {
+    pdl_wait();        // the coupling constants come from loss_finalize_kernel; the weights above are step constants
     for (int idx = tid; idx < 4 * 128; idx += nt) h.colc[idx] = p.colc[(int64_t)arm * 4 * 128 + idx];
+  }
 }
 
 // fc6 of one cell: lane i < L returns relu(W6[i,:C] . c + W6[i,C:] . s + b6[i]); c is spread over the lanes
@@ -133,7 +135,9 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_fwd_kernel(const HeadA
     __builtin_assume(C <= 128);
   }
   const HeadSmem h = head_carve(smem, L, C, S);
-  head_load_weights(p, h, arm, false);
+  pdl_trigger();
+  head_load_weights(p, h, arm, false);     // PDL: the weight staging overlaps the tail of the encoder chain
+  pdl_wait();
   if (p.bn_mode == 1) {
     const double* sums = p.bn_sums5 + (int64_t)arm * 256;
     for (int i = tid; i < L; i += blockDim.x) {
@@ -367,7 +371,8 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_bwd_kernel(const HeadA
     __builtin_assume(C <= 128);
   }
   const HeadSmem h = head_carve(smem, L, C, S);
-  head_load_weights(p, h, arm, true);
+  pdl_trigger();
+  head_load_weights(p, h, arm, true);      // (waits for the previous kernels before it reads the coupling constants)
   __syncthreads();
   const float* cw = h.colc;            // w
   const float* ccv = h.colc + 128;     // (var+eps)^-1.5 / (B-1)
@@ -528,14 +533,14 @@ static int head_attrs() {
     const size_t sm = head_smem_bytes(a.L, a.C, a.S);                                               \
     const bool c96 = a.C > 96;                                                                      \
     if (a.L == 10 && a.S == 2) {                                                                    \
-      if (c96) KERNEL<16, true, 10, 2><<<grid, kRowWarps * 32, sm, s>>>(a);                         \
-      else KERNEL<16, false, 10, 2><<<grid, kRowWarps * 32, sm, s>>>(a);                            \
+      if (c96) launch_pdl(KERNEL<16, true, 10, 2>, grid, dim3(kRowWarps * 32), sm, s, a);                         \
+      else launch_pdl(KERNEL<16, false, 10, 2>, grid, dim3(kRowWarps * 32), sm, s, a);                            \
     } else if (a.L <= 16) {                                                                         \
-      if (c96) KERNEL<16, true, 0, 0><<<grid, kRowWarps * 32, sm, s>>>(a);                          \
-      else KERNEL<16, false, 0, 0><<<grid, kRowWarps * 32, sm, s>>>(a);                             \
+      if (c96) launch_pdl(KERNEL<16, true, 0, 0>, grid, dim3(kRowWarps * 32), sm, s, a);                          \
+      else launch_pdl(KERNEL<16, false, 0, 0>, grid, dim3(kRowWarps * 32), sm, s, a);                             \
     } else {                                                                                        \
-      if (c96) KERNEL<32, true, 0, 0><<<grid, kRowWarps * 32, sm, s>>>(a);                          \
-      else KERNEL<32, false, 0, 0><<<grid, kRowWarps * 32, sm, s>>>(a);                             \
+      if (c96) launch_pdl(KERNEL<32, true, 0, 0>, grid, dim3(kRowWarps * 32), sm, s, a);                          \
+      else launch_pdl(KERNEL<32, false, 0, 0>, grid, dim3(kRowWarps * 32), sm, s, a);                             \
     }                                                                                               \
   } while (0)
 

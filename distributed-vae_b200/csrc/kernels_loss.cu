@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(kCoupWarps * 32) coupling_rows_kernel(const Co
     __builtin_assume(C > 96);
     __builtin_assume(C <= 128);
   }
+  pdl_trigger();       // PDL: the fc11 row pass may start filling its rings with x and fc11.weight tiles
+  pdl_wait();
   for (int idx = tid; idx < At * 128; idx += blockDim.x) {
     const int a = idx >> 7, k = idx & 127;
     float wv = 0.f;
@@ -194,6 +196,7 @@ int launch_coupling_rows(const CouplingArgs& a, cudaStream_t s) {
   CouplingArgs arg = a;
   void* args[] = {(void*)&arg};
   MVAE_CUDA(cudaLaunchKernel(fn, dim3(gx), dim3(kCoupWarps * 32), args, dyn, s));   // (At == 2: compile-time arm loops)
+  tl_pdl = 1;          // (an ordinary launch -- it follows the join with the side branch -- that can be a PDL primary)
   MVAE_LAUNCH_CHECK();
   return 0;
 }

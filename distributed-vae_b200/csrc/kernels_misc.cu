@@ -121,6 +121,16 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n4,
                                                    float lr, float b1, float b2, float eps, float wd, int adamw,
                                                    float step_size, float inv_sqrt_bc2, const uint64_t* step_dev) {
+  // PDL: parameters and moments are only ever written by this kernel, so the first round of their loads (21 of the 28
+  // bytes per parameter) goes out while the kernel that finishes the gradients is still running
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), mv = pv, vv = pv;
+  if (i0 < n4) {
+    pv = reinterpret_cast<float4*>(p)[i0];
+    mv = reinterpret_cast<float4*>(m)[i0];
+    vv = reinterpret_cast<float4*>(v)[i0];
+  }
+  pdl_wait();
   if (step_dev) {   // step counter on the device (replayed CUDA graph): same double-precision bias corrections as the host path
     __shared__ float sh[2];
     if (threadIdx.x == 0) {
@@ -133,11 +143,13 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     step_size = sh[0];
     inv_sqrt_bc2 = sh[1];
   }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 pv = reinterpret_cast<float4*>(p)[i];
+  for (int64_t i = i0; i < n4; i += stride) {
+    if (i != i0) {
+      pv = reinterpret_cast<float4*>(p)[i];
+      mv = reinterpret_cast<float4*>(m)[i];
+      vv = reinterpret_cast<float4*>(v)[i];
+    }
     float4 gv = reinterpret_cast<const float4*>(g)[i];
-    float4 mv = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
     float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -172,7 +184,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float l
   int gx = (int)((n4 + 255) / 256);
   if (gx > 148 * 8) gx = 148 * 8;
   if (gx < 1) gx = 1;
-  adam_kernel<<<gx, 256, 0, s>>>(p, g, m, v, n4, lr, b1, b2, eps, wd, adamw, step_size, inv_sqrt_bc2, step_dev);
+  launch_pdl(adam_kernel, dim3(gx), dim3(256), 0, s, p, g, m, v, n4, lr, b1, b2, eps, wd, adamw, step_size, inv_sqrt_bc2, step_dev);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -266,6 +278,8 @@ int launch_adam_peer(float* const* peer_params, const float* const* peer_grads, 
 __global__ void step_prep_kernel(uint64_t seed, uint64_t step_host, uint64_t* counters, int bump_adam, int arm_off,
                                  uint64_t* keys_out) {
   __shared__ uint64_t st;
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x == 0) {
     uint64_t s = step_host;
     if (counters) {
@@ -345,7 +359,7 @@ int launch_counter_inc(uint64_t* counter, cudaStream_t s) {
 }
 int launch_step_prep(uint64_t seed, uint64_t step_host, uint64_t* counters, int bump_adam, int arm_off, uint64_t* keys_out,
                      cudaStream_t s) {
-  step_prep_kernel<<<1, 64, 0, s>>>(seed, step_host, counters, bump_adam, arm_off, keys_out);
+  launch_pdl(step_prep_kernel, dim3(1), dim3(64), 0, s, seed, step_host, counters, bump_adam, arm_off, keys_out);
   MVAE_LAUNCH_CHECK();
   return 0;
 }

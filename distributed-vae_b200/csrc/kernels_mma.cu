@@ -631,6 +631,8 @@ __global__ void __launch_bounds__(512, SPLIT ? 1 : 2) wgrad2_kernel(const WgArgs
   float* bm = wsm;
   float* br = wsm + 128;
   float* stages = wsm + 256;
+  pdl_trigger();
+  pdl_wait();
   int pi = 0;
   while (pi + 1 < p.nprob && (int)blockIdx.x >= p.prob[pi + 1].cta_begin) ++pi;
   const WgProblem& pr = p.prob[pi];
@@ -754,6 +756,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce2_kernel(const WgArgs p) {
   const int64_t n = which ? pr.nout : (int64_t)pr.nout * pr.nin;
   const int64_t poff = which ? pr.poffB : pr.poffW;
   const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (e >= n) return;
   const float* part = p.part + (int64_t)arm * p.part_arm_stride + (poff - p.base_off) + e;
   float s = 0.f;
@@ -883,8 +887,8 @@ int launch_wgrad_mma(const WgArgs& a0, int split3, cudaStream_t s) {
         MVAE_CUDA(cudaFuncSetAttribute(wgrad2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_FLOATS * 4));
         MVAE_CUDA(cudaFuncSetAttribute(wgrad2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_FLOATS * 4));
       }
-      if (split3) wgrad2_kernel<true><<<dim3(ctas, a.A), 512, WG2_SMEM_FLOATS * 4, s>>>(a);
-      else wgrad2_kernel<false><<<dim3(ctas, a.A), 512, WG2_SMEM_FLOATS * 4, s>>>(a);
+      if (split3) launch_pdl(wgrad2_kernel<true>, dim3(ctas, a.A), dim3(512), (size_t)WG2_SMEM_FLOATS * 4, s, a);
+      else launch_pdl(wgrad2_kernel<false>, dim3(ctas, a.A), dim3(512), (size_t)WG2_SMEM_FLOATS * 4, s, a);
     }
   } else {
     for (int i = 0; i < a.nprob; ++i) a.prob[i].nsplit = a.nsplit;
@@ -898,7 +902,7 @@ int launch_wgrad_mma(const WgArgs& a0, int split3, cudaStream_t s) {
     if (n > maxn) maxn = n;
     if (a.prob[i].nout > maxn) maxn = a.prob[i].nout;
   }
-  wgrad_reduce2_kernel<<<dim3((unsigned)((maxn + 255) / 256), a.nprob * 2, a.A), 256, 0, s>>>(a);
+  launch_pdl(wgrad_reduce2_kernel, dim3((unsigned)((maxn + 255) / 256), a.nprob * 2, a.A), dim3(256), 0, s, a);
   MVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -93,6 +93,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the set-up above and the first fills of the x ring (x is an input of the step) overlap the tail of the previous
+  // kernel; everything else -- the small operand, the generator keys, the partial tiles -- waits for it
+  pdl_trigger();
+  if (warp != 0) pdl_wait();
 
   // first unit of this CTA; every role then advances (kt, arm, mt) and its ring slots incrementally (no divisions
   // inside the loops: the transform warps are instruction-issue bound)
@@ -362,6 +366,8 @@ __global__ void __launch_bounds__(256) w_lo_kernel(const float* __restrict__ w, 
   const int arm = blockIdx.y;
   const float4* src = reinterpret_cast<const float4*>(w + (int64_t)arm * w_arm_stride);
   float4* dst = reinterpret_cast<float4*>(lo + (int64_t)arm * lo_arm_stride);
+  pdl_trigger();
+  pdl_wait();      // (the scratch buffer W1_lo lives in is read by the previous step's last kernels)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = src[i];
     dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
@@ -383,6 +389,8 @@ __global__ void __launch_bounds__(256) fc1_fixup_kernel(const Fc1FixArgs p) {
   const int tid = threadIdx.x, r8 = tid >> 5, c4 = tid & 31;
   const int row0 = (blockIdx.x >> 3) * 128, sub0 = (blockIdx.x & 7) * 16;
   const int64_t t = (int64_t)(row0 >> 8) * p.batch + arm;
+  pdl_trigger();
+  pdl_wait();
   if (tid == 0) {
     cc[0] = (int)cta_of_unit(t * p.ktiles, p.U, p.G);
     cc[1] = (int)cta_of_unit(t * p.ktiles + p.ktiles - 1, p.U, p.G);
@@ -438,6 +446,8 @@ __global__ void __launch_bounds__(256) wgrad_fixup_kernel(const float* part, int
   const int gb = blockIdx.x >> 2, hq = blockIdx.x & 3;     // 128-gene block, quarter of the h rows
   const int gene = gb * 128 + 4 * g4;
   const int64_t t = (int64_t)(gb >> 1) * batch + arm;
+  pdl_trigger();
+  pdl_wait();
   if (tid == 0) {
     cc[0] = (int)cta_of_unit(t * ktiles, U, G);
     cc[1] = (int)cta_of_unit(t * ktiles + ktiles - 1, U, G);
@@ -494,7 +504,7 @@ int launch_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap&
   if (first_on_device(attr)) {
     MVAE_CUDA(cudaFuncSetAttribute(ts_gemm_kernel<WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
-  ts_gemm_kernel<WGRAD><<<dim3((unsigned)G), THREADS, smem, s>>>(tmX, tmW, tmWlo, a);
+  launch_pdl(ts_gemm_kernel<WGRAD>, dim3((unsigned)G), dim3(THREADS), smem, s, tmX, tmW, tmWlo, a);
   MVAE_LAUNCH_CHECK();
   *U_out = U; *G_out = G;
   return 0;
@@ -518,7 +528,7 @@ int ts_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state&
   const int64_t wlo_stride = (int64_t)128 * w.Dpad;
   if (split3) {
     const int64_t n4 = (int64_t)H * D / 4;
-    w_lo_kernel<<<dim3(148, A), 256, 0, s>>>(st.params + L.offset[FC1_W], L.arm_stride, wlo, wlo_stride, n4);
+    launch_pdl(w_lo_kernel, dim3(148, A), dim3(256), 0, s, (const float*)(st.params + L.offset[FC1_W]), L.arm_stride, wlo, wlo_stride, n4);
     MVAE_LAUNCH_CHECK();
   }
   TsArgs a;
@@ -552,7 +562,7 @@ int ts_fc1_forward(const mvae_dims& d, const mvae_hparams& hp, const mvae_state&
   f.scale = drop.mode ? drop.scale : 1.f;
   f.params = st.params; f.p_arm_stride = L.arm_stride; f.offB = L.offset[FC1_B];
   f.out = a1_out; f.stats_out = stats_out; f.B = B; f.H = H;
-  fc1_fixup_kernel<<<dim3((B + 127) / 128 * 8, A), 256, 0, s>>>(f);
+  launch_pdl(fc1_fixup_kernel, dim3((B + 127) / 128 * 8, A), dim3(256), 0, s, f);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -580,8 +590,8 @@ int ts_fc1_wgrad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
   int64_t U, G;
   rc = launch_ts<true>(tmX, tmW, tmW, a, &U, &G, s);
   if (rc) return rc;
-  wgrad_fixup_kernel<<<dim3((D + 127) / 128 * 4, A), 256, 0, s>>>(a.part, A, a.ktiles, U, G, drop.mode ? drop.scale : 1.f,
-                                                                   st.grads + L.offset[FC1_W], L.arm_stride, D, H);
+  launch_pdl(wgrad_fixup_kernel, dim3((D + 127) / 128 * 4, A), dim3(256), 0, s, (const float*)a.part, A, a.ktiles, U, G,
+             drop.mode ? drop.scale : 1.f, st.grads + L.offset[FC1_W], L.arm_stride, D, H);
   MVAE_LAUNCH_CHECK();
   return 0;
 }
