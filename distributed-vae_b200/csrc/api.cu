@@ -3,7 +3,6 @@
 // Step order follows mmidas/cpl_mixvae.py:434-463: zero_grad (implicit: every gradient is written,
 // never accumulated), forward, loss, backward, Adam.
 #include <math.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_tc.h"
@@ -43,17 +42,11 @@ static int check_device() {
   return ok == 1 ? 0 : -2;
 }
 
-// Programmatic dependent launch (see common.cuh).  MVAE_PDL=0 turns it off, =2 also lets the cooperative chain kernels be
-// primaries; per-group timing (events between the launches) measures the serial order and runs without it.
+// Programmatic dependent launch (see common.cuh).  mvae_pdl_enable(0) turns the attribute off (the test suite compares
+// both ways); per-group timing (events between the launches) measures the serial order and runs without it.
 thread_local int tl_pdl = 0;
-int pdl_level() {
-  static int level = -1;
-  if (level < 0) {
-    const char* e = getenv("MVAE_PDL");
-    level = e ? atoi(e) : 1;
-  }
-  return timing_enabled() ? 0 : level;
-}
+static int g_pdl_on = 1;
+bool pdl_enabled() { return g_pdl_on && !timing_enabled(); }
 
 // Side branch of the fused step (mvae_train_step): the coupling kernels run beside the decoder chain and the first fc11
 // pass, the loss finalisation beside the decoder's backward chain -- small latency-bound kernels that need no SM the main
@@ -63,6 +56,7 @@ int pdl_level() {
 struct SideBranch {
   cudaStream_t side = nullptr;
   cudaEvent_t head_done = nullptr, qstats_done = nullptr, fc11_done = nullptr, final_done = nullptr;
+  cudaEvent_t wg_fork = nullptr, wg_thin = nullptr, wg_wide = nullptr, wg_reduce = nullptr;
 };
 static SideBranch* side_branch(cudaStream_t s) {
   static thread_local SideBranch sb[64];
@@ -77,7 +71,11 @@ static SideBranch* side_branch(cudaStream_t s) {
                     cudaEventCreateWithFlags(&b.head_done, cudaEventDisableTiming) == cudaSuccess &&
                     cudaEventCreateWithFlags(&b.qstats_done, cudaEventDisableTiming) == cudaSuccess &&
                     cudaEventCreateWithFlags(&b.fc11_done, cudaEventDisableTiming) == cudaSuccess &&
-                    cudaEventCreateWithFlags(&b.final_done, cudaEventDisableTiming) == cudaSuccess;
+                    cudaEventCreateWithFlags(&b.final_done, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&b.wg_fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&b.wg_thin, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&b.wg_wide, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&b.wg_reduce, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) cudaGetLastError();
     state[dev] = ok ? 1 : -1;
   }
@@ -323,7 +321,7 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
       if (!cleared) MVAE_CUDA(cudaMemsetAsync(acc_loss, 0, (size_t)w.acc_loss_floats * 4, s));
       RC(launch_qstats(c, s));
     }
-    tl_pdl = 0;          // (join / memset / ordinary launches in front)
+    if (!fork) tl_pdl = 0;          // (memset / ordinary launches in front; behind the join the attribute stays)
     RC(launch_coupling_rows(c, s));
     timing_end(TG_COUPLING, s);
   }
@@ -331,7 +329,7 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
   // ---- reconstruction term: fc11 GEMM fused with loss (+ its own backward)
   timing_begin(TG_FC11, s);
   if (use_tc(p, hp)) {
-    RC(tc_fc11_loss_grad(p.d, hp, st, in, w, gscale, want_grad, s));
+    RC(tc_fc11_loss_grad(p.d, hp, st, in, w, gscale, want_grad, s, fork != nullptr));
   } else {
     GemmArgs g;
     memset(&g, 0, sizeof(g));
@@ -378,6 +376,10 @@ static int loss_impl(const Plan& p, const mvae_hparams& hp, const mvae_state& st
     MVAE_CUDA(cudaEventRecord(fork->fc11_done, s));
     MVAE_CUDA(cudaStreamWaitEvent(fork->side, fork->fc11_done, 0));
     RC(launch_loss_finalize(f, fork->side));        // (an ordinary launch; tl_pdl still describes the main branch)
+    {
+      const int rc = ts_fc11_gene_fixup(fork->side);   // d fc11.weight / d fc11.bias: nothing before Adam reads them
+      if (rc != 0 && rc != 1) return rc;
+    }
     MVAE_CUDA(cudaEventRecord(fork->final_done, fork->side));
   } else {
     RC(launch_loss_finalize(f, s));
@@ -451,8 +453,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   h.delta_z = work + w.delta_z; h.g_xlow = work + w.g_xlow;
   h.bnb_sums5 = acc_bwd + accb_bn(4, A, 0);
   if (fork) {
-    MVAE_CUDA(cudaStreamWaitEvent(s, fork->final_done, 0));      // join: coupling constants and the loss vector
-    tl_pdl = 0;
+    MVAE_CUDA(cudaStreamWaitEvent(s, fork->final_done, 0));      // join: coupling constants, the loss vector, d fc11.*
   }
   RC(launch_head_bwd(h, s));
 
@@ -515,7 +516,14 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   wg.part = work + w.wg_part; wg.part_arm_stride = w.wg_floats; wg.part_split_stride = (int64_t)A * w.wg_floats;
   wg.base_off = p.L.offset[FC1_B];
   wg.grads = st.grads; wg.g_arm_stride = p.L.arm_stride;
-  RC(hp.precision == 3 ? launch_wgrad(wg, s) : launch_wgrad_mma(wg, hp.precision == 1, s));
+  WgFork wf;
+  memset(&wf, 0, sizeof(wf));
+  const bool wg_forked = fork != nullptr && hp.precision != 3;
+  if (wg_forked) {
+    wf.side = fork->side; wf.fork_ev = fork->wg_fork; wf.thin_done = fork->wg_thin; wf.wide_done = fork->wg_wide;
+    wf.reduce_done = fork->wg_reduce;
+  }
+  RC(hp.precision == 3 ? launch_wgrad(wg, s) : launch_wgrad_mma(wg, hp.precision == 1, s, wg_forked ? &wf : nullptr));
   timing_end(TG_WGRAD, s);
   // ---- d fc1.weight = delta1^T * dropout(x)
   DropSpec drop = make_drop(p, hp, st, in);
@@ -536,6 +544,7 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
   }
 
   timing_end(TG_FC1_WGRAD, s);
+  if (wg_forked) MVAE_CUDA(cudaStreamWaitEvent(s, fork->wg_reduce, 0));      // join: the narrow layers' gradients are final
 
   if (grad_scale) RC(launch_scale(st.grads, (int64_t)A * p.L.arm_stride, grad_scale, s));
   return 0;
@@ -546,6 +555,12 @@ static int backward_impl(const Plan& p, const mvae_hparams& hp, const mvae_state
 using namespace mvae;
 
 extern "C" {
+
+int mvae_pdl_enable(int on) {
+  const int prev = g_pdl_on;
+  g_pdl_on = on ? 1 : 0;
+  return prev;
+}
 
 int mvae_forward(const mvae_dims* dims, const mvae_hparams* hp, const mvae_state* st, const mvae_inputs* in,
                  const mvae_outputs* out, void* stream) {

@@ -133,11 +133,13 @@ __host__ __device__ inline int64_t acc_bwd_doubles(int A) { return (int64_t)5 * 
 //     the step wrote and before it writes global memory at all; in front of it only step constants (parameters, x)
 //     may be read -- the kernels of a PDL chain cascade, so "earlier" is not just the direct predecessor;
 //   * tl_pdl says "the previous operation enqueued by this thread for this step was a kernel of the library on the same
-//     stream"; api.cu clears it at every entry point and around memsets, event edges and cooperative launches.
+//     stream"; api.cu clears it at every entry point and behind memsets, and keeps the main branch's value across the
+//     launches it puts on the side branch.  A kernel launched behind a join (cudaStreamWaitEvent) keeps the attribute: the
+//     event edge stays a full dependency and pdl_wait() covers the kernel edge.  Cooperative launches are never
+//     secondaries (measured: no gain) but trigger like every other kernel.
 // ---------------------------------------------------------------------------------------------
 extern thread_local int tl_pdl;
-int pdl_level();     // 0: off, 1: between ordinary launches, 2: cooperative kernels may be primaries too
-inline bool pdl_enabled() { return pdl_level() >= 1; }
+bool pdl_enabled();   // mvae_pdl_enable(0) turns the attribute off (a test compares both ways)
 template <typename... KP, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

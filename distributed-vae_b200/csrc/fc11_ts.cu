@@ -483,6 +483,7 @@ struct F11FixArgs {
   F11FixOne row, gene;
   const float* db_part; float* db_out; int64_t db_arm_stride; int D;
   int nblk_db;                   // ceil(D / 256) * batch blocks (256 genes each)
+  int b0;                        // first block of this launch in the (rows | genes | bias) sequence
 };
 
 // block = 16 rows of one 128-row tile; thread = (row mod 8, float4 column): 2 rows each (cols % 4 == 0 on this path)
@@ -533,7 +534,7 @@ __device__ __forceinline__ void f11_fix_bias(const F11FixArgs& p, int gene, int 
 
 __global__ void __launch_bounds__(256) f11_fixup_kernel(const F11FixArgs p) {
   __shared__ int cc[2];
-  int b = blockIdx.x;
+  int b = blockIdx.x + p.b0;
   pdl_trigger();
   pdl_wait();
   if (b < p.row.nblk) {
@@ -646,8 +647,11 @@ static int fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs
 }
 
 // d fc11.weight and d fc11.bias by the gene pass (x_hat recomputed)
+static thread_local F11FixArgs tl_gene_fix;
+static thread_local bool tl_gene_fix_pending = false;
+
 static int fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale,
-                      const F11FixOne* row_fix, cudaStream_t s) {
+                      const F11FixOne* row_fix, cudaStream_t s, bool defer_gene_fix) {
   mvae_layout L;
   compute_layout(d, &L);
   const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
@@ -677,7 +681,27 @@ static int fc11_genes(const mvae_dims& d, const mvae_state& st, const mvae_input
   fa.gene = fix_one(a.part, A, a.ktiles, U, G, st.grads + L.offset[FC11_W], L.arm_stride, H, D, H);
   fa.db_part = a.db_part; fa.db_out = st.grads + L.offset[FC11_B]; fa.db_arm_stride = L.arm_stride; fa.D = D;
   fa.nblk_db = (D + 255) / 256 * A;
+  if (defer_gene_fix && row_fix) {
+    launch_pdl(f11_fixup_kernel, dim3(fa.row.nblk), dim3(256), 0, s, fa);            // d h10: the backward chain waits for it
+    MVAE_LAUNCH_CHECK();
+    tl_gene_fix = fa;
+    tl_gene_fix.b0 = fa.row.nblk;
+    tl_gene_fix_pending = true;
+    return 0;
+  }
   launch_pdl(f11_fixup_kernel, dim3(fa.row.nblk + fa.gene.nblk + fa.nblk_db), dim3(256), 0, s, fa);
+  MVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int ts_fc11_gene_fixup(cudaStream_t s) {
+  if (!tl_gene_fix_pending) return 1;
+  tl_gene_fix_pending = false;
+  const F11FixArgs& fa = tl_gene_fix;
+  const int main_pdl = tl_pdl;
+  tl_pdl = 0;                          // an ordinary launch (side stream)
+  launch_pdl(f11_fixup_kernel, dim3(fa.gene.nblk + fa.nblk_db), dim3(256), 0, s, fa);
+  tl_pdl = main_pdl;
   MVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -690,11 +714,11 @@ int ts_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
 
 // both passes of the training step: row owner (loss sums, d h10), gene owner (d fc11.weight, d fc11.bias), one fix-up
 int ts_fc11_loss_grad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale,
-                      double* recon_acc, cudaStream_t s) {
+                      double* recon_acc, cudaStream_t s, bool defer_gene_fix) {
   F11FixOne row_fix;
   int rc = fc11_rows(d, st, in, w, gscale, 1, nullptr, recon_acc, &row_fix, s);
   if (rc) return rc;
-  return fc11_genes(d, st, in, w, gscale, &row_fix, s);
+  return fc11_genes(d, st, in, w, gscale, &row_fix, s, defer_gene_fix);
 }
 
 }  // namespace mvae

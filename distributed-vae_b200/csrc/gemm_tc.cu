@@ -843,7 +843,7 @@ bool tc_narrow_wgrad_ok(const WgArgs& a, const WgProblem& q) {
          (i & 15) == 0 && q.delta_arm_stride % 4 == 0 && q.in_arm_stride % 4 == 0;
 }
 
-int tc_narrow_wgrad(WgArgs& a, const int* idx, int n, int split3, cudaStream_t s) {
+int tc_narrow_wgrad(WgArgs& a, const int* idx, int n, int split3, cudaStream_t s, bool share_sm) {
   MVAE_CHECK_ARG(n >= 1 && n <= WGTC_MAX, "tc_narrow_wgrad: %d problems", n);
   WgTcParams P;
   memset(&P, 0, sizeof(P));
@@ -863,7 +863,8 @@ int tc_narrow_wgrad(WgArgs& a, const int* idx, int n, int split3, cudaStream_t s
   if (nsplit > ktiles) nsplit = ktiles;
   if (nsplit < 1) nsplit = 1;
   P.A = a.A; P.K = a.B; P.split3 = split3 ? 1 : 0;
-  P.stages = split3 ? 3 : 6;
+  // share_sm (fused step): 3 stages = 98 KB, so that a CTA of wgrad2 (105 KB), launched on the side branch, fits on the same SM
+  P.stages = (split3 || share_sm) ? 3 : 6;
   P.ktiles_per_split = (ktiles + nsplit - 1) / nsplit;
   nsplit = (ktiles + P.ktiles_per_split - 1) / P.ktiles_per_split;
   P.nsplit = nsplit;
@@ -945,7 +946,7 @@ static int tc_fc11_loss_grad_unfused(const mvae_dims& d, const mvae_hparams& hp,
 }
 
 int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
-                      const Work& w, float gscale, int want_grad, cudaStream_t s) {
+                      const Work& w, float gscale, int want_grad, cudaStream_t s, bool defer_gene_fix) {
   mvae_layout L;
   compute_layout(d, &L);
   const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
@@ -957,7 +958,7 @@ int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_sta
   if (hp.precision == 1) return tc_fc11_loss_grad_unfused(d, hp, st, in, w, gscale, want_grad, s);
   // fused passes: row owner (x_hat, loss sums, d h10), then gene owner (d fc11.weight, d fc11.bias)
   if (!want_grad) return ts_fc11_rows(d, st, in, w, gscale, 0, nullptr, acc_loss, s);
-  return ts_fc11_loss_grad(d, st, in, w, gscale, acc_loss, s);
+  return ts_fc11_loss_grad(d, st, in, w, gscale, acc_loss, s, defer_gene_fix);
 }
 
 int tc_fc1_wgrad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,

@@ -11,7 +11,7 @@ bool gemm_tc_supported(int B, int D, int H);
 
 // fc11 GEMM fused with the reconstruction loss and (want_grad) d fc11.weight / d fc11.bias / d h10.
 int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
-                      const Work& w, float gscale, int want_grad, cudaStream_t s);
+                      const Work& w, float gscale, int want_grad, cudaStream_t s, bool defer_gene_fix = false);
 
 // d fc1.weight = delta1^T * dropout(x)
 int tc_fc1_wgrad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
@@ -27,12 +27,15 @@ int ts_fc1_wgrad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in
 // fc11_ts.cu: second-generation fused fc11 passes (resident operand and dY in tensor memory, stream-K)
 int ts_fc11_rows(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale, int want_grad,
                  float* x_rec, double* recon_acc, cudaStream_t s);
+// defer_gene_fix: only the row pass's partials (d h10) are summed on s; ts_fc11_gene_fixup then sums the gene pass's
+// (d fc11.weight, d fc11.bias) on the stream it is given -- the side branch of the fused step (returns 1 if nothing is pending)
 int ts_fc11_loss_grad(const mvae_dims& d, const mvae_state& st, const mvae_inputs& in, const Work& w, float gscale,
-                      double* recon_acc, cudaStream_t s);
+                      double* recon_acc, cudaStream_t s, bool defer_gene_fix = false);
+int ts_fc11_gene_fixup(cudaStream_t s);
 // gemm_tc.cu: grouped tcgen05 weight-gradient GEMM of the wide narrow-layer problems (delta^T . bn(input), bias gradient
 // through a column of ones); partials in the layout of wgrad_reduce2_kernel
 bool tc_narrow_wgrad_ok(const WgArgs& a, const WgProblem& q);
-int tc_narrow_wgrad(WgArgs& a, const int* idx, int n, int split3, cudaStream_t s);
+int tc_narrow_wgrad(WgArgs& a, const int* idx, int n, int split3, cudaStream_t s, bool share_sm = false);
 // augmenter forward pieces (udagan.py:217-329, eval mode): folded BatchNorm/bias affine, Linear with fused affine + activation
 // epilogue on tcgen05, and the row-wise fma used by the reparameterisation
 int launch_fold_affine(const float* bias, const float* mean, const float* var, const float* gamma, const float* beta, float eps,

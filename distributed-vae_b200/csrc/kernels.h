@@ -128,7 +128,13 @@ struct WgArgs {
   float* grads; int64_t g_arm_stride;
 };
 int launch_wgrad(const WgArgs& a, cudaStream_t s);
-int launch_wgrad_mma(const WgArgs& a, int split3, cudaStream_t s);
+// side branch for the weight-gradient group of the fused step: the thin problems (wgrad2) run beside the grouped tcgen05
+// GEMM, the fixed-order sum of the partials beside the fc1 weight gradient (the caller joins reduce_done before Adam)
+struct WgFork {
+  cudaStream_t side;
+  cudaEvent_t fork_ev, thin_done, wide_done, reduce_done;
+};
+int launch_wgrad_mma(const WgArgs& a, int split3, cudaStream_t s, const WgFork* fork = nullptr);
 // decoder stack fc7..fc10 fused per direction (kernels_chain.cu)
 int launch_dec_chain_fwd(const float* params, int64_t p_arm_stride, const int64_t* off, int A, int B, int H, int L,
                          const float* h6, float* const hout[4], int split3, cudaStream_t s);

@@ -1146,7 +1146,7 @@ int launch_enc_chain_fwd(const float* params, int64_t p_arm_stride, const int64_
                          : (fast ? (const void*)enc_chain_fwd_kernel<MT, NWC, 100, 10> : (const void*)enc_chain_fwd_kernel<MT, NWC, 0, 0>);
   MVAE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MVAE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(gx, A), dim3(32 * MT * NWC), args, smem, s));
-  tl_pdl = pdl_level() >= 2 ? 1 : 0;      // a cooperative launch is never a PDL secondary; it may be a primary
+  tl_pdl = 1;                              // (never a PDL secondary itself, but a primary: the kernel triggers)
   MVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -1191,7 +1191,7 @@ int launch_enc_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
   void* args2[] = {(void*)&c, (void*)&g_scratch};
   MVAE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MVAE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(gx, A), dim3(32 * MT * NWC), multi ? args2 : args1, smem, s));
-  tl_pdl = pdl_level() >= 2 ? 1 : 0;
+  tl_pdl = 1;
   MVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -844,8 +844,10 @@ int launch_dense_bwd_mma(const DenseBwdArgs& a, int A, int split3, cudaStream_t 
   return 0;
 }
 
-int launch_wgrad_mma(const WgArgs& a0, int split3, cudaStream_t s) {
+int launch_wgrad_mma(const WgArgs& a0, int split3, cudaStream_t s, const WgFork* fork) {
   WgArgs a = a0;
+  const bool thin_side = fork != nullptr, red_side = fork != nullptr;
+  if (thin_side) MVAE_CUDA(cudaEventRecord(fork->fork_ev, s));
   bool fits = true;
   for (int i = 0; i < a.nprob; ++i) fits = fits && a.prob[i].nout <= 128 && a.prob[i].nin <= 127;
   if (fits) {
@@ -858,7 +860,7 @@ int launch_wgrad_mma(const WgArgs& a0, int split3, cudaStream_t s) {
       if (on_tc[i]) tc_idx[ntc++] = i;
     }
     if (ntc > 0) {
-      const int rc = tc_narrow_wgrad(a, tc_idx, ntc, split3, s);
+      const int rc = tc_narrow_wgrad(a, tc_idx, ntc, split3, s, thin_side);
       if (rc) return rc;
     }
     // the rest: split counts for one wave of two CTAs per SM; wide problems get twice the splits of narrow ones
@@ -887,8 +889,23 @@ int launch_wgrad_mma(const WgArgs& a0, int split3, cudaStream_t s) {
         MVAE_CUDA(cudaFuncSetAttribute(wgrad2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_FLOATS * 4));
         MVAE_CUDA(cudaFuncSetAttribute(wgrad2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_FLOATS * 4));
       }
-      if (split3) launch_pdl(wgrad2_kernel<true>, dim3(ctas, a.A), dim3(512), (size_t)WG2_SMEM_FLOATS * 4, s, a);
-      else launch_pdl(wgrad2_kernel<false>, dim3(ctas, a.A), dim3(512), (size_t)WG2_SMEM_FLOATS * 4, s, a);
+      cudaStream_t s2 = s;
+      const int main_pdl = tl_pdl;
+      if (thin_side) {           // beside the grouped GEMM: an ordinary launch on the side stream
+        MVAE_CUDA(cudaStreamWaitEvent(fork->side, fork->fork_ev, 0));
+        s2 = fork->side;
+        tl_pdl = 0;
+      }
+      if (split3) launch_pdl(wgrad2_kernel<true>, dim3(ctas, a.A), dim3(512), (size_t)WG2_SMEM_FLOATS * 4, s2, a);
+      else launch_pdl(wgrad2_kernel<false>, dim3(ctas, a.A), dim3(512), (size_t)WG2_SMEM_FLOATS * 4, s2, a);
+      if (thin_side) {
+        MVAE_CUDA(cudaEventRecord(fork->thin_done, fork->side));
+        tl_pdl = main_pdl;
+        if (!red_side) {
+          MVAE_CUDA(cudaStreamWaitEvent(s, fork->thin_done, 0));
+          tl_pdl = 0;
+        }
+      }
     }
   } else {
     for (int i = 0; i < a.nprob; ++i) a.prob[i].nsplit = a.nsplit;
@@ -902,7 +919,18 @@ int launch_wgrad_mma(const WgArgs& a0, int split3, cudaStream_t s) {
     if (n > maxn) maxn = n;
     if (a.prob[i].nout > maxn) maxn = a.prob[i].nout;
   }
-  launch_pdl(wgrad_reduce2_kernel, dim3((unsigned)((maxn + 255) / 256), a.nprob * 2, a.A), dim3(256), 0, s, a);
+  if (red_side) {
+    // the sum of the partials runs beside the fc1 weight gradient: behind both producers on the side stream
+    MVAE_CUDA(cudaEventRecord(fork->wide_done, s));
+    MVAE_CUDA(cudaStreamWaitEvent(fork->side, fork->wide_done, 0));
+    const int main_pdl = tl_pdl;
+    tl_pdl = 0;
+    launch_pdl(wgrad_reduce2_kernel, dim3((unsigned)((maxn + 255) / 256), a.nprob * 2, a.A), dim3(256), 0, fork->side, a);
+    MVAE_CUDA(cudaEventRecord(fork->reduce_done, fork->side));
+    tl_pdl = main_pdl;
+  } else {
+    launch_pdl(wgrad_reduce2_kernel, dim3((unsigned)((maxn + 255) / 256), a.nprob * 2, a.A), dim3(256), 0, s, a);
+  }
   MVAE_LAUNCH_CHECK();
   return 0;
 }

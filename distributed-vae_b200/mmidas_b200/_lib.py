@@ -59,7 +59,7 @@ PRECISIONS = {"tf32x3_fc1": 0, "tf32x3": 1, "tf32": 2, "fp32_simt": 3}
 EXPORTS = ("mvae_last_error", "mvae_abi_version", "mvae_compute_layout", "mvae_forward", "mvae_loss",
            "mvae_backward", "mvae_adam", "mvae_train_step", "mvae_grad_step", "mvae_argmax", "mvae_dropout_mask", "mvae_launch_count",
            "mvae_timing_enable", "mvae_timing_read", "mvae_debug_tc_gemm", "mvae_confmat", "mvae_fold_affine",
-           "mvae_linear_act", "mvae_fma_rows", "mvae_unpack_rows", "mvae_adam_peer")
+           "mvae_linear_act", "mvae_fma_rows", "mvae_unpack_rows", "mvae_adam_peer", "mvae_pdl_enable")
 
 _lib = None
 
@@ -110,6 +110,8 @@ def load():
     lib.mvae_debug_tc_gemm.restype = C.c_int
     lib.mvae_timing_enable.argtypes = [C.c_int]
     lib.mvae_timing_enable.restype = C.c_int
+    lib.mvae_pdl_enable.argtypes = [C.c_int]
+    lib.mvae_pdl_enable.restype = C.c_int
     lib.mvae_timing_read.argtypes = [P(C.c_float), P(C.c_int32), C.c_int32]
     lib.mvae_timing_read.restype = C.c_int
     for name in ("mvae_compute_layout", "mvae_forward", "mvae_loss", "mvae_backward", "mvae_adam",
@@ -134,6 +136,11 @@ def compute_layout(dims: Dims) -> Layout:
 
 
 TIMING_GROUPS = ("fc1_fwd", "fc11_loss_grad", "fc1_wgrad", "narrow_fwd", "narrow_bwd", "coupling", "narrow_wgrad", "adam")
+
+
+def pdl_enable(on: bool) -> bool:
+    """Programmatic dependent launch between the library's kernels (default on); returns the previous setting."""
+    return bool(load().mvae_pdl_enable(int(on)))
 
 
 def timing_enable(on: bool):

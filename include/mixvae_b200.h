@@ -200,6 +200,13 @@ int mvae_unpack_rows(const uint32_t* bitmap, const float* values, const int64_t*
 /* Number of kernels launched by the library in this process (for bench.py's gpu_launches). */
 int64_t mvae_launch_count(void);
 
+/* Programmatic dependent launch between the library's own kernels (on by default): a kernel launched right behind another
+ * kernel of the same call carries the programmatic-stream-serialization attribute (a programmatic edge in a captured
+ * graph) and runs its set-up and the loads of step constants while its predecessor drains; results do not depend on it.
+ * mvae_pdl_enable(0) launches every kernel fully ordered (diagnostics, tests); returns the previous setting.  Affects
+ * launches made (and graphs captured) afterwards, process-wide. */
+int mvae_pdl_enable(int on);
+
 /* Test hook for the tcgen05 GEMM kernel behind the gene-dimension layers:
  * C[split] (M x N, ldc) = A . B over K with fp32 storage and TF32 (flags 0) or error-compensated
  * 3xTF32 (flags 1|2) tensor-core math.  a_mn / b_mn: 0 = operand stored [M or N][K] (K contiguous),

@@ -436,6 +436,49 @@ def test_cuda_graph_replay_equals_eager_steps():
     assert torch.equal(res[1][1], res[2][1]) or float((res[1][1] - res[2][1]).abs().max()) <= 2 * hp.lr
 
 
+def test_dependent_launch_does_not_change_results():
+    """The fused step with programmatic dependent launch (the default: kernels start their set-up and constant loads while
+    their predecessor drains, side branches for the fix-ups and the narrow weight gradients) against the same steps
+    with every kernel fully ordered (mvae_pdl_enable(0)): eagerly launched and graph-replayed, a race would show here.
+    Full-width gene dimension (cfg1's 5032) so that the stream-K kernels run their real pipelines."""
+    from mmidas_b200 import FusedAdam, _lib
+    from mmidas_b200.nn_model import StepGraph
+    hp = O.HP(input_dim=5032, n_categories=92, state_dim=2, n_arm=2, x_drop=0.5, s_drop=0.0)
+    B, steps = 1000, 5
+    gen = torch.Generator().manual_seed(546)
+    xb = [O.synth_x(B, hp.input_dim, gen).cuda() for _ in range(steps)]
+    res = []
+    try:
+        for pdl, graphed in ((False, False), (True, False), (True, True), (False, True)):
+            _lib.pdl_enable(pdl)
+            torch.manual_seed(1234)
+            model = build_model(hp, "tf32x3_fc1")
+            opt = FusedAdam(model.parameters(), lr=hp.lr, model=model)
+            model.train()
+            buf = torch.empty(B, hp.input_dim, device="cuda")
+            losses = []
+            buf.copy_(xb[0])
+            losses.append(model.fused_train_step(buf.expand(2, -1, -1), hp.temp, opt)[0].item())
+            g = StepGraph(model, opt, lambda: model.fused_train_step(buf.expand(2, -1, -1), hp.temp, opt)) if graphed else None
+            for i in range(1, steps):
+                buf.copy_(xb[i])
+                lv = g.replay() if graphed else model.fused_train_step(buf.expand(2, -1, -1), hp.temp, opt)
+                losses.append(lv[0].item())
+            torch.cuda.synchronize()
+            m, v = opt.flat_state()
+            res.append((losses, model.flat_parameters().clone(), m.clone(), v.clone(), model._flat_bn.clone(),
+                        model.flat_grads().clone()))
+            del g
+    finally:
+        _lib.pdl_enable(True)
+    for other in res[1:]:
+        np.testing.assert_allclose(other[0], res[0][0], rtol=1e-6)
+        for i in (1, 2, 3, 4, 5):
+            d = (other[i] - res[0][i]).abs()
+            # fp64 atomics order the batch statistics differently from launch to launch: equal up to that
+            assert float((d > 1e-6 * (1 + res[0][i].abs())).float().mean()) < 1e-3, (i, float(d.max()))
+
+
 def test_trainer_uses_graphs_and_matches_eager_trainer():
     """cpl_mixVAE.train_batch replays graphs once a batch buffer repeats; results match the eager trainer."""
     from mmidas_b200.cpl_mixvae import HostBatchFeeder, cpl_mixVAE
