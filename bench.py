@@ -22,6 +22,7 @@ Prints ONE JSON line (rank 0).
   extra        N=4: BASELINE configs[2] (A=3, one arm per GPU on 3 of the 4 ranks); N=8: configs[3] (A=5 on 8 GPUs)
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -535,12 +536,17 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize()
             seen.clear()
-            t0 = time.perf_counter()
-            feeder = run(n_e2e)
-            torch.cuda.synchronize()
-            if grp is not None:
-                dist.barrier()
-            dt = time.perf_counter() - t0
+            gc.collect()                                                # a host-timed loop of ~20 ms: keep the collector's
+            gc.disable()                                                # pauses (several ms after the set-up above) out of it
+            try:
+                t0 = time.perf_counter()
+                feeder = run(n_e2e)
+                torch.cuda.synchronize()
+                if grp is not None:
+                    dist.barrier()
+                dt = time.perf_counter() - t0
+            finally:
+                gc.enable()
             tt = torch.tensor([dt], device=dev)
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)

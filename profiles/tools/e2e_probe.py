@@ -8,6 +8,10 @@ from bench import synth_x_device
 from mmidas_b200.cpl_mixvae import HostBatchFeeder, cpl_mixVAE
 from mmidas_b200.dataloader import PackedBatch
 
+from mmidas_b200 import _lib
+if len(sys.argv) > 1:
+    _lib.pdl_enable(bool(int(sys.argv[1])))
+    print("pdl", sys.argv[1])
 dev = torch.device("cuda", 0)
 B, D = 5000, 5032
 gen = torch.Generator(device=dev).manual_seed(1)

@@ -6,7 +6,8 @@ lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "distributed-vae_
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 cur, rows = None, collections.OrderedDict()
 pats = {"UTCMMA": r"\bUTC[A-Z]*MMA", "UTMALDG": r"\bUTMALDG", "LDTM": r"\bLDTM", "STTM": r"\bSTTM", "HMMA": r"\bHMMA", "SYNCS": r"\bSYNCS",
-        "LDGSTS": r"\bLDGSTS", "DADD/DFMA/DMUL": r"\bD(ADD|FMA|MUL)\b", "STL/LDL": r"\b(STL|LDL)"}
+        "LDGSTS": r"\bLDGSTS", "DADD/DFMA/DMUL": r"\bD(ADD|FMA|MUL)\b", "STL/LDL": r"\b(STL|LDL)",
+        "PDL (ACQBULK/PREEXIT)": r"\b(ACQBULK|PREEXIT)"}
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m:
