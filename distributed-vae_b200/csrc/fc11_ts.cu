@@ -39,6 +39,12 @@ constexpr uint32_t LT_BASE32B = 1;         // descriptor layout type
 #ifndef F11_NW
 #define F11_NW 4                           // T-tile ring depth (measured: 4 stages + 4 x slots beat 3 + 8)
 #endif
+#ifndef F11_NX
+#define F11_NX 4                           // x ring depth: a multiple of NG (see launch_f11)
+#endif
+// compile-time ring depths: every ring slot and mbarrier address is the shared base plus an immediate
+constexpr int NXC = F11_NX, NWC = F11_NW;
+static_assert(NXC % 4 == 0, "the x ring depth must be a multiple of the number of epilogue groups");
 constexpr int TILE_FLOATS = 128 * 128;
 constexpr uint32_t COL_ACC2 = 0, COL_ACC1 = 128, COL_A2 = 256, COL_R = 384;
 
@@ -105,14 +111,16 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const bool want_grad = TRAIN || a.want_grad;
   float* const x_rec = TRAIN ? nullptr : a.x_rec;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET in the shared window: the pointer stays derived from smem_raw, so the compiler keeps the
+  // shared address space (LDS / direct mbarrier addresses instead of generic loads and 64-bit window arithmetic)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto xs = [&](int s) { return smem + (size_t)s * X_BYTES; };
-  auto ts = [&](int s) { return smem + (size_t)a.nx * X_BYTES + (size_t)s * IMG_BYTES; };
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.nx * X_BYTES + (size_t)a.nw * IMG_BYTES);
-  uint64_t* x_full = bars;                 uint64_t* x_empty = x_full + a.nx;
-  uint64_t* w_full = x_empty + a.nx;       uint64_t* w_empty = w_full + a.nw;
-  uint64_t* acc1_full = w_empty + a.nw;    uint64_t* acc1_empty = acc1_full + NG;
+  auto ts = [&](int s) { return smem + (size_t)NXC * X_BYTES + (size_t)s * IMG_BYTES; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NXC * X_BYTES + (size_t)NWC * IMG_BYTES);
+  uint64_t* x_full = bars;                 uint64_t* x_empty = x_full + NXC;
+  uint64_t* w_full = x_empty + NXC;       uint64_t* w_empty = w_full + NWC;
+  uint64_t* acc1_full = w_empty + NWC;    uint64_t* acc1_empty = acc1_full + NG;
   uint64_t* a2_full = acc1_empty + NG;     uint64_t* a2_empty = a2_full + NG;
   uint64_t* r_full = a2_empty + NG;        // R of the current segment is in TMEM (and acc2 of the previous one drained)
   // segment s complete: barrier s % NG.  An epilogue group can be up to NG half-units -- hence several segments when a
@@ -126,8 +134,8 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int np = (int)(u1 - u0), nu = 2 * np;          // units and half-units of this CTA
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < a.nx; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 4); }
-    for (int s = 0; s < a.nw; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, want_grad ? 2 : 1); }
+    for (int s = 0; s < NXC; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 4); }
+    for (int s = 0; s < NWC; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, want_grad ? 2 : 1); }
     for (int s = 0; s < NG; ++s) {
       mbar_init(acc1_full + s, 1); mbar_init(acc1_empty + s, 4);
       mbar_init(a2_full + s, 4);   mbar_init(a2_empty + s, 1);
@@ -163,7 +171,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         else tma_load_3d(&tmX, x_full + sx, xs(sx), rb * 128, kt * UN, xb);          // [32 cells][128 genes], linear
       }
       __syncwarp();
-      if (++sx == a.nx) { sx = 0; phx ^= 1; }
+      if (++sx == NXC) { sx = 0; phx ^= 1; }
       if (++kt == KT) { kt = 0; if (++arm == a.batch) { arm = 0; ++rb; } }
     }
   } else if (warp == 1) {
@@ -178,7 +186,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         for (int q = 0; q < 4; ++q) tma_load_3d(&tmT, w_full + sw, ts(sw) + q * SLAB_BYTES, 32 * q, kp * 2 * UN, arm);
       }
       __syncwarp();
-      if (++sw == a.nw) { sw = 0; phw ^= 1; }
+      if (++sw == NWC) { sw = 0; phw ^= 1; }
       if (++kp == KP) { kp = 0; if (++arm == a.batch) arm = 0; }
     }
   } else if (warp == 2) {
@@ -219,7 +227,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (!want_grad && ((kp + 1 == KP) || (i == np - 1))) umma_commit(acc2_full + ((seg - 1) & (NG - 1)));   // loss-only: segment end marker
       }
       __syncwarp();
-      if (++sw == a.nw) { sw = 0; phw ^= 1; }
+      if (++sw == NWC) { sw = 0; phw ^= 1; }
       if (++kp == KP) kp = 0;
     }
   } else if (warp == 3) {
@@ -253,7 +261,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         __syncwarp();
         acc2 = last ? 0u : 1u;
         if (last) ++seg;
-        if (half && ++sw == a.nw) { sw = 0; phw ^= 1; }
+        if (half && ++sw == NWC) { sw = 0; phw ^= 1; }
         if (++kt == KT) kt = 0;
       }
     }
@@ -300,8 +308,8 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
     int kt = kt_first + grp, t = t_first, rb = rb_first, arm = arm_first;
     while (kt >= KT) { kt -= KT; ++t; if (++arm == a.batch) { arm = 0; ++rb; } }
-    int sx = grp % a.nx;
-    uint32_t phx = (uint32_t)((grp / a.nx) & 1), ph1 = 0, pha = 1;
+    int sx = grp % NXC;
+    uint32_t phx = (uint32_t)((grp / NXC) & 1), ph1 = 0, pha = 1;
     if (grp < 2) {
       uint32_t rv[8][8];
       fetch_R(rv, rb_first, arm_first);
@@ -461,7 +469,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
       }
       sx += NG;
-      if (sx >= a.nx) { sx -= a.nx; phx ^= 1; }
+      if (sx >= NXC) { sx -= NXC; phx ^= 1; }
       kt = kt_n; t = t_n; rb = rb_n; arm = arm_n;
     }
   }
@@ -578,12 +586,9 @@ int launch_f11(const CUtensorMap& tmX, const CUtensorMap& tmT, F11Args& a, int64
   // "its" fill k while fill k - 1 (the other group's; TMA completions are not ordered) is still in flight -- the parity
   // wait for fill k then succeeds on the completed fill k - 2 (stale tile, early release, two fills pending on one
   // barrier: intermittent launch failures when x rows are not 128-byte aligned, D = 5032 with 6 slots).
-  a.nw = F11_NW;
-#ifdef F11_NX
-  a.nx = F11_NX;
-#else
-  a.nx = (227 * 1024 - 2048 - a.nw * IMG_BYTES) / X_BYTES >= 2 * NG ? 2 * NG : NG;
-#endif
+  a.nw = NWC;
+  a.nx = NXC;
+  static_assert((size_t)NXC * X_BYTES + (size_t)NWC * IMG_BYTES + 2048 <= 227 * 1024, "rings exceed the shared memory of an SM");
   const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * IMG_BYTES + (2 * a.nx + 2 * a.nw + 5 * NG + 4) * 8 + 1024;
   int dev = 0;
   cudaGetDevice(&dev);

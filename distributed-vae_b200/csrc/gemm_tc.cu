@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment of every tile is required by SWIZZLE_128B (descriptor base_offset = 0)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET in the shared window: the pointer stays derived from smem_raw, so the compiler keeps the
+  // shared address space (LDS / direct mbarrier addresses instead of generic loads and 64-bit window arithmetic)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool splitA = args.flags & F_SPLIT_A, splitB = args.flags & F_SPLIT_B;
   const bool dropA = args.flags & F_DROP_A, dropB = args.flags & F_DROP_B;
@@ -345,7 +347,9 @@ __device__ __forceinline__ void wg_transform_b(float* hi, float* lo, bool do_spl
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) wg_tc_kernel(const __grid_constant__ WgTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET in the shared window: the pointer stays derived from smem_raw, so the compiler keeps the
+  // shared address space (LDS / direct mbarrier addresses instead of generic loads and 64-bit window arithmetic)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, pi = blockIdx.y, arm = blockIdx.z;
   const WgTcProblem& pr = P.prob[pi];
@@ -528,7 +532,9 @@ struct LinArgs {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const LinArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET in the shared window: the pointer stays derived from smem_raw, so the compiler keeps the
+  // shared address space (LDS / direct mbarrier addresses instead of generic loads and 64-bit window arithmetic)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool split3 = args.split3 != 0;
   const bool wide = args.BN > 128;                      // 256-column tiles (single-pass TF32 only): B tile = two TMA boxes

@@ -38,10 +38,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mvae tc_gemm: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
-    }
+    // (no printf here: its argument set-up and the spills around the call were hoisted into the fast path of every wait)
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 // Wait for two barriers whose results are independent: both try_waits are in flight together (a satisfied try_wait

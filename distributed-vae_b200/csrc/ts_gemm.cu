@@ -56,7 +56,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmWlo, const TsArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET in the shared window: the pointer stays derived from smem_raw, so the compiler keeps the
+  // shared address space (LDS / direct mbarrier addresses instead of generic loads and 64-bit window arithmetic)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w_stage_bytes = a.w_tile_bytes * (a.split3 ? 2 : 1);
   auto xs = [&](int s) { return smem + (size_t)s * X_BYTES; };
