@@ -51,10 +51,13 @@ struct TsArgs {
 
 __host__ __device__ inline int64_t cta_of_unit(int64_t u, int64_t U, int64_t G) { return ((u + 1) * G - 1) / U; }
 
-template <bool WGRAD>
+// NXT / NWT: compile-time ring depths (0: run-time values of a.nx / a.nw) -- with constants every ring slot and mbarrier
+// address is the shared base plus an immediate
+template <bool WGRAD, int NXT, int NWT>
 __global__ void __launch_bounds__(THREADS, 1)
 ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmWlo, const TsArgs a) {
+  const int NX = NXT ? NXT : a.nx, NW = NWT ? NWT : a.nw;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1 KB alignment by an OFFSET in the shared window: the pointer stays derived from smem_raw, so the compiler keeps the
   // shared address space (LDS / direct mbarrier addresses instead of generic loads and 64-bit window arithmetic)
@@ -62,13 +65,13 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w_stage_bytes = a.w_tile_bytes * (a.split3 ? 2 : 1);
   auto xs = [&](int s) { return smem + (size_t)s * X_BYTES; };
-  auto ws = [&](int s) { return smem + (size_t)a.nx * X_BYTES + (size_t)s * w_stage_bytes; };
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.nx * X_BYTES + (size_t)a.nw * w_stage_bytes);
+  auto ws = [&](int s) { return smem + (size_t)NX * X_BYTES + (size_t)s * w_stage_bytes; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NX * X_BYTES + (size_t)NW * w_stage_bytes);
   uint64_t* x_full = bars;
-  uint64_t* x_empty = x_full + a.nx;
-  uint64_t* w_full = x_empty + a.nx;
-  uint64_t* w_empty = w_full + a.nw;
-  uint64_t* a_full = w_empty + a.nw;
+  uint64_t* x_empty = x_full + NX;
+  uint64_t* w_full = x_empty + NX;
+  uint64_t* w_empty = w_full + NW;
+  uint64_t* a_full = w_empty + NW;
   uint64_t* a_empty = a_full + NA;
   // MMAs of segment s complete (both blocks): barrier s % NA.  A transform group can be up to NA units -- hence up to
   // NA segments when a CTA's share of a tile is a single unit -- ahead of the tensor pipe, which one parity bit
@@ -83,8 +86,8 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int nu = (int)(u1 - u0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < a.nx; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 4); }
-    for (int s = 0; s < a.nw; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
+    for (int s = 0; s < NX; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 4); }
+    for (int s = 0; s < NW; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
     for (int s = 0; s < NA; ++s) { mbar_init(a_full + s, 4); mbar_init(a_empty + s, 1); }
     for (int s = 0; s < NA; ++s) mbar_init(acc_full + s, 1);
     mbar_init(acc_empty, 4 * NB);
@@ -122,7 +125,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           else tma_load_3d(&tmX, x_full + sx, xs(sx), m0, kt * BK, xb);                // [32 cells][128 genes], linear
         }
         __syncwarp();
-        if (++sx == a.nx) { sx = 0; phx ^= 1; }
+        if (++sx == NX) { sx = 0; phx ^= 1; }
       }
       if (++kt == KT) { kt = 0; if (++arm == a.batch) { arm = 0; ++mt; } }
     }
@@ -143,7 +146,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
       }
       __syncwarp();
-      if (++sw == a.nw) { sw = 0; phw ^= 1; }
+      if (++sw == NW) { sw = 0; phw ^= 1; }
       if (++kt == KT) { kt = 0; if (++arm == a.batch) arm = 0; }
     }
   } else if (warp == 2) {
@@ -203,7 +206,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (seg_end) umma_commit(acc_full + (seg & (NA - 1)));          // this CTA's share of the tile is complete
       }
       __syncwarp();
-      if (++sw == a.nw) { sw = 0; phw ^= 1; }
+      if (++sw == NW) { sw = 0; phw ^= 1; }
       if (++kt == KT) kt = 0;
       if (seg_end) ++seg;
     }
@@ -224,8 +227,8 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     constexpr int ISTEP = NG / NB;
     int kt = kt_first + grp / NB, t = t_first, mt = mt_first, arm = arm_first;
     while (kt >= KT) { kt -= KT; ++t; if (++arm == a.batch) { arm = 0; ++mt; } }
-    int sx = grp % a.nx;
-    uint32_t phx = (uint32_t)((grp / a.nx) & 1);
+    int sx = grp % NX;
+    uint32_t phx = (uint32_t)((grp / NX) & 1);
     uint32_t pha = 1;                                     // parity for a_empty (first use passes)
     for (int i = grp / NB; i < nu; i += ISTEP) {
       const int m0 = (NB * mt + blk) * BM;                // first row (FWD: cell, WGRAD: gene) of this block
@@ -352,7 +355,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       // advance to x-unit j + NG (unit i + NG / NB)
       sx += NG;
-      if (sx >= a.nx) { sx -= a.nx; phx ^= 1; }
+      if (sx >= NX) { sx -= NX; phx ^= 1; }
       kt += ISTEP;
       while (kt >= KT) { kt -= KT; ++t; if (++arm == a.batch) { arm = 0; ++mt; } }
     }
@@ -504,9 +507,14 @@ int launch_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap&
   const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * w_stage + (2 * a.nx + 2 * a.nw + 3 * NA + 6) * 8 + 1024;
   static bool attr[64] = {};
   if (first_on_device(attr)) {
-    MVAE_CUDA(cudaFuncSetAttribute(ts_gemm_kernel<WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(ts_gemm_kernel<WGRAD, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(ts_gemm_kernel<WGRAD, 8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(ts_gemm_kernel<WGRAD, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
-  launch_pdl(ts_gemm_kernel<WGRAD>, dim3((unsigned)G), dim3(THREADS), smem, s, tmX, tmW, tmWlo, a);
+  // (the depths of the reference's fc_dim = 100: 8 + 3 for the 3xTF32 forward, 8 + 5 otherwise)
+  if (a.nx == 8 && a.nw == 5) launch_pdl(ts_gemm_kernel<WGRAD, 8, 5>, dim3((unsigned)G), dim3(THREADS), smem, s, tmX, tmW, tmWlo, a);
+  else if (a.nx == 8 && a.nw == 3) launch_pdl(ts_gemm_kernel<WGRAD, 8, 3>, dim3((unsigned)G), dim3(THREADS), smem, s, tmX, tmW, tmWlo, a);
+  else launch_pdl(ts_gemm_kernel<WGRAD, 0, 0>, dim3((unsigned)G), dim3(THREADS), smem, s, tmX, tmW, tmWlo, a);
   MVAE_LAUNCH_CHECK();
   *U_out = U; *G_out = G;
   return 0;

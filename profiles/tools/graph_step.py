@@ -6,6 +6,8 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "distributed-vae
 import bench
 from mmidas_b200.cpl_mixvae import cpl_mixVAE
 from mmidas_b200 import _lib
+if os.environ.get("MVAE_LIB"):            # (tool only: time an experimental build of the library)
+    _lib.LIB_PATH = os.environ["MVAE_LIB"]
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 40
