@@ -367,7 +367,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wg_tc_kernel(const __grid_cons
   uint64_t* empty = bars + 2 * S;
   uint64_t* tmem_full = bars + 3 * S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
-  float* bm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 3 * S + 2) + 15) & ~uintptr_t(15));   // [128] | [128]
+  uint8_t* bm_raw = reinterpret_cast<uint8_t*>(bars + 3 * S + 2);
+  float* bm = reinterpret_cast<float*>(bm_raw + ((16u - (smem_u32(bm_raw) & 15u)) & 15u));   // [128] | [128], 16-byte aligned
   float* br = bm + 128;
 
   const int BNp = (pr.N + 1 + 15) / 16 * 16;                 // UMMA N: inputs + the ones column

@@ -91,6 +91,13 @@ __device__ __forceinline__ void warp_gemm2(const float* __restrict__ As, int ap,
   }
 }
 
+// Two buffers of a ping-pong pair as "base + index * stride": a run-time index into an ARRAY of pointers makes the compiler
+// lose the shared address space (generic LD / ST with 64-bit addresses in the MMA loops of the multi-tile kernels)
+struct SmemPair {
+  float* base; int stride;
+  __device__ __forceinline__ float* operator[](int i) const { return base + i * stride; }
+};
+
 struct ChainArgs {
   int XP, WPB, Hp;               // pitches (floats) and round8(H)
   const float* params; int64_t p_arm_stride;
@@ -139,8 +146,8 @@ __global__ void __launch_bounds__(128 * MT) dec_chain_fwd_kernel(const ChainArgs
   async_tile(Ws1, WPF, par + p.offW[1], H, H, H, tid, CT);
   cp_async_commit();
 
-  float* Ws[2] = {Ws0, Ws1};
-  float* Xs[2] = {Xs0, Xs1};
+  const SmemPair Ws{Ws0, (int)(Ws1 - Ws0)};
+  const SmemPair Xs{Xs0, (int)(Xs1 - Xs0)};
   constexpr int NTW = 4;
   constexpr int UNR = FAST ? 4 : 1;
 #pragma unroll UNR
@@ -231,8 +238,8 @@ __global__ void __launch_bounds__(128 * MT) dec_chain_bwd_kernel(const ChainArgs
   async_tile(Ws1, WPB, par + p.offW[2], H, H, H, tid, CT);
   cp_async_commit();
 
-  float* Ws[2] = {Ws0, Ws1};
-  float* Ms[2] = {Ms0, Ms1};
+  const SmemPair Ws{Ws0, (int)(Ws1 - Ws0)};
+  const SmemPair Ms{Ms0, (int)(Ms1 - Ms0)};
   constexpr int NTW = 4;
   constexpr int UNR = FAST ? 4 : 1;
 #pragma unroll UNR
@@ -462,8 +469,8 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
     grid_barrier(p.bar + 3, nctas);
   }
 
-  float* Ws[2] = {Ws0, Ws1};
-  float* Xs[2] = {Xs0, Xs1};
+  const SmemPair Ws{Ws0, (int)(Ws1 - Ws0)};
+  const SmemPair Xs{Xs0, (int)(Xs1 - Xs0)};
   constexpr int UNR = FAST ? 4 : 1;
 #pragma unroll UNR
   for (int l = 0; l < 4; ++l) {
@@ -600,8 +607,8 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_multi_kernel(cons
     bias[idx] = j < nout ? par[p.offB[l] + j] : 0.f;
   }
   __syncthreads();
-  float* Ws[2] = {Ws0, Ws1};
-  float* Xs[2] = {Xs0, Xs1};
+  const SmemPair Ws{Ws0, (int)(Ws1 - Ws0)};
+  const SmemPair Xs{Xs0, (int)(Xs1 - Xs0)};
   auto load_tile = [&](int l, int j, float* dst) {      // input tile j of layer l (a1 / a2 / a3 / a4), valid rows only
     const int row0 = ((int)blockIdx.x + j * (int)gridDim.x) * CR;
     const float* src = (l == 0 ? p.a1 : p.aout[l - 1]) + ((int64_t)arm * B + row0) * H;
@@ -761,7 +768,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncB
   async_tile(Ws1, WPB, par + p.offW[3], H, H, H, tid, CT);
   cp_async_commit();
 
-  float* Ws[2] = {Ws0, Ws1};
+  const SmemPair Ws{Ws0, (int)(Ws1 - Ws0)};
   float* As[2] = {As0, As1};
   constexpr int UNR = FAST ? 5 : 1;
 #pragma unroll UNR
@@ -906,7 +913,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_multi_kernel(cons
   cp_async_commit();
   async_tile(Ws1, WPB, par + p.offW[3], H, H, H, tid, CT);
   cp_async_commit();
-  float* Ws[2] = {Ws0, Ws1};
+  const SmemPair Ws{Ws0, (int)(Ws1 - Ws0)};
 
   for (int it = 0; it < 5; ++it) {
     const int l = 4 - it;
