@@ -44,6 +44,8 @@ constexpr uint32_t LT_BASE32B = 1;         // descriptor layout type
 #endif
 // compile-time ring depths: every ring slot and mbarrier address is the shared base plus an immediate
 constexpr int NXC = F11_NX, NWC = F11_NW;
+constexpr int NBS = 2 * NXC;               // bias ring (ROW pass)
+static_assert(2 * NXC + 2 * NWC + 5 * 4 + 4 + 1 <= 64, "the barrier block is 64 words");
 static_assert(NXC % 4 == 0, "the x ring depth must be a multiple of the number of epilogue groups");
 constexpr int TILE_FLOATS = 128 * 128;
 constexpr uint32_t COL_ACC2 = 0, COL_ACC1 = 128, COL_A2 = 256, COL_R = 384;
@@ -93,6 +95,18 @@ __device__ __forceinline__ void dbg_wait(uint64_t* bar, uint32_t parity, int tag
 #else
 #define WAIT(bar, par, tag, idx) mbar_wait(bar, par)
 #endif
+#ifdef F11_STAMPS
+// development only (-DF11_STAMPS, built into a separate library by profiles/tools/f11_stamps.py): clock64 stamps of the
+// protocol events of CTA 0 and CTA 74, first 128 (half-)units, per pass
+__device__ long long g_f11_stamps[2][2][10][128];
+#define STAMP(ev, idx)                                                                                       \
+  do {                                                                                                       \
+    if ((blockIdx.x == 0 || blockIdx.x == 74) && (idx) < 128 && (threadIdx.x & 31) == 0)                     \
+      g_f11_stamps[GENE ? 1 : 0][blockIdx.x ? 1 : 0][ev][idx] = clock64();                                   \
+  } while (0)
+#else
+#define STAMP(ev, idx) do { } while (0)
+#endif
 __device__ __forceinline__ void mbar_wait3(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb, uint64_t* c, uint32_t pc) {
   const bool ra = mbar_try_wait(a, pa), rb = mbar_try_wait(b, pb), rc = mbar_try_wait(c, pc);
   if (!ra) mbar_wait(a, pa);
@@ -127,6 +141,10 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   // CTA's share of a tile is a single unit -- ahead of the tensor pipe; one parity bit cannot tell those apart.
   uint64_t* acc2_full = r_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + NG);
+  // ROW: the 32 bias values of a half-unit travel with its x tile (1-D bulk copy on the same mbarrier) into a ring twice as
+  // deep as the x ring: slot j % NBS is rewritten for half-unit j + NBS, whose copy is issued when the x slot of j + NXC
+  // comes back -- by then the group has finished half-unit j
+  float* bias_s = reinterpret_cast<float*>(bars + 64);          // [NBS][32], 512 bytes behind the (1 KB-aligned) barrier block
 
   const int KP = a.ktiles, KT = 2 * KP;
   const int64_t U = (int64_t)a.batch * a.rtiles * KP, G = gridDim.x;
@@ -165,10 +183,18 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     for (int j = 0; j < nu; ++j) {
       const int xb = a.x_batched ? arm : 0;
       WAIT(x_empty + sx, phx, 1, j);
+      STAMP(0, j);
       if (elect_one()) {
-        mbar_expect_tx(x_full + sx, X_BYTES);
-        if (!GENE) tma_load_3d(&tmX, x_full + sx, xs(sx), kt * UN, rb * 128, xb);    // [128 cells][32 genes], SW128
-        else tma_load_3d(&tmX, x_full + sx, xs(sx), rb * 128, kt * UN, xb);          // [32 cells][128 genes], linear
+        if (!GENE) {
+          const int g0 = kt * UN;
+          const int nb = max(0, min(UN, a.D - g0)) * 4;                              // bias bytes of this half-unit (D % 4 == 0)
+          mbar_expect_tx(x_full + sx, X_BYTES + nb);
+          tma_load_3d(&tmX, x_full + sx, xs(sx), g0, rb * 128, xb);                  // [128 cells][32 genes], SW128
+          if (nb > 0) bulk_load_1d(bias_s + (j % NBS) * UN, a.bias + (int64_t)arm * a.bias_arm_stride + g0, nb, x_full + sx);
+        } else {
+          mbar_expect_tx(x_full + sx, X_BYTES);
+          tma_load_3d(&tmX, x_full + sx, xs(sx), rb * 128, kt * UN, xb);             // [32 cells][128 genes], linear
+        }
       }
       __syncwarp();
       if (++sx == NXC) { sx = 0; phx ^= 1; }
@@ -180,6 +206,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     uint32_t phw = 1;
     for (int i = 0; i < np; ++i) {
       WAIT(w_empty + sw, phw, 2, i);
+      STAMP(1, i);
       if (elect_one()) {
         mbar_expect_tx(w_full + sw, IMG_BYTES);
 #pragma unroll
@@ -210,6 +237,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #else
       mbar_wait3(w_full + sw, phw, acc1_empty + g0, pe, acc1_empty + g0 + 1, pe);
 #endif
+      STAMP(2, i);
       tc_fence_after();
       const uint32_t ta = smem_u32(ts(sw));
       if (elect_one()) {
@@ -246,6 +274,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #else
         mbar_wait2(w_full + sw, phw, a2_full + g, (j / NG) & 1);
 #endif
+        STAMP(3, j);
         tc_fence_after();
         const uint32_t ta = smem_u32(ts(sw)) + (uint32_t)half * 4096u;
         if (elect_one()) {
@@ -329,7 +358,16 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (GENE) bj = row_ok ? __ldg(bias_arm + rb * 128 + r) : 0.f;
       }
       const int c0 = kt * UN;           // first gene (ROW) / cell (GENE) of the half-unit
+      if (quad == 0) STAMP(9, i);
+#ifdef F11_DEBUG
       WAIT(x_full + sx, phx, 9, i);
+      const bool acc1_ready = false;
+#else
+      // both barriers are polled together (a satisfied try_wait still costs its ~170 cycles of latency)
+      const bool x_ready = mbar_try_wait(x_full + sx, phx), acc1_ready = mbar_try_wait(acc1_full + grp, ph1);
+      if (!x_ready) mbar_wait(x_full + sx, phx);
+#endif
+      if (quad == 0) STAMP(4, i);
       const uint8_t* tile = xs(sx);
       // the x tile does not depend on MMA1: read it while the accumulator is still being produced
       float xv[32];
@@ -343,12 +381,14 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) xv[j] = *reinterpret_cast<const float*>(tile + j * 512 + r * 4);
       }
-      WAIT(acc1_full + grp, ph1, 10, i);
+      if (!acc1_ready) WAIT(acc1_full + grp, ph1, 10, i);
+      if (quad == 0) STAMP(5, i);
       tc_fence_after();
       uint32_t acc[32];
       tmem_ld16(tacc1, acc);
       tmem_ld16(tacc1 + 16u, acc + 16);
       tmem_ld_wait();
+      if (quad == 0) STAMP(6, i);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc1_empty + grp);        // the accumulator is in registers (tcgen05.wait::ld)
@@ -361,15 +401,15 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (!GENE) {
           float bb[16];
           const int g0 = c0 + 16 * half;
-          if (g0 + 16 <= a.D) {
+          const float* bsl = bias_s + (i % NBS) * UN + 16 * half;      // delivered with the x tile (broadcast reads)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_arm + g0 + 4 * q));
-              bb[4 * q] = b4.x; bb[4 * q + 1] = b4.y; bb[4 * q + 2] = b4.z; bb[4 * q + 3] = b4.w;
-            }
-          } else {
+          for (int q = 0; q < 4; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bsl + 4 * q);
+            bb[4 * q] = b4.x; bb[4 * q + 1] = b4.y; bb[4 * q + 2] = b4.z; bb[4 * q + 3] = b4.w;
+          }
+          if (g0 + 16 > a.D) {                                          // beyond the matrix the slot holds stale values
 #pragma unroll
-            for (int j = 0; j < 16; ++j) bb[j] = g0 + j < a.D ? __ldg(bias_arm + g0 + j) : 0.f;
+            for (int j = 0; j < 16; ++j) bb[j] = g0 + j < a.D ? bb[j] : 0.f;
           }
           float xh[16];
 #pragma unroll
@@ -402,6 +442,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (want_grad) {
           if (!a2_waited) {
             WAIT(a2_empty + grp, pha, 11, i);
+            if (quad == 0) STAMP(7, i);
             tc_fence_after();
             a2_waited = true;
           }
@@ -409,8 +450,11 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           tmem_st8(ta2 + 16u * half + 8u, dy + 8);
         }
       }
+      // The raw slot goes back only here, after the last USE of the values read from it.  Handing it back right behind the
+      // loads raced (round 1), and so did an arrive made dependent on an OR over all 32 loaded registers (round 2: run-to-run
+      // differences in test_large_batch_unaligned_rows_run_to_run_identical) -- measured, not explained.
       __syncwarp();
-      if (lane == 0) mbar_arrive(x_empty + sx);            // every value read from the x tile has been consumed by now
+      if (lane == 0) mbar_arrive(x_empty + sx);
       if (!GENE && row_ok) { sse += (double)fs; mism += (double)fm; }
       if (want_grad) {
         tmem_st_wait();
@@ -418,6 +462,7 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(a2_full + grp);
       }
+      if (quad == 0) STAMP(8, i);
       ph1 ^= 1;
       pha ^= 1;
       // this half-unit belongs to the last unit of the CTA's share of tile t (both of that unit's groups see it)
@@ -588,8 +633,8 @@ int launch_f11(const CUtensorMap& tmX, const CUtensorMap& tmT, F11Args& a, int64
   // barrier: intermittent launch failures when x rows are not 128-byte aligned, D = 5032 with 6 slots).
   a.nw = NWC;
   a.nx = NXC;
-  static_assert((size_t)NXC * X_BYTES + (size_t)NWC * IMG_BYTES + 2048 <= 227 * 1024, "rings exceed the shared memory of an SM");
-  const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * IMG_BYTES + (2 * a.nx + 2 * a.nw + 5 * NG + 4) * 8 + 1024;
+  static_assert((size_t)NXC * X_BYTES + (size_t)NWC * IMG_BYTES + 64 * 8 + (size_t)NBS * UN * 4 + 1024 <= 227 * 1024, "rings exceed the shared memory of an SM");
+  const size_t smem = (size_t)a.nx * X_BYTES + (size_t)a.nw * IMG_BYTES + 64 * 8 + (size_t)NBS * UN * 4 + 1024;   // rings | barriers | bias ring | alignment
   int dev = 0;
   cudaGetDevice(&dev);
   static bool attr[64] = {};
@@ -727,3 +772,9 @@ int ts_fc11_loss_grad(const mvae_dims& d, const mvae_state& st, const mvae_input
 }
 
 }  // namespace mvae
+
+#ifdef F11_STAMPS
+extern "C" int mvae_debug_f11_stamps(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, mvae::g_f11_stamps, sizeof(mvae::g_f11_stamps));
+}
+#endif
