@@ -44,7 +44,7 @@ constexpr uint32_t LT_BASE32B = 1;         // descriptor layout type
 #endif
 // compile-time ring depths: every ring slot and mbarrier address is the shared base plus an immediate
 constexpr int NXC = F11_NX, NWC = F11_NW;
-constexpr int NBS = 2 * NXC;               // bias ring (ROW pass)
+constexpr int NBS = NXC;                   // bias ring (ROW pass): one slot per x slot
 static_assert(2 * NXC + 2 * NWC + 5 * 4 + 4 + 1 <= 64, "the barrier block is 64 words");
 static_assert(NXC % 4 == 0, "the x ring depth must be a multiple of the number of epilogue groups");
 constexpr int TILE_FLOATS = 128 * 128;
@@ -141,9 +141,8 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   // CTA's share of a tile is a single unit -- ahead of the tensor pipe; one parity bit cannot tell those apart.
   uint64_t* acc2_full = r_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + NG);
-  // ROW: the 32 bias values of a half-unit travel with its x tile (1-D bulk copy on the same mbarrier) into a ring twice as
-  // deep as the x ring: slot j % NBS is rewritten for half-unit j + NBS, whose copy is issued when the x slot of j + NXC
-  // comes back -- by then the group has finished half-unit j
+  // ROW: the 32 bias values of a half-unit travel with its x tile (1-D bulk copy on the same mbarrier) into a slot of their
+  // own per x slot; the x slot is handed back after the last use of both
   float* bias_s = reinterpret_cast<float*>(bars + 64);          // [NBS][32], 512 bytes behind the (1 KB-aligned) barrier block
 
   const int KP = a.ktiles, KT = 2 * KP;
