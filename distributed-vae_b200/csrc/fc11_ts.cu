@@ -368,18 +368,9 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #endif
       if (quad == 0) STAMP(4, i);
       const uint8_t* tile = xs(sx);
-      // the x tile does not depend on MMA1: read it while the accumulator is still being produced
-      float xv[32];
-      if (!GENE) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 t4 = *reinterpret_cast<const float4*>(tile + r * 128 + ((q ^ (r & 7)) << 4));
-          xv[4 * q] = t4.x; xv[4 * q + 1] = t4.y; xv[4 * q + 2] = t4.z; xv[4 * q + 3] = t4.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) xv[j] = *reinterpret_cast<const float*>(tile + j * 512 + r * 4);
-      }
+      // (x is read from the slot chunk by chunk inside the math below: holding all 32 values next to the 32 accumulator
+      // columns spilled the loop state to local memory, which does not fit the small L1 beside 192 KB of shared memory --
+      // the stamps showed 730 cycles of "bookkeeping" per half-unit)
       if (!acc1_ready) WAIT(acc1_full + grp, ph1, 10, i);
       if (quad == 0) STAMP(5, i);
       tc_fence_after();
@@ -398,27 +389,30 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       for (int half = 0; half < 2; ++half) {
         uint32_t dy[16];
         if (!GENE) {
-          float bb[16];
           const int g0 = c0 + 16 * half;
           const float* bsl = bias_s + (i % NBS) * UN + 16 * half;      // delivered with the x tile (broadcast reads)
+          const bool tail = g0 + 16 > a.D;                              // beyond the matrix the bias slot holds stale values
+          float xh[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 b4 = *reinterpret_cast<const float4*>(bsl + 4 * q);
-            bb[4 * q] = b4.x; bb[4 * q + 1] = b4.y; bb[4 * q + 2] = b4.z; bb[4 * q + 3] = b4.w;
-          }
-          if (g0 + 16 > a.D) {                                          // beyond the matrix the slot holds stale values
+            const float4 x4 = *reinterpret_cast<const float4*>(tile + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+            float bq[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float xq[4] = {x4.x, x4.y, x4.z, x4.w};
+            if (tail) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) bb[j] = g0 + j < a.D ? bb[j] : 0.f;
-          }
-          float xh[16];
+              for (int e = 0; e < 4; ++e) bq[e] = g0 + 4 * q + e < a.D ? bq[e] : 0.f;
+            }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float xin = xv[16 * half + j];
-            xh[j] = fmaxf(__uint_as_float(acc[16 * half + j]) + bb[j], 0.f);
-            const float d = xh[j] - xin;
-            fs = fmaf(d, d, fs);
-            fm += ((xh[j] > 0.1f) != (xin > 0.1f)) ? 1.f : 0.f;
-            dy[j] = __float_as_uint(xh[j] > 0.f ? rscale * d : 0.f);
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * q + e;
+              const float xin = xq[e];
+              xh[j] = fmaxf(__uint_as_float(acc[16 * half + j]) + bq[e], 0.f);
+              const float d = xh[j] - xin;
+              fs = fmaf(d, d, fs);
+              fm += ((xh[j] > 0.1f) != (xin > 0.1f)) ? 1.f : 0.f;
+              dy[j] = __float_as_uint(xh[j] > 0.f ? rscale * d : 0.f);
+            }
           }
           if (x_rec && row_ok) {
             float* xr = x_rec + (int64_t)arm * a.xrec_arm_stride + (int64_t)(rb * 128 + r) * a.D + g0;
@@ -432,7 +426,8 @@ fc11_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float xh = fmaxf(__uint_as_float(acc[16 * half + j]) + bj, 0.f);
-            float v = xh > 0.f ? a.gscale * (xh - xv[16 * half + j]) : 0.f;
+            const float xin = *reinterpret_cast<const float*>(tile + (16 * half + j) * 512 + r * 4);
+            float v = xh > 0.f ? a.gscale * (xh - xin) : 0.f;
             if (!all && cell0 + j >= a.B) v = 0.f;
             dbsum += v;
             dy[j] = __float_as_uint(v);
