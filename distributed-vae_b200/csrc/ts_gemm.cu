@@ -230,8 +230,14 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     int sx = grp % NX;
     uint32_t phx = (uint32_t)((grp / NX) & 1);
     uint32_t pha = 1;                                     // parity for a_empty (first use passes)
+    uint64_t dkey = 0;                                    // generator key of (seed, step, global arm): re-read only when the arm changes
+    int key_arm = -1;                                     // (a load per half-unit sat in the middle of the group's latency chain)
     for (int i = grp / NB; i < nu; i += ISTEP) {
       const int m0 = (NB * mt + blk) * BM;                // first row (FWD: cell, WGRAD: gene) of this block
+      if (dp.mode == 2 && arm != key_arm) {
+        dkey = dp.keys[arm];
+        key_arm = arm;
+      }
       mbar_wait(x_full + sx, phx);
       const uint8_t* tile = xs(sx);
       bool waited = false;
@@ -252,7 +258,6 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         // ---- dropout: zero the dropped elements (the 1/(1-p) scale is applied by the fix-up kernel)
         if (dp.mode == 2) {
-          const uint64_t dkey = dp.keys[arm];             // generator key of (seed, step, global arm): L1/L2-resident table
           if (!WGRAD) {
             const uint64_t chunk = (uint64_t)(m0 + r) * Dq + (uint64_t)(kt * 8 + 4 * half);
 #pragma unroll
