@@ -91,6 +91,17 @@ __device__ __forceinline__ void warp_gemm2(const float* __restrict__ As, int ap,
   }
 }
 
+#ifdef CHAIN_STAMPS
+// development only (-DCHAIN_STAMPS, profiles/tools/chain_stamps.py): clock64 at the phase boundaries of CTA (0, 0)
+__device__ long long g_chain_stamps[2][64];
+#define CSTAMP(dir, k)                                                                          \
+  do {                                                                                          \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_chain_stamps[dir][k] = clock64(); \
+  } while (0)
+#else
+#define CSTAMP(dir, k) do { } while (0)
+#endif
+
 // Two buffers of a ping-pong pair as "base + index * stride": a run-time index into an ARRAY of pointers makes the compiler
 // lose the shared address space (generic LD / ST with 64-bit addresses in the MMA loops of the multi-tile kernels)
 struct SmemPair {
@@ -363,6 +374,7 @@ template <int MT, int NWC, int HC, int LC>
 __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncChainArgs p) {
   extern __shared__ __align__(16) float smem[];
   pdl_trigger();
+  CSTAMP(0, 0);
   constexpr int CR = 16 * MT, CT = 32 * MT * NWC, NTW = 16 / NWC;   // MT row groups x NWC column groups of warps
   constexpr bool FAST = HC > 0;
   const int XP = FAST ? (((HC + 7) & ~7) + 4) : p.XP, Hp = FAST ? ((HC + 7) & ~7) : p.Hp;
@@ -468,6 +480,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
     }
     grid_barrier(p.bar + 3, nctas);
   }
+  CSTAMP(0, 1);
 
   const SmemPair Ws{Ws0, (int)(Ws1 - Ws0)};
   const SmemPair Xs{Xs0, (int)(Xs1 - Xs0)};
@@ -492,6 +505,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
     }
     if (l < 3) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
+    CSTAMP(0, 2 + 5 * l);
     // ---- normalise the operand tile in place (rows beyond the batch stay zero)
     float* Xc = Xs[l & 1];
     for (int idx = tid; idx < rows_valid * H; idx += CT) {
@@ -499,6 +513,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
       Xc[r * XP + c] = (Xc[r * XP + c] - mean[c]) * rstd[c];
     }
     __syncthreads();
+    CSTAMP(0, 3 + 5 * l);
     float acc[NTW][4];
 #pragma unroll
     for (int nt = 0; nt < NTW; ++nt)
@@ -516,6 +531,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
         warp_gemm2<NTW, true, true>(Aw, XP, Bw, XP, (H + 7) / 8, nt_used, acc, lane);
       }
     }
+    CSTAMP(0, 4 + 5 * l);
     // ---- epilogue: bias + ReLU -> global a_{l+2}, the next operand tile, fp64 column sums of the valid rows
     float* out = p.aout[l] + ((int64_t)arm * B + row0) * nout;
     float* Xn = Xs[(l + 1) & 1];
@@ -547,6 +563,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
       }
     }
     __syncthreads();                       // Ws[l&1] / Xs[l&1] released, red complete
+    CSTAMP(0, 5 + 5 * l);
     for (int j = tid; j < 256; j += CT) {
       const int which = j >> 7, c = j & 127;
       if (c < nout) {
@@ -564,6 +581,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_fwd_kernel(const EncC
       cp_async_commit();
     }
     if (l < 3) grid_barrier(p.bar + l, nctas);
+    CSTAMP(0, 6 + 5 * l);
   }
 }
 
@@ -730,6 +748,7 @@ template <int MT, int NWC, bool SPLIT, int HC, int LC>
 __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncBwdArgs p) {
   extern __shared__ __align__(16) float smem[];
   pdl_trigger();
+  CSTAMP(1, 0);
   constexpr int CR = 16 * MT, CT = 32 * MT * NWC, NTW = 16 / NWC;
   constexpr bool FAST = HC > 0;
   constexpr int HPC = (HC + 7) & ~7;
@@ -789,6 +808,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncB
     }
     if (it < 4) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
+    CSTAMP(1, 1 + 5 * it);
     // ---- delta_l = bn_bwd(g_l) * relu'(a_l): in place in Gs and to global
     const float* Ac = As[it & 1];
     float* dout = p.delta[l] + rbase * nout;
@@ -804,6 +824,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncB
     if (l == 0) break;
     cp_async_wait<0>();                    // a_{l-1} (needed by the epilogue) has landed
     __syncthreads();
+    CSTAMP(1, 2 + 5 * it);
     float acc[NTW][4];
 #pragma unroll
     for (int nt = 0; nt < NTW; ++nt)
@@ -822,6 +843,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncB
       }
     }
     __syncthreads();                       // all warps have read delta_l before g_{l-1} overwrites it
+    CSTAMP(1, 3 + 5 * it);
     // ---- epilogue: g_{l-1} -> Gs; fp64 sums of g and g * n_{l-1} over the valid rows
     const float* An = As[(it + 1) & 1];
     const int ra = wr * 16 + g, rb = ra + 8;
@@ -852,6 +874,7 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncB
       }
     }
     __syncthreads();
+    CSTAMP(1, 4 + 5 * it);
     for (int j = tid; j < 256; j += CT) {
       const int which = j >> 7, c = j & 127;
       if (c < H) {
@@ -867,7 +890,9 @@ __global__ void __launch_bounds__(32 * MT * NWC) enc_chain_bwd_kernel(const EncB
     }
     cp_async_commit();
     grid_barrier(p.bar + it, nctas);
+    CSTAMP(1, 5 + 5 * it);
   }
+  CSTAMP(1, 26);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1204,3 +1229,9 @@ int launch_enc_chain_bwd(const float* params, int64_t p_arm_stride, const int64_
 }
 
 }  // namespace mvae
+
+#ifdef CHAIN_STAMPS
+extern "C" int mvae_debug_chain_stamps(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, mvae::g_chain_stamps, sizeof(mvae::g_chain_stamps));
+}
+#endif
