@@ -954,14 +954,7 @@ static int tc_fc11_loss_grad_unfused(const mvae_dims& d, const mvae_hparams& hp,
 
 int tc_fc11_loss_grad(const mvae_dims& d, const mvae_hparams& hp, const mvae_state& st, const mvae_inputs& in,
                       const Work& w, float gscale, int want_grad, cudaStream_t s, bool defer_gene_fix) {
-  mvae_layout L;
-  compute_layout(d, &L);
-  const int A = d.n_arm, B = d.batch, D = d.input_dim, H = d.fc_dim;
-  float* work = st.work;
-  double* acc_loss = reinterpret_cast<double*>(work + w.acc_loss);
-  const int split3 = hp.precision == 1 ? (F_SPLIT_A | F_SPLIT_B) : 0;
-  DropSpec nodrop;
-  memset(&nodrop, 0, sizeof(nodrop));
+  double* acc_loss = reinterpret_cast<double*>(st.work + w.acc_loss);
   if (hp.precision == 1) return tc_fc11_loss_grad_unfused(d, hp, st, in, w, gscale, want_grad, s);
   // fused passes: row owner (x_hat, loss sums, d h10), then gene owner (d fc11.weight, d fc11.bias)
   if (!want_grad) return ts_fc11_rows(d, st, in, w, gscale, 0, nullptr, acc_loss, s);

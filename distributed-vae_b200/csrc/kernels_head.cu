@@ -379,7 +379,6 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_bwd_kernel(const HeadA
   const float* cmean = h.colc + 256;   // column mean of q
   const float* cT = h.colc + 384;      // sum_b G*log q
   const int64_t ab = (int64_t)arm * B;
-  const float At = (float)p.At;
   double s1 = 0.0, s2 = 0.0;
 
   for (int row = blockIdx.x * kRowWarps + warp; row < B; row += gridDim.x * kRowWarps) {
@@ -451,7 +450,6 @@ __global__ void __launch_bounds__(kRowWarps * 32, 3) head_bwd_kernel(const HeadA
         const float dl = gq[k] * (gc[k] - dot);                 // d loss / d logits of y
         const float qe = q[k] + p.eps;
         const float lq = logf(qe);
-        const float rr = lq * cw[kk];
         const float G = p.g_coef * p.gdiff[r * C + kk];             // sum_b (r_a - r_b), coupling_rows_kernel
         float g = dl / (p.temp * qe);
         g += G * cw[kk] / qe - cT[kk] * ccv[kk] * (q[k] - cmean[kk]);
